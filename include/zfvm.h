@@ -1,0 +1,189 @@
+/* zfvm.h -- C ABI of the B200 residual path for ZisaFVM-style solvers.
+ *
+ * The reference (1uc/ZisaFVM) has no FFI layer: the operator API its hot path sits behind is the
+ * C++ virtual interface zisa::RateOfChange (include/zisa/ode/rate_of_change.hpp:23-43) plus the
+ * secondary interfaces TimeIntegration::compute_step (include/zisa/ode/time_integration.hpp:42-44),
+ * CFLCondition::operator() (include/zisa/model/cfl_condition.hpp:12-18), BoundaryCondition::apply
+ * (include/zisa/boundary/boundary_condition.hpp:17) and HaloExchange
+ * (include/zisa/parallelization/halo_exchange.hpp:11-21).  Each entry point below names the
+ * reference member function it stands in for; INTEGRATION.md shows the C++ adapter classes a
+ * maintainer adds on the ZisaFVM side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * code on failure with a message available from zfvm_last_error() (the reference reports errors
+ * with LOG_ERR, which prints and terminates -- the adapter turns non-zero into LOG_ERR).
+ * One context per GPU / rank; a context is driven from a single host thread, like
+ * RungeKutta::compute_step drives RateOfChange::compute.  State arrays are row-major
+ * [n_cells][5] doubles in the order (rho, rho v1, rho v2, rho v3, E), the layout of
+ * zisa::AllVariables::cvars (include/zisa/model/all_variables.hpp:31-35).
+ */
+#ifndef ZFVM_H_
+#define ZFVM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zfvm_grid zfvm_grid;         /* flattened host grid (mirrors zisa::Grid) */
+typedef struct zfvm_stencils zfvm_stencils; /* stencil families + least-squares matrices */
+typedef struct zfvm_ctx zfvm_ctx;           /* device context: one GPU, one (sub-)grid */
+
+enum zfvm_dtype { ZFVM_F64 = 0, ZFVM_I32 = 1, ZFVM_I64 = 2, ZFVM_U8 = 3 };
+
+/* ---- errors ---------------------------------------------------------------------------------- */
+const char *zfvm_last_error(void);
+int zfvm_version(void);
+
+/* ---- host precompute: grid ---------------------------------------------------------------------
+ * zfvm_grid_from_mesh  <->  zisa::Grid::Grid(element_type, vertices, vertex_indices, QRDegrees)
+ *                           (src/zisa/grid/grid.cpp:651-723); n_dims = 2 triangles, 3 tetrahedra.
+ * zfvm_grid_mask_ghost <->  zisa::mask_ghost_cells (src/zisa/grid/grid.cpp:1122-1136)
+ * zfvm_grid_set_flags       copies zisa::Grid::cell_flags verbatim (bit0 interior, bit1 ghost_cell,
+ *                           bit2 ghost_cell_l1; include/zisa/grid/cell_flags.hpp:9-15)
+ */
+int zfvm_grid_from_mesh(int n_dims, int64_t n_vertices, const double *vertices, int64_t n_cells,
+                        const int32_t *vertex_indices, int face_deg, int volume_deg, int moments_deg,
+                        zfvm_grid **out);
+int zfvm_grid_mask_ghost(zfvm_grid *grid, const uint8_t *mask);
+int zfvm_grid_set_flags(zfvm_grid *grid, const uint8_t *flags);
+/* Named array access, e.g. "volumes", "cell_centers", "left_right", "neighbours", "edge_indices",
+ * "cell_qp", "cell_qw", "face_qp", "face_qw", "face_normal", "moments", "cell_flags", "inradii", ...
+ * Pointers stay valid until zfvm_grid_free. */
+int zfvm_grid_get(const zfvm_grid *grid, const char *name, const void **data, int *dtype, int *ndim,
+                  int64_t shape[4]);
+int zfvm_grid_info(const zfvm_grid *grid, int64_t info[8]); /* n_dims, n_cells, n_vertices, n_edges,
+                                                               n_interior_edges, q_c, q_f, n_moments */
+void zfvm_grid_free(zfvm_grid *grid);
+
+/* Synthetic meshes (the reference ships no grids, rsync.exclude: grids/ *) and the Hilbert
+ * renumbering of src/renumber_grid.cpp:46-135.  Outputs are malloc'ed; free with zfvm_free. */
+int zfvm_mesh_square(int nx, int ny, double x0, double x1, double y0, double y1, double jitter, uint64_t seed,
+                     int hilbert, int64_t *n_vertices, double **vertices, int64_t *n_cells,
+                     int32_t **vertex_indices);
+int zfvm_mesh_cube(int nx, int ny, int nz, double h, double x0, double y0, double z0, double jitter,
+                   uint64_t seed, int hilbert, const int offset[3], const int global[3], int64_t *n_vertices,
+                   double **vertices, int64_t *n_cells, int32_t **vertex_indices);
+void zfvm_free(void *p);
+
+/* ---- host precompute: stencils -------------------------------------------------------------------
+ * zfvm_stencils_compute <-> zisa::compute_stencil_families (src/zisa/reconstruction/stencil_family.cpp:99-117)
+ *                           + LSQSolver ctor (src/zisa/reconstruction/lsq_solver.cpp:40-47) per stencil.
+ * biases: one char per stencil, 'c' central or 'b' one-sided (stencil_bias.cpp). */
+int zfvm_stencils_compute(const zfvm_grid *grid, int n_stencils, const int *orders, const char *biases,
+                          const double *overfit_factors, uint64_t seed, zfvm_stencils **out);
+/* names: "l2g_offset", "l2g", "order", "size", "local_offset", "local", "k_high", "n_family",
+ * "A_offset", "A" */
+int zfvm_stencils_get(const zfvm_stencils *st, const char *name, const void **data, int *dtype, int *ndim,
+                      int64_t shape[4]);
+void zfvm_stencils_free(zfvm_stencils *st);
+/* LSQSolver::A of stencil k of cell i, row-major rows x cols (lsq_solver.cpp:40-47,168-403) */
+int zfvm_stencil_matrix(const zfvm_grid *grid, const zfvm_stencils *st, int64_t i, int k, double *A, int max_count,
+                        int *rows, int *cols);
+/* all matrices: cell i, stencil k at A[i * A_stride + A_off[k]] */
+int zfvm_stencil_matrices(const zfvm_grid *grid, const zfvm_stencils *st, double *A, int64_t A_stride,
+                          const int64_t *A_off);
+/* W = pinv(A), cols x rows row-major: what the device applies instead of LDLT(A^T A).solve(A^T rhs)
+ * (lsq_solver.cpp:82) */
+int zfvm_pseudo_inverse(const double *A, int rows, int cols, double *W);
+/* reference rules: kind 1 EdgeRule (edge_rule.cpp), 2 TriangularRule (triangular_rule.cpp),
+ * 3 TetrahedralRule (tetrahedral_rule.cpp); Gauss-Legendre nodes by Fourier-Newton (gauss_legendre.hpp) */
+int zfvm_quadrature_rule(int kind, int deg, int *n_points, int *n_bary, double *weights, double *bary, int max_points);
+int zfvm_gauss_legendre(int n, double *points, double *weights);
+int zfvm_deduce_max_order(int stencil_size, double factor, int n_dims); /* stencil.cpp:158-165 */
+
+/* ---- scheme parameters ---------------------------------------------------------------------------- */
+typedef struct zfvm_params {
+  /* HybridWENOParams (include/zisa/reconstruction/hybrid_weno_params.hpp) */
+  int recon_mode;            /* 0 CWENO-AO (cweno_ao.cpp), 1 WENO-AO (weno_ao.cpp) */
+  double linear_weights[8];  /* un-normalised, one per stencil */
+  double epsilon, exponent;
+  /* "well-balancing.mode": 0 constant (NoEquilibrium), 1 isentropic (euler_experiment_impl.hpp:385-397) */
+  int well_balanced;
+  int scaling;               /* 0 UnityScaling, 1 EulerScaling (characteristic_scale.hpp) */
+  int flux;                  /* 0 HLLC (flux/hllc.hpp), 1 Rusanov (not in the reference) */
+  /* IdealGasEOS(gamma, specific_gas_constant) */
+  double gamma, gas_constant;
+  /* gravity (model/gravity_decl.hpp): kind 0 none, 1 constant g, 2 point mass (GM, X),
+   * 3 polytrope (rhoC, K, G), 4 radial table (set with zfvm_set_gravity_table),
+   * 5 user potentials at all quadrature points (zfvm_set_gravity_values);
+   * alignment 0 radial, 1 axial (axis) */
+  int gravity_kind, gravity_alignment;
+  double gravity_p[4];
+  double gravity_axis[3];
+  /* LocalRCParams{steps_per_recompute, recompute_threshold}: only steps_per_recompute == 1 is
+   * supported (the equilibrium is refreshed every stage, local_reconstruction.hpp:87-100) */
+  int steps_per_recompute;
+  int keep_polynomials;      /* diagnostics: store every cell's WENO polynomial */
+} zfvm_params;
+
+void zfvm_params_default(zfvm_params *p);
+
+/* ---- device context --------------------------------------------------------------------------------
+ * zfvm_create builds what EulerExperiment::choose_physical_rate_of_change builds
+ * (include/zisa/experiments/euler_experiment_impl.hpp:303-313): reconstruction array, flux loop,
+ * gravity source loop -- as device-resident weight / index / geometry tables.  The host arrays of
+ * `grid` and `stencils` are only borrowed during the call. */
+int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params, int device,
+                zfvm_ctx **out);
+void zfvm_destroy(zfvm_ctx *ctx);
+int zfvm_set_gravity_table(zfvm_ctx *ctx, const zfvm_grid *grid, int64_t n, const double *radii, const double *phi);
+int zfvm_set_gravity_values(zfvm_ctx *ctx, const double *phi_cell_qp, const double *grad_phi_cell_qp,
+                            const double *phi_face_qp);
+/* bytes of device memory held; algorithmic bytes per cell and RK stage (SURVEY.md 8d formula,
+ * evaluated on the actual stencils) */
+int zfvm_memory_info(const zfvm_ctx *ctx, int64_t *device_bytes, double *algorithmic_bytes_per_cell_stage);
+void *zfvm_stream(zfvm_ctx *ctx); /* cudaStream_t used by all kernels of this context */
+
+/* RateOfChange::compute(tendency, current_state, t) for Sum[FluxLoop, GravitySourceLoop]
+ * (fvm_loops/flux_loop.hpp:96-104, fvm_loops/gravity_source_loop.hpp:32-87,121-148).
+ * accumulate != 0: tendency += rate (the reference contract after ZeroRateOfChange);
+ * accumulate == 0: tendency  = rate (ZeroRateOfChange folded in).
+ * Host version: copies state in, tendency out (and in, when accumulating). */
+int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate);
+int zfvm_rate_of_change_device(zfvm_ctx *ctx, double *tendency_dev, const double *state_dev, double t,
+                               int accumulate);
+
+/* TimeIntegration::compute_step for RungeKutta (src/zisa/ode/runge_kutta.cpp:87-143).
+ * method: "forward_euler", "ssp2", "ssp3", "wicker", "rk4", "fehlberg" (make_tableau :145-213).
+ * The state lives on the device between calls. */
+int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method);
+int zfvm_upload_state(zfvm_ctx *ctx, const double *state_host);
+int zfvm_download_state(zfvm_ctx *ctx, double *state_host);
+double *zfvm_state_device(zfvm_ctx *ctx);
+/* FrozenBC (src/zisa/boundary/frozen_boundary_condition.cpp:11-55): ghost rows are reset to
+ * `steady_state_host` after every stage.  Pass NULL for NoBoundaryCondition. */
+int zfvm_set_frozen_bc(zfvm_ctx *ctx, const double *steady_state_host);
+int zfvm_apply_frozen_bc(zfvm_ctx *ctx, double *state_dev);
+/* One RK step on the resident state.  If dt_next / not_plausible are non-NULL the CFL time step
+ * cfl_number * min inradius/(|v|+a) (LocalCFL, model/local_cfl_condition_impl.hpp:25-40) and the
+ * SanityCheckFor<Euler> flag of the new state come back with it (one 16-byte D2H copy). */
+int zfvm_rk_step(zfvm_ctx *ctx, double t, double dt, double cfl_number, double *dt_next, int *not_plausible);
+/* Same with host buffers: u0_host -> u1_host (one H2D + one D2H copy of the state). */
+int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double t, double dt);
+/* LocalCFL on a device / the resident state */
+int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, double *dt, int *not_plausible);
+int zfvm_synchronize(zfvm_ctx *ctx);
+/* counters: [0] kernels launched since creation, [1] cells whose equilibrium solve failed */
+int zfvm_counters(zfvm_ctx *ctx, int64_t counters[4]);
+/* diagnostics (keep_polynomials): [n_cells][n_coef][5] coefficients in the scaled basis, [n_cells][5] scales */
+int zfvm_download_polynomials(zfvm_ctx *ctx, double *coeffs_host, double *scale_host, int *n_coef);
+int zfvm_download_work(zfvm_ctx *ctx, const char *name, double *host, int64_t max_count);
+
+/* ---- multi-GPU: HaloExchange (src/zisa/mpi/parallelization/mpi_halo_exchange.cpp:109-251) -----------
+ * Local cells are [0, n_owned) owned, then halo cells grouped contiguously per owner rank.
+ * recv_begin/recv_end: rows of the local state that peer p fills; send_index: local rows packed for
+ * peer p (concatenated, send_offset[n_peers+1]).  The exchange itself is NCCL send/recv in one group. */
+int zfvm_nccl_unique_id(char id_out[128]);
+int zfvm_comm_init(zfvm_ctx *ctx, const char id[128], int rank, int n_ranks);
+int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_rank, const int64_t *recv_begin,
+                  const int64_t *recv_end, const int64_t *send_offset, const int32_t *send_index);
+int zfvm_halo_exchange(zfvm_ctx *ctx, double *state_dev); /* post + wait (HaloExchange::operator(), wait) */
+int zfvm_allreduce_min(zfvm_ctx *ctx, double *value);     /* MPIAllReduce MIN (mpi_all_reduce.cpp:16-24) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZFVM_H_ */

@@ -1,0 +1,218 @@
+"""Synthetic set-ups of the BASELINE.json configurations.
+
+The reference ships neither grids nor these experiments; grids come from the seeded
+generators of the host library, initial data are cell averages of analytic fields taken with the cell
+quadrature rule (like ``average(cell, ic)`` in src/zisa/experiments/polytrope.cpp:45-49).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+from .grid import Grid, QRDegrees, WENO_PARAMS, compute_stencil_families, cube_mesh, square_mesh
+from .solver import EulerParams, Gravity
+
+
+@dataclass
+class Case:
+    name: str
+    grid: Grid
+    params: EulerParams
+    u0: np.ndarray          # [n_cells][5]
+    method: str             # Butcher tableau name
+    cfl: float
+    frozen_bc: bool = True
+    stencils: object = None
+
+    def ensure_stencils(self):
+        if self.stencils is None:
+            self.stencils = compute_stencil_families(self.grid, self.params.weno.stencil_family_params)
+        return self.stencils
+
+
+def cell_average(grid: Grid, f: Callable[[np.ndarray], np.ndarray]) -> np.ndarray:
+    """average(cell, f) with the grid's cell rule; f maps points [m][3] -> values [m][k]."""
+    qp = grid.array("cell_qp")          # [n][q][3]
+    qw = grid.array("cell_qw")          # [n][q]
+    vol = grid.array("volumes")
+    n, q, _ = qp.shape
+    vals = f(qp.reshape(-1, 3)).reshape(n, q, -1)
+    acc = qw[:, 0, None] * vals[:, 0]
+    for k in range(1, q):
+        acc = acc + qw[:, k, None] * vals[:, k]
+    return acc / vol[:, None]
+
+
+def cvars_from_primitive(rho, v, p, gamma):
+    u = np.zeros((rho.shape[0], 5))
+    u[:, 0] = rho
+    u[:, 1:4] = rho[:, None] * v
+    u[:, 4] = p / (gamma - 1.0) + 0.5 * rho * np.sum(v * v, axis=1)
+    return u
+
+
+def ghost_ring(grid: Grid, lo, hi, width):
+    """Cells whose centre is within `width` of the box boundary are ghost cells."""
+    c = grid.array("cell_centers")
+    nd = grid.n_dims
+    mask = np.zeros(grid.n_cells, dtype=bool)
+    for d in range(nd):
+        mask |= (c[:, d] < lo[d] + width) | (c[:, d] > hi[d] - width)
+    return mask
+
+
+# ---- C1: 2D isentropic vortex ------------------------------------------------------------------------
+def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: int = 0, jitter: float = 0.15) -> Case:
+    gamma = 1.4
+    verts, vi = square_mesh(n, n, 0.0, 10.0, 0.0, 10.0, jitter=jitter, seed=seed)
+    grid = Grid(2, verts, vi, QRDegrees(face_deg=3, volume_deg=3, moments_deg=4))
+    h = 10.0 / n
+    grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0), (10.0, 10.0), 3.0 * h))
+    beta = 5.0
+
+    def ic(x):
+        dx, dy = x[:, 0] - 5.0, x[:, 1] - 5.0
+        r2 = dx * dx + dy * dy
+        e = np.exp(0.5 * (1.0 - r2))
+        vel = np.zeros((x.shape[0], 3))
+        vel[:, 0] = -beta / (2 * np.pi) * e * dy
+        vel[:, 1] = beta / (2 * np.pi) * e * dx
+        T = 1.0 - (gamma - 1.0) * beta * beta / (8 * gamma * np.pi ** 2) * e * e
+        rho = T ** (1.0 / (gamma - 1.0))
+        return cvars_from_primitive(rho, vel, rho * T, gamma)
+
+    params = EulerParams(weno=WENO_PARAMS[f"2d_o{order}"], flux=flux, gamma=gamma)
+    return Case("isentropic_vortex", grid, params, cell_average(grid, ic), "ssp3", 0.4)
+
+
+# ---- C2: 2D well-balanced polytrope ------------------------------------------------------------------
+def polytrope_alpha(G=1.0, K=1.0):
+    return np.sqrt(2.0 * np.pi * G / K)
+
+
+def polytrope_2d(n: int = 158, order: int = 3, well_balanced: bool = True, amplitude: float = 0.0,
+                 width: float = 0.05, seed: int = 0) -> Case:
+    """gamma = 2 polytrope in hydrostatic equilibrium (src/zisa/experiments/polytrope.cpp:12-63)."""
+    gamma = 2.0
+    verts, vi = square_mesh(n, n, -0.6, 0.6, -0.6, 0.6, jitter=0.15, seed=seed)
+    grid = Grid(2, verts, vi, QRDegrees(face_deg=3, volume_deg=3, moments_deg=4))
+    c = grid.array("cell_centers")
+    grid.mask_ghost_cells(np.linalg.norm(c, axis=1) > 0.5)  # boundary_mask, polytrope.cpp:55-63
+    alpha = polytrope_alpha()
+
+    def ic(x):
+        r = np.linalg.norm(x, axis=1)
+        r_eff = alpha * (r + np.finfo(float).tiny)
+        rho = np.sin(r_eff) / r_eff
+        p = rho * rho * (1.0 + amplitude * np.exp(-((r / width) ** 2)))
+        return cvars_from_primitive(rho, np.zeros((x.shape[0], 3)), p, gamma)
+
+    params = EulerParams(
+        weno=WENO_PARAMS[f"2d_o{order}"], gamma=gamma,
+        well_balancing="isentropic" if well_balanced else "constant",
+        gravity=Gravity(kind="polytrope", params=(1.0, 1.0, 1.0), alignment="radial"),
+    )
+    return Case("polytrope_2d", grid, params, cell_average(grid, ic), "ssp3", 0.4)
+
+
+# ---- C3: 3D Sod / blast --------------------------------------------------------------------------------
+def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, ghost_cubes: int = 2,
+             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None) -> Case:
+    """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}."""
+    gamma = 1.4
+    gn = global_n or n
+    h = 1.0 / gn
+    nx, ny, nz = shape if shape is not None else (n, n, n)
+    verts, vi = cube_mesh(nx, ny, nz, h, jitter=0.1, seed=seed, hilbert=hilbert, offset=offset,
+                          global_shape=(gn, gn, gn) if offset is not None else None)
+    fdeg = 2 if order == 2 else 3
+    grid = Grid(3, verts, vi, QRDegrees(face_deg=fdeg, volume_deg=2, moments_deg=max(order - 1, 2)))
+    if ghost_cubes > 0:
+        grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), ghost_cubes * h))
+
+    def ic(x):
+        m = x.shape[0]
+        vel = np.zeros((m, 3))
+        if kind == "sod":
+            left = x[:, 0] < 0.5
+            rho = np.where(left, 1.0, 0.125)
+            p = np.where(left, 1.0, 0.1)
+        elif kind == "blast":
+            r = np.linalg.norm(x - 0.5, axis=1)
+            rho = np.ones(m)
+            p = np.where(r < 0.1, 10.0, 0.1)
+        else:  # smooth: moving density wave, used for accuracy / parity at high order
+            rho = 1.0 + 0.2 * np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1]) * np.cos(2 * np.pi * x[:, 2])
+            vel[:, 0], vel[:, 1], vel[:, 2] = 0.3, -0.2, 0.1
+            p = 1.0 + 0.1 * np.cos(2 * np.pi * x[:, 0])
+        return cvars_from_primitive(rho, vel, p, gamma)
+
+    params = EulerParams(weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma)
+    method = "ssp2" if order == 2 else "ssp3"
+    return Case(f"{kind}_3d_o{order}", grid, params, cell_average(grid, ic), method, 0.4)
+
+
+# ---- C4: 3D stellar atmosphere -----------------------------------------------------------------------------
+def stellar_atmosphere_3d(n: int = 12, order: int = 3, well_balanced: bool = True, amplitude: float = 1e-3,
+                          seed: int = 0) -> Case:
+    """Isentropic hydrostatic atmosphere in a softened point-mass potential, gamma = 5/3 ideal gas,
+    plus a pressure perturbation.  Orders 2 and 3 have compiled 3D kernels."""
+    gamma = 5.0 / 3.0
+    h = 2.0 / n
+    verts, vi = cube_mesh(n, n, n, h, origin=(-1.0, -1.0, -1.0), jitter=0.1, seed=seed)
+    vdeg = 3 if order >= 3 else 2
+    grid = Grid(3, verts, vi, QRDegrees(face_deg=min(order, 4), volume_deg=vdeg, moments_deg=max(order - 1, 2)))
+    grid.mask_ghost_cells(ghost_ring(grid, (-1.0,) * 3, (1.0,) * 3, 2 * h))
+    GM, X = -1.0, 1.0  # PointMassGravity: phi = GM / (X + r)
+    h_c, K = 4.0, 1.0
+
+    def ic(x):
+        r = np.linalg.norm(x, axis=1)
+        phi = GM / (X + r)
+        hh = h_c + GM / X - phi
+        rho = ((gamma - 1.0) / (gamma * K) * hh) ** (1.0 / (gamma - 1.0))
+        p = K * rho ** gamma * (1.0 + amplitude * np.exp(-((r / 0.3) ** 2)))
+        return cvars_from_primitive(rho, np.zeros((x.shape[0], 3)), p, gamma)
+
+    params = EulerParams(
+        weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma,
+        well_balancing="isentropic" if well_balanced else "constant",
+        gravity=Gravity(kind="point_mass", params=(GM, X), alignment="radial"),
+    )
+    return Case("stellar_atmosphere_3d", grid, params, cell_average(grid, ic), "ssp3", 0.4)
+
+
+def gravity_tables(grid: Grid, gravity: Gravity):
+    """phi / grad phi at all quadrature points, in numpy (independent of the host library's tables).
+    Follows include/zisa/model/gravity_impl.hpp:13-58 and RadialAlignment (gravity_decl.hpp:76-95)."""
+    def phi_dphi(chi):
+        kind, p = gravity.kind, gravity.params
+        if kind == "constant":
+            return p[0] * chi, np.full_like(chi, p[0])
+        if kind == "point_mass":
+            return p[0] / (p[1] + chi), -p[0] / (p[1] + chi) ** 2
+        if kind == "polytrope":
+            rhoC, K, G = p[:3]
+            alpha = np.sqrt(2.0 * np.pi * G / K)
+            ce = alpha * (chi + np.finfo(float).tiny)
+            return -2.0 * K * rhoC * np.sin(ce) / ce, -2.0 * K * rhoC * ((np.cos(ce) - np.sin(ce) / ce) / ce) * alpha
+        raise ValueError(kind)
+
+    def at(x):
+        if gravity.alignment == "radial":
+            r = np.sqrt(x[:, 0] ** 2 + x[:, 1] ** 2 + x[:, 2] ** 2)
+            ph, dph = phi_dphi(r)
+            return ph, dph[:, None] * (x / (r + 1e-50)[:, None])
+        ax = np.asarray(gravity.axis, dtype=float)
+        chi = x @ ax
+        ph, dph = phi_dphi(chi)
+        return ph, dph[:, None] * ax[None, :]
+
+    cq = grid.array("cell_qp").reshape(-1, 3)
+    fq = grid.array("face_qp").reshape(-1, 3)
+    phi_c, g_c = at(cq)
+    phi_f, _ = at(fq)
+    return (phi_c.reshape(grid.n_cells, grid.q_c), g_c.reshape(grid.n_cells, grid.q_c, 3),
+            phi_f.reshape(grid.n_edges, grid.q_f))

@@ -1,0 +1,786 @@
+// C ABI, device part: context creation (layout + upload), residual evaluation, fused
+// Runge-Kutta step, boundary condition, CFL (include/zfvm.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "ctx.hpp"
+
+using namespace zfvm;
+
+namespace {
+
+template <class T>
+int dev_alloc(zfvm_ctx *ctx, T **ptr, std::int64_t count, bool zero = false) {
+  const size_t bytes = (size_t)std::max<std::int64_t>(count, 1) * sizeof(T);
+  void *p = nullptr;
+  ZFVM_CUDA(cudaMalloc(&p, bytes));
+  if (zero) ZFVM_CUDA(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+  ctx->allocations.push_back(p);
+  ctx->device_bytes += (std::int64_t)bytes;
+  *ptr = (T *)p;
+  return 0;
+}
+
+template <class T>
+int dev_upload(zfvm_ctx *ctx, const T **ptr, const std::vector<T> &host) {
+  T *p = nullptr;
+  if (dev_alloc(ctx, &p, (std::int64_t)host.size())) return 1;
+  if (!host.empty()) ZFVM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *ptr = p;
+  return 0;
+}
+
+// Registers a caller-owned host buffer once so later copies run at full PCIe rate. The reference's
+// RungeKutta alternates between a handful of AllVariables buffers (runge_kutta.cpp:109-111).
+void register_host(zfvm_ctx *ctx, const void *p, size_t bytes) {
+  for (auto &r : ctx->registered)
+    if (r.first == p && r.second >= bytes) return;
+  if (ctx->registered.size() >= 32) return;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) {
+    ctx->registered.push_back({p, bytes});
+    return;
+  }
+  cudaGetLastError();
+  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+    ctx->registered.push_back({p, bytes});
+  else
+    cudaGetLastError();  // pageable copy still works
+}
+
+struct Tableau {
+  int n;
+  double a[MAX_RK_STAGES][MAX_RK_STAGES];
+  double b[MAX_RK_STAGES];
+};
+
+// make_tableau, src/zisa/ode/runge_kutta.cpp:145-213
+bool make_tableau(const std::string &m, Tableau &t) {
+  std::memset(&t, 0, sizeof(t));
+  if (m == "forward_euler") {
+    t.n = 1;
+    t.b[0] = 1.0;
+  } else if (m == "ssp2") {
+    t.n = 2;
+    t.a[1][0] = 1.0;
+    t.b[0] = 0.5;
+    t.b[1] = 0.5;
+  } else if (m == "ssp3") {
+    t.n = 3;
+    t.a[1][0] = 1.0;
+    t.a[2][0] = 0.25;
+    t.a[2][1] = 0.25;
+    t.b[0] = 1.0 / 6;
+    t.b[1] = 1.0 / 6;
+    t.b[2] = 2.0 / 3;
+  } else if (m == "wicker") {
+    t.n = 3;
+    t.a[1][0] = 1.0 / 3;
+    t.a[2][1] = 0.5;
+    t.b[2] = 1.0;
+  } else if (m == "rk4") {
+    t.n = 4;
+    t.a[1][0] = 0.5;
+    t.a[2][1] = 0.5;
+    t.a[3][2] = 1.0;
+    t.b[0] = 1.0 / 6;
+    t.b[1] = 1.0 / 3;
+    t.b[2] = 1.0 / 3;
+    t.b[3] = 1.0 / 6;
+  } else if (m == "fehlberg") {
+    t.n = 6;
+    t.a[1][0] = 0.25;
+    t.a[2][0] = 3.0 / 32.0;
+    t.a[2][1] = 9.0 / 32.0;
+    t.a[3][0] = 1932.0 / 2197.0;
+    t.a[3][1] = -7200.0 / 2197.0;
+    t.a[3][2] = 7296.0 / 2197.0;
+    t.a[4][0] = 439.0 / 216.0;
+    t.a[4][1] = -8.0;
+    t.a[4][2] = 3680.0 / 513.0;
+    t.a[4][3] = -845.0 / 4104;
+    t.a[5][0] = -8.0 / 27.0;
+    t.a[5][1] = 2.0;
+    t.a[5][2] = -3544.0 / 2565.0;
+    t.a[5][3] = 1859.0 / 4104.0;
+    t.a[5][4] = -11.0 / 40.0;
+    t.b[0] = 16.0 / 135.0;
+    t.b[2] = 6656.0 / 12825.0;
+    t.b[3] = 28561.0 / 56430.0;
+    t.b[4] = -9.0 / 50.0;
+    t.b[5] = 2.0 / 55.0;
+  } else {
+    return false;
+  }
+  return true;
+}
+
+// One residual evaluation: K1 (reconstruction + traces + source), K2 (face fluxes), K3 (gather /
+// update).  In a multi-rank context the halo exchange is posted first and the tiles whose stencils
+// touch no halo cell are reconstructed while it is in flight (flux_loop.hpp:96-104, with a correct
+// interior set, see SURVEY.md 5 "Distributed backend").
+int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd);
+
+}  // namespace
+
+int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev);
+int zfvm_halo_wait_internal(zfvm_ctx *ctx);
+int zfvm_allreduce_min_internal(zfvm_ctx *ctx, double *dev_value);
+
+namespace {
+
+int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
+  int rc;
+  if (ctx->n_ranks > 1 && ctx->nccl_comm) {
+    if (zfvm_halo_post_internal(ctx, const_cast<double *>(state))) return 1;
+    rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_interior,
+                      ctx->n_tiles_interior, ctx->stream);
+    if (rc) return fail("no reconstruction kernel is compiled for this scheme");
+    if (zfvm_halo_wait_internal(ctx)) return 1;
+    launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_exterior, ctx->n_tiles_exterior,
+                 ctx->stream);
+    ctx->launches += 2;
+  } else {
+    rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, nullptr, ctx->n_tiles, ctx->stream);
+    if (rc) return fail("no reconstruction kernel is compiled for this scheme");
+    ctx->launches += 1;
+  }
+  launch_flux(ctx->plan, ctx->sc, nullptr, ctx->plan.n_interior_edges, ctx->stream);
+  launch_update(ctx->plan, ctx->n_dims, upd, ctx->stream);
+  ctx->launches += 2;
+  ZFVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+UpdateArgs base_update_args(zfvm_ctx *ctx) {
+  UpdateArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.n_cells_update = ctx->n_cells;
+  A.has_source = ctx->sc.has_gravity;
+  A.gamma = ctx->sc.gamma;
+  A.inradius = ctx->inradius;
+  return A;
+}
+
+}  // namespace
+
+extern "C" {
+
+void zfvm_params_default(zfvm_params *p) {
+  std::memset(p, 0, sizeof(*p));
+  p->recon_mode = RECON_CWENO_AO;
+  for (int k = 0; k < 8; ++k) p->linear_weights[k] = 1.0;
+  p->linear_weights[0] = 100.0;
+  p->epsilon = 1e-10;
+  p->exponent = 4.0;
+  p->well_balanced = 0;
+  p->scaling = SCALING_EULER;
+  p->flux = FLUX_HLLC;
+  p->gamma = 1.4;
+  p->gas_constant = 1.0;
+  p->gravity_kind = GRAVITY_NONE;
+  p->steps_per_recompute = 1;
+}
+
+int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params, int device,
+                zfvm_ctx **out) {
+  zfvm_ctx *ctx = nullptr;
+  try {
+    const HostGrid &g = grid->g;
+    const HostStencils &S = stencils->s;
+    const int nd = g.n_dims, F = g.max_neighbours, ns = S.n_stencils;
+    if (S.n_cells != g.n_cells) return fail("zfvm_create: stencils do not belong to this grid");
+    if (params->steps_per_recompute != 1)
+      return fail("zfvm_create: only steps_per_recompute == 1 is supported (local_reconstruction.hpp:87-100)");
+    if (params->well_balanced && params->gravity_kind == GRAVITY_NONE)
+      return fail("zfvm_create: isentropic well-balancing needs a gravity model");
+    if (g.q_f > MAX_QF || g.q_c > MAX_QC) return fail("zfvm_create: quadrature rule too large");
+    if (ns > MAX_STENCILS) return fail("zfvm_create: too many stencils");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+      return fail("zfvm_create: no CUDA device available (the B200 path has no CPU fallback)");
+    ZFVM_CUDA(cudaSetDevice(device));
+
+    ctx = new zfvm_ctx();
+    ctx->device = device;
+    ctx->params = *params;
+    ctx->n_dims = nd;
+    ctx->n_cells = g.n_cells;
+    ctx->n_owned = g.n_cells;
+    const std::int64_t n = g.n_cells, T = (n + TILE - 1) / TILE, E = g.n_edges, EI = g.n_interior_edges;
+    ctx->n_tiles = T;
+    ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+
+    // ---- scheme constants ------------------------------------------------------------------
+    SchemeConst &sc = ctx->sc;
+    std::memset(&sc, 0, sizeof(sc));
+    sc.n_dims = nd;
+    sc.n_stencils = ns;
+    sc.q_f = g.q_f;
+    sc.q_c = g.q_c;
+    sc.recon_mode = params->recon_mode;
+    sc.scaling = params->scaling;
+    sc.flux = params->flux;
+    sc.well_balanced = params->well_balanced;
+    sc.has_gravity = params->gravity_kind != GRAVITY_NONE;
+    sc.epsilon = params->epsilon;
+    sc.exponent = params->exponent;
+    sc.gamma = params->gamma;
+    ctx->deg_hi = S.params.orders[0] - 1;
+    ctx->deg_lo = 0;
+    for (int k = 1; k < ns; ++k) ctx->deg_lo = std::max(ctx->deg_lo, S.params.orders[(size_t)k] - 1);
+    if (ctx->deg_lo > ctx->deg_hi)
+      return fail("zfvm_create: the first stencil must have the highest order (all reference parameter sets do)");
+    if (ns == 1) ctx->deg_lo = std::min(ctx->deg_hi, 1);
+    if ((nd == 2 && ctx->deg_hi >= 5) || (nd == 3 && ctx->deg_hi >= 4))
+      return fail("zfvm_create: LSQ matrices exist up to order 5 in 2D and 4 in 3D (lsq_solver.cpp:288,399)");
+    if (g.n_moments < poly_dof(ctx->deg_hi, nd))
+      return fail("zfvm_create: grid moments_deg is lower than the polynomial degree");
+    double wsum = 0.0;
+    for (int k = 0; k < ns; ++k) wsum += params->linear_weights[k];
+    for (int k = 0; k < ns; ++k) {
+      sc.lin_w[k] = params->linear_weights[k] / wsum;  // hybrid_weno.cpp:26-31
+      sc.rows_max[k] = S.max_size[(size_t)k] - 1;
+      sc.ncoef[k] = poly_dof(k == 0 ? ctx->deg_hi : ctx->deg_lo, nd) - 1;
+    }
+    for (int q = 0; q < g.q_f; ++q) {
+      sc.face_w[q] = g.face_rule.weights[(size_t)q];
+      for (int b = 0; b < g.face_rule.n_bary; ++b) sc.face_bary[q][b] = g.face_rule.bary[(size_t)(q * g.face_rule.n_bary + b)];
+    }
+    for (int q = 0; q < g.q_c; ++q) {
+      sc.cell_w[q] = g.cell_rule.weights[(size_t)q];
+      for (int b = 0; b < g.cell_rule.n_bary; ++b) sc.cell_bary[q][b] = g.cell_rule.bary[(size_t)(q * g.cell_rule.n_bary + b)];
+    }
+
+    DevicePlan &P = ctx->plan;
+    std::memset(&P, 0, sizeof(P));
+    P.n_cells = n;
+    P.n_tiles = T;
+    P.n_edges = E;
+    P.n_interior_edges = EI;
+
+    // ---- stencil indices, weights, meta: built and uploaded in chunks of tiles -----------------
+    std::vector<std::uint64_t> meta((size_t)(T * TILE), 0ull);
+    ctx->tile_max_ref.assign((size_t)T, 0);
+    for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
+    double bytes_W = 0.0, bytes_idx = 0.0, bytes_m = 0.0;
+    std::int64_t n_counted = 0;
+    for (int k = 0; k < ns; ++k) {
+      const int RM = sc.rows_max[k], NC = sc.ncoef[k];
+      std::int32_t *d_sidx = nullptr;
+      double *d_W = nullptr;
+      if (dev_alloc(ctx, &d_sidx, T * RM * TILE) || dev_alloc(ctx, &d_W, T * (std::int64_t)RM * NC * TILE)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+      P.sidx[k] = d_sidx;
+      P.W[k] = d_W;
+      const std::int64_t chunk = 2048;  // tiles per upload
+      std::vector<std::int32_t> h_sidx((size_t)(chunk * RM * TILE));
+      std::vector<double> h_W((size_t)(chunk * RM * NC * TILE));
+      for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
+        const std::int64_t t1 = std::min(T, t0 + chunk);
+        std::fill(h_W.begin(), h_W.end(), 0.0);
+#pragma omp parallel
+        {
+          std::vector<double> A, W;
+#pragma omp for schedule(dynamic, 8)
+          for (std::int64_t t = t0; t < t1; ++t) {
+            for (int lane = 0; lane < TILE; ++lane) {
+              const std::int64_t i = t * TILE + lane;
+              const std::int64_t ic = std::min(i, n - 1);
+              std::int32_t *si = &h_sidx[(size_t)(((t - t0) * RM) * TILE + lane)];
+              for (int j = 0; j < RM; ++j) si[(size_t)j * TILE] = (std::int32_t)ic;
+              if (i >= n || k >= S.n_family[(size_t)i]) continue;
+              const int order = S.order[(size_t)(i * ns + k)];
+              if (order <= 1) continue;
+              int rows, cols;
+              stencil_matrix(A, rows, cols, g, S, i, k);
+              if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
+              W.resize((size_t)(rows * cols));
+              pseudo_inverse(A.data(), rows, cols, W.data());
+              std::int32_t mx = 0;
+              for (int j = 0; j < rows; ++j) {
+                si[(size_t)j * TILE] = S.global(i, k, j + 1);
+                mx = std::max(mx, si[(size_t)j * TILE]);
+              }
+#pragma omp critical(zfvm_tile_max)
+              ctx->tile_max_ref[(size_t)t] = std::max(ctx->tile_max_ref[(size_t)t], mx);
+              double *w = &h_W[(size_t)(((t - t0) * RM) * NC * TILE + lane)];
+              for (int j = 0; j < rows; ++j)
+                for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+#pragma omp atomic
+              meta[(size_t)i] |= ((std::uint64_t)rows) << (8 * k);
+            }
+          }
+        }
+        ZFVM_CUDA(cudaMemcpy(d_sidx + t0 * RM * TILE, h_sidx.data(), (size_t)((t1 - t0) * RM * TILE) * sizeof(std::int32_t),
+                             cudaMemcpyHostToDevice));
+        ZFVM_CUDA(cudaMemcpy(d_W + t0 * RM * NC * TILE, h_W.data(), (size_t)((t1 - t0) * RM * NC * TILE) * sizeof(double),
+                             cudaMemcpyHostToDevice));
+      }
+    }
+    for (std::int64_t i = 0; i < n; ++i) {
+      const bool single = S.n_family[(size_t)i] == 1;
+      meta[(size_t)i] |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
+      if (single) meta[(size_t)i] |= 1ull << 60;
+      if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
+        ++n_counted;
+        bytes_m += S.l2g_size[(size_t)i];
+        for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+          const int order = S.order[(size_t)(i * ns + k)], size = S.size[(size_t)(i * ns + k)];
+          if (order > 1) bytes_W += 8.0 * (size - 1) * (poly_dof(order - 1, nd) - 1);
+          bytes_idx += 4.0 * (size - 1);
+        }
+      }
+    }
+    if (dev_upload(ctx, &P.meta, meta)) {
+      zfvm_destroy(ctx);
+      return 1;
+    }
+
+    // ---- geometry -----------------------------------------------------------------------------
+    const int D = poly_dof(ctx->deg_hi, nd);
+    P.n_mom = std::max(D - 3, 0);
+    {
+      std::vector<double> vtx((size_t)(T * F * 3 * TILE), 0.0), center((size_t)(T * 3 * TILE), 0.0),
+          inv_len((size_t)(T * TILE), 1.0), volume((size_t)(T * TILE), 1.0),
+          mom((size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
+      std::vector<std::uint32_t> fref((size_t)(T * F * TILE), 0u);
+      std::vector<std::uint8_t> fslots((size_t)(T * F * TILE), 0);
+#pragma omp parallel for schedule(static)
+      for (std::int64_t i = 0; i < n; ++i) {
+        const std::int64_t t = i / TILE;
+        const int lane = (int)(i % TILE);
+        for (int k = 0; k < F; ++k) {
+          const Vec3 v = g.vertex(i, k);
+          for (int d = 0; d < 3; ++d) vtx[(size_t)(((t * F + k) * 3 + d) * TILE + lane)] = v[d];
+          const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
+          const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+          std::uint32_t r = (std::uint32_t)e & FREF_EDGE_MASK;
+          if (iL != (std::int32_t)i) r |= FREF_SIDE;
+          if (iR != INVALID) {
+            r |= FREF_INTERIOR;
+            const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+            if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
+          }
+          fref[(size_t)((t * F + k) * TILE + lane)] = r;
+          fslots[(size_t)((t * F + k) * TILE + lane)] = g.face_vertex_slots[(size_t)(i * F + k)];
+        }
+        for (int d = 0; d < 3; ++d) center[(size_t)((t * 3 + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * i + d)];
+        inv_len[(size_t)i] = 1.0 / g.characteristic_length[(size_t)i];
+        volume[(size_t)i] = g.volumes[(size_t)i];
+        for (int m = 0; m < P.n_mom; ++m)
+          mom[(size_t)((t * P.n_mom + m) * TILE + lane)] = g.moments[(size_t)(i * g.n_moments + 3 + m)];
+      }
+      if (E > (std::int64_t)FREF_EDGE_MASK) {
+        zfvm_destroy(ctx);
+        return fail("zfvm_create: too many faces for the packed face reference");
+      }
+      if (dev_upload(ctx, &P.vtx, vtx) || dev_upload(ctx, &P.center, center) || dev_upload(ctx, &P.inv_len, inv_len) ||
+          dev_upload(ctx, &P.volume, volume) || dev_upload(ctx, &P.moments, mom) || dev_upload(ctx, &P.face_ref, fref) ||
+          dev_upload(ctx, &P.face_slots, fslots) || dev_upload(ctx, &P.cell_flags, g.cell_flags)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+      const double *inr = nullptr;
+      if (dev_upload(ctx, &inr, g.inradii)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+      ctx->inradius = const_cast<double *>(inr);
+    }
+    // ---- faces ----------------------------------------------------------------------------------
+    {
+      std::vector<std::int32_t> lr((size_t)(2 * E));
+      std::vector<double> frame((size_t)(10 * E));
+#pragma omp parallel for schedule(static)
+      for (std::int64_t e = 0; e < E; ++e) {
+        std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+        bool skip = (iR == INVALID);
+        if (!skip) skip = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+        lr[(size_t)(2 * e)] = skip ? -1 : iL;
+        lr[(size_t)(2 * e + 1)] = iR;
+        for (int d = 0; d < 3; ++d) {
+          frame[(size_t)(10 * e + d)] = g.face_normal[(size_t)(3 * e + d)];
+          frame[(size_t)(10 * e + 3 + d)] = g.face_t1[(size_t)(3 * e + d)];
+          frame[(size_t)(10 * e + 6 + d)] = g.face_t2[(size_t)(3 * e + d)];
+        }
+        frame[(size_t)(10 * e + 9)] = g.face_area[(size_t)e];
+      }
+      if (dev_upload(ctx, &P.left_right, lr) || dev_upload(ctx, &P.face_frame, frame)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+    }
+    // ---- gravity ----------------------------------------------------------------------------------
+    if (sc.has_gravity) {
+      double *a = nullptr, *b = nullptr, *c = nullptr;
+      if (dev_alloc(ctx, &a, n * g.q_c, true) || dev_alloc(ctx, &b, n * g.q_c * 3, true) ||
+          dev_alloc(ctx, &c, E * g.q_f, true)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+      P.phi_cqp = a;
+      P.gradphi_cqp = b;
+      P.phi_fqp = c;
+      if (params->gravity_kind >= GRAVITY_CONSTANT && params->gravity_kind <= GRAVITY_POLYTROPE) {
+        GravityModel gm;
+        gm.kind = params->gravity_kind;
+        gm.alignment = params->gravity_alignment;
+        for (int q = 0; q < 4; ++q) gm.p[q] = params->gravity_p[q];
+        if (gm.kind == GRAVITY_POINT_MASS && params->gravity_p[2] != 0.0) {
+          // PointMassGravity(G, M, X): GM = G * M
+          gm.p[0] = params->gravity_p[0] * params->gravity_p[1];
+          gm.p[1] = params->gravity_p[2];
+        }
+        for (int d = 0; d < 3; ++d) gm.axis[d] = params->gravity_axis[d];
+        std::vector<double> h_a, h_b, h_c;
+        tabulate_gravity(gm, g, h_a, h_b, h_c);
+        ZFVM_CUDA(cudaMemcpy(a, h_a.data(), h_a.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ZFVM_CUDA(cudaMemcpy(b, h_b.data(), h_b.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ZFVM_CUDA(cudaMemcpy(c, h_c.data(), h_c.size() * sizeof(double), cudaMemcpyHostToDevice));
+      }
+    }
+    // ---- work arrays ------------------------------------------------------------------------------
+    if (dev_alloc(ctx, &P.trace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * NVARS, true) ||
+        dev_alloc(ctx, &P.flux, std::max<std::int64_t>(EI, 1) * NVARS, true) || dev_alloc(ctx, &P.source, n * NVARS, true) ||
+        dev_alloc(ctx, &ctx->eq_fail_dev, 1, true) || dev_alloc(ctx, &ctx->reduce_dev, 1, true)) {
+      zfvm_destroy(ctx);
+      return 1;
+    }
+    P.eq_fail = ctx->eq_fail_dev;
+    P.n_poly_coef = D;
+    if (params->keep_polynomials) {
+      if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+    }
+    ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));
+    // ghost cells (FrozenBC::count_ghost_cells)
+    {
+      std::vector<std::int32_t> gi;
+      for (std::int64_t i = 0; i < n; ++i)
+        if (g.cell_flags[(size_t)i] & FLAG_GHOST) gi.push_back((std::int32_t)i);
+      ctx->n_ghost = (std::int64_t)gi.size();
+      const std::int32_t *p = nullptr;
+      if (dev_upload(ctx, &p, gi)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+      ctx->ghost_index = const_cast<std::int32_t *>(p);
+    }
+    // resident state / RK buffers
+    if (dev_alloc(ctx, &ctx->u_cur, n * NVARS, true) || dev_alloc(ctx, &ctx->u_tmp, n * NVARS, true) ||
+        dev_alloc(ctx, &ctx->tend_work, n * NVARS, true) || dev_alloc(ctx, &ctx->state_work, n * NVARS, true)) {
+      zfvm_destroy(ctx);
+      return 1;
+    }
+
+    // ---- algorithmic bytes per cell and stage -----------------------------------------
+    {
+      const double nc = (double)std::max<std::int64_t>(n_counted, 1);
+      const double B_W = bytes_W / nc, B_idx = bytes_idx / nc + 4.0 * bytes_m / nc, m = bytes_m / nc;
+      const double B_state = 80.0, B_poly = 2.0 * 40.0 * D;
+      const double B_cell = 8.0 * (3 + 1 + 1 + D + 5) + (sc.has_gravity ? 8.0 * 4 * g.q_c : 0.0);
+      const double B_face = (F / 2.0) * (8.0 * (9 + 4 * g.q_f) + 8.0);
+      const double B_wb = sc.well_balanced ? 8.0 * (2 * m + 4.0 * (g.q_c + F * g.q_f)) : 0.0;
+      ctx->algorithmic_bytes = B_W + B_idx + B_state + B_poly + B_cell + B_face + B_wb;  // + B_rk added per tableau
+    }
+    if (zfvm_set_time_integration(ctx, "ssp3")) {
+      zfvm_destroy(ctx);
+      return 1;
+    }
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return 0;
+  } catch (const std::exception &e) {
+    if (ctx) zfvm_destroy(ctx);
+    return fail(std::string("zfvm_create: ") + e.what());
+  }
+}
+
+void zfvm_destroy(zfvm_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto &r : ctx->registered) cudaHostUnregister(const_cast<void *>(r.first));
+  cudaGetLastError();
+  for (void *p : ctx->allocations) cudaFree(p);
+  if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+}
+
+int zfvm_set_gravity_values(zfvm_ctx *ctx, const double *phi_cell_qp, const double *grad_phi_cell_qp,
+                            const double *phi_face_qp) {
+  if (!ctx->sc.has_gravity) return fail("zfvm_set_gravity_values: context was created without gravity");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  const std::int64_t n = ctx->n_cells, E = ctx->plan.n_edges;
+  ZFVM_CUDA(cudaMemcpy(const_cast<double *>(ctx->plan.phi_cqp), phi_cell_qp, (size_t)(n * ctx->sc.q_c) * sizeof(double),
+                       cudaMemcpyHostToDevice));
+  ZFVM_CUDA(cudaMemcpy(const_cast<double *>(ctx->plan.gradphi_cqp), grad_phi_cell_qp,
+                       (size_t)(n * ctx->sc.q_c * 3) * sizeof(double), cudaMemcpyHostToDevice));
+  ZFVM_CUDA(cudaMemcpy(const_cast<double *>(ctx->plan.phi_fqp), phi_face_qp, (size_t)(E * ctx->sc.q_f) * sizeof(double),
+                       cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int zfvm_set_gravity_table(zfvm_ctx *ctx, const zfvm_grid *grid, int64_t n, const double *radii, const double *phi) {
+  if (!ctx->sc.has_gravity) return fail("zfvm_set_gravity_table: context was created without gravity");
+  if (n < 2) return fail("zfvm_set_gravity_table: need at least two table points");
+  GravityModel gm;
+  gm.kind = GRAVITY_TABLE;
+  gm.alignment = ctx->params.gravity_alignment;
+  for (int d = 0; d < 3; ++d) gm.axis[d] = ctx->params.gravity_axis[d];
+  gm.table_r.assign(radii, radii + n);
+  gm.table_phi.assign(phi, phi + n);
+  std::vector<double> a, b, c;
+  tabulate_gravity(gm, grid->g, a, b, c);
+  return zfvm_set_gravity_values(ctx, a.data(), b.data(), c.data());
+}
+
+int zfvm_memory_info(const zfvm_ctx *ctx, int64_t *device_bytes, double *algorithmic_bytes_per_cell_stage) {
+  if (device_bytes) *device_bytes = ctx->device_bytes;
+  if (algorithmic_bytes_per_cell_stage)
+    *algorithmic_bytes_per_cell_stage = ctx->algorithmic_bytes + 40.0 * (1.0 + ctx->n_k_avg) + 40.0;
+  return 0;
+}
+
+void *zfvm_stream(zfvm_ctx *ctx) { return (void *)ctx->stream; }
+
+int zfvm_rate_of_change_device(zfvm_ctx *ctx, double *tendency_dev, const double *state_dev, double /*t*/,
+                               int accumulate) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  UpdateArgs A = base_update_args(ctx);
+  A.tendency = tendency_dev;
+  A.accumulate = accumulate;
+  return residual(ctx, state_dev, A);
+}
+
+int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
+  register_host(ctx, state_host, bytes);
+  register_host(ctx, tendency_host, bytes);
+  ZFVM_CUDA(cudaMemcpyAsync(ctx->state_work, state_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (accumulate)
+    ZFVM_CUDA(cudaMemcpyAsync(ctx->tend_work, tendency_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (zfvm_rate_of_change_device(ctx, ctx->tend_work, ctx->state_work, t, accumulate)) return 1;
+  ZFVM_CUDA(cudaMemcpyAsync(tendency_host, ctx->tend_work, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->n_ranks > 1) {
+    // FluxLoop fills the halo rows of the caller's state (flux_loop.hpp:100, const_cast)
+    for (auto &p : ctx->peers) {
+      const size_t off = (size_t)(p.recv_begin * NVARS), cnt = (size_t)((p.recv_end - p.recv_begin) * NVARS);
+      ZFVM_CUDA(cudaMemcpyAsync(const_cast<double *>(state_host) + off, ctx->state_work + off, cnt * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method) {
+  Tableau t;
+  if (!make_tableau(method, t)) return fail(std::string("Unknown Butcher Tableau. [") + method + "]");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ctx->n_stages = t.n;
+  std::memcpy(ctx->tab_a, t.a, sizeof(t.a));
+  std::memcpy(ctx->tab_b, t.b, sizeof(t.b));
+  double nk = 0.0;
+  for (int s = 1; s <= t.n; ++s) {
+    const double *row = (s < t.n) ? t.a[s] : t.b;
+    for (int j = 0; j < t.n; ++j) nk += (row[j] != 0.0);
+  }
+  ctx->n_k_avg = nk / t.n;
+  for (int s = 0; s + 1 < t.n; ++s)
+    if (!ctx->k[s] && dev_alloc(ctx, &ctx->k[s], ctx->n_cells * NVARS, true)) return 1;
+  return 0;
+}
+
+int zfvm_upload_state(zfvm_ctx *ctx, const double *state_host) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaMemcpyAsync(ctx->u_cur, state_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int zfvm_download_state(zfvm_ctx *ctx, double *state_host) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaMemcpyAsync(state_host, ctx->u_cur, (size_t)(ctx->n_cells * NVARS) * sizeof(double),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+double *zfvm_state_device(zfvm_ctx *ctx) { return ctx->u_cur; }
+
+int zfvm_set_frozen_bc(zfvm_ctx *ctx, const double *steady_state_host) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  if (!steady_state_host) {
+    ctx->frozen = nullptr;
+    return 0;
+  }
+  double *f = nullptr;
+  if (dev_alloc(ctx, &f, ctx->n_cells * NVARS)) return 1;
+  ZFVM_CUDA(cudaMemcpy(f, steady_state_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->frozen = f;
+  return 0;
+}
+
+int zfvm_apply_frozen_bc(zfvm_ctx *ctx, double *state_dev) {
+  if (!ctx->frozen) return 0;
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  launch_frozen_bc(state_dev, ctx->frozen, ctx->ghost_index, ctx->n_ghost, ctx->stream);
+  ctx->launches += 1;
+  ZFVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// RungeKutta::compute_step (runge_kutta.cpp:87-112). Each stage's K3 also forms the next stage
+// state u0 + dt * sum_j a[s+1][j] k_j (or the final sum with b) and applies the boundary condition,
+// so there is no separate axpy pass over the state.
+static int rk_step_impl(zfvm_ctx *ctx, double dt, bool reduce) {
+  const int S = ctx->n_stages;
+  if (reduce) {
+    launch_reset_reduce(ctx->reduce_dev, ctx->stream);
+    ctx->launches += 1;
+  }
+  for (int s = 0; s < S; ++s) {
+    const double *in = (s == 0) ? ctx->u_cur : ctx->u_tmp;
+    const double *coefs = (s + 1 < S) ? ctx->tab_a[s + 1] : ctx->tab_b;
+    UpdateArgs A = base_update_args(ctx);
+    // k_s is needed again iff a later sum uses it
+    bool needed_later = false;
+    for (int r = s + 2; r <= S; ++r) {
+      const double *row = (r < S) ? ctx->tab_a[r] : ctx->tab_b;
+      if (row[s] != 0.0) needed_later = true;
+    }
+    A.tendency = needed_later ? ctx->k[s] : nullptr;
+    A.accumulate = 0;
+    A.u_next = ctx->u_tmp;
+    A.u_base = ctx->u_cur;
+    A.n_prev = s;
+    for (int j = 0; j < s; ++j) {
+      A.k_prev[j] = ctx->k[j];
+      A.coef_prev[j] = coefs[j];
+    }
+    A.coef_cur = coefs[s];
+    A.dt = dt;
+    A.frozen = ctx->frozen;
+    A.reduce_out = (reduce && s + 1 == S) ? ctx->reduce_dev : nullptr;
+    if (residual(ctx, in, A)) return 1;
+  }
+  std::swap(ctx->u_cur, ctx->u_tmp);
+  return 0;
+}
+
+
+int zfvm_rk_step(zfvm_ctx *ctx, double /*t*/, double dt, double cfl_number, double *dt_next, int *not_plausible) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  const bool reduce = (dt_next != nullptr) || (not_plausible != nullptr);
+  if (rk_step_impl(ctx, dt, reduce)) return 1;
+  if (reduce) {
+    if (ctx->n_ranks > 1 && ctx->nccl_comm && zfvm_allreduce_min_internal(ctx, &ctx->reduce_dev->min_dx_over_ev)) return 1;
+    ZFVM_CUDA(cudaMemcpyAsync(ctx->reduce_host, ctx->reduce_dev, sizeof(ReduceOut), cudaMemcpyDeviceToHost, ctx->stream));
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (dt_next) *dt_next = cfl_number * ctx->reduce_host->min_dx_over_ev;
+    if (not_plausible) *not_plausible = ctx->reduce_host->not_plausible;
+  }
+  return 0;
+}
+
+int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double /*t*/, double dt) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
+  register_host(ctx, u0_host, bytes);
+  register_host(ctx, u1_host, bytes);
+  ZFVM_CUDA(cudaMemcpyAsync(ctx->u_cur, u0_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (rk_step_impl(ctx, dt, false)) return 1;
+  ZFVM_CUDA(cudaMemcpyAsync(u1_host, ctx->u_cur, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, double *dt, int *not_plausible) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  if (!state_dev) state_dev = ctx->u_cur;
+  launch_reset_reduce(ctx->reduce_dev, ctx->stream);
+  // owned + physical ghost cells; halo rows are refreshed by the next exchange and are left out
+  // (deviation from local_cfl_condition_impl.hpp:25-40, which also scans stale halo rows)
+  launch_cfl(state_dev, ctx->inradius, ctx->n_ranks > 1 ? ctx->n_owned : ctx->n_cells, ctx->sc.gamma, ctx->reduce_dev,
+             ctx->stream);
+  ctx->launches += 2;
+  if (ctx->n_ranks > 1 && ctx->nccl_comm && zfvm_allreduce_min_internal(ctx, &ctx->reduce_dev->min_dx_over_ev)) return 1;
+  ZFVM_CUDA(cudaMemcpyAsync(ctx->reduce_host, ctx->reduce_dev, sizeof(ReduceOut), cudaMemcpyDeviceToHost, ctx->stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (dt) *dt = cfl_number * ctx->reduce_host->min_dx_over_ev;
+  if (not_plausible) *not_plausible = ctx->reduce_host->not_plausible;
+  return 0;
+}
+
+int zfvm_synchronize(zfvm_ctx *ctx) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int zfvm_counters(zfvm_ctx *ctx, int64_t counters[4]) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  int fails = 0;
+  ZFVM_CUDA(cudaMemcpyAsync(&fails, ctx->eq_fail_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  counters[0] = ctx->launches;
+  counters[1] = fails;
+  counters[2] = ctx->n_tiles_interior;
+  counters[3] = ctx->n_tiles_exterior;
+  return 0;
+}
+
+int zfvm_download_polynomials(zfvm_ctx *ctx, double *coeffs_host, double *scale_host, int *n_coef) {
+  if (!ctx->plan.poly) return fail("zfvm_download_polynomials: create the context with keep_polynomials = 1");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const std::int64_t n = ctx->n_cells;
+  *n_coef = ctx->plan.n_poly_coef;
+  ZFVM_CUDA(cudaMemcpy(coeffs_host, ctx->plan.poly, (size_t)(n * ctx->plan.n_poly_coef * NVARS) * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+  ZFVM_CUDA(cudaMemcpy(scale_host, ctx->plan.poly_scale, (size_t)(n * NVARS) * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int zfvm_download_work(zfvm_ctx *ctx, const char *name, double *host, int64_t max_count) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const std::string s(name);
+  const double *src = nullptr;
+  std::int64_t count = 0;
+  if (s == "trace") {
+    src = ctx->plan.trace;
+    count = ctx->plan.n_interior_edges * 2 * ctx->sc.q_f * NVARS;
+  } else if (s == "flux") {
+    src = ctx->plan.flux;
+    count = ctx->plan.n_interior_edges * NVARS;
+  } else if (s == "source") {
+    src = ctx->plan.source;
+    count = ctx->n_cells * NVARS;
+  } else {
+    return fail("zfvm_download_work: unknown array");
+  }
+  if (count > max_count) return fail("zfvm_download_work: buffer too small");
+  ZFVM_CUDA(cudaMemcpy(host, src, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

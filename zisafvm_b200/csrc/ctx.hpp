@@ -1,0 +1,77 @@
+// Internal definition of the opaque handles of include/zfvm.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zfvm.h"
+#include "device/layout.hpp"
+#include "host/gravity.hpp"
+#include "host/handles.hpp"
+#include "kernels/kernels.hpp"
+
+struct HaloPeer {
+  int rank;
+  std::int64_t recv_begin, recv_end;
+  std::int64_t send_begin, send_end;  // rows in the packed send buffer
+};
+
+struct zfvm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  zfvm::SchemeConst sc{};
+  zfvm::DevicePlan plan{};
+  zfvm_params params{};
+  int n_dims = 0, deg_hi = 0, deg_lo = 0;
+  std::int64_t n_cells = 0, n_tiles = 0;
+  std::vector<void *> allocations;
+  std::int64_t device_bytes = 0;
+  double algorithmic_bytes = 0.0;
+  std::int64_t launches = 0;
+
+  // resident state and Runge-Kutta buffers
+  double *u_cur = nullptr, *u_tmp = nullptr;
+  double *k[zfvm::MAX_RK_STAGES] = {nullptr};
+  double *tend_work = nullptr;  // device tendency for the host entry point
+  double *state_work = nullptr; // device state for the host entry point
+  double *frozen = nullptr;
+  double *inradius = nullptr;
+  std::int32_t *ghost_index = nullptr;
+  std::int64_t n_ghost = 0;
+  zfvm::ReduceOut *reduce_dev = nullptr;
+  zfvm::ReduceOut *reduce_host = nullptr;  // pinned
+  int *eq_fail_dev = nullptr;
+  int n_stages = 0;
+  double tab_a[zfvm::MAX_RK_STAGES][zfvm::MAX_RK_STAGES] = {{0}};
+  double tab_b[zfvm::MAX_RK_STAGES] = {0};
+  double tab_c[zfvm::MAX_RK_STAGES] = {0};
+  double n_k_avg = 2.0;
+
+  // host buffers registered for fast PCIe copies
+  std::vector<std::pair<const void *, size_t>> registered;
+
+  // multi-GPU
+  void *nccl_comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  std::int64_t n_owned = 0;
+  std::vector<HaloPeer> peers;
+  std::int32_t *send_index_dev = nullptr;
+  double *send_buf = nullptr;
+  std::int64_t n_send = 0;
+  std::vector<std::int32_t> tile_max_ref;  // per tile: largest cell index any of its stencils reads
+  std::int32_t *tiles_interior = nullptr, *tiles_exterior = nullptr;
+  std::int64_t n_tiles_interior = 0, n_tiles_exterior = 0;
+};
+
+namespace zfvm {
+void set_error(const std::string &msg);
+int fail(const std::string &msg);
+#define ZFVM_CUDA(call)                                                                     \
+  do {                                                                                      \
+    cudaError_t err__ = (call);                                                             \
+    if (err__ != cudaSuccess)                                                               \
+      return ::zfvm::fail(std::string(#call) + ": " + cudaGetErrorString(err__));           \
+  } while (0)
+}  // namespace zfvm

@@ -1,0 +1,87 @@
+// Device data layout for the per-stage residual path (see DESIGN.md "Data layout in HBM").
+//
+// Cells are grouped in *tiles* of 32 consecutive cells (one warp). Every per-cell array that is
+// only read by the owning cell is stored tile-interleaved, [tile][field][32], so that a warp's
+// access to one field is one fully coalesced 256-byte (FP64) or 128-byte (int32) transaction.
+// Arrays that are gathered through indices (the state, equilibrium potentials, face fluxes) stay
+// row-major AoS, the layout of zisa::GridVariables (grid_variables_decl.hpp:17).
+#pragma once
+#include <cstdint>
+
+namespace zfvm {
+
+constexpr int TILE = 32;
+constexpr int MAX_STENCILS = 6;
+constexpr int NVARS = 5;        // rho, m1, m2, m3, E  (euler_variables.hpp:30-36)
+constexpr int MAX_QF = 8;
+constexpr int MAX_QC = 16;
+
+// face_ref bit layout
+constexpr std::uint32_t FREF_EDGE_MASK = 0x0FFFFFFFu;  // edge index
+constexpr std::uint32_t FREF_SIDE = 1u << 28;           // 0: this cell is the left cell, 1: right
+constexpr std::uint32_t FREF_TRACE = 1u << 29;          // the flux loop needs this cell's trace here
+constexpr std::uint32_t FREF_INTERIOR = 1u << 30;       // edge has two cells
+
+enum GravityKind : int {
+  GRAVITY_NONE = 0,
+  GRAVITY_CONSTANT = 1,     // ConstantGravity       gravity_impl.hpp:13-20
+  GRAVITY_POINT_MASS = 2,   // PointMassGravity      gravity_impl.hpp:22-29
+  GRAVITY_POLYTROPE = 3,    // PolytropeGravity      gravity_impl.hpp:31-58
+  GRAVITY_TABLE = 4,        // SphericalGravity (piecewise-linear table)
+  GRAVITY_USER = 5,         // potentials supplied by the caller at all quadrature points
+};
+enum AlignmentKind : int { ALIGN_RADIAL = 0, ALIGN_AXIAL = 1 };
+enum ScalingKind : int { SCALING_UNITY = 0, SCALING_EULER = 1 };  // characteristic_scale.hpp:14-46
+enum FluxKind : int { FLUX_HLLC = 0, FLUX_RUSANOV = 1 };
+enum ReconMode : int { RECON_CWENO_AO = 0, RECON_WENO_AO = 1 };
+
+/// Quadrature tables and scheme constants, passed by value to kernels (fits the 4 KB param space).
+struct SchemeConst {
+  int n_dims, n_stencils, q_f, q_c;
+  int recon_mode, scaling, flux, well_balanced, has_gravity;
+  int rows_max[MAX_STENCILS];    // padded rows of W_k (= max stencil size - 1)
+  int ncoef[MAX_STENCILS];       // padded coefficient count of stencil k (without the constant)
+  double lin_w[MAX_STENCILS];    // normalised linear weights (hybrid_weno.cpp:26-31)
+  double epsilon, exponent;
+  double gamma;
+  double face_w[MAX_QF];         // reference weights (sum to 1)
+  double face_bary[MAX_QF][3];   // barycentric coordinates w.r.t. the left cell's face vertices
+  double cell_w[MAX_QC];
+  double cell_bary[MAX_QC][4];
+};
+
+/// Raw device pointers of one context. Sizes in comments use n = n_cells, T = n_tiles, E = n_edges.
+struct DevicePlan {
+  std::int64_t n_cells, n_tiles, n_edges, n_interior_edges;
+  // reconstruction
+  const std::int32_t *sidx[MAX_STENCILS];   // [T][rows_max_k][32]  global index of stencil member
+  const double *W[MAX_STENCILS];            // [T][rows_max_k][ncoef_k][32]
+  const std::uint64_t *meta;                // [T][32] byte k: rows of stencil k; byte 7: k_high | single<<4
+  // geometry (tile-interleaved)
+  const double *vtx;                        // [T][F][3][32]
+  const double *center;                     // [T][3][32]
+  const double *inv_len;                    // [T][32]   1 / characteristic_length
+  const double *volume;                     // [T][32]
+  const double *moments;                    // [T][n_mom][32]  c(3 .. n_mom+2)
+  int n_mom;
+  const std::uint32_t *face_ref;            // [T][F][32]
+  const std::uint8_t *face_slots;           // [T][F][32]
+  const std::uint8_t *cell_flags;           // [n]
+  // faces
+  const std::int32_t *left_right;           // [E][2]; left = -1 for faces the flux loop skips
+  const double *face_frame;                 // [E][10]: n(3) t1(3) t2(3) area
+  // gravity tables
+  const double *phi_cqp;                    // [n][q_c]
+  const double *gradphi_cqp;                // [n][q_c][3]
+  const double *phi_fqp;                    // [E][q_f]
+  // work arrays
+  double *trace;                            // [E][2][q_f][5]
+  double *flux;                             // [E][5]
+  double *source;                           // [n][5]
+  double *poly;                             // optional diagnostics [n][n_poly_coef][5]; may be null
+  double *poly_scale;                       // optional [n][5]
+  int n_poly_coef;
+  int *eq_fail;                             // counter of cells whose equilibrium solve failed
+};
+
+}  // namespace zfvm

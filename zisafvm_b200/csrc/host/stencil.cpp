@@ -1,0 +1,428 @@
+// Stencil selection and least-squares matrices.
+//   region-grown candidates, distance sort, truncation   stencil.cpp:192-258
+//   biased stencils: cone at off-vertex, cone at centre, random retry  stencil.cpp:260-393
+//   local/global index bookkeeping                        stencil.cpp:82-104
+//   family: k_biased counter, k_high, achieved order      stencil_family.cpp:15-45,120-136
+//   o1 families for cells that are neither interior nor ghost_l1  stencil_family.cpp:99-117
+//   A assembly                                            lsq_solver.cpp:168-403
+#include <algorithm>
+#include <cmath>
+#include <random>
+#include <stdexcept>
+
+#include "vec3.hpp"
+#include "zfvm_host.hpp"
+
+namespace zfvm {
+
+namespace {
+
+struct Region {
+  int kind = 0;  // 0 full sphere, 2 triangular cone, 3 tetrahedral cone
+  Vec3 A, dB, dC, dD;
+  bool is_inside(Vec3 x) const {
+    if (kind == 0) return true;
+    Vec3 dx = x - A;
+    if (kind == 2) return cross(dB, dx).z >= 0.0 && cross(dx, dC).z >= 0.0;  // cone.cpp:11-14
+    return det3(dB, dC, dx) >= 0.0 && det3(dC, dD, dx) >= 0.0 && det3(dD, dB, dx) >= 0.0;  // :23-32
+  }
+};
+
+struct Selector {
+  const HostGrid &g;
+  RefRule query_rule;  // MAX_*_RULE_DEGREE rule, stencil.cpp:178-190
+  explicit Selector(const HostGrid &g_)
+      : g(g_),
+        query_rule(g_.n_dims == 2 ? make_triangular_rule(MAX_TRIANGULAR_RULE_DEGREE)
+                                  : make_tetrahedral_rule(MAX_TETRAHEDRAL_RULE_DEGREE)) {}
+
+  bool cell_inside(const Region &region, i32 cand) const {
+    if (region.kind == 0) return true;
+    const int F = g.max_neighbours;
+    Vec3 v[4];
+    for (int k = 0; k < F; ++k) v[k] = g.vertex(cand, k);
+    for (int q = 0; q < query_rule.n_points; ++q) {
+      const double *lam = &query_rule.bary[(size_t)q * F];
+      Vec3 x = v[0] * lam[0] + v[1] * lam[1] + v[2] * lam[2];
+      if (F == 4) x = x + v[3] * lam[3];
+      if (region.is_inside(x)) return true;
+    }
+    return region.is_inside(g.center(cand));
+  }
+
+  void candidates(std::vector<i32> &cands, i32 i_center, int n_points, const Region &region) const {
+    const int F = g.max_neighbours;
+    const size_t max_points = (size_t)5 * n_points;
+    cands.clear();
+    cands.push_back(i_center);
+    for (size_t p = 0; p < max_points; ++p) {
+      if (p >= cands.size()) break;
+      i32 j = cands[p];
+      for (int k = 0; k < F; ++k) {
+        i32 cand = g.neighbours[(i64)j * F + k];
+        if (cand == INVALID) continue;
+        if (std::find(cands.begin(), cands.end(), cand) != cands.end()) continue;
+        if (cell_inside(region, cand)) cands.push_back(cand);
+      }
+    }
+  }
+
+  void region_stencil(std::vector<i32> &cands, i32 i_center, int n_points, const Region &region) const {
+    candidates(cands, i_center, n_points, region);
+    Vec3 xc = g.center(i_center);
+    auto closer = [&](i32 a, i32 b) { return norm(g.center(a) - xc) < norm(g.center(b) - xc); };
+    std::sort(cands.begin(), cands.end(), closer);
+    if ((int)cands.size() > n_points) cands.resize((size_t)n_points);
+  }
+
+  Region make_cone(i32 i, Vec3 apex, int k) const {
+    Region r;
+    r.A = apex;
+    r.dB = g.vertex(i, relative_vertex_index(g.n_dims, k, 0)) - apex;
+    r.dC = g.vertex(i, relative_vertex_index(g.n_dims, k, 1)) - apex;
+    if (g.n_dims == 2) {
+      r.kind = 2;
+    } else {
+      r.kind = 3;
+      r.dD = g.vertex(i, relative_vertex_index(g.n_dims, k, 2)) - apex;
+    }
+    return r;
+  }
+
+  bool is_good(const i32 *s, int n, int order) const {
+    std::vector<double> A;
+    int rows, cols;
+    assemble_weno_ao_matrix(A, rows, cols, g, s, n, order);
+    return matrix_rank(A.data(), rows, cols) == cols;
+  }
+
+  // stencil.cpp:355-393; returns false on the reference's LOG_ERR paths.
+  bool biased(std::vector<i32> &s, i32 i, int k, int n_points, int order, std::mt19937 &rng,
+              std::string &err) const {
+    Region r1 = make_cone(i, g.vertex(i, relative_off_vertex_index(g.n_dims, k)), k);
+    region_stencil(s, i, n_points, r1);
+    if ((int)s.size() == n_points && is_good(s.data(), n_points, order)) return true;
+
+    Region r2 = make_cone(i, g.center(i), k);
+    region_stencil(s, i, n_points, r2);
+    if ((int)s.size() == n_points && is_good(s.data(), n_points, order)) return true;
+
+    i64 e = g.edge_indices[(i64)i * g.max_neighbours + k];
+    Vec3 fc{g.face_centers[3 * e], g.face_centers[3 * e + 1], g.face_centers[3 * e + 2]};
+    Region r3 = make_cone(i, fc, k);
+    candidates(s, i, n_points, r3);
+    if ((int)s.size() < n_points) {
+      s.assign(1, i);
+      return true;
+    }
+    if (!is_good(s.data(), (int)s.size(), order)) {
+      err = "It is impossible to find a suitable stencil. i_center = " + std::to_string(i);
+      return false;
+    }
+    // Deviation: the reference re-seeds from std::random_device each iteration
+    // (stencil.cpp:332-334); we use a deterministic per-cell generator.
+    for (int iter = 0; iter < 100; ++iter) {
+      std::shuffle(s.begin() + 1, s.end(), rng);
+      if (is_good(s.data(), n_points, order)) {
+        s.resize((size_t)n_points);
+        return true;
+      }
+    }
+    err = "Did not find a suitable stencil given the candidates. i_center = " + std::to_string(i);
+    return false;
+  }
+};
+
+}  // namespace
+
+// ---- LSQ matrix (lsq_solver.cpp:168-403) ------------------------------------------------------
+void assemble_weno_ao_matrix(std::vector<double> &A, int &n_rows, int &n_cols, const HostGrid &g,
+                             const i32 *stencil, int n, int order) {
+  const int nd = g.n_dims;
+  if (order <= 0) throw std::runtime_error("a non-positive convergence order?");
+  if (order == 1) {
+    n_rows = 1;
+    n_cols = 1;
+    A.assign(1, 1.0);
+    return;
+  }
+  if ((nd == 2 && order >= 6) || (nd == 3 && order >= 5)) throw std::runtime_error("LSQ order not implemented");
+  n_rows = n - 1;
+  n_cols = poly_dof(order - 1, nd) - 1;
+  A.assign((size_t)n_rows * n_cols, 0.0);
+
+  const i32 i0 = stencil[0];
+  const Vec3 x0 = g.center(i0);
+  const double l0 = g.characteristic_length[i0];
+  const double *C0 = &g.moments[(size_t)i0 * g.n_moments];
+  auto idx = [nd](int a, int b) { return nd == 2 ? poly_index2(a, b) : poly_index3(a, b, 0); };
+
+  for (int ii = 0; ii < n_rows; ++ii) {
+    const i32 j = stencil[ii + 1];
+    double *row = &A[(size_t)ii * n_cols];
+    const Vec3 d = (g.center(j) - x0) / l0;
+    const double x_10 = d.x, x_01 = d.y;
+    const double lj = g.characteristic_length[j] / l0;
+    const double *Cj = &g.moments[(size_t)j * g.n_moments];
+
+    row[idx(1, 0) - 1] = x_10;
+    row[idx(0, 1) - 1] = x_01;
+    if (order >= 3) {
+      const int i_20 = idx(2, 0), i_11 = idx(1, 1), i_02 = idx(0, 2);
+      const double x_20 = x_10 * x_10, x_11 = x_10 * x_01, x_02 = x_01 * x_01;
+      const double lj_2 = lj * lj;
+      row[i_20 - 1] = x_20 - C0[i_20] + lj_2 * Cj[i_20];
+      row[i_11 - 1] = x_11 - C0[i_11] + lj_2 * Cj[i_11];
+      row[i_02 - 1] = x_02 - C0[i_02] + lj_2 * Cj[i_02];
+      if (order >= 4) {
+        const int i_30 = idx(3, 0), i_21 = idx(2, 1), i_12 = idx(1, 2), i_03 = idx(0, 3);
+        const double x_30 = x_20 * x_10, x_21 = x_20 * x_01, x_12 = x_11 * x_01, x_03 = x_02 * x_01;
+        const double lj_3 = lj_2 * lj;
+        row[i_30 - 1] = x_30 - C0[i_30] + 3.0 * x_10 * lj_2 * Cj[i_20] + lj_3 * Cj[i_30];
+        row[i_21 - 1] = x_21 - C0[i_21] + x_01 * lj_2 * Cj[i_20] + 2.0 * x_10 * lj_2 * Cj[i_11] + lj_3 * Cj[i_21];
+        row[i_12 - 1] = x_12 - C0[i_12] + x_10 * lj_2 * Cj[i_02] + 2.0 * x_01 * lj_2 * Cj[i_11] + lj_3 * Cj[i_12];
+        row[i_03 - 1] = x_03 - C0[i_03] + 3.0 * x_01 * lj_2 * Cj[i_02] + lj_3 * Cj[i_03];
+        if (order >= 5) {
+          const int i_40 = idx(4, 0), i_31 = idx(3, 1), i_22 = idx(2, 2), i_13 = idx(1, 3), i_04 = idx(0, 4);
+          const double x_40 = x_30 * x_10, x_31 = x_30 * x_01, x_22 = x_21 * x_01, x_13 = x_12 * x_01,
+                       x_04 = x_03 * x_01;
+          const double lj_4 = lj_3 * lj;
+          row[i_40 - 1] = x_40 - C0[i_40] + 6.0 * x_20 * lj_2 * Cj[i_20] + 4.0 * x_10 * lj_3 * Cj[i_30] +
+                          lj_4 * Cj[i_40];
+          row[i_31 - 1] = x_31 - C0[i_31] + 3 * x_11 * lj_2 * Cj[i_20] + 3.0 * x_20 * lj_2 * Cj[i_11] +
+                          x_01 * lj_3 * Cj[i_30] + 3.0 * x_10 * lj_3 * Cj[i_21] + lj_4 * Cj[i_31];
+          row[i_22 - 1] = x_22 - C0[i_22] + x_02 * lj_2 * Cj[i_20] + x_20 * lj_2 * Cj[i_02] +
+                          4 * x_11 * lj_2 * Cj[i_11] + 2.0 * x_01 * lj_3 * Cj[i_21] +
+                          2 * x_10 * lj_3 * Cj[i_12] + lj_4 * Cj[i_22];
+          row[i_13 - 1] = x_13 - C0[i_13] + 3 * x_11 * lj_2 * Cj[i_02] + 3.0 * x_02 * lj_2 * Cj[i_11] +
+                          x_10 * lj_3 * Cj[i_03] + 3.0 * x_01 * lj_3 * Cj[i_12] + lj_4 * Cj[i_13];
+          row[i_04 - 1] = x_04 - C0[i_04] + 6.0 * x_02 * lj_2 * Cj[i_02] + 4.0 * x_01 * lj_3 * Cj[i_03] +
+                          lj_4 * Cj[i_04];
+        }
+      }
+    }
+    if (nd == 3) {
+      const double x = d.x, y = d.y, z = d.z;
+      row[poly_index3(0, 0, 1) - 1] = z;
+      if (order >= 3) {
+        const int i_002 = poly_index3(0, 0, 2), i_101 = poly_index3(1, 0, 1), i_011 = poly_index3(0, 1, 1);
+        const double lj_2 = lj * lj;
+        row[i_002 - 1] = z * z - C0[i_002] + lj_2 * Cj[i_002];
+        row[i_101 - 1] = x * z - C0[i_101] + lj_2 * Cj[i_101];
+        row[i_011 - 1] = y * z - C0[i_011] + lj_2 * Cj[i_011];
+        if (order >= 4) {
+          const int i_003 = poly_index3(0, 0, 3), i_102 = poly_index3(1, 0, 2), i_012 = poly_index3(0, 1, 2),
+                    i_201 = poly_index3(2, 0, 1), i_111 = poly_index3(1, 1, 1), i_021 = poly_index3(0, 2, 1),
+                    i_200 = poly_index3(2, 0, 0), i_020 = poly_index3(0, 2, 0), i_110 = poly_index3(1, 1, 0);
+          const double lj_3 = lj * lj * lj;
+          row[i_003 - 1] = z * z * z - C0[i_003] + 3.0 * z * lj_2 * Cj[i_002] + lj_3 * Cj[i_003];
+          row[i_102 - 1] = x * z * z - C0[i_102] + x * lj_2 * Cj[i_002] + 2.0 * z * lj_2 * Cj[i_101] +
+                           lj_3 * Cj[i_102];
+          row[i_012 - 1] = y * z * z - C0[i_012] + y * lj_2 * Cj[i_002] + 2.0 * z * lj_2 * Cj[i_011] +
+                           lj_3 * Cj[i_012];
+          row[i_201 - 1] = x * x * z - C0[i_201] + z * lj_2 * Cj[i_200] + 2.0 * x * lj_2 * Cj[i_101] +
+                           lj_3 * Cj[i_201];
+          row[i_021 - 1] = y * y * z - C0[i_021] + z * lj_2 * Cj[i_020] + 2.0 * y * lj_2 * Cj[i_011] +
+                           lj_3 * Cj[i_021];
+          row[i_111 - 1] = x * y * z - C0[i_111] + z * lj_2 * Cj[i_110] + y * lj_2 * Cj[i_101] +
+                           x * lj_2 * Cj[i_011] + lj_3 * Cj[i_111];
+        }
+      }
+    }
+  }
+}
+
+// ---- tiny dense linear algebra -------------------------------------------------------------------
+// Singular values by one-sided (Hestenes) Jacobi rotations; rank with Eigen's default
+// threshold  sigma_i > sigma_max * min(rows, cols) * eps  (JacobiSVD::rank()).
+int matrix_rank(const double *A, int rows, int cols) {
+  if (rows < cols) return rows < 0 ? 0 : std::min(rows, cols - 1);  // under-determined: never full column rank
+  std::vector<double> U(A, A + (size_t)rows * cols);
+  auto col_dot = [&](int p, int q) {
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += U[(size_t)r * cols + p] * U[(size_t)r * cols + q];
+    return s;
+  };
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < cols - 1; ++p)
+      for (int q = p + 1; q < cols; ++q) {
+        double app = col_dot(p, p), aqq = col_dot(q, q), apq = col_dot(p, q);
+        if (std::abs(apq) <= 1e-15 * std::sqrt(app * aqq) || apq == 0.0) continue;
+        rotated = true;
+        double zeta = (aqq - app) / (2.0 * apq);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+        for (int r = 0; r < rows; ++r) {
+          double up = U[(size_t)r * cols + p], uq = U[(size_t)r * cols + q];
+          U[(size_t)r * cols + p] = c * up - s * uq;
+          U[(size_t)r * cols + q] = s * up + c * uq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double smax = 0.0;
+  std::vector<double> sv((size_t)cols);
+  for (int p = 0; p < cols; ++p) {
+    sv[(size_t)p] = std::sqrt(col_dot(p, p));
+    smax = std::max(smax, sv[(size_t)p]);
+  }
+  if (smax == 0.0) return 0;
+  const double thresh = smax * std::min(rows, cols) * 2.220446049250313e-16;
+  int rank = 0;
+  for (int p = 0; p < cols; ++p)
+    if (sv[(size_t)p] > thresh) ++rank;
+  return rank;
+}
+
+// W = R^{-1} Q^T by Householder QR in extended precision (rows >= cols, full column rank).
+void pseudo_inverse(const double *A, int rows, int cols, double *W) {
+  using real = long double;
+  std::vector<real> R((size_t)rows * cols), Qt((size_t)rows * rows, 0.0L);
+  for (size_t a = 0; a < R.size(); ++a) R[a] = A[a];
+  for (int r = 0; r < rows; ++r) Qt[(size_t)r * rows + r] = 1.0L;
+  std::vector<real> v((size_t)rows);
+  for (int k = 0; k < cols; ++k) {
+    real nrm = 0.0L;
+    for (int r = k; r < rows; ++r) nrm += R[(size_t)r * cols + k] * R[(size_t)r * cols + k];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0.0L) continue;
+    real alpha = (R[(size_t)k * cols + k] > 0 ? -nrm : nrm);
+    real vn = 0.0L;
+    for (int r = k; r < rows; ++r) {
+      v[(size_t)r] = R[(size_t)r * cols + k] - (r == k ? alpha : 0.0L);
+      vn += v[(size_t)r] * v[(size_t)r];
+    }
+    if (vn == 0.0L) continue;
+    for (int c = k; c < cols; ++c) {
+      real s = 0.0L;
+      for (int r = k; r < rows; ++r) s += v[(size_t)r] * R[(size_t)r * cols + c];
+      s = 2.0L * s / vn;
+      for (int r = k; r < rows; ++r) R[(size_t)r * cols + c] -= s * v[(size_t)r];
+    }
+    for (int c = 0; c < rows; ++c) {
+      real s = 0.0L;
+      for (int r = k; r < rows; ++r) s += v[(size_t)r] * Qt[(size_t)r * rows + c];
+      s = 2.0L * s / vn;
+      for (int r = k; r < rows; ++r) Qt[(size_t)r * rows + c] -= s * v[(size_t)r];
+    }
+  }
+  // back substitution: W[:, c] = R^{-1} Qt[0:cols, c]
+  for (int c = 0; c < rows; ++c) {
+    for (int i = cols - 1; i >= 0; --i) {
+      real s = Qt[(size_t)i * rows + c];
+      for (int j = i + 1; j < cols; ++j) s -= R[(size_t)i * cols + j] * v[(size_t)j];
+      v[(size_t)i] = s / R[(size_t)i * cols + i];
+    }
+    for (int i = 0; i < cols; ++i) W[(size_t)i * rows + c] = (double)v[(size_t)i];
+  }
+}
+
+// ---- families --------------------------------------------------------------------------------------
+void compute_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyParams &params, std::uint64_t seed) {
+  const i64 n = g.n_cells;
+  const int ns = params.n_stencils();
+  const int nd = g.n_dims;
+  S = HostStencils();
+  S.n_cells = n;
+  S.n_dims = nd;
+  S.n_stencils = ns;
+  S.params = params;
+  S.max_size.resize((size_t)ns);
+  S.local_off.assign((size_t)ns + 1, 0);
+  for (int k = 0; k < ns; ++k) {
+    S.max_size[(size_t)k] = required_stencil_size(params.orders[(size_t)k] - 1, params.overfit_factors[(size_t)k], nd);
+    S.local_off[(size_t)k + 1] = S.local_off[(size_t)k] + S.max_size[(size_t)k];
+  }
+  const int L = S.local_off[(size_t)ns];
+  S.l2g_stride = L;
+  S.l2g_size.assign((size_t)n, 1);
+  S.l2g.assign((size_t)(n * L), INVALID);
+  S.local.assign((size_t)(n * L), 0);
+  S.order.assign((size_t)(n * ns), 1);
+  S.size.assign((size_t)(n * ns), 0);
+  S.k_high.assign((size_t)n, 0);
+  S.family_order.assign((size_t)n, 1);
+  S.n_family.assign((size_t)n, 1);
+  Selector sel(g);
+  int error = 0;
+  std::string error_msg;
+
+#pragma omp parallel
+  {
+    std::vector<i32> s;
+#pragma omp for schedule(dynamic, 256)
+    for (i64 i = 0; i < n; ++i) {
+      i32 *l2g = &S.l2g[(size_t)(i * L)];
+      i32 *local = &S.local[(size_t)(i * L)];
+      i32 *order = &S.order[(size_t)(i * ns)];
+      i32 *size = &S.size[(size_t)(i * ns)];
+      int n_l2g = 0;
+      const bool full = (g.cell_flags[i] & FLAG_INTERIOR) || (g.cell_flags[i] & FLAG_GHOST_L1);
+      if (!full) {  // StencilFamilyParams{{1}, {"c"}, {1.0}}
+        l2g[0] = (i32)i;
+        S.l2g_size[(size_t)i] = 1;
+        order[0] = 1;
+        size[0] = 1;
+        continue;
+      }
+      std::mt19937 rng((std::uint32_t)(seed * 2654435761u + (std::uint64_t)i));
+      int k_biased = 0;
+      for (int k = 0; k < ns; ++k) {
+        const int max_order = params.orders[(size_t)k];
+        const double factor = params.overfit_factors[(size_t)k];
+        const int max_size = S.max_size[(size_t)k];
+        if (params.biases[(size_t)k] == 1) {
+          std::string err;
+          if (!sel.biased(s, (i32)i, k_biased, max_size, max_order, rng, err)) {
+#pragma omp critical
+            {
+              error = 1;
+              error_msg = err;
+            }
+            s.assign(1, (i32)i);
+          }
+          ++k_biased;
+        } else {
+          Region full_sphere;
+          sel.region_stencil(s, (i32)i, max_size, full_sphere);
+        }
+        // assign_local_indices, stencil.cpp:82-104 (every found cell enters l2g)
+        i32 *loc = local + S.local_off[(size_t)k];
+        for (size_t a = 0; a < s.size(); ++a) {
+          i32 *it = std::find(l2g, l2g + n_l2g, s[a]);
+          loc[a] = (i32)(it - l2g);
+          if (it == l2g + n_l2g) l2g[n_l2g++] = s[a];
+        }
+        order[k] = deduce_max_order((int)s.size(), factor, nd);
+        size[k] = required_stencil_size(order[k] - 1, factor, nd);
+      }
+      S.l2g_size[(size_t)i] = n_l2g;
+      S.n_family[(size_t)i] = ns;
+      int fo = 1;
+      for (int k = 0; k < ns; ++k) fo = std::max(fo, (int)order[k]);
+      S.family_order[(size_t)i] = fo;
+      int kh = 0;  // highest_order_central_stencil, stencil_family.cpp:120-136
+      for (int k = 1; k < ns; ++k) {
+        if (order[k] > order[kh])
+          kh = k;
+        else if (order[k] == order[kh] && params.biases[(size_t)k] == 0)
+          kh = k;
+      }
+      S.k_high[(size_t)i] = kh;
+    }
+  }
+  S.error = error;
+  S.error_msg = error_msg;
+}
+
+void stencil_matrix(std::vector<double> &A, int &rows, int &cols, const HostGrid &g, const HostStencils &s,
+                    i64 i, int k) {
+  const int size = s.size[(size_t)(i * s.n_stencils + k)];
+  const int order = s.order[(size_t)(i * s.n_stencils + k)];
+  i32 glob[128];
+  for (int j = 0; j < size; ++j) glob[j] = s.global(i, k, j);
+  assemble_weno_ao_matrix(A, rows, cols, g, glob, size, order);
+}
+
+}  // namespace zfvm

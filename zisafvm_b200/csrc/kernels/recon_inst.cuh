@@ -1,0 +1,50 @@
+// Instantiation helper: one translation unit per (n_dims, high degree) keeps nvcc compile times parallel.
+#pragma once
+#include "kernels.hpp"
+#include "recon.cuh"
+
+namespace zfvm {
+
+template <int ND, int DEG_HI, int DEG_LO, int NS>
+int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const double *state,
+                          const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream) {
+  ReconArgs args;
+  args.plan = plan;
+  args.state = state;
+  args.tile_list = tile_list;
+  args.n_tiles_launch = n_tiles;
+  if (n_tiles <= 0) return 0;
+  const int block = 128;  // 4 tiles per CTA
+  const unsigned grid = (unsigned)((n_tiles + 3) / 4);
+  if (sc.well_balanced)
+    recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED><<<grid, block, 0, stream>>>(args, sc);
+  else if (sc.has_gravity)
+    recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_GRAVITY><<<grid, block, 0, stream>>>(args, sc);
+  else
+    recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_PLAIN><<<grid, block, 0, stream>>>(args, sc);
+  return 0;
+}
+
+#define ZFVM_DECLARE_RECON(ND, DEG_HI)                                                                   \
+  int launch_recon_##ND##d_deg##DEG_HI(const DevicePlan &plan, const SchemeConst &sc, int deg_lo,       \
+                                       const double *state, const std::int32_t *tile_list,              \
+                                       std::int64_t n_tiles, cudaStream_t stream)
+
+#define ZFVM_DEFINE_RECON(ND, DEG_HI)                                                                    \
+  ZFVM_DECLARE_RECON(ND, DEG_HI) {                                                                       \
+    if (sc.n_stencils != ND + 2) return 1;                                                               \
+    if (deg_lo == 1 || (DEG_HI == 0 && deg_lo == 0))                                                     \
+      return launch_recon_variants<ND, DEG_HI, (DEG_HI >= 1 ? 1 : 0), ND + 2>(plan, sc, state, tile_list, \
+                                                                               n_tiles, stream);         \
+    return 1;                                                                                            \
+  }
+
+ZFVM_DECLARE_RECON(2, 1);
+ZFVM_DECLARE_RECON(2, 2);
+ZFVM_DECLARE_RECON(2, 3);
+ZFVM_DECLARE_RECON(2, 4);
+ZFVM_DECLARE_RECON(3, 1);
+ZFVM_DECLARE_RECON(3, 2);
+ZFVM_DECLARE_RECON(3, 3);
+
+}  // namespace zfvm
