@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the per-RK-stage residual path (BASELINE.json metric: cell-updates/s per RK stage).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores (oracle port)
+
+One "step" is one SSP-RK time step = `stages` passes of the hot path (reconstruction, face fluxes, gather +
+stage update + boundary condition) over the whole grid.  `value` = owned non-ghost cells x stages x K / time with
+the state resident in HBM; `e2e` = the same metric through the reference-facing call RateOfChange::compute
+(zfvm_rate_of_change) with HOST buffers, i.e. one H2D copy of the state and one D2H copy of the tendency per stage.
+
+Workload at N=1: BASELINE config[2] "3D Sod/blast on synthetic ~10M-tetrahedra grid, order 3, single B200"
+(118^3 cubes x 6 = 9 858 192 tets, CWENO-AO {3,2,2,2,2}, HLLC, SSP3) -- the configuration the north-star's
+">= 60 % of HBM roofline on one B200" target is quoted on.  N>1: weak scaling, every rank owns an equal box of a
+global lattice (NCCL halo exchange per stage).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cell_updates_per_sec_per_rk_stage"
+UNIT = "cell-updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("ZFVM_BENCH_N", "118")), help="cubes per direction per GPU")
+    ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--kind", default="blast")
+    ap.add_argument("--cpu-n", type=int, default=32, help="cubes per direction of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def rank_box(rank: int, n_ranks: int):
+    """Weak scaling: ranks tile a (px, py, pz) arrangement of equal boxes."""
+    shapes = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+    if n_ranks not in shapes:
+        raise SystemExit(f"--gpus must be one of {sorted(shapes)}")
+    px, py, pz = shapes[n_ranks]
+    return (px, py, pz), (rank % px, (rank // px) % py, rank // (px * py))
+
+
+def cpu_reference_run(args, steps: int, warmup: int):
+    """The reference algorithm (CPU oracle port, OpenMP on all host cores) on a bounded sample of the workload."""
+    from oracle import binding as ob
+    from zisafvm_b200 import cases
+
+    case = cases.blast_3d(n=args.cpu_n, order=args.order, kind=args.kind)
+    st = case.ensure_stencils()
+    ora = ob.Oracle(case.grid, st, case.params)
+    ora.set_frozen_bc(case.u0)
+    n_int = int((~case.grid.is_ghost).sum())
+    stages = {"ssp3": 3, "ssp2": 2}[case.method]
+    dt = ora.cfl_dt(case.u0, case.cfl)
+    u = case.u0
+    for _ in range(warmup):
+        u = ora.rk_step(case.method, u, dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u = ora.rk_step(case.method, u, dt)
+    el = time.perf_counter() - t0
+    value = n_int * stages * steps / el
+    sample = (f"{case.grid.n_cells} tets ({args.cpu_n}^3 cubes x 6) of the same 3D {args.kind} order-{args.order} workload, "
+              f"{steps} {case.method} steps")
+    return value, el / steps * 1e3, ob.num_threads(), sample, case
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    value, ms, cores, sample, case = cpu_reference_run(args, steps, warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D {args.kind}, CWENO-AO order {args.order}, HLLC, {case.method}; reference algorithm "
+                               f"restated on the CPU (oracle port; the reference binary cannot be built here)",
+                   "cells": int(case.grid.n_cells), "l2_flush": "state + weights larger than any cache"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import zisafvm_b200 as z
+    from zisafvm_b200 import cases
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if world != args.gpus:
+            raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+
+    t_setup = time.perf_counter()
+    if distributed:
+        from zisafvm_b200 import distributed as zd
+
+        sub = zd.make_weak_scaling_case(rank, world, n=args.n, order=args.order, kind=args.kind)
+        case, ctx = sub.case, sub.ctx
+        n_counted = sub.n_counted
+    else:
+        case = cases.blast_3d(n=args.n, order=args.order, kind=args.kind)
+        st = case.ensure_stencils()
+        ctx = z.CudaContext(case.grid, st, case.params, device=local_rank)
+        n_counted = int((~case.grid.is_ghost).sum())
+    n = case.grid.n_cells
+    rk = z.CudaRungeKutta(ctx, case.method)
+    z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+    stages = {"ssp3": 3, "ssp2": 2}[case.method]
+    rk.upload(z.AllVariables(n, case.u0))
+    dt_next, bad = z.LocalCFL(ctx, case.cfl)()
+    dt = 0.5 * dt_next
+    setup_s = time.perf_counter() - t_setup
+    dev_bytes, alg_bytes = ctx.memory_info()
+
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+
+    # ---- device-resident timing --------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        rk.step(0.0, dt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.counters()["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        rk.step(0.0, dt)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.counters()["launches"] - launches0
+    if distributed:
+        tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+        cnt = torch.tensor([n_counted], device="cuda", dtype=torch.int64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_counted = int(cnt.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    else:
+        total_counted = n_counted
+    value = total_counted * stages * args.steps / (ms_total * 1e-3)
+    state_ok = not rk.step(0.0, dt, case.cfl)[1]
+
+    # ---- per-kernel timing for the roofline (separate pass; event pairs around every launch) ----------------
+    ctx.profile(True)
+    prof_steps = max(2, min(args.steps, 5))
+    for _ in range(prof_steps):
+        rk.step(0.0, dt)
+    kms, kcnt = ctx.profile_read()
+    ctx.profile(False)
+    peak, peak_src = measured_peak_gbs()
+    D = {2: 4, 3: 10, 4: 20}[args.order]
+    b_k2 = 40.0 * D + 2.0 * (8.0 * (9 + 4 * case.grid.q_f) + 8.0)      # polynomial read + face data  (F/2 = 2)
+    b_k3 = 40.0 + 40.0 * (1.0 + {3: 2.0, 2: 1.5}[stages]) + 40.0        # tendency write + RK sum
+    b_k1 = alg_bytes - b_k2 - b_k3
+    t_k1 = kms[0] / max(kcnt[0], 1) * 1e-3
+    ach_k1 = n_counted * b_k1 / t_k1 / 1e9
+    t_stage = sum(kms) / max(kcnt[0], 1) * 1e-3
+    roofline = {
+        "bound": "hbm", "kernel": "recon_kernel (K1: stencil-weight apply + CWENO-AO + traces)",
+        "achieved": ach_k1, "peak": peak, "unit": "GB/s", "frac": ach_k1 / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_cell": {"K1": b_k1, "K2": b_k2, "K3": b_k3, "stage": alg_bytes},
+        "kernel_ms": {"K1_recon": kms[0] / max(kcnt[0], 1), "K2_flux": kms[1] / max(kcnt[1], 1),
+                      "K3_update": kms[2] / max(kcnt[2], 1)},
+        "stage": {"achieved": n_counted * alg_bytes / t_stage / 1e9, "frac": n_counted * alg_bytes / t_stage / 1e9 / peak},
+    }
+
+    # ---- end to end through RateOfChange::compute with host buffers ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        roc = z.CudaEulerRateOfChange(ctx)
+        h_state = torch.from_numpy(case.u0.copy()).pin_memory()
+        h_tend = torch.zeros_like(h_state).pin_memory()
+        s_av = z.AllVariables(n, h_state.numpy())
+        t_av = z.AllVariables(n, h_tend.numpy())
+        calls = max(3, min(3 * args.steps, 9))
+        for _ in range(2):
+            roc.compute(t_av, s_av, 0.0, accumulate=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            roc.compute(t_av, s_av, 0.0, accumulate=False)
+        barrier()
+        el = time.perf_counter() - t0
+        if distributed:
+            tm = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            el = float(tm.item())
+        checksum = float(np.abs(t_av.cvars).sum())
+        e2e = {"value": total_counted * calls / el, "unit": UNIT, "h2d_bytes_per_step": int(n * 40 * stages),
+               "d2h_bytes_per_step": int(n * 40 * stages), "call": "zfvm_rate_of_change (RateOfChange::compute), host buffers",
+               "calls": calls, "tendency_l1": checksum}
+        # TimeIntegration::compute_step with host buffers (one H2D + one D2H per time step)
+        u_av = z.AllVariables(n, h_state.numpy())
+        rk.compute_step(u_av, 0.0, dt)
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            rk.compute_step(u_av, 0.0, dt)
+        barrier()
+        el2 = time.perf_counter() - t0
+        e2e["compute_step_value"] = n_counted * stages * reps / el2 * (world if distributed else 1)
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline and not distributed:
+        v, ms, cores, sample, _ = cpu_reference_run(args, steps=2, warmup=1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets per GPU, CWENO-AO order {args.order} "
+                            f"{{3,2,2,2,2}}, HLLC, {case.method}, FrozenBC ghost shell",
+                "cells_per_gpu": int(n), "counted_cells": int(total_counted), "stages_per_step": stages,
+                "device_bytes": int(dev_bytes), "setup_seconds": round(setup_s, 1),
+                "l2_flush": "inputs larger than L2 (weights + state >> 126 MB per stage)",
+                "parallelism": f"domain decomposition x{world}" if distributed else "single GPU",
+            },
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "state_plausible": bool(state_ok),
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -166,6 +166,10 @@ int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, dou
 /* LocalCFL on a device / the resident state */
 int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, double *dt, int *not_plausible);
 int zfvm_synchronize(zfvm_ctx *ctx);
+/* per-kernel device timing: CUDA events around K1 (reconstruction), K2 (face flux), K3 (update) of every
+ * residual evaluation while enabled; read returns the summed milliseconds and the launch counts */
+int zfvm_profile_enable(zfvm_ctx *ctx, int enable);
+int zfvm_profile_read(zfvm_ctx *ctx, double ms[3], int64_t counts[3]);
 /* counters: [0] kernels launched since creation, [1] cells whose equilibrium solve failed */
 int zfvm_counters(zfvm_ctx *ctx, int64_t counters[4]);
 /* diagnostics (keep_polynomials): [n_cells][n_coef][5] coefficients in the scaled basis, [n_cells][5] scales */

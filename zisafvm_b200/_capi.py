@@ -101,6 +101,8 @@ _SIGNATURES = {
     "zfvm_cfl_dt": (C.c_int, [_vp, _vp, C.c_double, c_double_p, C.POINTER(C.c_int)]),
     "zfvm_synchronize": (C.c_int, [_vp]),
     "zfvm_counters": (C.c_int, [_vp, c_int64_p]),
+    "zfvm_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "zfvm_profile_read": (C.c_int, [_vp, c_double_p, c_int64_p]),
     "zfvm_download_polynomials": (C.c_int, [_vp, c_double_p, c_double_p, C.POINTER(C.c_int)]),
     "zfvm_download_work": (C.c_int, [_vp, C.c_char_p, c_double_p, C.c_int64]),
     "zfvm_nccl_unique_id": (C.c_int, [C.c_char_p]),

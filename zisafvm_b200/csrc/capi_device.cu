@@ -132,8 +132,17 @@ int zfvm_allreduce_min_internal(zfvm_ctx *ctx, double *dev_value);
 
 namespace {
 
+void prof_mark(zfvm_ctx *ctx, int which) {
+  if (!ctx->prof_enabled) return;
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  cudaEventRecord(ev, ctx->stream);
+  ctx->prof_events[which].push_back(ev);
+}
+
 int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
   int rc;
+  prof_mark(ctx, 0);
   if (ctx->n_ranks > 1 && ctx->nccl_comm) {
     if (zfvm_halo_post_internal(ctx, const_cast<double *>(state))) return 1;
     rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_interior,
@@ -148,8 +157,13 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     ctx->launches += 1;
   }
+  prof_mark(ctx, 0);
+  prof_mark(ctx, 1);
   launch_flux(ctx->plan, ctx->sc, nullptr, ctx->plan.n_interior_edges, ctx->stream);
+  prof_mark(ctx, 1);
+  prof_mark(ctx, 2);
   launch_update(ctx->plan, ctx->n_dims, upd, ctx->stream);
+  prof_mark(ctx, 2);
   ctx->launches += 2;
   ZFVM_CUDA(cudaGetLastError());
   return 0;
@@ -727,6 +741,32 @@ int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, doubl
   ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (dt) *dt = cfl_number * ctx->reduce_host->min_dx_over_ev;
   if (not_plausible) *not_plausible = ctx->reduce_host->not_plausible;
+  return 0;
+}
+
+int zfvm_profile_enable(zfvm_ctx *ctx, int enable) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &v : ctx->prof_events) {
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+  }
+  ctx->prof_enabled = enable != 0;
+  return 0;
+}
+
+int zfvm_profile_read(zfvm_ctx *ctx, double ms[3], int64_t counts[3]) {
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int w = 0; w < 3; ++w) {
+    ms[w] = 0.0;
+    counts[w] = (int64_t)ctx->prof_events[w].size() / 2;
+    for (size_t a = 0; a + 1 < ctx->prof_events[w].size(); a += 2) {
+      float t = 0.f;
+      ZFVM_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[w][a], ctx->prof_events[w][a + 1]));
+      ms[w] += t;
+    }
+  }
   return 0;
 }
 

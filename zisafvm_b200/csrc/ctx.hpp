@@ -49,6 +49,10 @@ struct zfvm_ctx {
   double tab_c[zfvm::MAX_RK_STAGES] = {0};
   double n_k_avg = 2.0;
 
+  // optional per-kernel timing (cudaEvent pairs around K1 / K2 / K3), see zfvm_profile_*
+  bool prof_enabled = false;
+  std::vector<cudaEvent_t> prof_events[3];
+
   // host buffers registered for fast PCIe copies
   std::vector<std::pair<const void *, size_t>> registered;
 

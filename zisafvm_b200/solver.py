@@ -125,6 +125,16 @@ class CudaContext:
         check(lib.zfvm_counters(self._h, c))
         return {"launches": int(c[0]), "eq_failures": int(c[1]), "tiles_interior": int(c[2]), "tiles_exterior": int(c[3])}
 
+    def profile(self, enable: bool):
+        check(lib.zfvm_profile_enable(self._h, int(enable)))
+
+    def profile_read(self):
+        """Summed device milliseconds and launch counts of (reconstruction, face flux, update) kernels."""
+        ms = (C.c_double * 3)()
+        cnt = (C.c_int64 * 3)()
+        check(lib.zfvm_profile_read(self._h, ms, cnt))
+        return [float(x) for x in ms], [int(x) for x in cnt]
+
     def stream(self) -> int:
         return int(lib.zfvm_stream(self._h) or 0)
 
