@@ -904,6 +904,19 @@ bool make_tableau(const std::string &m, Tableau &t) {
     t.b[1] = 1.0 / 3;
     t.b[2] = 1.0 / 3;
     t.b[3] = 1.0 / 6;
+  } else if (m == "fehlberg") {
+    t.n = 6;
+    const double a[6][6] = {{0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+                            {0.25, 0.0, 0.0, 0.0, 0.0, 0.0},
+                            {3.0 / 32.0, 9.0 / 32.0, 0.0, 0.0, 0.0, 0.0},
+                            {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0, 0.0, 0.0, 0.0},
+                            {439.0 / 216.0, -8.0, 3680.0 / 513.0, -845.0 / 4104, 0.0, 0.0},
+                            {-8.0 / 27.0, 2.0, -3544.0 / 2565.0, 1859.0 / 4104.0, -11.0 / 40.0, 0.0}};
+    const double b[6] = {16.0 / 135.0, 0.0, 6656.0 / 12825.0, 28561.0 / 56430.0, -9.0 / 50.0, 2.0 / 55.0};
+    for (int r = 0; r < 6; ++r) {
+      t.b[r] = b[r];
+      for (int c = 0; c < 6; ++c) t.a[r][c] = a[r][c];
+    }
   } else {
     return false;
   }
