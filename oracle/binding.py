@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         _lib.oracle_reconstruct.argtypes = [C.c_void_p, dp, dp, C.c_int, dp]
         _lib.oracle_point_value.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, dp]
         _lib.oracle_eval_at.argtypes = [C.c_void_p, C.c_int64, dp, dp]
+        _lib.oracle_cell_point_values.argtypes = [C.c_void_p, dp]
         _lib.oracle_rk_step.argtypes = [C.c_void_p, C.c_char_p, dp, dp, C.c_double]
         _lib.oracle_rk_step.restype = C.c_int
         _lib.oracle_cfl_dt.argtypes = [C.c_void_p, dp, C.c_double]
@@ -169,6 +170,12 @@ class Oracle:
         u = np.zeros(5)
         lib().oracle_point_value(self._h, i, kind, k, q, _p(u))
         return u
+
+    def cell_point_values(self, q_c):
+        """rc(i)(x) at all cell Gauss points, [n][q_c][5]; call after reconstruct() / rate_of_change()."""
+        out = np.zeros((self.n_cells, q_c, 5))
+        lib().oracle_cell_point_values(self._h, _p(out))
+        return out
 
     def eval_at(self, i, x):
         u = np.zeros(5)

@@ -1071,6 +1071,17 @@ void oracle_point_value(void *h, int64_t i, int kind, int k, int q, double *u) {
   }
 }
 
+/* rc(i)(x) at every cell Gauss point of every cell: out[n_cells][q_c][5] (after oracle_reconstruct) */
+void oracle_cell_point_values(void *h, double *out) {
+  Oracle *o = (Oracle *)h;
+  const Grid &g = o->g;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < g.n_cells; ++i)
+    for (int q = 0; q < g.q_c; ++q)
+      o->point_value(i, &g.cell_qp[(size_t)((i * g.q_c + q) * 3)],
+                     o->prm.well_balanced ? &o->pv_cell[(size_t)(i * g.q_c + q)] : nullptr, &out[(size_t)((i * g.q_c + q) * NV)]);
+}
+
 void oracle_eval_at(void *h, int64_t i, const double *x, double *u) { ((Oracle *)h)->point_value(i, x, nullptr, u); }
 
 /* RungeKutta::compute_step, runge_kutta.cpp:87-112 with Sum[Zero, Sum[FluxLoop, GravitySourceLoop]] */

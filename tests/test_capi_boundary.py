@@ -1,0 +1,72 @@
+"""The C-ABI boundary: libzfvm_b200.so loads, exports every symbol include/zfvm.h declares, and fails loudly
+(no CPU fallback) when no CUDA device is present.  No compute calls are made; no GPU is needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import zisafvm_b200 as z
+from zisafvm_b200 import _capi, cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "zfvm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zfvm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    lib = C.CDLL(_capi.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 45
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_the_header():
+    assert sorted(_capi.DECLARED_SYMBOLS) == declared_symbols()
+
+
+def test_params_struct_layout_matches_header():
+    """zfvm_params_default writes through the ctypes mirror of the struct: field offsets must agree."""
+    p = _capi.ZfvmParams()
+    _capi.lib.zfvm_params_default(C.byref(p))
+    assert p.recon_mode == 0 and list(p.linear_weights)[:2] == [100.0, 1.0]
+    assert p.epsilon == 1e-10 and p.exponent == 4.0 and p.gamma == 1.4 and p.steps_per_recompute == 1
+    assert p.keep_polynomials == 0 and p.flux == 0 and p.scaling == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    case = cases.isentropic_vortex(n=8)
+    st = case.ensure_stencils()
+    with pytest.raises(_capi.ZfvmError, match="no CUDA device|no CPU fallback|cuda"):
+        z.CudaContext(case.grid, st, case.params)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under zisafvm_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "zisafvm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_unknown_tableau_is_rejected_like_the_reference():
+    """make_tableau LOG_ERRs 'Unknown Butcher Tableau. [name]' (runge_kutta.cpp:212); checked on the host-only path
+    of the oracle here and on the device context in the GPU tests."""
+    from oracle import binding as ob
+
+    case = cases.isentropic_vortex(n=8)
+    ora = ob.Oracle(case.grid, case.ensure_stencils(), case.params)
+    with pytest.raises(ValueError, match="Unknown Butcher Tableau"):
+        ora.rk_step("heun17", case.u0, 1e-3)

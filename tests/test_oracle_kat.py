@@ -14,6 +14,7 @@ import pytest
 from oracle import binding as ob
 
 dp = ob.dp
+RHS = C.CFUNCTYPE(None, C.c_double, dp, dp, C.c_int64)
 
 
 def _arr(x):
@@ -31,6 +32,7 @@ def L():
     lib.oracle_poly_index2.restype = C.c_int
     lib.oracle_poly_index3.restype = C.c_int
     lib.oracle_rk_generic.restype = C.c_int
+    lib.oracle_rk_generic.argtypes = [C.c_char_p, RHS, dp, C.c_int64, C.c_double, C.c_double]
     return lib
 
 
@@ -192,7 +194,6 @@ def test_local_equilibrium_solve_and_extrapolate(L):
 
 
 # ---- ode/runge_kutta.cpp:172-199 -----------------------------------------------------------------------------------------
-RHS = C.CFUNCTYPE(None, C.c_double, dp, dp, C.c_int64)
 
 
 def _rk_error(L, ode, method, dt):
