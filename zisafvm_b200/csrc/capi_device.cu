@@ -33,22 +33,83 @@ int dev_upload(zfvm_ctx *ctx, const T **ptr, const std::vector<T> &host) {
   return 0;
 }
 
-// Registers a caller-owned host buffer once so later copies run at full PCIe rate. The reference's
-// RungeKutta alternates between a handful of AllVariables buffers (runge_kutta.cpp:109-111).
-void register_host(zfvm_ctx *ctx, const void *p, size_t bytes) {
-  for (auto &r : ctx->registered)
-    if (r.first == p && r.second >= bytes) return;
-  if (ctx->registered.size() >= 32) return;
+// Host <-> device copies of caller-owned buffers.  The reference's RungeKutta hands us plain
+// zisa::array storage that alternates between calls (runge_kutta.cpp:109-111).  Buffers the caller has
+// pinned go straight to the copy engine; pageable ones are staged through two internal pinned chunks that
+// OpenMP threads fill / drain while the other chunk is in flight.  Caller memory is never registered here:
+// its lifetime is not ours.
+constexpr size_t STAGE_BYTES = 16u << 20;
+
+bool is_pinned(const void *p) {
   cudaPointerAttributes attr;
-  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) {
-    ctx->registered.push_back({p, bytes});
-    return;
-  }
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;
   cudaGetLastError();
-  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
-    ctx->registered.push_back({p, bytes});
-  else
-    cudaGetLastError();  // pageable copy still works
+  return false;
+}
+
+int ensure_stage(zfvm_ctx *ctx) {
+  if (ctx->stage[0]) return 0;
+  for (int b = 0; b < 2; ++b) {
+    ZFVM_CUDA(cudaMallocHost(&ctx->stage[b], STAGE_BYTES));
+    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+void parallel_copy(void *dst, const void *src, size_t bytes) {
+  const std::int64_t blk = 1 << 20, nb = (std::int64_t)((bytes + blk - 1) / blk);
+#pragma omp parallel for schedule(static)
+  for (std::int64_t b = 0; b < nb; ++b) {
+    const size_t off = (size_t)(b * blk);
+    std::memcpy((char *)dst + off, (const char *)src + off, std::min<size_t>((size_t)blk, bytes - off));
+  }
+}
+
+// asynchronous with respect to the host only for pinned sources
+int copy_h2d(zfvm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (is_pinned(src_host)) {
+    ZFVM_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+  }
+  if (ensure_stage(ctx)) return 1;
+  int b = 0;
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES, b ^= 1) {
+    const size_t nb = std::min(STAGE_BYTES, bytes - off);
+    ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));  // the previous transfer out of this chunk is done
+    parallel_copy(ctx->stage[b], (const char *)src_host + off, nb);
+    ZFVM_CUDA(cudaMemcpyAsync((char *)dst_dev + off, ctx->stage[b], nb, cudaMemcpyHostToDevice, ctx->stream));
+    ZFVM_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+  }
+  return 0;
+}
+
+// returns after the data is in dst_host
+int copy_d2h(zfvm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (is_pinned(dst_host)) {
+    ZFVM_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  if (ensure_stage(ctx)) return 1;
+  int b = 0;
+  size_t prev_off = 0, prev_nb = 0;
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES, b ^= 1) {
+    const size_t nb = std::min(STAGE_BYTES, bytes - off);
+    ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));
+    ZFVM_CUDA(cudaMemcpyAsync(ctx->stage[b], (const char *)src_dev + off, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    ZFVM_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    if (prev_nb) {  // drain the other chunk while this one is in flight
+      ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b ^ 1]));
+      parallel_copy((char *)dst_host + prev_off, ctx->stage[b ^ 1], prev_nb);
+    }
+    prev_off = off;
+    prev_nb = nb;
+  }
+  ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b ^ 1]));
+  parallel_copy((char *)dst_host + prev_off, ctx->stage[b ^ 1], prev_nb);
+  return 0;
 }
 
 struct Tableau {
@@ -279,71 +340,82 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     P.n_edges = E;
     P.n_interior_edges = EI;
 
-    // ---- stencil indices, weights, meta: built and uploaded in chunks of tiles -----------------
-    std::vector<std::uint64_t> meta((size_t)(T * TILE), 0ull);
+    // ---- tile records (meta | sidx_k | W_k), built and uploaded in chunks of tiles -------------------
     ctx->tile_max_ref.assign((size_t)T, 0);
     for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
     double bytes_W = 0.0, bytes_idx = 0.0, bytes_m = 0.0;
     std::int64_t n_counted = 0;
-    for (int k = 0; k < ns; ++k) {
-      const int RM = sc.rows_max[k], NC = sc.ncoef[k];
-      std::int32_t *d_sidx = nullptr;
-      double *d_W = nullptr;
-      if (dev_alloc(ctx, &d_sidx, T * RM * TILE) || dev_alloc(ctx, &d_W, T * (std::int64_t)RM * NC * TILE)) {
+    {
+      int off = TILE * (int)sizeof(std::uint64_t);
+      for (int k = 0; k < ns; ++k) {
+        P.off_sidx[k] = off;
+        off += sc.rows_max[k] * TILE * (int)sizeof(std::int32_t);
+      }
+      P.hdr_bytes = off;
+      for (int k = 0; k < ns; ++k) {
+        P.off_W[k] = off;
+        off += sc.rows_max[k] * sc.ncoef[k] * TILE * (int)sizeof(double);
+      }
+      P.rec_bytes = off;  // every section is a multiple of 128 bytes
+    }
+    {
+      char *d_rec = nullptr;
+      if (dev_alloc(ctx, &d_rec, T * P.rec_bytes)) {
         zfvm_destroy(ctx);
         return 1;
       }
-      P.sidx[k] = d_sidx;
-      P.W[k] = d_W;
-      const std::int64_t chunk = 2048;  // tiles per upload
-      std::vector<std::int32_t> h_sidx((size_t)(chunk * RM * TILE));
-      std::vector<double> h_W((size_t)(chunk * RM * NC * TILE));
+      P.rec = d_rec;
+      const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / P.rec_bytes));
+      std::vector<char> h_rec((size_t)(chunk * P.rec_bytes));
       for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
         const std::int64_t t1 = std::min(T, t0 + chunk);
-        std::fill(h_W.begin(), h_W.end(), 0.0);
+        std::memset(h_rec.data(), 0, h_rec.size());
 #pragma omp parallel
         {
           std::vector<double> A, W;
 #pragma omp for schedule(dynamic, 8)
           for (std::int64_t t = t0; t < t1; ++t) {
+            char *rec = h_rec.data() + (size_t)((t - t0) * P.rec_bytes);
+            std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec);
+            std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
             for (int lane = 0; lane < TILE; ++lane) {
               const std::int64_t i = t * TILE + lane;
               const std::int64_t ic = std::min(i, n - 1);
-              std::int32_t *si = &h_sidx[(size_t)(((t - t0) * RM) * TILE + lane)];
-              for (int j = 0; j < RM; ++j) si[(size_t)j * TILE] = (std::int32_t)ic;
-              if (i >= n || k >= S.n_family[(size_t)i]) continue;
-              const int order = S.order[(size_t)(i * ns + k)];
-              if (order <= 1) continue;
-              int rows, cols;
-              stencil_matrix(A, rows, cols, g, S, i, k);
-              if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
-              W.resize((size_t)(rows * cols));
-              pseudo_inverse(A.data(), rows, cols, W.data());
-              std::int32_t mx = 0;
-              for (int j = 0; j < rows; ++j) {
-                si[(size_t)j * TILE] = S.global(i, k, j + 1);
-                mx = std::max(mx, si[(size_t)j * TILE]);
+              std::uint64_t m = 0;
+              for (int k = 0; k < ns; ++k) {
+                const int RM = sc.rows_max[k], NC = sc.ncoef[k];
+                std::int32_t *si = reinterpret_cast<std::int32_t *>(rec + P.off_sidx[k]) + lane;
+                for (int j = 0; j < RM; ++j) si[(size_t)j * TILE] = (std::int32_t)ic;  // padded rows: rhs == 0
+                if (i >= n || k >= S.n_family[(size_t)i]) continue;
+                const int order = S.order[(size_t)(i * ns + k)];
+                if (order <= 1) continue;
+                int rows, cols;
+                stencil_matrix(A, rows, cols, g, S, i, k);
+                if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
+                W.resize((size_t)(rows * cols));
+                pseudo_inverse(A.data(), rows, cols, W.data());
+                for (int j = 0; j < rows; ++j) {
+                  si[(size_t)j * TILE] = S.global(i, k, j + 1);
+                  tile_mx = std::max(tile_mx, si[(size_t)j * TILE]);
+                }
+                double *w = reinterpret_cast<double *>(rec + P.off_W[k]) + lane;
+                for (int j = 0; j < rows; ++j)
+                  for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+                m |= ((std::uint64_t)rows) << (8 * k);
               }
-#pragma omp critical(zfvm_tile_max)
-              ctx->tile_max_ref[(size_t)t] = std::max(ctx->tile_max_ref[(size_t)t], mx);
-              double *w = &h_W[(size_t)(((t - t0) * RM) * NC * TILE + lane)];
-              for (int j = 0; j < rows; ++j)
-                for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
-#pragma omp atomic
-              meta[(size_t)i] |= ((std::uint64_t)rows) << (8 * k);
+              if (i < n) {
+                m |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
+                if (S.n_family[(size_t)i] == 1) m |= 1ull << 60;
+              }
+              meta[lane] = m;
             }
+            ctx->tile_max_ref[(size_t)t] = tile_mx;
           }
         }
-        ZFVM_CUDA(cudaMemcpy(d_sidx + t0 * RM * TILE, h_sidx.data(), (size_t)((t1 - t0) * RM * TILE) * sizeof(std::int32_t),
-                             cudaMemcpyHostToDevice));
-        ZFVM_CUDA(cudaMemcpy(d_W + t0 * RM * NC * TILE, h_W.data(), (size_t)((t1 - t0) * RM * NC * TILE) * sizeof(double),
-                             cudaMemcpyHostToDevice));
+        ZFVM_CUDA(cudaMemcpy(d_rec + t0 * P.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * P.rec_bytes), cudaMemcpyHostToDevice));
       }
     }
     for (std::int64_t i = 0; i < n; ++i) {
-      const bool single = S.n_family[(size_t)i] == 1;
-      meta[(size_t)i] |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
-      if (single) meta[(size_t)i] |= 1ull << 60;
       if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
         ++n_counted;
         bytes_m += S.l2g_size[(size_t)i];
@@ -353,10 +425,6 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
           bytes_idx += 4.0 * (size - 1);
         }
       }
-    }
-    if (dev_upload(ctx, &P.meta, meta)) {
-      zfvm_destroy(ctx);
-      return 1;
     }
 
     // ---- geometry -----------------------------------------------------------------------------
@@ -525,8 +593,10 @@ void zfvm_destroy(zfvm_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (auto &r : ctx->registered) cudaHostUnregister(const_cast<void *>(r.first));
-  cudaGetLastError();
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
+    if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
+  }
   for (void *p : ctx->allocations) cudaFree(p);
   if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -585,23 +655,17 @@ int zfvm_rate_of_change_device(zfvm_ctx *ctx, double *tendency_dev, const double
 int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
-  register_host(ctx, state_host, bytes);
-  register_host(ctx, tendency_host, bytes);
-  ZFVM_CUDA(cudaMemcpyAsync(ctx->state_work, state_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (accumulate)
-    ZFVM_CUDA(cudaMemcpyAsync(ctx->tend_work, tendency_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (copy_h2d(ctx, ctx->state_work, state_host, bytes)) return 1;
+  if (accumulate && copy_h2d(ctx, ctx->tend_work, tendency_host, bytes)) return 1;
   if (zfvm_rate_of_change_device(ctx, ctx->tend_work, ctx->state_work, t, accumulate)) return 1;
-  ZFVM_CUDA(cudaMemcpyAsync(tendency_host, ctx->tend_work, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (ctx->n_ranks > 1) {
     // FluxLoop fills the halo rows of the caller's state (flux_loop.hpp:100, const_cast)
     for (auto &p : ctx->peers) {
       const size_t off = (size_t)(p.recv_begin * NVARS), cnt = (size_t)((p.recv_end - p.recv_begin) * NVARS);
-      ZFVM_CUDA(cudaMemcpyAsync(const_cast<double *>(state_host) + off, ctx->state_work + off, cnt * sizeof(double),
-                                cudaMemcpyDeviceToHost, ctx->stream));
+      if (copy_d2h(ctx, const_cast<double *>(state_host) + off, ctx->state_work + off, cnt * sizeof(double))) return 1;
     }
   }
-  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return copy_d2h(ctx, tendency_host, ctx->tend_work, bytes);
 }
 
 int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method) {
@@ -624,18 +688,14 @@ int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method) {
 
 int zfvm_upload_state(zfvm_ctx *ctx, const double *state_host) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
-  ZFVM_CUDA(cudaMemcpyAsync(ctx->u_cur, state_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double),
-                            cudaMemcpyHostToDevice, ctx->stream));
+  if (copy_h2d(ctx, ctx->u_cur, state_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double))) return 1;
   ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
 int zfvm_download_state(zfvm_ctx *ctx, double *state_host) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
-  ZFVM_CUDA(cudaMemcpyAsync(state_host, ctx->u_cur, (size_t)(ctx->n_cells * NVARS) * sizeof(double),
-                            cudaMemcpyDeviceToHost, ctx->stream));
-  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return copy_d2h(ctx, state_host, ctx->u_cur, (size_t)(ctx->n_cells * NVARS) * sizeof(double));
 }
 
 double *zfvm_state_device(zfvm_ctx *ctx) { return ctx->u_cur; }
@@ -718,13 +778,9 @@ int zfvm_rk_step(zfvm_ctx *ctx, double /*t*/, double dt, double cfl_number, doub
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double /*t*/, double dt) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
-  register_host(ctx, u0_host, bytes);
-  register_host(ctx, u1_host, bytes);
-  ZFVM_CUDA(cudaMemcpyAsync(ctx->u_cur, u0_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes)) return 1;
   if (rk_step_impl(ctx, dt, false)) return 1;
-  ZFVM_CUDA(cudaMemcpyAsync(u1_host, ctx->u_cur, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return copy_d2h(ctx, u1_host, ctx->u_cur, bytes);
 }
 
 int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, double *dt, int *not_plausible) {

@@ -53,8 +53,9 @@ struct zfvm_ctx {
   bool prof_enabled = false;
   std::vector<cudaEvent_t> prof_events[3];
 
-  // host buffers registered for fast PCIe copies
-  std::vector<std::pair<const void *, size_t>> registered;
+  // pinned staging chunks for copies from / to pageable caller memory
+  void *stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 
   // multi-GPU
   void *nccl_comm = nullptr;

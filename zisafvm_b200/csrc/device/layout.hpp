@@ -1,12 +1,20 @@
 // Device data layout for the per-stage residual path (see DESIGN.md "Data layout in HBM").
 //
-// Cells are grouped in *tiles* of 32 consecutive cells (one warp). Every per-cell array that is
-// only read by the owning cell is stored tile-interleaved, [tile][field][32], so that a warp's
-// access to one field is one fully coalesced 256-byte (FP64) or 128-byte (int32) transaction.
+// Cells are grouped in *tiles* of 32 consecutive cells. Every per-cell array that is only read by
+// the owning cell is stored tile-interleaved, [tile][field][32], so that a warp's access to one
+// field is one fully coalesced 256-byte (FP64) or 128-byte (int32) transaction.
+// The reconstruction tables of a tile (stencil meta data, stencil member indices, pseudo-inverse
+// weights) form one contiguous *tile record*, so that the reconstruction kernel can stream them
+// with a handful of TMA bulk copies (cp.async.bulk) per tile:
+//   record = | meta u64[32] | sidx_0 i32[RM_0][32] | .. | sidx_{NS-1} | W_0 f64[RM_0][NC_0][32] | .. | W_{NS-1} |
 // Arrays that are gathered through indices (the state, equilibrium potentials, face fluxes) stay
 // row-major AoS, the layout of zisa::GridVariables (grid_variables_decl.hpp:17).
 #pragma once
 #include <cstdint>
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
 
 namespace zfvm {
 
@@ -53,10 +61,13 @@ struct SchemeConst {
 /// Raw device pointers of one context. Sizes in comments use n = n_cells, T = n_tiles, E = n_edges.
 struct DevicePlan {
   std::int64_t n_cells, n_tiles, n_edges, n_interior_edges;
-  // reconstruction
-  const std::int32_t *sidx[MAX_STENCILS];   // [T][rows_max_k][32]  global index of stencil member
-  const double *W[MAX_STENCILS];            // [T][rows_max_k][ncoef_k][32]
-  const std::uint64_t *meta;                // [T][32] byte k: rows of stencil k; byte 7: k_high | single<<4
+  // reconstruction: tile records (layout above). All offsets in bytes from the start of a record.
+  const char *rec;                          // [T][rec_bytes]
+  std::int64_t rec_bytes;                   // multiple of 128
+  int hdr_bytes;                            // meta + all sidx_k (= offset of W_0)
+  int off_sidx[MAX_STENCILS];               // sidx_k: [rows_max_k][32] global index of stencil member
+  int off_W[MAX_STENCILS];                  // W_k:    [rows_max_k][ncoef_k][32]
+  // meta (offset 0): [32] u64, byte k: rows of stencil k; byte 7: k_high | single<<4
   // geometry (tile-interleaved)
   const double *vtx;                        // [T][F][3][32]
   const double *center;                     // [T][3][32]
@@ -78,6 +89,16 @@ struct DevicePlan {
   double *trace;                            // [E][2][q_f][5]
   double *flux;                             // [E][5]
   double *source;                           // [n][5]
+  // helpers
+  __host__ __device__ const std::uint64_t *meta_of(std::int64_t tile) const {
+    return reinterpret_cast<const std::uint64_t *>(rec + tile * rec_bytes);
+  }
+  __host__ __device__ const std::int32_t *sidx_of(std::int64_t tile, int k) const {
+    return reinterpret_cast<const std::int32_t *>(rec + tile * rec_bytes + off_sidx[k]);
+  }
+  __host__ __device__ const double *W_of(std::int64_t tile, int k) const {
+    return reinterpret_cast<const double *>(rec + tile * rec_bytes + off_W[k]);
+  }
   double *poly;                             // optional diagnostics [n][n_poly_coef][5]; may be null
   double *poly_scale;                       // optional [n][5]
   int n_poly_coef;

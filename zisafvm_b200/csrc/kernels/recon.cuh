@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
   const bool active = cell < P.n_cells;
   const std::int64_t ci = active ? cell : P.n_cells - 1;  // padded lanes mirror the last cell, write nothing
 
-  const std::uint64_t meta = active ? P.meta[tile * TILE + lane] : 0ull;
+  const std::uint64_t meta = active ? P.meta_of(tile)[lane] : 0ull;
   const int kh = (int)((meta >> 56) & 0xF);
   const bool single = ((meta >> 60) & 1) != 0;
 
@@ -236,9 +236,8 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
     const int NC = (k == 0) ? CHI : CLO;  // compile-time after unrolling
     const int rows = (int)((meta >> (8 * k)) & 0xFF);
     const int rows_warp = __reduce_max_sync(0xffffffffu, rows);
-    const int RM = sc.rows_max[k];
-    const std::int32_t *sidx = P.sidx[k] + (tile * RM) * TILE + lane;
-    const double *Wk = P.W[k] + (tile * RM) * (std::int64_t)NC * TILE + lane;
+    const std::int32_t *sidx = P.sidx_of(tile, k) + lane;
+    const double *Wk = P.W_of(tile, k) + lane;
     for (int j = 0; j < rows_warp; ++j) {
       if (j < rows) {
         const std::int64_t g = ld_stream(sidx + (std::int64_t)j * TILE);

@@ -1,7 +1,12 @@
 // Instantiation helper: one translation unit per (n_dims, high degree) keeps nvcc compile times parallel.
 #pragma once
+#include <algorithm>
+
 #include "kernels.hpp"
 #include "recon.cuh"
+#include "recon_stream.cuh"
+
+#include <cstdlib>
 
 namespace zfvm {
 
@@ -14,6 +19,30 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
   args.tile_list = tile_list;
   args.n_tiles_launch = n_tiles;
   if (n_tiles <= 0) return 0;
+  if constexpr (DEG_HI >= 1) {
+    // streaming kernel (recon_stream.cuh); ZFVM_RECON=v1 selects the thread-per-cell kernel for comparisons
+    static const bool force_v1 = [] {
+      const char *e = std::getenv("ZFVM_RECON");
+      return e && e[0] == 'v' && e[1] == '1';
+    }();
+    if (!sc.well_balanced && !sc.has_gravity && !force_v1) {
+      int dev = 0, optin = 0, n_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      int budget = optin;
+      if (const char *e = std::getenv("ZFVM_STREAM_SMEM_KB")) budget = std::min(optin, std::atoi(e) * 1024);
+      StreamCfg cfg;
+      if (stream_config<ND, DEG_HI, DEG_LO, NS>(plan, sc, budget, cfg)) {
+        auto kern = recon_stream_kernel<ND, DEG_HI, DEG_LO, NS>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.total_bytes);
+        const unsigned grid = (unsigned)std::min<std::int64_t>(n_tiles, n_sm);
+        const int block = 32 * (1 + STREAM_NVAR_WARPS + ND + 1);
+        kern<<<grid, block, (size_t)cfg.total_bytes, stream>>>(args, sc, cfg);
+        return 0;
+      }
+    }
+  }
   const int block = 128;  // 4 tiles per CTA
   const unsigned grid = (unsigned)((n_tiles + 3) / 4);
   if (sc.well_balanced)
