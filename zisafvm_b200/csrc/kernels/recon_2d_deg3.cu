@@ -1,5 +1,5 @@
 // recon_kernel instantiations for n_dims = 2, high-order stencil degree 3 (order 4).
 #include "recon_inst.cuh"
 namespace zfvm {
-ZFVM_DEFINE_RECON(2, 3)
+ZFVM_DEFINE_RECON(2, 3, 18, 3)
 }

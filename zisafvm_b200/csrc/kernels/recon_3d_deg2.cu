@@ -1,5 +1,5 @@
 // recon_kernel instantiations for n_dims = 3, high-order stencil degree 2 (order 3).
 #include "recon_inst.cuh"
 namespace zfvm {
-ZFVM_DEFINE_RECON(3, 2)
+ZFVM_DEFINE_RECON(3, 2, 18, 4)
 }

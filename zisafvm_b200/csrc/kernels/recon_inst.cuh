@@ -10,7 +10,7 @@
 
 namespace zfvm {
 
-template <int ND, int DEG_HI, int DEG_LO, int NS>
+template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO>
 int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const double *state,
                           const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream) {
   ReconArgs args;
@@ -33,11 +33,11 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
       int budget = optin;
       if (const char *e = std::getenv("ZFVM_STREAM_SMEM_KB")) budget = std::min(optin, std::atoi(e) * 1024);
       StreamCfg cfg;
-      if (stream_config<ND, DEG_HI, DEG_LO, NS>(plan, sc, budget, cfg)) {
-        auto kern = recon_stream_kernel<ND, DEG_HI, DEG_LO, NS>;
+      if (stream_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO>(plan, sc, budget, cfg)) {
+        auto kern = recon_stream_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.total_bytes);
         const unsigned grid = (unsigned)std::min<std::int64_t>(n_tiles, n_sm);
-        const int block = 32 * (1 + STREAM_NVAR_WARPS + ND + 1);
+        const int block = 32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO>::N_WARPS;
         kern<<<grid, block, (size_t)cfg.total_bytes, stream>>>(args, sc, cfg);
         return 0;
       }
@@ -59,12 +59,14 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
                                        const double *state, const std::int32_t *tile_list,              \
                                        std::int64_t n_tiles, cudaStream_t stream)
 
-#define ZFVM_DEFINE_RECON(ND, DEG_HI)                                                                    \
+// RM0 / RLO: rows (stencil size - 1) of the central / one-sided stencils of the reference's parameter set for this
+// order; the streaming kernel is compiled for exactly these, other sizes run the thread-per-cell kernel.
+#define ZFVM_DEFINE_RECON(ND, DEG_HI, RM0, RLO)                                                          \
   ZFVM_DECLARE_RECON(ND, DEG_HI) {                                                                       \
     if (sc.n_stencils != ND + 2) return 1;                                                               \
     if (deg_lo == 1 || (DEG_HI == 0 && deg_lo == 0))                                                     \
-      return launch_recon_variants<ND, DEG_HI, (DEG_HI >= 1 ? 1 : 0), ND + 2>(plan, sc, state, tile_list, \
-                                                                               n_tiles, stream);         \
+      return launch_recon_variants<ND, DEG_HI, (DEG_HI >= 1 ? 1 : 0), ND + 2, RM0, RLO>(                 \
+          plan, sc, state, tile_list, n_tiles, stream);                                                  \
     return 1;                                                                                            \
   }
 
