@@ -2,23 +2,28 @@
 //
 // Same arithmetic as recon.cuh (EulerGlobalReconstruction::compute + LocalReconstruction::compute +
 // HybridWENO::compute_polys_impl / eno_hybridize + CWENO_AO::reconstruct_impl + rc(i)(x) at the face
-// Gauss points; reference lines are listed there), restructured around the memory system:
+// Gauss points; reference lines are listed there), restructured around the memory system as a
+// four-stage pipeline inside one persistent CTA per SM (tiles of 32 cells, stride gridDim.x):
 //
-//   * one CTA per SM, looping over tiles (32 cells) with stride gridDim.x;
-//   * warp 0 (one elected lane) is the *producer*: it streams each tile record -- header (meta +
-//     stencil member indices) and pseudo-inverse weights in row segments of <= ~24 KB -- from HBM into
-//     shared-memory rings with TMA bulk copies (cp.async.bulk.shared::cluster.global + mbarrier
-//     complete_tx), L2 evict-first, so the bytes in flight do not depend on occupancy;
-//   * two *apply* groups of five warps take alternate tiles: thread = (cell, variable), the five
-//     variables of a cell sit in adjacent lanes, so a weight is read from shared memory once per
-//     warp-row as a broadcast and a gathered neighbour state row (40 B) is read by five adjacent
-//     lanes.  They accumulate coef = W_k * rhs, exchange smoothness indicators through shared
-//     memory, hybridise, and hand the final polynomial (times the characteristic scale) to the trace
-//     group through shared memory;
-//   * the *trace* group (one warp per local face, thread = (cell, face)) evaluates the polynomial at
-//     the face Gauss points and writes trace[e][side][q][5].
+//   producer (warp 0, one elected lane)
+//       streams each tile record -- header (meta + stencil member indices) and pseudo-inverse weights in
+//       row segments of <= ~24 KB -- from HBM into shared-memory rings with TMA bulk copies
+//       (cp.async.bulk.shared::cluster.global + mbarrier complete_tx, L2 evict-first): the bytes in flight
+//       do not depend on occupancy.
+//   gather group (5 warps, thread = (cell, variable), the five variables of a cell in adjacent lanes)
+//       reads the neighbour states of a segment's stencil rows (a 40-byte state row is read by five
+//       adjacent lanes: every L1 wavefront serves 6-7 rows), forms rhs = (u_j / scale - u_0 / scale) and
+//       stores it next to the segment's weights in the same ring slot, [row][cell][5].  Loads of segment
+//       s+1 are issued before segment s is stored, so L2 latency is hidden without occupancy.
+//   apply groups (2 groups x G warps, alternate tiles; thread = (cell, coefficient group g), all 5 variables)
+//       coef += W * rhs entirely out of shared memory: per stencil row 5 rhs loads + 1..3 weight loads feed
+//       5..15 DFMAs (register tiling; thread g owns low-order coefficient g of every stencil and every
+//       G-th high-order coefficient of the central one, so the CWENO-AO combination is thread-local).
+//       Smoothness indicators are summed across the G threads of a cell through shared memory; the
+//       non-linear weights are computed once per stencil, not once per thread.
+//   trace group (one warp per local face, thread = (cell, face))
+//       evaluates the hybridised polynomial at the face Gauss points and writes trace[e][side][q][5].
 //
-// The gather of segment s+1 is issued before the FMAs of segment s, so L2 latency overlaps the math.
 // Stencil sizes are compile-time (RM0 rows for the central stencil, RLO for every one-sided one): all
 // shared-memory offsets fold into immediates and no row loop carries a predicate.  Other stencil sizes
 // use the thread-per-cell kernel of recon.cuh.
@@ -31,15 +36,15 @@ namespace zfvm {
 
 struct StreamCfg {
   int n_w_slots;
-  int off_hdr, off_w, off_coef, off_is;  // byte offsets into dynamic shared memory (barriers at 0)
+  int off_hdr, off_info, off_w, off_xchg, off_alpha;  // byte offsets into dynamic shared memory (barriers at 0)
   int total_bytes;
 };
 
-constexpr int STREAM_VAR_WARPS = 5;  // one apply group: 160 threads = 32 cells x 5 variables
+constexpr int STREAM_VAR_WARPS = 5;  // gather group: 160 threads = 32 cells x 5 variables
 constexpr int STREAM_GROUPS = 2;     // apply groups (alternate tiles)
-constexpr int STREAM_HDR_SLOTS = 4;
+constexpr int STREAM_HDR_SLOTS = 3;
 constexpr int STREAM_BARS_BYTES = 1024;
-constexpr int COEF_PAD = 33;         // coef exchange row pitch (doubles): spreads (cell, var) writes over banks
+constexpr int COEF_PAD = 33;         // coef exchange row pitch (doubles)
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO>
 struct StreamTraits {
@@ -48,6 +53,8 @@ struct StreamTraits {
   static constexpr int CHI = D - 1;
   static constexpr int CLO = dof_of(DEG_LO, ND) - 1;
   static constexpr int NHI = CHI - CLO;
+  static constexpr int G = CLO;                                 // apply warps per group = coefficient groups
+  static constexpr int HPT = (NHI + G - 1) / (G > 0 ? G : 1);  // high-order coefficients per apply thread
   static constexpr int R_CAP0 = 24576 / (CHI * TILE * 8);
   static constexpr int R_CAP = R_CAP0 < 1 ? 1 : (R_CAP0 > 12 ? 12 : R_CAP0);
   static constexpr int N_HI = (RM0 + R_CAP - 1) / R_CAP;       // central-stencil segments
@@ -55,19 +62,24 @@ struct StreamTraits {
   static constexpr int R_TAIL = RM0 - (N_HI - 1) * R_HI;       // rows of the last one
   static constexpr int N_LO = NS / 2;                          // two one-sided stencils per segment
   static constexpr int N_SEGS = N_HI + N_LO;
-  static constexpr int RAW = R_HI > 2 * RLO ? R_HI : 2 * RLO;
+  static constexpr int RAW = R_HI > 2 * RLO ? R_HI : 2 * RLO;  // rows of the largest segment
   static constexpr int HI_BYTES = R_HI * CHI * TILE * 8;
   static constexpr int LO_BYTES = 2 * RLO * CLO * TILE * 8;
-  static constexpr int SLOT_BYTES = HI_BYTES > LO_BYTES ? HI_BYTES : LO_BYTES;
+  static constexpr int W_BYTES = HI_BYTES > LO_BYTES ? HI_BYTES : LO_BYTES;
+  static constexpr int RHS_BYTES = RAW * TILE * NVARS * 8;      // [row][cell][5]
+  static constexpr int SLOT_BYTES = W_BYTES + RHS_BYTES;
   // tile record layout (device/layout.hpp) for these stencil sizes
   static constexpr int OFF_SIDX0 = TILE * 8;
   static constexpr __host__ __device__ int off_sidx(int k) { return OFF_SIDX0 + 4 * TILE * (k == 0 ? 0 : RM0 + (k - 1) * RLO); }
   static constexpr int HDR_BYTES = OFF_SIDX0 + 4 * TILE * (RM0 + (NS - 1) * RLO);
   static constexpr __host__ __device__ int off_W(int k) { return HDR_BYTES + 8 * TILE * (k == 0 ? 0 : RM0 * CHI + (k - 1) * RLO * CLO); }
   static constexpr int REC_BYTES = HDR_BYTES + 8 * TILE * (RM0 * CHI + (NS - 1) * RLO * CLO);
-  static constexpr int COEF_BYTES = D * NVARS * COEF_PAD * 8;     // per apply group
-  static constexpr int IS_BYTES = 2 * NS * NVARS * TILE * 8;      // per apply group (two parities)
-  static constexpr int N_WARPS = 1 + STREAM_GROUPS * STREAM_VAR_WARPS + F;
+  static constexpr int INFO_BYTES = TILE * 2 * NVARS * 8;         // per header slot: q0s[5], scale[5] per cell
+  static constexpr int COEF_BYTES = D * NVARS * COEF_PAD * 8;     // polynomial handed to the trace group
+  static constexpr int PART_BYTES = G * NS * NVARS * TILE * 8;    // smoothness-indicator partial sums
+  static constexpr int XCHG_BYTES = COEF_BYTES > PART_BYTES ? COEF_BYTES : PART_BYTES;  // per apply group (aliased)
+  static constexpr int ALPHA_BYTES = NS * TILE * 8;               // per apply group
+  static constexpr int N_WARPS = 1 + STREAM_VAR_WARPS + STREAM_GROUPS * G + F;
   static constexpr int VARS_PER_PASS = (20 / D) < 1 ? 1 : ((20 / D) > NVARS ? NVARS : (20 / D));  // trace group
 };
 
@@ -119,10 +131,10 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
     recon_stream_kernel(const __grid_constant__ ReconArgs args, const __grid_constant__ SchemeConst sc,
                         const __grid_constant__ StreamCfg cfg) {
   using T = StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO>;
-  constexpr int F = T::F, D = T::D, CHI = T::CHI, CLO = T::CLO, NHI = T::NHI;
+  constexpr int F = T::F, D = T::D, CHI = T::CHI, CLO = T::CLO, NHI = T::NHI, G = T::G, HPT = T::HPT;
   constexpr int N_HI = T::N_HI, R_HI = T::R_HI, R_TAIL = T::R_TAIL, N_LO = T::N_LO, N_SEGS = T::N_SEGS;
   constexpr int RAW = T::RAW, HS = STREAM_HDR_SLOTS, NG = STREAM_GROUPS;
-  constexpr int N_APPLY = 32 * STREAM_VAR_WARPS;
+  constexpr int FIRST_APPLY_WARP = 1 + STREAM_VAR_WARPS, FIRST_TRACE_WARP = FIRST_APPLY_WARP + NG * G;
   const DevicePlan &P = args.plan;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -133,21 +145,27 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
   std::uint64_t *w_full = coef_empty + NG, *w_empty = w_full + WS;
   unsigned char *hdr_base = smem + cfg.off_hdr;
   unsigned char *w_base = smem + cfg.off_w;
+  double *info_base = reinterpret_cast<double *>(smem + cfg.off_info);  // [HS][32][10]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const std::int64_t n_launch = args.n_tiles_launch;
+  auto tile_of = [&](int m) -> std::int64_t {
+    const std::int64_t idx = blockIdx.x + (std::int64_t)m * gridDim.x;
+    return args.tile_list ? (std::int64_t)args.tile_list[idx] : idx;
+  };
+  auto has_tile = [&](int m) { return blockIdx.x + (std::int64_t)m * gridDim.x < n_launch; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < HS; ++s) {
       ptx::mbar_init(&hdr_full[s], 1);
-      ptx::mbar_init(&hdr_empty[s], STREAM_VAR_WARPS);
+      ptx::mbar_init(&hdr_empty[s], STREAM_VAR_WARPS + G);  // gather warps + the apply group that owns the tile
     }
     for (int s = 0; s < WS; ++s) {
-      ptx::mbar_init(&w_full[s], 1);
-      ptx::mbar_init(&w_empty[s], STREAM_VAR_WARPS);
+      ptx::mbar_init(&w_full[s], 1 + STREAM_VAR_WARPS);  // TMA transaction + rhs rows of the gather warps
+      ptx::mbar_init(&w_empty[s], G);
     }
     for (int g = 0; g < NG; ++g) {
-      ptx::mbar_init(&coef_full[g], STREAM_VAR_WARPS);
+      ptx::mbar_init(&coef_full[g], G);
       ptx::mbar_init(&coef_empty[g], F);
     }
     ptx::fence_barrier_init();
@@ -159,9 +177,8 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
     if (lane == 0) {
       const std::uint64_t pol = ptx::policy_evict_first();
       int hs = 0, hph = 0, ws = 0, wph = 0;
-      for (std::int64_t idx = blockIdx.x; idx < n_launch; idx += gridDim.x) {
-        const std::int64_t tile = args.tile_list ? (std::int64_t)args.tile_list[idx] : idx;
-        const char *rec = P.rec + tile * T::REC_BYTES;
+      for (int m = 0; has_tile(m); ++m) {
+        const char *rec = P.rec + tile_of(m) * T::REC_BYTES;
         ptx::mbar_wait(&hdr_empty[hs], hph ^ 1);
         ptx::mbar_expect_tx(&hdr_full[hs], T::HDR_BYTES);
         ptx::bulk_g2s(hdr_base + hs * T::HDR_BYTES, rec, T::HDR_BYTES, &hdr_full[hs], pol);
@@ -187,27 +204,15 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
     return;
   }
 
-  // =============================== apply groups: thread = (cell, variable) ==========================
-  if (warp <= NG * STREAM_VAR_WARPS) {
-    const int grp = (warp - 1) / STREAM_VAR_WARPS;
-    const int ta = threadIdx.x - 32 - grp * N_APPLY;
+  // =============================== gather group: thread = (cell, variable) ==========================
+  if (warp < FIRST_APPLY_WARP) {
+    const int ta = threadIdx.x - 32;
     const int cell = ta / NVARS, var = ta - cell * NVARS;
-    double *coef_x = reinterpret_cast<double *>(smem + cfg.off_coef + grp * T::COEF_BYTES);
-    double *is_x = reinterpret_cast<double *>(smem + cfg.off_is + grp * T::IS_BYTES);
+    int cur_m = 0, cur_seg = 0;
+    double raw_cur[RAW], raw_nxt[RAW], u0[NVARS];
+    double inv_scale_v = 1.0, q0s = 0.0;
 
-    // cursor over (tile, segment): m = position of the tile in this CTA's sequence
-    int cur_m = grp, cur_seg = 0;
-    // u0: own-cell state of the tile whose first segment was gathered last; it is consumed at that
-    // tile's first segment, before the next tile's first gather overwrites it
-    double raw_cur[RAW], raw_nxt[RAW], u0c[NVARS];
-
-    auto tile_of = [&](int m) -> std::int64_t {
-      const std::int64_t idx = blockIdx.x + (std::int64_t)m * gridDim.x;
-      return args.tile_list ? (std::int64_t)args.tile_list[idx] : idx;
-    };
-    auto has_tile = [&](int m) { return blockIdx.x + (std::int64_t)m * gridDim.x < n_launch; };
-
-    // issue the gather of one segment: raw neighbour values of this thread's variable
+    // issue the loads of one segment: raw neighbour values of this thread's variable
     auto issue_gather = [&](int m, int seg, double *raw) {
       const int hs = m % HS;
       const unsigned char *hdr = hdr_base + hs * T::HDR_BYTES;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
         ptx::mbar_wait(&hdr_full[hs], (m / HS) & 1);
         const std::int64_t cell_idx = min(tile_of(m) * TILE + cell, P.n_cells - 1);
 #pragma unroll
-        for (int v = 0; v < NVARS; ++v) u0c[v] = args.state[cell_idx * NVARS + v];
+        for (int v = 0; v < NVARS; ++v) u0[v] = args.state[cell_idx * NVARS + v];
       }
       if (seg < N_HI) {
         const std::int32_t *si = reinterpret_cast<const std::int32_t *>(hdr + T::OFF_SIDX0) + seg * R_HI * TILE + cell;
@@ -240,218 +245,54 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       }
     };
 
-    // per-tile state
-    double lo[NS][CLO > 0 ? CLO : 1], hi[NHI > 0 ? NHI : 1];
-    double scale_v = 1.0, inv_scale_v = 1.0, q0s = 0.0;
-    std::uint64_t meta = 0;
-
-    bool have_cur = has_tile(cur_m);
-    if (have_cur) issue_gather(cur_m, 0, raw_cur);
+    bool have_cur = has_tile(0);
+    if (have_cur) issue_gather(0, 0, raw_cur);
 #pragma unroll 1
     while (have_cur) {
       int nxt_m = cur_m, nxt_seg = cur_seg + 1;
       if (nxt_seg == N_SEGS) {
         nxt_seg = 0;
-        nxt_m += NG;
+        nxt_m += 1;
       }
       const bool have_nxt = has_tile(nxt_m);
-
-      if (cur_seg == 0) {  // N_SEGS >= 2: the gather issued below never belongs to another tile here
-        const unsigned char *hdr = hdr_base + (cur_m % HS) * T::HDR_BYTES;
-        meta = reinterpret_cast<const std::uint64_t *>(hdr)[cell];
-        const double ekin0 = 0.5 * (u0c[1] * u0c[1] + u0c[2] * u0c[2] + u0c[3] * u0c[3]) / u0c[0];
-        const double eint0 = u0c[4] - ekin0;
+      const int hs = cur_m % HS;
+      if (cur_seg == 0) {  // per-tile scalars of this (cell, variable); N_SEGS >= 2 keeps u0 intact until here
+        const double ekin0 = 0.5 * (u0[1] * u0[1] + u0[2] * u0[2] + u0[3] * u0[3]) / u0[0];
+        const double eint0 = u0[4] - ekin0;
+        double scale_v = 1.0;
         if (sc.scaling == SCALING_EULER) {  // characteristic_scale.hpp:24-33
           const double p = eint0 * (sc.gamma - 1.0);
-          const double cs = sqrt(sc.gamma * p / u0c[0]);
-          scale_v = (var == 0) ? u0c[0] : ((var == 4) ? eint0 : cs);
-        } else {
-          scale_v = 1.0;
+          const double cs = sqrt(sc.gamma * p / u0[0]);
+          scale_v = (var == 0) ? u0[0] : ((var == 4) ? eint0 : cs);
         }
         inv_scale_v = 1.0 / scale_v;
-        double own = u0c[0];
+        double own = u0[0];
 #pragma unroll
         for (int v = 1; v < NVARS; ++v)
-          if (var == v) own = u0c[v];
+          if (var == v) own = u0[v];
         q0s = own * inv_scale_v;
-#pragma unroll
-        for (int k = 0; k < NS; ++k)
-#pragma unroll
-          for (int c = 0; c < CLO; ++c) lo[k][c] = 0.0;
-#pragma unroll
-        for (int c = 0; c < NHI; ++c) hi[c] = 0.0;
+        double *info = info_base + (hs * TILE + cell) * (2 * NVARS);
+        info[var] = q0s;
+        info[NVARS + var] = scale_v;
       }
-
       if (have_nxt) issue_gather(nxt_m, nxt_seg, raw_nxt);
 
-      // ---- coef += W_seg * rhs ------------------------------------------------------------------
-      const int gseg = cur_m * N_SEGS + cur_seg;  // position in the weight ring
+      // ---- rhs rows of the current segment -> ring slot ---------------------------------------------
+      const int gseg = cur_m * N_SEGS + cur_seg;
       const int ws = gseg % WS;
-      ptx::mbar_wait(&w_full[ws], (gseg / WS) & 1);
-      const double *wslot = reinterpret_cast<const double *>(w_base + ws * T::SLOT_BYTES) + cell;
-      auto hi_rows = [&](auto n_rows_tag) {
-        constexpr int NR = decltype(n_rows_tag)::value;
+      ptx::mbar_wait(&w_empty[ws], ((gseg / WS) & 1) ^ 1);
+      double *rhs = reinterpret_cast<double *>(w_base + ws * T::SLOT_BYTES + T::W_BYTES) + ta;  // [row][cell][5]
+      int n_rows = 2 * RLO;
+      if (cur_seg < N_HI)
+        n_rows = (cur_seg == N_HI - 1) ? R_TAIL : R_HI;
+      else if ((NS - 1) % 2 == 1 && 1 + 2 * (cur_seg - N_HI) + 1 >= NS)
+        n_rows = RLO;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const double rhs = raw_cur[r] * inv_scale_v - q0s;
-#pragma unroll
-          for (int c = 0; c < CHI; ++c) {
-            const double wv = wslot[(r * CHI + c) * TILE];
-            if (c < CLO)
-              lo[0][c] = fma(wv, rhs, lo[0][c]);
-            else
-              hi[c - CLO] = fma(wv, rhs, hi[c - CLO]);
-          }
-        }
-      };
-      // the segment number is resolved by explicit branches so that lo[k][c] is only ever indexed with
-      // compile-time k (the accumulators must stay in registers)
-      auto lo_rows = [&](auto seg_tag) {
-        constexpr int s = decltype(seg_tag)::value;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          constexpr int k_first = 1 + 2 * s;
-          if (k_first + kk < NS) {
-#pragma unroll
-            for (int r = 0; r < RLO; ++r) {
-              const double rhs = raw_cur[kk * RLO + r] * inv_scale_v - q0s;
-#pragma unroll
-              for (int c = 0; c < CLO; ++c) {
-                const double wv = wslot[((kk * RLO + r) * CLO + c) * TILE];
-                constexpr int ka = k_first < NS ? k_first : 0, kb = k_first + 1 < NS ? k_first + 1 : 0;
-                if (kk == 0)
-                  lo[ka][c] = fma(wv, rhs, lo[ka][c]);
-                else
-                  lo[kb][c] = fma(wv, rhs, lo[kb][c]);
-              }
-            }
-          }
-        }
-      };
-      if (cur_seg < N_HI) {
-        if (R_TAIL != R_HI && cur_seg == N_HI - 1)
-          hi_rows(std::integral_constant<int, R_TAIL>{});
-        else
-          hi_rows(std::integral_constant<int, R_HI>{});
-      } else {
-        const int ls = cur_seg - N_HI;
-        if (ls == 0)
-          lo_rows(std::integral_constant<int, 0>{});
-        else if (N_LO > 1 && ls == 1)
-          lo_rows(std::integral_constant<int, (N_LO > 1 ? 1 : 0)>{});
-        else if (N_LO > 2 && ls == 2)
-          lo_rows(std::integral_constant<int, (N_LO > 2 ? 2 : 0)>{});
-      }
+      for (int r = 0; r < RAW; ++r)
+        if (r < n_rows) rhs[r * TILE * NVARS] = raw_cur[r] * inv_scale_v - q0s;
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&w_empty[ws]);
-
-      // ---- end of tile: hybridise and hand over ----------------------------------------------------
-      if (cur_seg == N_SEGS - 1) {
-        if (lane == 0) ptx::mbar_arrive(&hdr_empty[cur_m % HS]);  // ordered after the __syncwarp above
-        const int j_tile = cur_m / NG;  // tiles finished by this group
-        const int kh = (int)((meta >> 56) & 0xF);
-        const bool single = ((meta >> 60) & 1) != 0;
-        const int n_eff = single ? 1 : NS;
-        double a0h = q0s;  // constant coefficient of stencil kh after the CWENO correction
-        if (sc.recon_mode == RECON_CWENO_AO) {  // cweno_ao.cpp:41-50
-          double cor[CLO > 0 ? CLO : 1];
-#pragma unroll
-          for (int c = 0; c < CLO; ++c) {
-            cor[c] = 0.0;
-#pragma unroll
-            for (int k = 0; k < NS; ++k)
-              if (k == kh) cor[c] = lo[k][c];
-          }
-#pragma unroll
-          for (int k = 0; k < NS; ++k) {
-            if (k != kh && k < n_eff) {
-              const double g = sc.lin_w[k];
-              a0h -= g * q0s;
-#pragma unroll
-              for (int c = 0; c < CLO; ++c) cor[c] -= g * lo[k][c];
-            }
-          }
-          double gh = 1.0;
-#pragma unroll
-          for (int k = 0; k < NS; ++k)
-            if (k == kh) gh = single ? 1.0 : sc.lin_w[k];
-          const double inv_gh = 1.0 / gh;
-          a0h *= inv_gh;
-#pragma unroll
-          for (int c = 0; c < CLO; ++c) {
-            const double val = inv_gh * cor[c];
-#pragma unroll
-            for (int k = 0; k < NS; ++k)
-              if (k == kh) lo[k][c] = val;
-          }
-          if (kh == 0) {
-#pragma unroll
-            for (int c = 0; c < NHI; ++c) hi[c] *= inv_gh;
-          }
-        }
-        // smoothness indicators: this thread's variable -> shared memory -> max over variables
-        double *isb = is_x + (j_tile & 1) * (NS * NVARS * TILE);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-          double beta = 0.0;
-#pragma unroll
-          for (int c = 0; c < CLO; ++c) beta += lo[k][c] * lo[k][c];
-          if (k == 0) {
-#pragma unroll
-            for (int c = 0; c < NHI; ++c) beta += hi[c] * hi[c];
-          }
-          isb[(k * NVARS + var) * TILE + cell] = beta;
-        }
-        ptx::named_bar_sync(1 + grp, N_APPLY);
-        double alpha[NS];
-        double al_tot = 0.0;
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-          double is_max = isb[(k * NVARS) * TILE + cell];
-#pragma unroll
-          for (int v = 1; v < NVARS; ++v) is_max = fmax(is_max, isb[(k * NVARS + v) * TILE + cell]);
-          double is_pow;
-          if (sc.exponent == 4.0) {
-            const double s2 = is_max * is_max;
-            is_pow = s2 * s2;
-          } else if (sc.exponent == 2.0) {
-            is_pow = is_max * is_max;
-          } else {
-            is_pow = pow(is_max, sc.exponent);
-          }
-          const double g = single ? 1.0 : sc.lin_w[k];
-          alpha[k] = (k < n_eff) ? g / (sc.epsilon + is_pow) : 0.0;
-          al_tot += alpha[k];
-        }
-        double coef[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) coef[i] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-          const double wk = alpha[k] / al_tot;
-          coef[0] += wk * ((k == kh) ? a0h : q0s);
-#pragma unroll
-          for (int c = 0; c < CLO; ++c) coef[1 + c] += wk * lo[k][c];
-          if (k == 0) {
-#pragma unroll
-            for (int c = 0; c < NHI; ++c) coef[1 + CLO + c] += wk * hi[c];
-          }
-        }
-        if (P.poly != nullptr) {
-          const std::int64_t ci = tile_of(cur_m) * TILE + cell;
-          if (ci < P.n_cells) {
-            for (int i = 0; i < D; ++i) P.poly[(ci * P.n_poly_coef + i) * NVARS + var] = coef[i];
-            P.poly_scale[ci * NVARS + var] = scale_v;
-          }
-        }
-        // hand the polynomial (times the characteristic scale) to the trace group
-        ptx::mbar_wait(&coef_empty[grp], (j_tile & 1) ^ 1);
-        double *cx = coef_x + var * COEF_PAD + cell;
-#pragma unroll
-        for (int i = 0; i < D; ++i) cx[i * NVARS * COEF_PAD] = coef[i] * scale_v;
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&coef_full[grp]);
-      }
+      if (lane == 0) ptx::mbar_arrive(&w_full[ws]);
+      if (cur_seg == N_SEGS - 1 && lane == 0) ptx::mbar_arrive(&hdr_empty[hs]);  // indices of this tile are consumed
 
 #pragma unroll
       for (int r = 0; r < RAW; ++r) raw_cur[r] = raw_nxt[r];
@@ -462,13 +303,241 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
     return;
   }
 
+  // =============================== apply groups: thread = (cell, coefficient group) =================
+  if (warp < FIRST_TRACE_WARP) {
+    const int grp = (warp - FIRST_APPLY_WARP) / G;
+    const int g = (warp - FIRST_APPLY_WARP) - grp * G;
+    const int cell = lane;
+    constexpr int N_GROUP_THREADS = 32 * G;
+    double *xchg = reinterpret_cast<double *>(smem + cfg.off_xchg + grp * T::XCHG_BYTES);     // partial IS | coefficients
+    double *alpha_x = reinterpret_cast<double *>(smem + cfg.off_alpha + grp * T::ALPHA_BYTES);  // [NS][32]
+
+#pragma unroll 1
+    for (int m = grp; has_tile(m); m += NG) {
+      double lo[NS][NVARS], hi[HPT > 0 ? HPT : 1][NVARS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) lo[k][v] = 0.0;
+#pragma unroll
+      for (int h = 0; h < HPT; ++h)
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) hi[h][v] = 0.0;
+
+#pragma unroll 1
+      for (int seg = 0; seg < N_SEGS; ++seg) {
+        const int gseg = m * N_SEGS + seg;
+        const int ws = gseg % WS;
+        ptx::mbar_wait(&w_full[ws], (gseg / WS) & 1);
+        const double *wslot = reinterpret_cast<const double *>(w_base + ws * T::SLOT_BYTES) + g * TILE + cell;
+        const double *rslot = reinterpret_cast<const double *>(w_base + ws * T::SLOT_BYTES + T::W_BYTES) + cell * NVARS;
+        auto hi_rows = [&](auto n_rows_tag) {
+          constexpr int NR = decltype(n_rows_tag)::value;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            double rhs[NVARS];
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) rhs[v] = rslot[r * TILE * NVARS + v];
+            const double wl = wslot[(r * CHI) * TILE];  // low-order coefficient g of the central stencil
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) lo[0][v] = fma(wl, rhs[v], lo[0][v]);
+#pragma unroll
+            for (int h = 0; h < HPT; ++h) {
+              if (NHI % G == 0 || h * G + g < NHI) {  // high-order coefficient CLO + h*G + g
+                const double wh = wslot[(r * CHI + CLO + h * G) * TILE];
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v) hi[h][v] = fma(wh, rhs[v], hi[h][v]);
+              }
+            }
+          }
+        };
+        // the segment number is resolved by explicit branches so that lo[k][v] is only ever indexed with
+        // compile-time k (the accumulators must stay in registers)
+        auto lo_rows = [&](auto seg_tag) {
+          constexpr int s = decltype(seg_tag)::value;
+          constexpr int k_first = 1 + 2 * s;
+          constexpr int ka = k_first < NS ? k_first : 0, kb = k_first + 1 < NS ? k_first + 1 : 0;
+#pragma unroll
+          for (int r = 0; r < RLO; ++r) {  // the two stencils interleaved: independent accumulator chains
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              if (k_first + kk < NS) {
+                double rhs[NVARS];
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v) rhs[v] = rslot[(kk * RLO + r) * TILE * NVARS + v];
+                const double wv = wslot[((kk * RLO + r) * CLO) * TILE];
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v) {
+                  if (kk == 0)
+                    lo[ka][v] = fma(wv, rhs[v], lo[ka][v]);
+                  else
+                    lo[kb][v] = fma(wv, rhs[v], lo[kb][v]);
+                }
+              }
+            }
+          }
+        };
+        if (seg < N_HI) {
+          if (R_TAIL != R_HI && seg == N_HI - 1)
+            hi_rows(std::integral_constant<int, R_TAIL>{});
+          else
+            hi_rows(std::integral_constant<int, R_HI>{});
+        } else {
+          const int ls = seg - N_HI;
+          if (ls == 0)
+            lo_rows(std::integral_constant<int, 0>{});
+          else if (N_LO > 1 && ls == 1)
+            lo_rows(std::integral_constant<int, (N_LO > 1 ? 1 : 0)>{});
+          else if (N_LO > 2 && ls == 2)
+            lo_rows(std::integral_constant<int, (N_LO > 2 ? 2 : 0)>{});
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&w_empty[ws]);
+      }
+
+      // ---- hybridise (cweno_ao.cpp:36-53, hybrid_weno.cpp:110-128) -----------------------------------
+      const int hs = m % HS;
+      const int j_tile = m / NG;  // tiles finished by this group
+      const std::uint64_t meta = reinterpret_cast<const std::uint64_t *>(hdr_base + hs * T::HDR_BYTES)[cell];
+      const int kh = (int)((meta >> 56) & 0xF);
+      const bool single = ((meta >> 60) & 1) != 0;
+      const int n_eff = single ? 1 : NS;
+      double inv_gh = 1.0;
+      if (sc.recon_mode == RECON_CWENO_AO) {
+        double gh = 1.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+          if (k == kh) gh = single ? 1.0 : sc.lin_w[k];
+        inv_gh = 1.0 / gh;
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) {
+          double cor = 0.0;
+#pragma unroll
+          for (int k = 0; k < NS; ++k)
+            if (k == kh) cor = lo[k][v];
+#pragma unroll
+          for (int k = 0; k < NS; ++k)
+            if (k != kh && k < n_eff) cor -= sc.lin_w[k] * lo[k][v];
+          const double val = inv_gh * cor;
+#pragma unroll
+          for (int k = 0; k < NS; ++k)
+            if (k == kh) lo[k][v] = val;
+        }
+        if (kh == 0) {
+#pragma unroll
+          for (int h = 0; h < HPT; ++h)
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) hi[h][v] *= inv_gh;
+        }
+      }
+      // partial smoothness indicators of this thread's coefficients -> shared memory
+      ptx::mbar_wait(&coef_empty[grp], (j_tile & 1) ^ 1);  // the exchange area aliases the previous polynomial
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) {
+          double beta = lo[k][v] * lo[k][v];
+          if (k == 0) {
+#pragma unroll
+            for (int h = 0; h < HPT; ++h) beta += hi[h][v] * hi[h][v];  // unused slots hold exact zeros
+          }
+          xchg[((g * NS + k) * NVARS + v) * TILE + cell] = beta;
+        }
+      ptx::named_bar_sync(1 + grp, N_GROUP_THREADS);
+      // non-linear weight of stencil k: computed by thread k % G
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (k % G == g) {
+          double is_max = 0.0;
+#pragma unroll
+          for (int v = 0; v < NVARS; ++v) {
+            // same summation order as a single thread would use: low-order coefficients first (g = 0, 1, ..)
+            double beta = xchg[((0 * NS + k) * NVARS + v) * TILE + cell];
+#pragma unroll
+            for (int gg = 1; gg < G; ++gg) beta += xchg[((gg * NS + k) * NVARS + v) * TILE + cell];
+            is_max = (v == 0) ? beta : fmax(is_max, beta);
+          }
+          double is_pow;
+          if (sc.exponent == 4.0) {
+            const double s2 = is_max * is_max;
+            is_pow = s2 * s2;
+          } else if (sc.exponent == 2.0) {
+            is_pow = is_max * is_max;
+          } else {
+            is_pow = pow(is_max, sc.exponent);
+          }
+          const double gk = single ? 1.0 : sc.lin_w[k];
+          alpha_x[k * TILE + cell] = (k < n_eff) ? gk / (sc.epsilon + is_pow) : 0.0;
+        }
+      }
+      ptx::named_bar_sync(1 + grp, N_GROUP_THREADS);
+      double wk[NS];
+      {
+        double al_tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+          wk[k] = alpha_x[k * TILE + cell];
+          al_tot += wk[k];
+        }
+        const double inv_tot = 1.0 / al_tot;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) wk[k] *= inv_tot;
+      }
+      // this thread's coefficients of the hybridised polynomial, times the characteristic scale -> trace group
+      const double *info = info_base + (hs * TILE + cell) * (2 * NVARS);
+      const std::int64_t ci = tile_of(m) * TILE + cell;
+      const bool keep = P.poly != nullptr && ci < P.n_cells;
+      double *cx = xchg + cell;
+#pragma unroll
+      for (int v = 0; v < NVARS; ++v) {
+        const double scale_v = info[NVARS + v];
+        double c_lo = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) c_lo += wk[k] * lo[k][v];
+        cx[((1 + g) * NVARS + v) * COEF_PAD] = c_lo * scale_v;
+        if (keep) P.poly[(ci * P.n_poly_coef + 1 + g) * NVARS + v] = c_lo;
+#pragma unroll
+        for (int h = 0; h < HPT; ++h) {
+          if (NHI % G == 0 || h * G + g < NHI) {
+            const double c_hi = wk[0] * hi[h][v];
+            cx[((1 + CLO + h * G + g) * NVARS + v) * COEF_PAD] = c_hi * scale_v;
+            if (keep) P.poly[(ci * P.n_poly_coef + 1 + CLO + h * G + g) * NVARS + v] = c_hi;
+          }
+        }
+        if (g == 0) {  // constant coefficient: q0 for every stencil but kh, whose value carries the CWENO correction
+          const double q0 = info[v];
+          double a0h = q0;
+          if (sc.recon_mode == RECON_CWENO_AO) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (k != kh && k < n_eff) a0h -= sc.lin_w[k] * q0;
+            a0h *= inv_gh;
+          }
+          double c0 = 0.0;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) c0 += wk[k] * ((k == kh) ? a0h : q0);
+          cx[v * COEF_PAD] = c0 * scale_v;
+          if (keep) {
+            P.poly[(ci * P.n_poly_coef) * NVARS + v] = c0;
+            P.poly_scale[ci * NVARS + v] = scale_v;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&coef_full[grp]);
+        ptx::mbar_arrive(&hdr_empty[hs]);
+      }
+    }
+    return;
+  }
+
   // =============================== trace group: thread = (cell, face) ===============================
   {
-    const int k = warp - (1 + NG * STREAM_VAR_WARPS);  // local face
-    std::int64_t m = 0;
+    const int k = warp - FIRST_TRACE_WARP;  // local face
 #pragma unroll 1
-    for (std::int64_t idx = blockIdx.x; idx < n_launch; idx += gridDim.x, ++m) {
-      const std::int64_t tile = args.tile_list ? (std::int64_t)args.tile_list[idx] : idx;
+    for (int m = 0; has_tile(m); ++m) {
+      const std::int64_t tile = tile_of(m);
       const std::int64_t cell = tile * TILE + lane;
       const bool active = cell < P.n_cells;
       // geometry of the cell (issued before the wait: the loads overlap the apply groups' work)
@@ -494,9 +563,9 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       const int side = (fref & FREF_SIDE) ? 1 : 0;
       const bool want_trace = (fref & FREF_TRACE) != 0;
 
-      const int grp = (int)(m % NG);
-      ptx::mbar_wait(&coef_full[grp], (int)((m / NG) & 1));
-      const double *cx = reinterpret_cast<const double *>(smem + cfg.off_coef + grp * T::COEF_BYTES) + lane;
+      const int grp = m % NG;
+      ptx::mbar_wait(&coef_full[grp], (m / NG) & 1);
+      const double *cx = reinterpret_cast<const double *>(smem + cfg.off_xchg + grp * T::XCHG_BYTES) + lane;
       constexpr int VP = T::VARS_PER_PASS;
 #pragma unroll
       for (int v0 = 0; v0 < NVARS; v0 += VP) {
@@ -511,28 +580,25 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
           if (lane == 0) ptx::mbar_arrive(&coef_empty[grp]);
         }
         if (want_trace) {
-#pragma unroll
           for (int q = 0; q < sc.q_f; ++q) {
-            {
-              double xs[3] = {0.0, 0.0, 0.0};
+            double xs[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-              for (int d = 0; d < ND; ++d) {
-                const double x = (ND == 2) ? sc.face_bary[q][0] * fv[0][d] + sc.face_bary[q][1] * fv[1][d]
-                                           : fv[0][d] * sc.face_bary[q][0] + fv[1][d] * sc.face_bary[q][1] +
-                                                 fv[ND - 1][d] * sc.face_bary[q][2];
-                xs[d] = (x - xc[d]) * inv_len;
-              }
-              double mono[D];
-              PolyEval<ND, DEG_HI>::monomials(xs[0], xs[1], xs[2], cmom, mono);
-              double *tr = P.trace + ((e * 2 + side) * sc.q_f + q) * NVARS;
+            for (int d = 0; d < ND; ++d) {
+              const double x = (ND == 2) ? sc.face_bary[q][0] * fv[0][d] + sc.face_bary[q][1] * fv[1][d]
+                                         : fv[0][d] * sc.face_bary[q][0] + fv[1][d] * sc.face_bary[q][1] +
+                                               fv[ND - 1][d] * sc.face_bary[q][2];
+              xs[d] = (x - xc[d]) * inv_len;
+            }
+            double mono[D];
+            PolyEval<ND, DEG_HI>::monomials(xs[0], xs[1], xs[2], cmom, mono);
+            double *tr = P.trace + ((e * 2 + side) * sc.q_f + q) * NVARS;
 #pragma unroll
-              for (int v = 0; v < VP; ++v) {
-                if (v0 + v < NVARS) {
-                  double s = coef[0][v];
+            for (int v = 0; v < VP; ++v) {
+              if (v0 + v < NVARS) {
+                double s = coef[0][v];
 #pragma unroll
-                  for (int i = 1; i < D; ++i) s = fma(coef[i][v], mono[i], s);
-                  tr[v0 + v] = s;
-                }
+                for (int i = 1; i < D; ++i) s = fma(coef[i][v], mono[i], s);
+                tr[v0 + v] = s;
               }
             }
           }
@@ -553,16 +619,18 @@ bool stream_config(const DevicePlan &P, const SchemeConst &sc, int smem_budget, 
   if (P.rec_bytes != T::REC_BYTES || P.hdr_bytes != T::HDR_BYTES) return false;
   for (int k = 0; k < NS; ++k)
     if (P.off_sidx[k] != T::off_sidx(k) || P.off_W[k] != T::off_W(k)) return false;
-  const int fixed = STREAM_BARS_BYTES + STREAM_HDR_SLOTS * T::HDR_BYTES + STREAM_GROUPS * (T::COEF_BYTES + T::IS_BYTES);
+  const int fixed = STREAM_BARS_BYTES + STREAM_HDR_SLOTS * (T::HDR_BYTES + T::INFO_BYTES) +
+                    STREAM_GROUPS * (T::XCHG_BYTES + T::ALPHA_BYTES);
   int ws = (smem_budget - fixed) / T::SLOT_BYTES;
   if (ws > 12) ws = 12;
   if (ws < 3) return false;
   c.n_w_slots = ws;
   c.off_hdr = STREAM_BARS_BYTES;
-  c.off_w = c.off_hdr + STREAM_HDR_SLOTS * T::HDR_BYTES;
-  c.off_coef = c.off_w + ws * T::SLOT_BYTES;
-  c.off_is = c.off_coef + STREAM_GROUPS * T::COEF_BYTES;
-  c.total_bytes = c.off_is + STREAM_GROUPS * T::IS_BYTES;
+  c.off_info = c.off_hdr + STREAM_HDR_SLOTS * T::HDR_BYTES;
+  c.off_w = c.off_info + STREAM_HDR_SLOTS * T::INFO_BYTES;
+  c.off_xchg = c.off_w + ws * T::SLOT_BYTES;
+  c.off_alpha = c.off_xchg + STREAM_GROUPS * T::XCHG_BYTES;
+  c.total_bytes = c.off_alpha + STREAM_GROUPS * T::ALPHA_BYTES;
   return 2 * STREAM_HDR_SLOTS + 2 * STREAM_GROUPS + 2 * ws <= STREAM_BARS_BYTES / 8;
 }
 
