@@ -21,10 +21,8 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
   if (n_tiles <= 0) return 0;
   if constexpr (DEG_HI >= 1) {
     // streaming kernel (recon_stream.cuh); ZFVM_RECON=v1 selects the thread-per-cell kernel for comparisons
-    static const bool force_v1 = [] {
-      const char *e = std::getenv("ZFVM_RECON");
-      return e && e[0] == 'v' && e[1] == '1';
-    }();
+    const char *e_recon = std::getenv("ZFVM_RECON");
+    const bool force_v1 = e_recon && e_recon[0] == 'v' && e_recon[1] == '1';
     if (!sc.well_balanced && !sc.has_gravity && !force_v1) {
       int dev = 0, optin = 0, n_sm = 0;
       cudaGetDevice(&dev);
@@ -36,7 +34,10 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
       if (stream_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO>(plan, sc, budget, cfg)) {
         auto kern = recon_stream_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.total_bytes);
-        const unsigned grid = (unsigned)std::min<std::int64_t>(n_tiles, n_sm);
+        // one persistent CTA per SM; ZFVM_STREAM_MAX_CTAS lowers the count (tests use it to put many tiles on a CTA)
+        const char *e_ctas = std::getenv("ZFVM_STREAM_MAX_CTAS");
+        const int max_ctas = e_ctas ? std::max(1, std::atoi(e_ctas)) : (1 << 30);
+        const unsigned grid = (unsigned)std::min<std::int64_t>(n_tiles, std::min(n_sm, max_ctas));
         const int block = 32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO>::N_WARPS;
         kern<<<grid, block, (size_t)cfg.total_bytes, stream>>>(args, sc, cfg);
         return 0;

@@ -36,7 +36,9 @@ namespace zfvm {
 
 struct StreamCfg {
   int n_w_slots;
-  int off_hdr, off_info, off_w, off_xchg, off_alpha;  // byte offsets into dynamic shared memory (barriers at 0)
+  int n_groups;  // apply groups in use (1 or STREAM_GROUPS)
+  int off_hdr, off_info, off_w, off_xchg, off_alpha, off_stage;  // byte offsets into dynamic shared memory (barriers at 0)
+  int stage_pitch;  // doubles per lane in the trace staging area (odd: conflict-free 64-bit accesses)
   int total_bytes;
 };
 
@@ -55,7 +57,7 @@ struct StreamTraits {
   static constexpr int NHI = CHI - CLO;
   static constexpr int G = CLO;                                 // apply warps per group = coefficient groups
   static constexpr int HPT = (NHI + G - 1) / (G > 0 ? G : 1);  // high-order coefficients per apply thread
-  static constexpr int R_CAP0 = 24576 / (CHI * TILE * 8);
+  static constexpr int R_CAP0 = 16384 / (CHI * TILE * 8);       // weight segments of <= 16 KB
   static constexpr int R_CAP = R_CAP0 < 1 ? 1 : (R_CAP0 > 12 ? 12 : R_CAP0);
   static constexpr int N_HI = (RM0 + R_CAP - 1) / R_CAP;       // central-stencil segments
   static constexpr int R_HI = (RM0 + N_HI - 1) / N_HI;         // rows per segment (balanced)
@@ -133,16 +135,17 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
   using T = StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO>;
   constexpr int F = T::F, D = T::D, CHI = T::CHI, CLO = T::CLO, NHI = T::NHI, G = T::G, HPT = T::HPT;
   constexpr int N_HI = T::N_HI, R_HI = T::R_HI, R_TAIL = T::R_TAIL, N_LO = T::N_LO, N_SEGS = T::N_SEGS;
-  constexpr int RAW = T::RAW, HS = STREAM_HDR_SLOTS, NG = STREAM_GROUPS;
-  constexpr int FIRST_APPLY_WARP = 1 + STREAM_VAR_WARPS, FIRST_TRACE_WARP = FIRST_APPLY_WARP + NG * G;
+  constexpr int RAW = T::RAW, HS = STREAM_HDR_SLOTS;
+  constexpr int FIRST_APPLY_WARP = 1 + STREAM_VAR_WARPS, FIRST_TRACE_WARP = FIRST_APPLY_WARP + STREAM_GROUPS * G;
+  const int NG = cfg.n_groups;
   const DevicePlan &P = args.plan;
 
   extern __shared__ __align__(128) unsigned char smem[];
   std::uint64_t *bars = reinterpret_cast<std::uint64_t *>(smem);
   const int WS = cfg.n_w_slots;
   std::uint64_t *hdr_full = bars, *hdr_empty = bars + HS;
-  std::uint64_t *coef_full = bars + 2 * HS, *coef_empty = coef_full + NG;
-  std::uint64_t *w_full = coef_empty + NG, *w_empty = w_full + WS;
+  std::uint64_t *coef_full = bars + 2 * HS, *coef_empty = coef_full + STREAM_GROUPS;
+  std::uint64_t *w_full = coef_empty + STREAM_GROUPS, *w_empty = w_full + WS;
   unsigned char *hdr_base = smem + cfg.off_hdr;
   unsigned char *w_base = smem + cfg.off_w;
   double *info_base = reinterpret_cast<double *>(smem + cfg.off_info);  // [HS][32][10]
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       ptx::mbar_init(&w_full[s], 1 + STREAM_VAR_WARPS);  // TMA transaction + rhs rows of the gather warps
       ptx::mbar_init(&w_empty[s], G);
     }
-    for (int g = 0; g < NG; ++g) {
+    for (int g = 0; g < STREAM_GROUPS; ++g) {
       ptx::mbar_init(&coef_full[g], G);
       ptx::mbar_init(&coef_empty[g], F);
     }
@@ -307,6 +310,7 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
   if (warp < FIRST_TRACE_WARP) {
     const int grp = (warp - FIRST_APPLY_WARP) / G;
     const int g = (warp - FIRST_APPLY_WARP) - grp * G;
+    if (grp >= NG) return;
     const int cell = lane;
     constexpr int N_GROUP_THREADS = 32 * G;
     double *xchg = reinterpret_cast<double *>(smem + cfg.off_xchg + grp * T::XCHG_BYTES);     // partial IS | coefficients
@@ -403,31 +407,47 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       const bool single = ((meta >> 60) & 1) != 0;
       const int n_eff = single ? 1 : NS;
       double inv_gh = 1.0;
+      // all 32 cells of the warp have the full family with the central stencil as the highest-order one
+      // (true away from boundaries): compile-time stencil indices, no select chains
+      const bool fast = __all_sync(0xffffffffu, kh == 0 && !single);
       if (sc.recon_mode == RECON_CWENO_AO) {
-        double gh = 1.0;
+        if (fast) {
+          inv_gh = 1.0 / sc.lin_w[0];
 #pragma unroll
-        for (int k = 0; k < NS; ++k)
-          if (k == kh) gh = single ? 1.0 : sc.lin_w[k];
-        inv_gh = 1.0 / gh;
+          for (int v = 0; v < NVARS; ++v) {
+            double cor = lo[0][v];
 #pragma unroll
-        for (int v = 0; v < NVARS; ++v) {
-          double cor = 0.0;
+            for (int k = 1; k < NS; ++k) cor -= sc.lin_w[k] * lo[k][v];
+            lo[0][v] = inv_gh * cor;
 #pragma unroll
-          for (int k = 0; k < NS; ++k)
-            if (k == kh) cor = lo[k][v];
-#pragma unroll
-          for (int k = 0; k < NS; ++k)
-            if (k != kh && k < n_eff) cor -= sc.lin_w[k] * lo[k][v];
-          const double val = inv_gh * cor;
+            for (int h = 0; h < HPT; ++h) hi[h][v] *= inv_gh;
+          }
+        } else {
+          double gh = 1.0;
 #pragma unroll
           for (int k = 0; k < NS; ++k)
-            if (k == kh) lo[k][v] = val;
-        }
-        if (kh == 0) {
+            if (k == kh) gh = single ? 1.0 : sc.lin_w[k];
+          inv_gh = 1.0 / gh;
 #pragma unroll
-          for (int h = 0; h < HPT; ++h)
+          for (int v = 0; v < NVARS; ++v) {
+            double cor = 0.0;
 #pragma unroll
-            for (int v = 0; v < NVARS; ++v) hi[h][v] *= inv_gh;
+            for (int k = 0; k < NS; ++k)
+              if (k == kh) cor = lo[k][v];
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (k != kh && k < n_eff) cor -= sc.lin_w[k] * lo[k][v];
+            const double val = inv_gh * cor;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (k == kh) lo[k][v] = val;
+          }
+          if (kh == 0) {
+#pragma unroll
+            for (int h = 0; h < HPT; ++h)
+#pragma unroll
+              for (int v = 0; v < NVARS; ++v) hi[h][v] *= inv_gh;
+          }
         }
       }
       // partial smoothness indicators of this thread's coefficients -> shared memory
@@ -563,6 +583,7 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       const int side = (fref & FREF_SIDE) ? 1 : 0;
       const bool want_trace = (fref & FREF_TRACE) != 0;
 
+      double *stage = reinterpret_cast<double *>(smem + cfg.off_stage) + k * TILE * cfg.stage_pitch;
       const int grp = m % NG;
       ptx::mbar_wait(&coef_full[grp], (m / NG) & 1);
       const double *cx = reinterpret_cast<const double *>(smem + cfg.off_xchg + grp * T::XCHG_BYTES) + lane;
@@ -579,7 +600,7 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&coef_empty[grp]);
         }
-        if (want_trace) {
+        {  // every lane evaluates (lanes without a trace hold finite garbage that is never written out)
           for (int q = 0; q < sc.q_f; ++q) {
             double xs[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -591,19 +612,39 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
             }
             double mono[D];
             PolyEval<ND, DEG_HI>::monomials(xs[0], xs[1], xs[2], cmom, mono);
-            double *tr = P.trace + ((e * 2 + side) * sc.q_f + q) * NVARS;
 #pragma unroll
             for (int v = 0; v < VP; ++v) {
               if (v0 + v < NVARS) {
                 double s = coef[0][v];
 #pragma unroll
                 for (int i = 1; i < D; ++i) s = fma(coef[i][v], mono[i], s);
-                tr[v0 + v] = s;
+                stage[lane * cfg.stage_pitch + q * NVARS + v0 + v] = s;
               }
             }
           }
         }
       }
+      // coalesced write-out: consecutive lanes write consecutive doubles of a cell's 40*q_f-byte trace block
+      // (a lane-per-cell store would touch 32 cache lines per instruction)
+      __syncwarp();
+      {
+        const int qv = sc.q_f * NVARS;
+        const std::int64_t my_base = ((e * 2 + side) * sc.q_f) * NVARS;
+        int owner = lane / qv, j = lane - owner * qv;
+        const int step_o = TILE / qv, step_j = TILE - step_o * qv;
+        for (int it = 0; it < qv; ++it) {
+          const std::int64_t base = __shfl_sync(0xffffffffu, my_base, owner);
+          const int want = __shfl_sync(0xffffffffu, (int)want_trace, owner);
+          if (want) P.trace[base + j] = stage[owner * cfg.stage_pitch + j];
+          owner += step_o;
+          j += step_j;
+          if (j >= qv) {
+            j -= qv;
+            ++owner;
+          }
+        }
+      }
+      __syncwarp();  // the staging area is reused for the next tile
     }
   }
 }
@@ -619,18 +660,26 @@ bool stream_config(const DevicePlan &P, const SchemeConst &sc, int smem_budget, 
   if (P.rec_bytes != T::REC_BYTES || P.hdr_bytes != T::HDR_BYTES) return false;
   for (int k = 0; k < NS; ++k)
     if (P.off_sidx[k] != T::off_sidx(k) || P.off_W[k] != T::off_W(k)) return false;
+  c.stage_pitch = (sc.q_f * NVARS) | 1;
+  const int stage_bytes = T::F * TILE * c.stage_pitch * 8;
   const int fixed = STREAM_BARS_BYTES + STREAM_HDR_SLOTS * (T::HDR_BYTES + T::INFO_BYTES) +
-                    STREAM_GROUPS * (T::XCHG_BYTES + T::ALPHA_BYTES);
+                    STREAM_GROUPS * (T::XCHG_BYTES + T::ALPHA_BYTES) + stage_bytes;
   int ws = (smem_budget - fixed) / T::SLOT_BYTES;
   if (ws > 12) ws = 12;
-  if (ws < 3) return false;
+  // mbarrier waits see one parity bit: an apply group may only wait for use u of a slot once use u-1 has
+  // completed.  Its previous segment is N_SEGS + 1 ring positions back when it moves on to its next tile
+  // (the other group's tile lies in between), and fills complete in ring order, so WS >= N_SEGS + 1 makes
+  // use u-1 of the slot (WS positions back) no younger than a segment the group has already consumed.
+  c.n_groups = (ws >= T::N_SEGS + 1) ? STREAM_GROUPS : 1;
+  if (ws < 2) return false;
   c.n_w_slots = ws;
   c.off_hdr = STREAM_BARS_BYTES;
   c.off_info = c.off_hdr + STREAM_HDR_SLOTS * T::HDR_BYTES;
   c.off_w = c.off_info + STREAM_HDR_SLOTS * T::INFO_BYTES;
   c.off_xchg = c.off_w + ws * T::SLOT_BYTES;
   c.off_alpha = c.off_xchg + STREAM_GROUPS * T::XCHG_BYTES;
-  c.total_bytes = c.off_alpha + STREAM_GROUPS * T::ALPHA_BYTES;
+  c.off_stage = c.off_alpha + STREAM_GROUPS * T::ALPHA_BYTES;
+  c.total_bytes = c.off_stage + stage_bytes;
   return 2 * STREAM_HDR_SLOTS + 2 * STREAM_GROUPS + 2 * ws <= STREAM_BARS_BYTES / 8;
 }
 
