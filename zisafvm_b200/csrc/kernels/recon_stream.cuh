@@ -211,55 +211,69 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
   if (warp < FIRST_APPLY_WARP) {
     const int ta = threadIdx.x - 32;
     const int cell = ta / NVARS, var = ta - cell * NVARS;
-    int cur_m = 0, cur_seg = 0;
-    double raw_cur[RAW], raw_nxt[RAW], u0[NVARS];
+    constexpr int N_LOW_ROWS = (NS - 1) * RLO;
+    // Two register buffers hold the raw neighbour values of a whole tile: the central-stencil rows and the
+    // one-sided-stencil rows.  While one half is being scaled and stored into ring slots, the loads of the
+    // same half of the NEXT tile are already in flight (17..34 independent loads per thread), which is what
+    // hides the L2 / HBM latency of the gather without any occupancy.
+    double raw_hi[RM0], raw_lo[N_LOW_ROWS], u0[NVARS];
     double inv_scale_v = 1.0, q0s = 0.0;
 
-    // issue the loads of one segment: raw neighbour values of this thread's variable
-    auto issue_gather = [&](int m, int seg, double *raw) {
+    auto load_hi = [&](int m) {  // waits for the tile's header; also fetches the cell's own state
       const int hs = m % HS;
       const unsigned char *hdr = hdr_base + hs * T::HDR_BYTES;
-      if (seg == 0) {
-        ptx::mbar_wait(&hdr_full[hs], (m / HS) & 1);
-        const std::int64_t cell_idx = min(tile_of(m) * TILE + cell, P.n_cells - 1);
+      ptx::mbar_wait(&hdr_full[hs], (m / HS) & 1);
+      const std::int64_t cell_idx = min(tile_of(m) * TILE + cell, P.n_cells - 1);
 #pragma unroll
-        for (int v = 0; v < NVARS; ++v) u0[v] = args.state[cell_idx * NVARS + v];
+      for (int v = 0; v < NVARS; ++v) u0[v] = args.state[cell_idx * NVARS + v];
+      const std::int32_t *si = reinterpret_cast<const std::int32_t *>(hdr + T::OFF_SIDX0) + cell;
+#pragma unroll
+      for (int r = 0; r < RM0; ++r) raw_hi[r] = args.state[(std::int64_t)si[r * TILE] * NVARS + var];
+    };
+    auto load_lo = [&](int m) {
+      const unsigned char *hdr = hdr_base + (m % HS) * T::HDR_BYTES;
+      const std::int32_t *si = reinterpret_cast<const std::int32_t *>(hdr + T::off_sidx(1)) + cell;
+#pragma unroll
+      for (int r = 0; r < N_LOW_ROWS; ++r) raw_lo[r] = args.state[(std::int64_t)si[r * TILE] * NVARS + var];
+    };
+    // scale and store rows [first, first + count) of `raw` into the rhs part of the ring slot of segment `seg`
+    auto store_rows = [&](int m, int seg, const double *raw, auto first_tag, auto count_tag) {
+      constexpr int FIRST = decltype(first_tag)::value, COUNT = decltype(count_tag)::value;
+      const int gseg = m * N_SEGS + seg;
+      const int ws = gseg % WS;
+      ptx::mbar_wait(&w_empty[ws], ((gseg / WS) & 1) ^ 1);
+      double *rhs = reinterpret_cast<double *>(w_base + ws * T::SLOT_BYTES + T::W_BYTES) + ta;  // [row][cell][5]
+#pragma unroll
+      for (int r = 0; r < COUNT; ++r) rhs[r * TILE * NVARS] = raw[FIRST + r] * inv_scale_v - q0s;
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&w_full[ws]);
+    };
+    auto for_each_hi_seg = [&](int m, auto self, auto seg_tag) -> void {
+      constexpr int S = decltype(seg_tag)::value;
+      if constexpr (S < N_HI) {
+        store_rows(m, S, raw_hi, std::integral_constant<int, S * R_HI>{},
+                   std::integral_constant<int, (S == N_HI - 1 ? R_TAIL : R_HI)>{});
+        self(m, self, std::integral_constant<int, S + 1>{});
       }
-      if (seg < N_HI) {
-        const std::int32_t *si = reinterpret_cast<const std::int32_t *>(hdr + T::OFF_SIDX0) + seg * R_HI * TILE + cell;
-        if (R_TAIL != R_HI && seg == N_HI - 1) {
-#pragma unroll
-          for (int r = 0; r < R_TAIL; ++r) raw[r] = args.state[(std::int64_t)si[r * TILE] * NVARS + var];
-        } else {
-#pragma unroll
-          for (int r = 0; r < R_HI; ++r) raw[r] = args.state[(std::int64_t)si[r * TILE] * NVARS + var];
-        }
-      } else {
-        // one-sided stencils k0, k0 + 1: their index rows are contiguous in the header
-        const int k0 = 1 + 2 * (seg - N_HI);
-        const std::int32_t *si = reinterpret_cast<const std::int32_t *>(hdr + T::off_sidx(1)) + (k0 - 1) * RLO * TILE + cell;
-        if ((NS - 1) % 2 == 1 && k0 + 1 >= NS) {
-#pragma unroll
-          for (int r = 0; r < RLO; ++r) raw[r] = args.state[(std::int64_t)si[r * TILE] * NVARS + var];
-        } else {
-#pragma unroll
-          for (int r = 0; r < 2 * RLO; ++r) raw[r] = args.state[(std::int64_t)si[r * TILE] * NVARS + var];
-        }
+    };
+    auto for_each_lo_seg = [&](int m, auto self, auto seg_tag) -> void {
+      constexpr int S = decltype(seg_tag)::value;
+      if constexpr (S < N_LO) {
+        constexpr int K0 = 1 + 2 * S;
+        store_rows(m, N_HI + S, raw_lo, std::integral_constant<int, (K0 - 1) * RLO>{},
+                   std::integral_constant<int, (K0 + 1 < NS ? 2 : 1) * RLO>{});
+        self(m, self, std::integral_constant<int, S + 1>{});
       }
     };
 
-    bool have_cur = has_tile(0);
-    if (have_cur) issue_gather(0, 0, raw_cur);
+    if (has_tile(0)) {
+      load_hi(0);
+      load_lo(0);
+    }
 #pragma unroll 1
-    while (have_cur) {
-      int nxt_m = cur_m, nxt_seg = cur_seg + 1;
-      if (nxt_seg == N_SEGS) {
-        nxt_seg = 0;
-        nxt_m += 1;
-      }
-      const bool have_nxt = has_tile(nxt_m);
-      const int hs = cur_m % HS;
-      if (cur_seg == 0) {  // per-tile scalars of this (cell, variable); N_SEGS >= 2 keeps u0 intact until here
+    for (int m = 0; has_tile(m); ++m) {
+      const int hs = m % HS;
+      {  // per-tile scalars of this (cell, variable)
         const double ekin0 = 0.5 * (u0[1] * u0[1] + u0[2] * u0[2] + u0[3] * u0[3]) / u0[0];
         const double eint0 = u0[4] - ekin0;
         double scale_v = 1.0;
@@ -278,30 +292,13 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
         info[var] = q0s;
         info[NVARS + var] = scale_v;
       }
-      if (have_nxt) issue_gather(nxt_m, nxt_seg, raw_nxt);
-
-      // ---- rhs rows of the current segment -> ring slot ---------------------------------------------
-      const int gseg = cur_m * N_SEGS + cur_seg;
-      const int ws = gseg % WS;
-      ptx::mbar_wait(&w_empty[ws], ((gseg / WS) & 1) ^ 1);
-      double *rhs = reinterpret_cast<double *>(w_base + ws * T::SLOT_BYTES + T::W_BYTES) + ta;  // [row][cell][5]
-      int n_rows = 2 * RLO;
-      if (cur_seg < N_HI)
-        n_rows = (cur_seg == N_HI - 1) ? R_TAIL : R_HI;
-      else if ((NS - 1) % 2 == 1 && 1 + 2 * (cur_seg - N_HI) + 1 >= NS)
-        n_rows = RLO;
-#pragma unroll
-      for (int r = 0; r < RAW; ++r)
-        if (r < n_rows) rhs[r * TILE * NVARS] = raw_cur[r] * inv_scale_v - q0s;
+      const bool have_nxt = has_tile(m + 1);
+      for_each_hi_seg(m, for_each_hi_seg, std::integral_constant<int, 0>{});
+      if (have_nxt) load_hi(m + 1);  // raw_hi and u0 are free again
+      for_each_lo_seg(m, for_each_lo_seg, std::integral_constant<int, 0>{});
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&w_full[ws]);
-      if (cur_seg == N_SEGS - 1 && lane == 0) ptx::mbar_arrive(&hdr_empty[hs]);  // indices of this tile are consumed
-
-#pragma unroll
-      for (int r = 0; r < RAW; ++r) raw_cur[r] = raw_nxt[r];
-      cur_m = nxt_m;
-      cur_seg = nxt_seg;
-      have_cur = have_nxt;
+      if (lane == 0) ptx::mbar_arrive(&hdr_empty[hs]);  // the index rows of this tile are consumed
+      if (have_nxt) load_lo(m + 1);
     }
     return;
   }
@@ -583,7 +580,8 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       const int side = (fref & FREF_SIDE) ? 1 : 0;
       const bool want_trace = (fref & FREF_TRACE) != 0;
 
-      double *stage = reinterpret_cast<double *>(smem + cfg.off_stage) + k * TILE * cfg.stage_pitch;
+      double *stage = reinterpret_cast<double *>(smem + cfg.off_stage) + k * (TILE * cfg.stage_pitch + TILE);
+      long long *stage_base = reinterpret_cast<long long *>(stage + TILE * cfg.stage_pitch);
       const int grp = m % NG;
       ptx::mbar_wait(&coef_full[grp], (m / NG) & 1);
       const double *cx = reinterpret_cast<const double *>(smem + cfg.off_xchg + grp * T::XCHG_BYTES) + lane;
@@ -626,16 +624,15 @@ __global__ void __launch_bounds__(32 * StreamTraits<ND, DEG_HI, DEG_LO, NS, RM0,
       }
       // coalesced write-out: consecutive lanes write consecutive doubles of a cell's 40*q_f-byte trace block
       // (a lane-per-cell store would touch 32 cache lines per instruction)
+      stage_base[lane] = want_trace ? (long long)(((e * 2 + side) * sc.q_f) * NVARS) : -1ll;
       __syncwarp();
       {
         const int qv = sc.q_f * NVARS;
-        const std::int64_t my_base = ((e * 2 + side) * sc.q_f) * NVARS;
         int owner = lane / qv, j = lane - owner * qv;
         const int step_o = TILE / qv, step_j = TILE - step_o * qv;
         for (int it = 0; it < qv; ++it) {
-          const std::int64_t base = __shfl_sync(0xffffffffu, my_base, owner);
-          const int want = __shfl_sync(0xffffffffu, (int)want_trace, owner);
-          if (want) P.trace[base + j] = stage[owner * cfg.stage_pitch + j];
+          const long long base = stage_base[owner];
+          if (base >= 0) P.trace[base + j] = stage[owner * cfg.stage_pitch + j];
           owner += step_o;
           j += step_j;
           if (j >= qv) {
@@ -661,7 +658,7 @@ bool stream_config(const DevicePlan &P, const SchemeConst &sc, int smem_budget, 
   for (int k = 0; k < NS; ++k)
     if (P.off_sidx[k] != T::off_sidx(k) || P.off_W[k] != T::off_W(k)) return false;
   c.stage_pitch = (sc.q_f * NVARS) | 1;
-  const int stage_bytes = T::F * TILE * c.stage_pitch * 8;
+  const int stage_bytes = T::F * (TILE * c.stage_pitch * 8 + TILE * 8);  // values + one block base per lane
   const int fixed = STREAM_BARS_BYTES + STREAM_HDR_SLOTS * (T::HDR_BYTES + T::INFO_BYTES) +
                     STREAM_GROUPS * (T::XCHG_BYTES + T::ALPHA_BYTES) + stage_bytes;
   int ws = (smem_budget - fixed) / T::SLOT_BYTES;
