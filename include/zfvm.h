@@ -79,6 +79,12 @@ int zfvm_stencils_compute(const zfvm_grid *grid, int n_stencils, const int *orde
 int zfvm_stencils_get(const zfvm_stencils *st, const char *name, const void **data, int *dtype, int *ndim,
                       int64_t shape[4]);
 void zfvm_stencils_free(zfvm_stencils *st);
+/* Stencils of a sub-grid cut out of the grid `src` belongs to: local cell a is cell local_to_src[a] of the
+ * source grid (extraction of a partition's stencils, src/domain_decomposition.cpp /
+ * src/zisa/grid/domain_decomposition.cpp:412-447).  Every used stencil member must be part of the sub-grid. */
+int zfvm_stencils_extract(const zfvm_stencils *src, int64_t n_local, const int32_t *local_to_src, zfvm_stencils **out);
+/* Hilbert ordering of cell centres [n][3] (src/renumber_grid.cpp:60-126): perm[new] = old. */
+int zfvm_hilbert_permutation(int n_dims, int64_t n, const double *centers, int32_t *perm);
 /* LSQSolver::A of stencil k of cell i, row-major rows x cols (lsq_solver.cpp:40-47,168-403) */
 int zfvm_stencil_matrix(const zfvm_grid *grid, const zfvm_stencils *st, int64_t i, int k, double *A, int max_count,
                         int *rows, int *cols);

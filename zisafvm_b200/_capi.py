@@ -75,6 +75,8 @@ _SIGNATURES = {
     "zfvm_stencils_compute": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.c_char_p, c_double_p, C.c_uint64, C.POINTER(_vp)]),
     "zfvm_stencils_get": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(C.c_int), c_int64_p]),
     "zfvm_stencils_free": (None, [_vp]),
+    "zfvm_stencils_extract": (C.c_int, [_vp, C.c_int64, c_int32_p, C.POINTER(_vp)]),
+    "zfvm_hilbert_permutation": (C.c_int, [C.c_int, C.c_int64, c_double_p, c_int32_p]),
     "zfvm_stencil_matrix": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, c_double_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "zfvm_stencil_matrices": (C.c_int, [_vp, _vp, c_double_p, C.c_int64, c_int64_p]),
     "zfvm_pseudo_inverse": (C.c_int, [c_double_p, C.c_int, C.c_int, c_double_p]),
@@ -129,7 +131,13 @@ def check(rc: int) -> None:
 _DTYPES = {0: np.float64, 1: np.int32, 2: np.int64, 3: np.uint8}
 
 
-def named_array(getter, handle, name: str) -> np.ndarray:
+class _HandleView(np.ndarray):
+    """ndarray view of library-owned storage that keeps the owning Python object (and so the handle) alive."""
+
+    _owner = None
+
+
+def named_array(getter, handle, name: str, owner=None) -> np.ndarray:
     """Zero-copy numpy view of a named array owned by a grid / stencil handle."""
     data = _vp()
     dtype = C.c_int()
@@ -142,7 +150,9 @@ def named_array(getter, handle, name: str) -> np.ndarray:
     if count == 0 or not data.value:
         return np.zeros(shp, dtype=np_dtype)
     buf = (C.c_char * (count * np_dtype.itemsize)).from_address(data.value)
-    return np.frombuffer(buf, dtype=np_dtype).reshape(shp)
+    out = np.frombuffer(buf, dtype=np_dtype).reshape(shp).view(_HandleView)
+    out._owner = owner
+    return out
 
 
 def as_f64(a) -> np.ndarray:

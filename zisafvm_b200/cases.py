@@ -117,20 +117,8 @@ def polytrope_2d(n: int = 158, order: int = 3, well_balanced: bool = True, ampli
     return Case("polytrope_2d", grid, params, cell_average(grid, ic), "ssp3", 0.4)
 
 
-# ---- C3: 3D Sod / blast --------------------------------------------------------------------------------
-def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, ghost_cubes: int = 2,
-             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None) -> Case:
-    """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}."""
-    gamma = 1.4
-    gn = global_n or n
-    h = 1.0 / gn
-    nx, ny, nz = shape if shape is not None else (n, n, n)
-    verts, vi = cube_mesh(nx, ny, nz, h, jitter=0.1, seed=seed, hilbert=hilbert, offset=offset,
-                          global_shape=(gn, gn, gn) if offset is not None else None)
-    fdeg = 2 if order == 2 else 3
-    grid = Grid(3, verts, vi, QRDegrees(face_deg=fdeg, volume_deg=2, moments_deg=max(order - 1, 2)))
-    if ghost_cubes > 0:
-        grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), ghost_cubes * h))
+def blast_ic(kind: str, gamma: float = 1.4):
+    """Initial data of the 3D set-ups on [0,1]^3: ``kind`` in {"blast", "sod", "smooth"}."""
 
     def ic(x):
         m = x.shape[0]
@@ -148,6 +136,38 @@ def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, gh
             vel[:, 0], vel[:, 1], vel[:, 2] = 0.3, -0.2, 0.1
             p = 1.0 + 0.1 * np.cos(2 * np.pi * x[:, 0])
         return cvars_from_primitive(rho, vel, p, gamma)
+
+    return ic
+
+
+def blast_qr(order: int) -> QRDegrees:
+    return QRDegrees(face_deg=2 if order == 2 else 3, volume_deg=2, moments_deg=max(order - 1, 2))
+
+
+def blast_3d_on_grid(grid: Grid, order: int = 3, kind: str = "blast", stencils=None) -> Case:
+    """The C3 set-up on a grid whose ghost flags are already set (sub-domains of a decomposed run)."""
+    gamma = 1.4
+    params = EulerParams(weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma)
+    method = "ssp2" if order == 2 else "ssp3"
+    return Case(f"{kind}_3d_o{order}", grid, params, cell_average(grid, blast_ic(kind, gamma)), method, 0.4,
+                stencils=stencils)
+
+
+# ---- C3: 3D Sod / blast --------------------------------------------------------------------------------
+def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, ghost_cubes: int = 2,
+             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None) -> Case:
+    """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}."""
+    gamma = 1.4
+    gn = global_n or n
+    h = 1.0 / gn
+    nx, ny, nz = shape if shape is not None else (n, n, n)
+    verts, vi = cube_mesh(nx, ny, nz, h, jitter=0.1, seed=seed, hilbert=hilbert, offset=offset,
+                          global_shape=(gn, gn, gn) if offset is not None else None)
+    grid = Grid(3, verts, vi, blast_qr(order))
+    if ghost_cubes > 0:
+        grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), ghost_cubes * h))
+
+    ic = blast_ic(kind, gamma)
 
     params = EulerParams(weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma)
     method = "ssp2" if order == 2 else "ssp3"

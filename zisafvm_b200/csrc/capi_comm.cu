@@ -152,6 +152,7 @@ int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_r
   // tiles whose stencils reference no halo row can be reconstructed before the exchange completes
   std::vector<int32_t> ti, te;
   for (int64_t t = 0; t < ctx->n_tiles; ++t) {
+    if (!ctx->tile_needed[(size_t)t]) continue;
     if (ctx->tile_max_ref[(size_t)t] >= n_owned)
       te.push_back((int32_t)t);
     else

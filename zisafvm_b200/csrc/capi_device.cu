@@ -214,7 +214,8 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
                  ctx->stream);
     ctx->launches += 2;
   } else {
-    rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, nullptr, ctx->n_tiles, ctx->stream);
+    rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_needed, ctx->n_tiles_needed,
+                      ctx->stream);
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     ctx->launches += 1;
   }
@@ -233,7 +234,8 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
 UpdateArgs base_update_args(zfvm_ctx *ctx) {
   UpdateArgs A;
   std::memset(&A, 0, sizeof(A));
-  A.n_cells_update = ctx->n_cells;
+  // halo rows are refreshed by the next exchange: a decomposed run updates (and reduces over) owned rows only
+  A.n_cells_update = (ctx->n_ranks > 1) ? ctx->n_owned : ctx->n_cells;
   A.has_source = ctx->sc.has_gravity;
   A.gamma = ctx->sc.gamma;
   A.inradius = ctx->inradius;
@@ -461,6 +463,16 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
         for (int m = 0; m < P.n_mom; ++m)
           mom[(size_t)((t * P.n_mom + m) * TILE + lane)] = g.moments[(size_t)(i * g.n_moments + 3 + m)];
       }
+      // tiles none of whose cells contributes a trace to the flux loop (ghost cells deeper than the l1 layer)
+      // are not reconstructed at all -- unless the caller wants every cell's polynomial back
+      ctx->tile_needed.assign((size_t)T, 1);
+      if (!params->keep_polynomials && params->gravity_kind == GRAVITY_NONE) {  // (the source loop visits every cell)
+        for (std::int64_t t = 0; t < T; ++t) {
+          bool any = false;
+          for (std::int64_t a = t * F * TILE; a < (t + 1) * F * TILE && !any; ++a) any = (fref[(size_t)a] & FREF_TRACE) != 0;
+          ctx->tile_needed[(size_t)t] = any ? 1 : 0;
+        }
+      }
       if (E > (std::int64_t)FREF_EDGE_MASK) {
         zfvm_destroy(ctx);
         return fail("zfvm_create: too many faces for the packed face reference");
@@ -543,6 +555,20 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
         zfvm_destroy(ctx);
         return 1;
+      }
+    }
+    {
+      std::vector<std::int32_t> tl;
+      for (std::int64_t t = 0; t < T; ++t)
+        if (ctx->tile_needed[(size_t)t]) tl.push_back((std::int32_t)t);
+      ctx->n_tiles_needed = (std::int64_t)tl.size();
+      if (ctx->n_tiles_needed < T) {
+        const std::int32_t *p = nullptr;
+        if (dev_upload(ctx, &p, tl)) {
+          zfvm_destroy(ctx);
+          return 1;
+        }
+        ctx->tiles_needed = const_cast<std::int32_t *>(p);
       }
     }
     ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));

@@ -285,4 +285,30 @@ int zfvm_deduce_max_order(int stencil_size, double factor, int n_dims) {
 
 void zfvm_stencils_free(zfvm_stencils *st) { delete st; }
 
+int zfvm_stencils_extract(const zfvm_stencils *src, int64_t n_local, const int32_t *local_to_src, zfvm_stencils **out) {
+  try {
+    auto *h = new zfvm_stencils();
+    std::string err;
+    if (!extract_stencils(h->s, src->s, n_local, local_to_src, err)) {
+      delete h;
+      return fail("zfvm_stencils_extract: " + err);
+    }
+    *out = h;
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_stencils_extract: ") + e.what());
+  }
+}
+
+int zfvm_hilbert_permutation(int n_dims, int64_t n, const double *centers, int32_t *perm) {
+  try {
+    if (n_dims != 2 && n_dims != 3) return fail("zfvm_hilbert_permutation: n_dims must be 2 or 3");
+    const std::vector<i32> p = hilbert_permutation(n_dims, n, centers);
+    std::memcpy(perm, p.data(), (size_t)n * sizeof(int32_t));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_hilbert_permutation: ") + e.what());
+  }
+}
+
 }  // extern "C"

@@ -66,6 +66,9 @@ struct zfvm_ctx {
   double *send_buf = nullptr;
   std::int64_t n_send = 0;
   std::vector<std::int32_t> tile_max_ref;  // per tile: largest cell index any of its stencils reads
+  std::vector<std::uint8_t> tile_needed;   // per tile: some cell contributes a trace to the flux loop
+  std::int32_t *tiles_needed = nullptr;    // device list of those tiles (null: all tiles)
+  std::int64_t n_tiles_needed = 0;
   std::int32_t *tiles_interior = nullptr, *tiles_exterior = nullptr;
   std::int64_t n_tiles_interior = 0, n_tiles_exterior = 0;
 };

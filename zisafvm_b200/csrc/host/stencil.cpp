@@ -425,4 +425,70 @@ void stencil_matrix(std::vector<double> &A, int &rows, int &cols, const HostGrid
   assemble_weno_ao_matrix(A, rows, cols, g, glob, size, order);
 }
 
+bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, const i32 *local_to_src,
+                      std::string &err) {
+  const int ns = src.n_stencils, L = src.l2g_stride;
+  out = HostStencils();
+  out.n_cells = n_local;
+  out.n_dims = src.n_dims;
+  out.n_stencils = ns;
+  out.params = src.params;
+  out.max_size = src.max_size;
+  out.local_off = src.local_off;
+  out.l2g_stride = L;
+  out.l2g_size.assign((size_t)n_local, 1);
+  out.l2g.assign((size_t)(n_local * L), INVALID);
+  out.local.assign((size_t)(n_local * L), 0);
+  out.order.assign((size_t)(n_local * ns), 1);
+  out.size.assign((size_t)(n_local * ns), 0);
+  out.k_high.assign((size_t)n_local, 0);
+  out.family_order.assign((size_t)n_local, 1);
+  out.n_family.assign((size_t)n_local, 1);
+  std::vector<i32> src_to_local((size_t)src.n_cells, INVALID);
+  for (i64 a = 0; a < n_local; ++a) {
+    const i32 i = local_to_src[a];
+    if (i < 0 || i >= src.n_cells) {
+      err = "extract_stencils: source cell index out of range";
+      return false;
+    }
+    src_to_local[(size_t)i] = (i32)a;
+  }
+  i64 bad = -1;
+#pragma omp parallel for schedule(static)
+  for (i64 a = 0; a < n_local; ++a) {
+    const i64 i = local_to_src[a];
+    i32 *l2g = &out.l2g[(size_t)(a * L)];
+    i32 *local = &out.local[(size_t)(a * L)];
+    int n_l2g = 0;
+    l2g[n_l2g++] = (i32)a;
+    const int nf = src.n_family[(size_t)i];
+    for (int k = 0; k < nf; ++k) {
+      const int size = src.size[(size_t)(i * ns + k)];
+      out.order[(size_t)(a * ns + k)] = src.order[(size_t)(i * ns + k)];
+      out.size[(size_t)(a * ns + k)] = size;
+      i32 *loc = local + src.local_off[(size_t)k];
+      for (int j = 0; j < size; ++j) {
+        const i32 m = src_to_local[(size_t)src.global(i, k, j)];
+        if (m == INVALID) {
+#pragma omp critical
+          bad = i;
+          continue;
+        }
+        i32 *it = std::find(l2g, l2g + n_l2g, m);
+        loc[j] = (i32)(it - l2g);
+        if (it == l2g + n_l2g) l2g[n_l2g++] = m;
+      }
+    }
+    out.l2g_size[(size_t)a] = n_l2g;
+    out.n_family[(size_t)a] = nf;
+    out.family_order[(size_t)a] = src.family_order[(size_t)i];
+    out.k_high[(size_t)a] = src.k_high[(size_t)i];
+  }
+  if (bad >= 0) {
+    err = "extract_stencils: a stencil member of source cell " + std::to_string(bad) + " is not part of the sub-grid";
+    return false;
+  }
+  return true;
+}
+
 }  // namespace zfvm

@@ -192,22 +192,11 @@ int matrix_rank(const double *A, int rows, int cols);
 void pseudo_inverse(const double *A, int rows, int cols, double *W);
 
 // ---- domain decomposition -------------------------------------------------------------------
-struct Partition {
-  int n_parts = 0;
-  std::vector<i32> part_of_cell;  // [n_cells] owner rank (cells must be SFC ordered for sfc chunks)
-};
-/// compute_partitioned_grid_by_sfc: contiguous equal chunks (domain_decomposition.cpp:577-609).
-Partition partition_by_chunks(i64 n_cells, int n_parts);
-
-struct SubGrid {
-  RawMesh mesh;                        // local cells: owned first, then halo grouped by owner
-  std::vector<i64> global_cell_index;  // [n_local]
-  std::vector<i32> owner;              // [n_local]
-  i64 n_owned = 0;
-};
-/// extract_subgrid (domain_decomposition.cpp:371-447,451-575): owned cells of `rank` plus every
-/// cell within `n_layers` face-neighbour rings (oversized halo; the needed subset is decided
-/// after stencils are computed, see StencilBasedIndicator :300-326).
-SubGrid extract_subgrid(const HostGrid &global, const Partition &part, int rank, int n_layers);
+/// Stencils of a sub-grid cut out of the grid `src` was computed on (the reference extracts the stencils
+/// of a partition from the global ones, domain_decomposition.cpp:412-447): local cell a is cell
+/// local_to_src[a] of the source grid.  Families keep their members (renumbered); every used member
+/// must be part of the sub-grid.  Returns false and sets `err` otherwise.
+bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, const i32 *local_to_src,
+                      std::string &err);
 
 }  // namespace zfvm

@@ -53,7 +53,7 @@ class Grid:
             self._h = None
 
     def array(self, name: str) -> np.ndarray:
-        return named_array(lib.zfvm_grid_get, self._h, name)
+        return named_array(lib.zfvm_grid_get, self._h, name, owner=self)
 
     def __getattr__(self, name: str):
         # grid.volumes, grid.cell_centers, grid.left_right, ... (names of zisa::Grid members)
@@ -158,6 +158,21 @@ class StencilFamilies:
         self.params = params
         self.n_stencils = ns
 
+    @classmethod
+    def extract(cls, src: "StencilFamilies", local_grid: Grid, local_to_src: np.ndarray) -> "StencilFamilies":
+        """Stencils of a sub-grid cut out of ``src.grid``: local cell ``a`` is source cell ``local_to_src[a]``
+        (what the reference's partitioner does with the global stencils, domain_decomposition.cpp:412-447)."""
+        idx = np.ascontiguousarray(local_to_src, dtype=np.int32)
+        assert idx.shape == (local_grid.n_cells,)
+        h = C.c_void_p()
+        check(lib.zfvm_stencils_extract(src._h, idx.size, idx.ctypes.data_as(_capi.c_int32_p), C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        self.grid = local_grid
+        self.params = src.params
+        self.n_stencils = src.n_stencils
+        return self
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -165,7 +180,7 @@ class StencilFamilies:
             self._h = None
 
     def array(self, name: str) -> np.ndarray:
-        return named_array(lib.zfvm_stencils_get, self._h, name)
+        return named_array(lib.zfvm_stencils_get, self._h, name, owner=self)
 
     def stencil(self, i: int, k: int) -> np.ndarray:
         """Global indices of stencil k of cell i (``Stencil::global()``, truncated to ``size()``)."""
@@ -203,3 +218,12 @@ class StencilFamilies:
 
 def compute_stencil_families(grid: Grid, params: StencilFamilyParams, seed: int = 0) -> StencilFamilies:
     return StencilFamilies(grid, params, seed)
+
+
+def hilbert_permutation(n_dims: int, centers: np.ndarray) -> np.ndarray:
+    """Hilbert-curve order of cell centres ``[n][3]`` (src/renumber_grid.cpp:60-126): ``perm[new] = old``."""
+    c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+    perm = np.zeros(c.shape[0], dtype=np.int32)
+    check(lib.zfvm_hilbert_permutation(n_dims, c.shape[0], c.ctypes.data_as(_capi.c_double_p),
+                                       perm.ctypes.data_as(_capi.c_int32_p)))
+    return perm
