@@ -24,6 +24,12 @@ import sys
 import threading
 import time
 
+# torchrun pins OMP_NUM_THREADS=1; the host precompute (stencils, pseudo-inverses) is OpenMP code, so give every
+# rank its share of the host cores before any OpenMP runtime is loaded
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    _lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(_lws, 1)))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -183,7 +189,7 @@ def run_b200(args):
     if distributed:
         from zisafvm_b200 import distributed as zd
 
-        sub = zd.make_weak_scaling_case(rank, world, n=args.n, order=args.order, kind=args.kind)
+        sub = zd.make_weak_scaling_case(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank)
         case, ctx = sub.case, sub.ctx
         n_counted = sub.n_counted
     else:
