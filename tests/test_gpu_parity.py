@@ -179,28 +179,32 @@ def test_equilibrium_preservation():
 
 
 @pytest.mark.parametrize("maker", ["vortex_o3_hllc", "vortex_o4", "blast_o2", "blast_o3"])
-def test_streaming_kernel_many_tiles_per_cta(maker, monkeypatch):
-    """The persistent streaming reconstruction kernel with 3 CTAs (every CTA walks many tiles: ring wrap-around,
-    both apply groups, header-slot reuse) gives bit-identical tendencies to the one-tile-per-CTA launch, and the
-    thread-per-cell kernel (ZFVM_RECON=v1) agrees with both to round-off."""
+def test_reconstruction_kernels_agree(maker, monkeypatch):
+    """The persistent reconstruction kernel with 3 CTAs or 1 CTA (every warp walks many tiles: ring wrap-around,
+    header-buffer and table reuse) gives bit-identical tendencies to the default launch; the older streaming
+    kernel (ZFVM_RECON=stream) and the thread-per-cell kernel (ZFVM_RECON=v1), which read differently laid out
+    records chosen at context creation, agree with it to round-off."""
     case = CASES[maker]()
     st = case.ensure_stencils()
     n = case.grid.n_cells
-    ctx = z.CudaContext(case.grid, st, case.params)
-    roc = z.CudaEulerRateOfChange(ctx)
     out = {}
     for key, env in [("default", {}), ("few_ctas", {"ZFVM_STREAM_MAX_CTAS": "3"}), ("one_cta", {"ZFVM_STREAM_MAX_CTAS": "1"}),
-                     ("v1", {"ZFVM_RECON": "v1"})]:
-        for k in ("ZFVM_STREAM_MAX_CTAS", "ZFVM_RECON"):
+                     ("one_warp", {"ZFVM_TILE_WARPS": "1", "ZFVM_STREAM_MAX_CTAS": "2"}),
+                     ("stream", {"ZFVM_RECON": "stream"}), ("v1", {"ZFVM_RECON": "v1"})]:
+        for k in ("ZFVM_STREAM_MAX_CTAS", "ZFVM_RECON", "ZFVM_TILE_WARPS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
+        ctx = z.CudaContext(case.grid, st, case.params)
+        roc = z.CudaEulerRateOfChange(ctx)
         t = z.AllVariables(n)
         for _ in range(2):  # twice: the second call re-uses every buffer
             roc.compute(t, z.AllVariables(n, case.u0), accumulate=False)
         out[key] = t.cvars.copy()
+        ctx.close()
     assert np.array_equal(out["default"], out["few_ctas"])
     assert np.array_equal(out["default"], out["one_cta"])
+    assert np.array_equal(out["default"], out["one_warp"])
     scale = tendency_scales(case.u0, case.params.gamma, case.grid.array("inradii"))
     assert (np.abs(out["default"] - out["v1"]).max(axis=0) / scale).max() < 1e-12
-    ctx.close()
+    assert (np.abs(out["default"] - out["stream"]).max(axis=0) / scale).max() < 1e-12

@@ -2,6 +2,7 @@
 // Runge-Kutta step, boundary condition, CFL (include/zfvm.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -360,7 +361,186 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       }
       P.rec_bytes = off;  // every section is a multiple of 128 bytes
     }
+    // ---- tile kernel records (kernels/recon_tile.cuh): header | one-sided W | central W | geometry ----------
+    // Built instead of the records above whenever the tile kernel is compiled for the scheme (plain Euler,
+    // no gravity terms inside K1); ZFVM_RECON=v1|stream keeps the older kernels for comparisons.
+    bool use_tile = false;
     {
+      const char *e_recon = std::getenv("ZFVM_RECON");
+      const bool other = e_recon && (e_recon[0] == 'v' || e_recon[0] == 's');
+      use_tile = !other && !sc.well_balanced && !sc.has_gravity && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
+    }
+    if (use_tile) {
+      // distinct cells read by a tile's stencils
+      std::vector<std::int32_t> n_union((size_t)T, 0);
+#pragma omp parallel
+      {
+        std::vector<std::int32_t> seen;
+#pragma omp for schedule(dynamic, 64)
+        for (std::int64_t t = 0; t < T; ++t) {
+          seen.clear();
+          for (int lane = 0; lane < TILE; ++lane) {
+            const std::int64_t i = t * TILE + lane;
+            seen.push_back((std::int32_t)std::min(i, n - 1));
+            if (i >= n) continue;
+            for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+              if (S.order[(size_t)(i * ns + k)] <= 1) continue;
+              const int size = S.size[(size_t)(i * ns + k)];
+              for (int j = 1; j < size; ++j) seen.push_back(S.global(i, k, j));
+            }
+          }
+          std::sort(seen.begin(), seen.end());
+          // the own cells occupy 32 list entries even when the last tile repeats the last cell
+          const std::int64_t n_own_distinct = std::min<std::int64_t>(TILE, n - t * TILE);
+          n_union[(size_t)t] = (std::int32_t)((std::unique(seen.begin(), seen.end()) - seen.begin()) + (TILE - n_own_distinct));
+        }
+      }
+      int cap = TILE;
+      for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
+      cap = (cap + 31) / 32 * 32;
+      if (cap > 1024) use_tile = false;  // the shared-memory table would not fit; fall back to the older kernels
+      P.rec2_cap = cap;
+    }
+    if (use_tile) {
+      const int D2 = poly_dof(ctx->deg_hi, nd);
+      const TileRecLayout L = tile_rec_layout(sc, nd, D2, P.rec2_cap);
+      P.rec2_bytes = L.rec_bytes;
+      char *d_rec = nullptr;
+      if (dev_alloc(ctx, &d_rec, T * L.rec_bytes)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+      P.rec2 = d_rec;
+      std::vector<int> lo_row0((size_t)ns, 0), lo_w0((size_t)ns, 0);  // row / byte offsets of the one-sided stencils
+      {
+        int r = 0, b = 0;
+        for (int k = 1; k < ns; ++k) {
+          lo_row0[(size_t)k] = r;
+          lo_w0[(size_t)k] = b;
+          r += sc.rows_max[k];
+          b += sc.rows_max[k] * sc.ncoef[k] * TILE * 8;
+        }
+        lo_row0[0] = r;  // the central stencil's rows come last
+      }
+      const int n_mom2 = std::max(D2 - 3, 0);
+      const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / L.rec_bytes));
+      std::vector<char> h_rec((size_t)(chunk * L.rec_bytes));
+      for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
+        const std::int64_t t1 = std::min(T, t0 + chunk);
+        std::memset(h_rec.data(), 0, h_rec.size());
+#pragma omp parallel
+        {
+          std::vector<double> A, W;
+          std::vector<std::pair<std::int32_t, std::int32_t>> map;  // (global, local), sorted by global
+          std::vector<std::int32_t> refs;
+#pragma omp for schedule(dynamic, 8)
+          for (std::int64_t t = t0; t < t1; ++t) {
+            char *rec = h_rec.data() + (size_t)((t - t0) * L.rec_bytes);
+            std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec + TILE_OFF_META);
+            std::int32_t *list = reinterpret_cast<std::int32_t *>(rec + L.off_list);
+            unsigned char *lidx = reinterpret_cast<unsigned char *>(rec + L.off_lidx);
+            auto put_lidx = [&](int row, int lane_, int value) {
+              if (L.lidx_elem == 1)
+                lidx[(size_t)row * TILE + lane_] = (unsigned char)value;
+              else
+                reinterpret_cast<std::uint16_t *>(lidx)[(size_t)row * TILE + lane_] = (std::uint16_t)value;
+            };
+            std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
+            // pass 1: the row list (own cells first, then the other stencil members in ascending order)
+            refs.clear();
+            for (int lane = 0; lane < TILE; ++lane) {
+              const std::int64_t i = t * TILE + lane;
+              list[lane] = (std::int32_t)std::min(i, n - 1);
+              if (i >= n) continue;
+              for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+                if (S.order[(size_t)(i * ns + k)] <= 1) continue;
+                const int size = S.size[(size_t)(i * ns + k)];
+                for (int j = 1; j < size; ++j) refs.push_back(S.global(i, k, j));
+              }
+            }
+            std::sort(refs.begin(), refs.end());
+            refs.erase(std::unique(refs.begin(), refs.end()), refs.end());
+            map.clear();
+            const std::int32_t own_lo = (std::int32_t)(t * TILE), own_hi = (std::int32_t)std::min<std::int64_t>(n, (t + 1) * TILE);
+            int n_list = TILE;
+            for (std::int32_t gidx : refs) {
+              if (gidx >= own_lo && gidx < own_hi) {
+                map.emplace_back(gidx, gidx - own_lo);
+              } else {
+                list[n_list] = gidx;
+                map.emplace_back(gidx, n_list++);
+              }
+              tile_mx = std::max(tile_mx, gidx);
+            }
+            *reinterpret_cast<std::int32_t *>(rec) = n_list;
+            auto local_of = [&](std::int32_t gidx) {
+              auto it = std::lower_bound(map.begin(), map.end(), std::make_pair(gidx, (std::int32_t)-1));
+              return (int)it->second;
+            };
+            // pass 2: per cell meta, local indices, weights, geometry
+            double *geo = reinterpret_cast<double *>(rec + L.off_geo);
+            std::uint32_t *gref = reinterpret_cast<std::uint32_t *>(rec + L.off_geo + (size_t)L.geo_doubles * TILE * 8);
+            for (int lane = 0; lane < TILE; ++lane) {
+              const std::int64_t i = t * TILE + lane;
+              std::uint64_t m = 0;
+              for (int k = 0; k < ns; ++k) {
+                const int RM = sc.rows_max[k], NC = sc.ncoef[k];
+                const int row0 = lo_row0[(size_t)k];
+                for (int j = 0; j < RM; ++j) put_lidx(row0 + j, lane, lane);  // padded rows: rhs == 0
+                if (i >= n || k >= S.n_family[(size_t)i]) continue;
+                const int order = S.order[(size_t)(i * ns + k)];
+                if (order <= 1) continue;
+                int rows, cols;
+                stencil_matrix(A, rows, cols, g, S, i, k);
+                if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
+                W.resize((size_t)(rows * cols));
+                pseudo_inverse(A.data(), rows, cols, W.data());
+                for (int j = 0; j < rows; ++j) put_lidx(row0 + j, lane, local_of(S.global(i, k, j + 1)));
+                double *w = reinterpret_cast<double *>(rec + (k == 0 ? L.off_whi : L.off_wlo + lo_w0[(size_t)k])) + lane;
+                for (int j = 0; j < rows; ++j)
+                  for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+                m |= ((std::uint64_t)rows) << (8 * k);
+              }
+              if (i < n) {
+                m |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
+                if (S.n_family[(size_t)i] == 1) m |= 1ull << 60;
+              }
+              meta[lane] = m;
+              // geometry: vtx[F][nd] | centre[nd] | 1/len | moments | face_ref u32[F] | face slots (byte k: face k)
+              const std::int64_t ic = std::min(i, n - 1);
+              for (int k = 0; k < F; ++k) {
+                const Vec3 v = g.vertex(ic, k);
+                for (int d = 0; d < nd; ++d) geo[(size_t)((k * nd + d) * TILE + lane)] = v[d];
+              }
+              for (int d = 0; d < nd; ++d) geo[(size_t)((F * nd + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * ic + d)];
+              geo[(size_t)((F * nd + nd) * TILE + lane)] = 1.0 / g.characteristic_length[(size_t)ic];
+              for (int mm = 0; mm < n_mom2; ++mm)
+                geo[(size_t)((F * nd + nd + 1 + mm) * TILE + lane)] = g.moments[(size_t)(ic * g.n_moments + 3 + mm)];
+              std::uint32_t slots_all = 0;
+              for (int k = 0; k < F; ++k) {
+                std::uint32_t r = 0;
+                if (i < n) {
+                  const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
+                  const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+                  r = (std::uint32_t)e & FREF_EDGE_MASK;
+                  if (iL != (std::int32_t)i) r |= FREF_SIDE;
+                  if (iR != INVALID) {
+                    r |= FREF_INTERIOR;
+                    const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+                    if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
+                  }
+                  slots_all |= ((std::uint32_t)g.face_vertex_slots[(size_t)(i * F + k)] & 0xFFu) << (8 * k);
+                }
+                gref[(size_t)(k * TILE + lane)] = r;
+              }
+              gref[(size_t)(F * TILE + lane)] = slots_all;
+            }
+            ctx->tile_max_ref[(size_t)t] = tile_mx;
+          }
+        }
+        ZFVM_CUDA(cudaMemcpy(d_rec + t0 * L.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * L.rec_bytes), cudaMemcpyHostToDevice));
+      }
+    } else {
       char *d_rec = nullptr;
       if (dev_alloc(ctx, &d_rec, T * P.rec_bytes)) {
         zfvm_destroy(ctx);
@@ -543,7 +723,8 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       }
     }
     // ---- work arrays ------------------------------------------------------------------------------
-    if (dev_alloc(ctx, &P.trace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * NVARS, true) ||
+    // (+ dump blocks for the tile kernel's branch-free trace write-out)
+    if (dev_alloc(ctx, &P.trace, (std::max<std::int64_t>(EI, 1) + TRACE_DUMP_BLOCKS / 2) * 2 * g.q_f * NVARS, true) ||
         dev_alloc(ctx, &P.flux, std::max<std::int64_t>(EI, 1) * NVARS, true) || dev_alloc(ctx, &P.source, n * NVARS, true) ||
         dev_alloc(ctx, &ctx->eq_fail_dev, 1, true) || dev_alloc(ctx, &ctx->reduce_dev, 1, true)) {
       zfvm_destroy(ctx);
@@ -848,6 +1029,13 @@ int zfvm_profile_read(zfvm_ctx *ctx, double ms[3], int64_t counts[3]) {
       ZFVM_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[w][a], ctx->prof_events[w][a + 1]));
       ms[w] += t;
     }
+  }
+  unsigned long long tp[16];
+  if (tile_prof_read(tp) && tp[8] > 0) {  // ZFVM_TILE_PROF=1: phase timers of warp 0 of the tile kernel
+    static const char *names[8] = {"table_wait", "one_sided", "central", "table_issue", "hybridise", "geo_wait", "trace", "(ring waits)"};
+    std::fprintf(stderr, "[zfvm tile prof] %llu tiles, cycles per tile:", tp[8]);
+    for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %s %.0f", names[k], (double)tp[k] / (double)tp[8]);
+    std::fprintf(stderr, "\n");
   }
   return 0;
 }

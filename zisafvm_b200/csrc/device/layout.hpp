@@ -68,6 +68,10 @@ struct DevicePlan {
   int off_sidx[MAX_STENCILS];               // sidx_k: [rows_max_k][32] global index of stencil member
   int off_W[MAX_STENCILS];                  // W_k:    [rows_max_k][ncoef_k][32]
   // meta (offset 0): [32] u64, byte k: rows of stencil k; byte 7: k_high | single<<4
+  // reconstruction, tile kernel (kernels/recon_tile.cuh): self-contained tile records; null if not built
+  const char *rec2;                         // [T][rec2_bytes]
+  std::int64_t rec2_bytes;
+  int rec2_cap;                             // capacity of a record's row list
   // geometry (tile-interleaved)
   const double *vtx;                        // [T][F][3][32]
   const double *center;                     // [T][3][32]

@@ -16,26 +16,23 @@ namespace zfvm {
 
 namespace {
 
-ZFVM_DEVICE void euler_flux(const double u[NVARS], double p, double f[NVARS]) {
-  const double v = u[1] / u[0];
-  f[0] = u[1];
-  f[1] = v * u[1] + p;
-  f[2] = v * u[2];
-  f[3] = v * u[3];
-  f[4] = v * (u[4] + p);
-}
-
+// HLLCBatten::flux (flux/hllc.hpp:36-81,143-176) with the reciprocals 1/rho_L, 1/rho_R and 1/(1 + sqrt(rho_R/rho_L))
+// formed once: 6 divisions and 4 square roots per Gauss point instead of 21 and 4 (FP64 divisions are what made
+// the first version of this kernel FP64-pipe bound); results differ from the operation-by-operation form by rounding only.
 ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], double gamma, double nf[NVARS]) {
-  const double pL = pressure_of(uL, gamma), pR = pressure_of(uR, gamma);
-  const double aL = sqrt(gamma * pL / uL[0]), aR = sqrt(gamma * pR / uR[0]);
+  const double iL = 1.0 / uL[0], iR = 1.0 / uR[0];
+  const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (gamma - 1.0);
+  const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (gamma - 1.0);
+  const double aL = sqrt(gamma * pL * iL), aR = sqrt(gamma * pR * iR);
 
-  const double roe_ratio = sqrt(uR[0] / uL[0]);
-  const double vL = uL[1] / uL[0], vR = uR[1] / uR[0];
-  const double v_tilda = (vL + vR * roe_ratio) / (1.0 + roe_ratio);
-  const double HL = (uL[4] + pL) / uL[0], HR = (uR[4] + pR) / uR[0];
-  const double H_tilda = (HL + HR * roe_ratio) / (1.0 + roe_ratio);
-  const double w2 = (uL[2] / uL[0] + uR[2] / uR[0] * roe_ratio) / (1.0 + roe_ratio);
-  const double w3 = (uL[3] / uL[0] + uR[3] / uR[0] * roe_ratio) / (1.0 + roe_ratio);
+  const double roe_ratio = sqrt(uR[0] * iL);
+  const double inv_den = 1.0 / (1.0 + roe_ratio);
+  const double vL = uL[1] * iL, vR = uR[1] * iR;
+  const double v_tilda = (vL + vR * roe_ratio) * inv_den;
+  const double HL = (uL[4] + pL) * iL, HR = (uR[4] + pR) * iR;
+  const double H_tilda = (HL + HR * roe_ratio) * inv_den;
+  const double w2 = (uL[2] * iL + uR[2] * iR * roe_ratio) * inv_den;
+  const double w3 = (uL[3] * iL + uR[3] * iR * roe_ratio) * inv_den;
   const double vroe_square = v_tilda * v_tilda + w2 * w2 + w3 * w3;
   const double a_tilda = sqrt((gamma - 1.0) * (H_tilda - 0.5 * vroe_square));
 
@@ -49,10 +46,14 @@ ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], doubl
 #pragma unroll
   for (int v = 0; v < NVARS; ++v) uK[v] = left ? uL[v] : uR[v];
   const double pK = left ? pL : pR;
-  euler_flux(uK, pK, nf);
+  const double vK = left ? vL : vR;
+  nf[0] = uK[1];  // Euler::flux, euler_impl.hpp:23-36
+  nf[1] = vK * uK[1] + pK;
+  nf[2] = vK * uK[2];
+  nf[3] = vK * uK[3];
+  nf[4] = vK * (uK[4] + pK);
   if (sL < 0.0 && 0.0 <= sR) {
     const double sK = left ? sL : sR;
-    const double vK = left ? vL : vR;
     const double cK = (sK - vK) / (sK - s_star);
     nf[0] += sK * (cK * uK[0] - uK[0]);
     nf[1] += sK * (cK * uK[0] * s_star - uK[1]);
@@ -64,25 +65,68 @@ ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], doubl
 
 // Not in the reference: local Lax-Friedrichs in the face frame.
 ZFVM_DEVICE void rusanov_flux(const double uL[NVARS], const double uR[NVARS], double gamma, double nf[NVARS]) {
-  const double pL = pressure_of(uL, gamma), pR = pressure_of(uR, gamma);
-  const double aL = sqrt(gamma * pL / uL[0]), aR = sqrt(gamma * pR / uR[0]);
+  const double iL = 1.0 / uL[0], iR = 1.0 / uR[0];
+  const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (gamma - 1.0);
+  const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (gamma - 1.0);
+  const double aL = sqrt(gamma * pL * iL), aR = sqrt(gamma * pR * iR);
+  const double vL = uL[1] * iL, vR = uR[1] * iR;
   double fL[NVARS], fR[NVARS];
-  euler_flux(uL, pL, fL);
-  euler_flux(uR, pR, fR);
-  const double lam = fmax(fabs(uL[1] / uL[0]) + aL, fabs(uR[1] / uR[0]) + aR);
+  fL[0] = uL[1];
+  fL[1] = vL * uL[1] + pL;
+  fL[2] = vL * uL[2];
+  fL[3] = vL * uL[3];
+  fL[4] = vL * (uL[4] + pL);
+  fR[0] = uR[1];
+  fR[1] = vR * uR[1] + pR;
+  fR[2] = vR * uR[2];
+  fR[3] = vR * uR[3];
+  fR[4] = vR * (uR[4] + pR);
+  const double lam = fmax(fabs(vL) + aL, fabs(vR) + aR);
 #pragma unroll
   for (int v = 0; v < NVARS; ++v) nf[v] = 0.5 * (fL[v] + fR[v]) - 0.5 * lam * (uR[v] - uL[v]);
 }
 
-__global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
-                                                   const std::int32_t *__restrict__ face_list,
-                                                   std::int64_t n_faces) {
-  const std::int64_t t = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_faces) return;
+ZFVM_DEVICE void cp_async16(void *dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((std::uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+
+// K2.  One warp owns 32 faces, one thread one face.  A face's two traces are one contiguous 80 q_f-byte block and
+// its frame one 80-byte row, so a thread-per-face load touches 32 cache lines per instruction; instead the warp
+// copies its faces' blocks into shared memory with 16-byte cp.async (fully coalesced when the faces are
+// consecutive) and the threads read their rows from there (row pitch padded against bank conflicts).  The
+// fluxes go back the same way.
+template <int FLUX>
+__global__ void __launch_bounds__(64) flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                  const std::int32_t *__restrict__ face_list, std::int64_t n_faces,
+                                                  int pitch) {
+  extern __shared__ __align__(16) double flux_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  double *tr = flux_smem + (size_t)warp * (TILE * pitch + TILE * 10);
+  double *frs = tr + TILE * pitch;
+  const std::int64_t t0 = ((std::int64_t)blockIdx.x * wpc + warp) * TILE;
+  if (t0 >= n_faces) return;
+  const std::int64_t t = min(t0 + lane, n_faces - 1);
+  const bool in_range = t0 + lane < n_faces;
   const std::int64_t e = face_list ? (std::int64_t)face_list[t] : t;
-  const std::int32_t iL = P.left_right[2 * e];
-  if (iL < 0) return;
-  const double *fr = P.face_frame + e * 10;
+
+  const int chunks = sc.q_f * NVARS;  // 16-byte chunks of a face's trace block [2][q_f][5]
+  for (int c = lane; c < TILE * chunks; c += TILE) {
+    const int f = c / chunks, part = c - f * chunks;
+    const std::int64_t ef = __shfl_sync(0xffffffffu, e, f);
+    cp_async16(tr + f * pitch + part * 2, P.trace + ef * (2 * chunks) + part * 2);
+  }
+  for (int c = lane; c < TILE * 5; c += TILE) {
+    const int f = c / 5, part = c - f * 5;
+    const std::int64_t ef = __shfl_sync(0xffffffffu, e, f);
+    cp_async16(frs + f * 10 + part * 2, P.face_frame + ef * 10 + part * 2);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const bool skip = !in_range || P.left_right[2 * e] < 0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  const double *fr = frs + lane * 10;
   double n[3], t1[3], t2[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -92,124 +136,130 @@ __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __g
   }
   const double area = fr[9];
   double nf[NVARS] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  const double *trL = P.trace + (e * 2) * sc.q_f * NVARS;
+  const double *trL = tr + lane * pitch;
   const double *trR = trL + sc.q_f * NVARS;
-  for (int q = 0; q < sc.q_f; ++q) {
-    double uL[NVARS], uR[NVARS];
+  if (!skip) {
+    for (int q = 0; q < sc.q_f; ++q) {
+      double uL[NVARS], uR[NVARS];
 #pragma unroll
-    for (int v = 0; v < NVARS; ++v) {
-      uL[v] = __ldcs(trL + q * NVARS + v);
-      uR[v] = __ldcs(trR + q * NVARS + v);
+      for (int v = 0; v < NVARS; ++v) {
+        uL[v] = trL[q * NVARS + v];
+        uR[v] = trR[q * NVARS + v];
+      }
+      auto rot = [&](double u[NVARS]) {
+        const double un = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
+        const double ut1 = u[1] * t1[0] + u[2] * t1[1] + u[3] * t1[2];
+        const double ut2 = u[1] * t2[0] + u[2] * t2[1] + u[3] * t2[2];
+        u[1] = un;
+        u[2] = ut1;
+        u[3] = ut2;
+      };
+      rot(uL);
+      rot(uR);
+      double f[NVARS];
+      if (FLUX == FLUX_HLLC)
+        hllc_flux(uL, uR, sc.gamma, f);
+      else
+        rusanov_flux(uL, uR, sc.gamma, f);
+      const double wq = area * sc.face_w[q];
+#pragma unroll
+      for (int v = 0; v < NVARS; ++v) nf[v] += wq * f[v];
     }
-    auto rot = [&](double u[NVARS]) {
-      const double un = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
-      const double ut1 = u[1] * t1[0] + u[2] * t1[1] + u[3] * t1[2];
-      const double ut2 = u[1] * t2[0] + u[2] * t2[1] + u[3] * t2[2];
-      u[1] = un;
-      u[2] = ut1;
-      u[3] = ut2;
-    };
-    rot(uL);
-    rot(uR);
-    double f[NVARS];
-    if (sc.flux == FLUX_HLLC)
-      hllc_flux(uL, uR, sc.gamma, f);
-    else
-      rusanov_flux(uL, uR, sc.gamma, f);
-    const double wq = area * sc.face_w[q];
-#pragma unroll
-    for (int v = 0; v < NVARS; ++v) nf[v] += wq * f[v];
   }
   const double fx = nf[1] * n[0] + nf[2] * t1[0] + nf[3] * t2[0];
   const double fy = nf[1] * n[1] + nf[2] * t1[1] + nf[3] * t2[1];
   const double fz = nf[1] * n[2] + nf[2] * t1[2] + nf[3] * t2[2];
-  double *out = P.flux + e * NVARS;
+  __syncwarp();  // all lanes are done with the staged traces: reuse the area for the fluxes
+  double *out = tr + lane * NVARS;
   out[0] = nf[0];
   out[1] = fx;
   out[2] = fy;
   out[3] = fz;
   out[4] = nf[4];
+  __syncwarp();
+  for (int j = lane; j < TILE * NVARS; j += TILE) {
+    const int f = j / NVARS;
+    const std::int64_t ef = __shfl_sync(0xffffffffu, e, f);
+    const int skip_f = __shfl_sync(0xffffffffu, (int)skip, f);
+    if (!skip_f) P.flux[ef * NVARS + (j - f * NVARS)] = tr[j];
+  }
 }
 
+// K3.  One thread owns one (cell, variable) pair and a block two tiles of 32 cells: every access to the row-major
+// [n][5] arrays (state, tendencies, fluxes) is then contiguous across the warp, and a face's flux row is read by
+// five adjacent lanes.  The face fluxes are gathered in the fixed order of the cell's face list (no atomics).
 template <int F>
-__global__ void __launch_bounds__(256) update_kernel(const DevicePlan P, const UpdateArgs A) {
-  const std::int64_t i = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(320) update_kernel(const DevicePlan P, const UpdateArgs A) {
+  constexpr int CELLS = 2 * TILE;
+  __shared__ double s_un[CELLS * NVARS];
+  const int cl = threadIdx.x / NVARS, v = threadIdx.x - cl * NVARS;  // cell within the block, variable
+  const std::int64_t i = (std::int64_t)blockIdx.x * CELLS + cl;
   const bool active = i < A.n_cells_update;
-  double dx_over_ev = 1e300;
-  int bad = 0;
+  double un = 1.0;
   if (active) {
     const std::int64_t tile = i / TILE;
     const int lane = (int)(i % TILE);
-    const double vol = P.volume[tile * TILE + lane];
-    double t[NVARS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double inv_vol = 1.0 / P.volume[i];
+    double t = 0.0;
 #pragma unroll
     for (int k = 0; k < F; ++k) {
       const std::uint32_t fref = P.face_ref[(tile * F + k) * TILE + lane];
       if (!(fref & FREF_TRACE)) continue;
       const std::int64_t e = fref & FREF_EDGE_MASK;
-      const double *fl = P.flux + e * NVARS;
-      if (fref & FREF_SIDE) {
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) t[v] += fl[v] / vol;
-      } else {
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) t[v] -= fl[v] / vol;
-      }
+      const double fl = P.flux[e * NVARS + v];
+      t += ((fref & FREF_SIDE) ? fl : -fl) * inv_vol;
     }
-    if (A.has_source) {
-#pragma unroll
-      for (int v = 0; v < NVARS; ++v) t[v] += P.source[i * NVARS + v];
-    }
+    const std::int64_t iv = i * NVARS + v;
+    if (A.has_source) t += P.source[iv];
     if (A.tendency) {
-      if (A.accumulate) {
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) A.tendency[i * NVARS + v] += t[v];
-      } else {
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) A.tendency[i * NVARS + v] = t[v];
-      }
+      if (A.accumulate)
+        A.tendency[iv] += t;
+      else
+        A.tendency[iv] = t;
     }
     if (A.u_next) {
       // runge_kutta_sum: stages in index order, the stage just computed is the last one
-      double un[NVARS];
-#pragma unroll
-      for (int v = 0; v < NVARS; ++v) {
-        double dudt = 0.0;
-        for (int s = 0; s < A.n_prev; ++s)
-          if (A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * A.k_prev[s][i * NVARS + v];
-        if (A.coef_cur != 0.0) dudt += A.coef_cur * t[v];
-        un[v] = A.u_base[i * NVARS + v] + A.dt * dudt;
-      }
-      if (A.frozen && (P.cell_flags[i] & 2)) {
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) un[v] = A.frozen[i * NVARS + v];
-      }
-#pragma unroll
-      for (int v = 0; v < NVARS; ++v) A.u_next[i * NVARS + v] = un[v];
-      if (A.reduce_out) {
-        const double p = pressure_of(un, A.gamma);
-        const double a = sqrt(A.gamma * p / un[0]);
-        const double v2 = (un[1] * un[1] + un[2] * un[2] + un[3] * un[3]) / (un[0] * un[0]);
-        dx_over_ev = A.inradius[i] / (sqrt(v2) + a);
-        bool finite = true;
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) finite = finite && isfinite(un[v]);
-        bad = (un[0] <= 0.0 || un[4] <= 0.0 || !finite) ? 1 : 0;
-      }
+      double dudt = 0.0;
+      for (int s = 0; s < A.n_prev; ++s)
+        if (A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * A.k_prev[s][iv];
+      if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
+      un = A.u_base[iv] + A.dt * dudt;
+      if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[iv];
+      A.u_next[iv] = un;
     }
   }
-  if (A.reduce_out) {
+  if (A.reduce_out) {  // LocalCFL + plausibility over the updated state (uniform branch)
+    s_un[threadIdx.x] = un;
+    __syncthreads();
+    if (threadIdx.x < CELLS) {
+      const std::int64_t ic = (std::int64_t)blockIdx.x * CELLS + threadIdx.x;
+      double dx_over_ev = 1e300;
+      int bad = 0;
+      if (ic < A.n_cells_update && A.u_next) {
+        double u[NVARS];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      dx_over_ev = fmin(dx_over_ev, __shfl_xor_sync(0xffffffffu, dx_over_ev, o));
-      bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      // positive doubles order like their bit patterns; NaN (from a bad state) is caught by `bad`
-      if (dx_over_ev == dx_over_ev)
-        atomicMin(reinterpret_cast<unsigned long long *>(&A.reduce_out->min_dx_over_ev),
-                  (unsigned long long)__double_as_longlong(fmax(dx_over_ev, 0.0)));
-      if (bad) atomicOr(&A.reduce_out->not_plausible, 1);
+        for (int w = 0; w < NVARS; ++w) u[w] = s_un[threadIdx.x * NVARS + w];
+        const double p = pressure_of(u, A.gamma);
+        const double a = sqrt(A.gamma * p / u[0]);
+        const double v2 = (u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) / (u[0] * u[0]);
+        dx_over_ev = A.inradius[ic] / (sqrt(v2) + a);
+        bool finite = true;
+#pragma unroll
+        for (int w = 0; w < NVARS; ++w) finite = finite && isfinite(u[w]);
+        bad = (u[0] <= 0.0 || u[4] <= 0.0 || !finite) ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dx_over_ev = fmin(dx_over_ev, __shfl_xor_sync(0xffffffffu, dx_over_ev, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        // positive doubles order like their bit patterns; NaN (from a bad state) is caught by `bad`
+        if (dx_over_ev == dx_over_ev)
+          atomicMin(reinterpret_cast<unsigned long long *>(&A.reduce_out->min_dx_over_ev),
+                    (unsigned long long)__double_as_longlong(fmax(dx_over_ev, 0.0)));
+        if (bad) atomicOr(&A.reduce_out->not_plausible, 1);
+      }
     }
   }
 }
@@ -281,14 +331,20 @@ __global__ void axpy_stage_kernel(double *__restrict__ u_next, const double *__r
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
                  cudaStream_t stream) {
   if (n_faces <= 0) return;
-  const int block = 128;
-  flux_kernel<<<(unsigned)((n_faces + block - 1) / block), block, 0, stream>>>(P, sc, face_list, n_faces);
+  const int block = 64, wpc = block / 32;
+  const int pitch = 2 * sc.q_f * NVARS + 2;  // doubles per staged face row: 16-byte aligned, 2-way bank conflicts at most
+  const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
+  const unsigned grid = (unsigned)((n_faces + block - 1) / block);
+  if (sc.flux == FLUX_HLLC)
+    flux_kernel<FLUX_HLLC><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+  else
+    flux_kernel<FLUX_RUSANOV><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
 }
 
 void launch_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream) {
   if (A.n_cells_update <= 0) return;
-  const int block = 256;
-  const unsigned grid = (unsigned)((A.n_cells_update + block - 1) / block);
+  const int block = 2 * TILE * NVARS;
+  const unsigned grid = (unsigned)((A.n_cells_update + 2 * TILE - 1) / (2 * TILE));
   if (n_dims == 2)
     update_kernel<3><<<grid, block, 0, stream>>>(P, A);
   else

@@ -42,6 +42,43 @@ struct UpdateArgs {
   double gamma;
 };
 
+constexpr int TILE_OFF_META = 16;
+constexpr int TRACE_DUMP_BLOCKS = 2048;  // per-warp dump blocks behind the trace array (tile kernel write-out)
+
+/// Generic description of the tile record for a scheme (used by the host when it builds the records).
+struct TileRecLayout {
+  int cap, rows, lidx_elem, off_list, off_lidx, off_wlo, off_whi, off_geo, geo_doubles;
+  std::int64_t rec_bytes;
+};
+
+inline TileRecLayout tile_rec_layout(const SchemeConst &sc, int n_dims, int dof_hi, int cap) {
+  TileRecLayout L{};
+  const int ns = sc.n_stencils, F = n_dims + 1;
+  L.cap = cap;
+  L.rows = 0;
+  for (int k = 0; k < ns; ++k) L.rows += sc.rows_max[k];
+  L.lidx_elem = cap <= 256 ? 1 : 2;
+  L.off_list = TILE_OFF_META + TILE * 8;
+  L.off_lidx = (L.off_list + cap * 4 + 127) / 128 * 128;
+  L.off_wlo = (L.off_lidx + L.rows * TILE * L.lidx_elem + 127) / 128 * 128;
+  int lo = 0;
+  for (int k = 1; k < ns; ++k) lo += sc.rows_max[k] * sc.ncoef[k] * TILE * 8;
+  L.off_whi = L.off_wlo + lo;
+  L.off_geo = L.off_whi + sc.rows_max[0] * sc.ncoef[0] * TILE * 8;
+  L.geo_doubles = F * n_dims + n_dims + 1 + (dof_hi > 3 ? dof_hi - 3 : 0);
+  const int geo_bytes = L.geo_doubles * TILE * 8 + F * TILE * 4 + TILE * 4;
+  L.rec_bytes = L.off_geo + (geo_bytes + 127) / 128 * 128;
+  return L;
+}
+
+/// Phase timers of the tile kernel (ZFVM_TILE_PROF=1): device buffer of 16 counters, or null when profiling is off.
+unsigned long long *tile_prof_buffer();
+/// Copies the counters to the host and clears them; returns false when profiling is off.
+bool tile_prof_read(unsigned long long out[16]);
+
+/// True if the tile kernel (recon_tile.cuh) is compiled for this scheme's dimension, degrees and stencil sizes.
+bool recon_tile_compiled(const SchemeConst &sc, int deg_hi, int deg_lo);
+
 /// Returns 0 on success, 1 if no kernel is compiled for this (n_dims, orders, n_stencils) combination.
 int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int deg_lo, const double *state,
                  const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);

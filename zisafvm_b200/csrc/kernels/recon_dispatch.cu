@@ -22,4 +22,48 @@ int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int 
   return 1;
 }
 
+namespace {
+unsigned long long *g_tile_prof = nullptr;
+bool g_tile_prof_init = false;
+}  // namespace
+
+unsigned long long *tile_prof_buffer() {
+  if (!g_tile_prof_init) {
+    g_tile_prof_init = true;
+    const char *e = std::getenv("ZFVM_TILE_PROF");
+    if (e && e[0] == '1' && cudaMalloc((void **)&g_tile_prof, 16 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(g_tile_prof, 0, 16 * sizeof(unsigned long long));
+    else
+      g_tile_prof = nullptr;
+  }
+  return g_tile_prof;
+}
+
+bool tile_prof_read(unsigned long long out[16]) {
+  if (!g_tile_prof) return false;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_tile_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_tile_prof, 0, 16 * sizeof(unsigned long long));
+  return true;
+}
+
+bool recon_tile_compiled(const SchemeConst &sc, int deg_hi, int deg_lo) {
+  if (deg_lo != 1) return false;
+  if (sc.n_dims == 2) {
+    switch (deg_hi) {
+      case 1: return recon_tile_sizes_2d_deg1(sc);
+      case 2: return recon_tile_sizes_2d_deg2(sc);
+      case 3: return recon_tile_sizes_2d_deg3(sc);
+      case 4: return recon_tile_sizes_2d_deg4(sc);
+    }
+  } else if (sc.n_dims == 3) {
+    switch (deg_hi) {
+      case 1: return recon_tile_sizes_3d_deg1(sc);
+      case 2: return recon_tile_sizes_3d_deg2(sc);
+      case 3: return recon_tile_sizes_3d_deg3(sc);
+    }
+  }
+  return false;
+}
+
 }  // namespace zfvm

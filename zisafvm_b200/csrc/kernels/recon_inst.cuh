@@ -5,10 +5,51 @@
 #include "kernels.hpp"
 #include "recon.cuh"
 #include "recon_stream.cuh"
+#include "recon_tile.cuh"
 
 #include <cstdlib>
 
 namespace zfvm {
+
+/// Face quadrature sizes the tile kernel is compiled for (edge rules of degree 2-5, triangle rules of degree 2-3).
+constexpr bool tile_kernel_qf(int nd, int q_f) { return nd == 2 ? (q_f == 2 || q_f == 3) : (q_f == 3 || q_f == 4); }
+
+template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
+int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_tiles, cudaStream_t stream) {
+  using T = TileTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>;
+  int dev = 0, optin = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  // one CTA per SM; as many warps (= tiles in flight) as fit with `slots` ring slots each, at most 8
+  int slots = 4;
+  if (const char *e = std::getenv("ZFVM_TILE_SLOTS")) slots = std::max(2, std::min(13, std::atoi(e)));
+  TileCfg cfg;
+  if (!tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, 1 << 20, slots, cfg)) return 1;
+  int wpc = std::min(8, optin / cfg.warp_bytes);
+  if (const char *e = std::getenv("ZFVM_TILE_WARPS")) wpc = std::max(1, std::min(wpc, std::atoi(e)));
+  if (wpc < 1) return 1;
+  // spend what is left on deeper rings
+  if (!std::getenv("ZFVM_TILE_SLOTS")) tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, (optin / wpc) / 128 * 128, 13, cfg);
+  cfg.prof = tile_prof_buffer();
+  const int smem_bytes = cfg.warp_bytes * wpc;
+  const char *e_ctas = std::getenv("ZFVM_STREAM_MAX_CTAS");
+  const int max_ctas = e_ctas ? std::max(1, std::atoi(e_ctas)) : (1 << 30);
+  const unsigned grid = (unsigned)std::min<std::int64_t>((n_tiles + wpc - 1) / wpc, std::min(n_sm, max_ctas));
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    kern<<<grid, 32 * wpc, (size_t)smem_bytes, stream>>>(args, sc, cfg);
+  };
+  if (args.plan.rec2_cap <= 256)
+    go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint8_t>);
+  else
+    go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint16_t>);
+  (void)sizeof(T);
+  return 0;
+}
+
+/// The tile kernel keeps (dof - 1) x 5 accumulators of the central stencil in registers: compiled up to 9 coefficients.
+constexpr bool tile_kernel_enabled(int nd, int deg_hi) { return dof_of(deg_hi, nd) - 1 <= 9; }
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO>
 int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const double *state,
@@ -19,6 +60,20 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
   args.tile_list = tile_list;
   args.n_tiles_launch = n_tiles;
   if (n_tiles <= 0) return 0;
+  if constexpr (DEG_HI >= 1 && tile_kernel_enabled(ND, DEG_HI)) {
+    // tile kernel (recon_tile.cuh): used whenever the context carries tile records (zfvm_create decides)
+    if (plan.rec2 != nullptr) {
+      int rc = 1;
+      if constexpr (ND == 2) {
+        if (sc.q_f == 2) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 2>(args, sc, n_tiles, stream);
+        if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream);
+      } else {
+        if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream);
+        if (sc.q_f == 4) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 4>(args, sc, n_tiles, stream);
+      }
+      return rc;
+    }
+  }
   if constexpr (DEG_HI >= 1) {
     // streaming kernel (recon_stream.cuh); ZFVM_RECON=v1 selects the thread-per-cell kernel for comparisons
     const char *e_recon = std::getenv("ZFVM_RECON");
@@ -63,6 +118,14 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
 // RM0 / RLO: rows (stencil size - 1) of the central / one-sided stencils of the reference's parameter set for this
 // order; the streaming kernel is compiled for exactly these, other sizes run the thread-per-cell kernel.
 #define ZFVM_DEFINE_RECON(ND, DEG_HI, RM0, RLO)                                                          \
+  bool recon_tile_sizes_##ND##d_deg##DEG_HI(const SchemeConst &sc) {                                     \
+    if (!tile_kernel_enabled(ND, DEG_HI) || DEG_HI < 1 || sc.n_stencils != ND + 2) return false;          \
+    if (!tile_kernel_qf(ND, sc.q_f)) return false;                                                       \
+    if (sc.rows_max[0] != RM0) return false;                                                             \
+    for (int k = 1; k < sc.n_stencils; ++k)                                                              \
+      if (sc.rows_max[k] != RLO) return false;                                                           \
+    return true;                                                                                         \
+  }                                                                                                      \
   ZFVM_DECLARE_RECON(ND, DEG_HI) {                                                                       \
     if (sc.n_stencils != ND + 2) return 1;                                                               \
     if (deg_lo == 1 || (DEG_HI == 0 && deg_lo == 0))                                                     \
@@ -71,6 +134,14 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
     return 1;                                                                                            \
   }
 
+#define ZFVM_DECLARE_TILE_SIZES(ND, DEG_HI) bool recon_tile_sizes_##ND##d_deg##DEG_HI(const SchemeConst &sc)
+ZFVM_DECLARE_TILE_SIZES(2, 1);
+ZFVM_DECLARE_TILE_SIZES(2, 2);
+ZFVM_DECLARE_TILE_SIZES(2, 3);
+ZFVM_DECLARE_TILE_SIZES(2, 4);
+ZFVM_DECLARE_TILE_SIZES(3, 1);
+ZFVM_DECLARE_TILE_SIZES(3, 2);
+ZFVM_DECLARE_TILE_SIZES(3, 3);
 ZFVM_DECLARE_RECON(2, 1);
 ZFVM_DECLARE_RECON(2, 2);
 ZFVM_DECLARE_RECON(2, 3);
