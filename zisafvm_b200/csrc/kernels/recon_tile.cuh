@@ -76,6 +76,7 @@ struct TileCfg {
   const char *rec;
   // shared memory of one warp
   int n_slots, s_list, s_lidx, s_table, s_ring, s_stage, warp_bytes;
+  int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
 };
 
@@ -84,6 +85,17 @@ enum TilePhase : int { TP_TABLE_WAIT = 0, TP_LO = 1, TP_HI = 2, TP_TABLE_ISSUE =
 namespace ptx {
 ZFVM_DEVICE void cp_async8(void *dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+/// expect_tx + TMA bulk copy global -> shared, both predicated on `pred` inside one asm block (no divergent branch).
+ZFVM_DEVICE void bulk_g2s_if(bool pred, void *dst, const void *src, std::uint32_t bytes, std::uint64_t *bar,
+                             std::uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy), "r"((std::uint32_t)pred)
+      : "memory");
 }
 ZFVM_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 ZFVM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -165,24 +177,15 @@ __global__ void __launch_bounds__(256, 1)
   const char *iss_ptr = cfg.rec + tile_of(0) * cfg.rec_bytes + cfg.off_wlo;
   const char *nxt_ptr = nullptr;
   auto issue_seg = [&](int slot) {
-    if (iss_ptr != nullptr) {
-      int bytes = T::LO_ST_BYTES;
-      if (iss_s >= N_LO) bytes = R_HI * T::HI_ROW_BYTES;
-      if (iss_s == N_LO + N_HI - 1) bytes = R_TAIL * T::HI_ROW_BYTES;
-      if (iss_s >= N_LO + N_HI) bytes = T::SLOT_BYTES;
-      if (iss_s == N_SEG - 1) bytes = T::GEO_TAIL_BYTES;
-      if (lane == 0) {
-        std::uint64_t *bar = &seg_full[slot];
-        ptx::mbar_expect_tx(bar, (std::uint32_t)bytes);
-        ptx::bulk_g2s(ring + (size_t)slot * T::SLOT_BYTES, iss_ptr, (std::uint32_t)bytes, bar, pol);
-      }
-      iss_ptr += bytes;
-      if (++iss_s == N_SEG) {
-        iss_s = 0;
-        iss_ptr = nxt_ptr;
-        nxt_ptr = nullptr;
-      }
-    }
+    // branch-free: when the tile list is exhausted iss_ptr is null and nothing is issued
+    const bool live = iss_ptr != nullptr;
+    const int bytes = live ? cfg.seg_bytes[iss_s] : 0;
+    ptx::bulk_g2s_if(live && lane == 0, ring + (size_t)slot * T::SLOT_BYTES, iss_ptr, (std::uint32_t)bytes, &seg_full[slot],
+                     pol);
+    const bool last = (iss_s == N_SEG - 1);
+    iss_ptr = last ? nxt_ptr : (live ? iss_ptr + bytes : nullptr);
+    nxt_ptr = last ? nullptr : nxt_ptr;
+    iss_s = last ? 0 : iss_s + 1;
   };
   // ---- consume side ---------------------------------------------------------------------------------
   int cslot = 0, cphase = 0;
@@ -686,6 +689,15 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   if (ns < 2) return false;
   c.n_slots = ns;
   c.warp_bytes = c.s_ring + ns * T::SLOT_BYTES;
+  if (T::N_SEG > 64) return false;
+  for (int i = 0; i < T::N_SEG; ++i) {
+    int bytes = T::LO_ST_BYTES;
+    if (i >= T::N_LO) bytes = T::R_HI * T::HI_ROW_BYTES;
+    if (i == T::N_LO + T::N_HI - 1) bytes = T::R_TAIL * T::HI_ROW_BYTES;
+    if (i >= T::N_LO + T::N_HI) bytes = T::SLOT_BYTES;
+    if (i == T::N_SEG - 1) bytes = T::GEO_TAIL_BYTES;
+    c.seg_bytes[i] = bytes;
+  }
   c.prof = nullptr;
   return true;
 }
