@@ -9,6 +9,8 @@
 //   FrozenBC::apply                                 src/zisa/boundary/frozen_boundary_condition.cpp:39-55
 //   LocalCFL                                        model/local_cfl_condition_impl.hpp:25-40
 //   SanityCheckFor<Euler> / notplausible            model/euler_impl.hpp:44-46
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -16,17 +18,39 @@ namespace zfvm {
 
 namespace {
 
-// HLLCBatten::flux (flux/hllc.hpp:36-81,143-176) with the reciprocals 1/rho_L, 1/rho_R and 1/(1 + sqrt(rho_R/rho_L))
-// formed once: 6 divisions and 4 square roots per Gauss point instead of 21 and 4 (FP64 divisions are what made
-// the first version of this kernel FP64-pipe bound); results differ from the operation-by-operation form by rounding only.
+// Reciprocal and reciprocal square root from the hardware's 2^-23 approximations plus two Newton steps: full
+// double precision to within an ulp or two, at about a third of the FP64-pipe cost of the IEEE division /
+// square root sequences (which is what bounds the flux kernel).  Arguments here are densities, pressures and
+// wave-speed differences: finite, normal numbers; a non-positive argument of rsqrt yields NaN like sqrt would.
+ZFVM_DEVICE double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+ZFVM_DEVICE double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+// HLLCBatten::flux (flux/hllc.hpp:36-81,143-176).  1/rho and sqrt(rho_R/rho_L) come from rsqrt(rho_L), rsqrt(rho_R);
+// the sound speeds from rsqrt(gamma p); the remaining quotients from fast_rcp: 5 rsqrt + 4 rcp per Gauss point
+// instead of 21 divisions and 4 square roots.  Results differ from the operation-by-operation form by rounding only.
 ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], double gamma, double nf[NVARS]) {
-  const double iL = 1.0 / uL[0], iR = 1.0 / uR[0];
+  const double rL = fast_rsqrt(uL[0]), rR = fast_rsqrt(uR[0]);
+  const double iL = rL * rL, iR = rR * rR;
   const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (gamma - 1.0);
   const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (gamma - 1.0);
-  const double aL = sqrt(gamma * pL * iL), aR = sqrt(gamma * pR * iR);
+  const double gpL = gamma * pL, gpR = gamma * pR;
+  const double aL = gpL * fast_rsqrt(gpL) * rL, aR = gpR * fast_rsqrt(gpR) * rR;  // sqrt(gamma p / rho)
 
-  const double roe_ratio = sqrt(uR[0] * iL);
-  const double inv_den = 1.0 / (1.0 + roe_ratio);
+  const double roe_ratio = (uR[0] * rR) * rL;  // sqrt(rho_R / rho_L)
+  const double inv_den = fast_rcp(1.0 + roe_ratio);
   const double vL = uL[1] * iL, vR = uR[1] * iR;
   const double v_tilda = (vL + vR * roe_ratio) * inv_den;
   const double HL = (uL[4] + pL) * iL, HR = (uR[4] + pR) * iR;
@@ -34,12 +58,13 @@ ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], doubl
   const double w2 = (uL[2] * iL + uR[2] * iR * roe_ratio) * inv_den;
   const double w3 = (uL[3] * iL + uR[3] * iR * roe_ratio) * inv_den;
   const double vroe_square = v_tilda * v_tilda + w2 * w2 + w3 * w3;
-  const double a_tilda = sqrt((gamma - 1.0) * (H_tilda - 0.5 * vroe_square));
+  const double a2 = (gamma - 1.0) * (H_tilda - 0.5 * vroe_square);
+  const double a_tilda = a2 * fast_rsqrt(a2);
 
   const double sL = fmin(vL - aL, v_tilda - a_tilda);
   const double sR = fmax(vR + aR, v_tilda + a_tilda);
   const double s_star =
-      (uR[1] * (sR - vR) - uL[1] * (sL - vL) + pL - pR) / (uR[0] * (sR - vR) - uL[0] * (sL - vL));
+      (uR[1] * (sR - vR) - uL[1] * (sL - vL) + pL - pR) * fast_rcp(uR[0] * (sR - vR) - uL[0] * (sL - vL));
 
   const bool left = (0.0 <= s_star);
   double uK[NVARS];
@@ -54,12 +79,12 @@ ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], doubl
   nf[4] = vK * (uK[4] + pK);
   if (sL < 0.0 && 0.0 <= sR) {
     const double sK = left ? sL : sR;
-    const double cK = (sK - vK) / (sK - s_star);
+    const double cK = (sK - vK) * fast_rcp(sK - s_star);
     nf[0] += sK * (cK * uK[0] - uK[0]);
     nf[1] += sK * (cK * uK[0] * s_star - uK[1]);
     nf[2] += sK * (cK * uK[2] - uK[2]);
     nf[3] += sK * (cK * uK[3] - uK[3]);
-    nf[4] += sK * (cK * (uK[4] + (s_star - vK) * (uK[0] * s_star + pK / (sK - vK))) - uK[4]);
+    nf[4] += sK * (cK * (uK[4] + (s_star - vK) * (uK[0] * s_star + pK * fast_rcp(sK - vK))) - uK[4]);
   }
 }
 
@@ -91,13 +116,119 @@ ZFVM_DEVICE void cp_async16(void *dst_smem, const void *src) {
                : "memory");
 }
 
+// K2.  One thread owns one (face, Gauss point) pair: LPF = QF rounded up to a power of two lanes per face,
+// 32 / LPF faces per warp.  The Riemann solver is a long chain of dependent FP64 divisions and square roots;
+// spreading a face's Gauss points over lanes shortens the chain per thread by QF and keeps the FP64 pipe busy.
+// A face's two traces are one contiguous 80 QF-byte block and its frame one 80-byte row: the warp copies its
+// faces' blocks into shared memory with 16-byte cp.async (fully coalesced when the faces are consecutive), the
+// threads read their points from there, lane q = 0 of a face adds the weighted point fluxes in the reference's
+// order (point 0 first, quadrature.hpp:43-48) and the fluxes go back through shared memory as contiguous rows.
+template <int FLUX, int QF>
+__global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces) {
+  constexpr int LPF = QF <= 1 ? 1 : (QF <= 2 ? 2 : (QF <= 4 ? 4 : 8));  // lanes per face
+  constexpr int FPW = 32 / LPF;                                          // faces per warp
+  constexpr int CHUNKS = QF * NVARS;                                     // 16-byte chunks of a trace block [2][QF][5]
+  constexpr int PITCH = 2 * QF * NVARS + 2;                              // doubles per staged face row
+  __shared__ __align__(16) double flux_smem[4 * FPW * (PITCH + 10)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *tr = flux_smem + warp * FPW * (PITCH + 10);
+  double *frs = tr + FPW * PITCH;
+  const std::int64_t t0 = ((std::int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * FPW;
+  if (t0 >= n_faces) return;
+  const int f = lane / LPF, q = lane - f * LPF;  // face within the warp, Gauss point
+  const std::int64_t t = min(t0 + f, n_faces - 1);
+  const bool in_range = t0 + f < n_faces;
+  const std::int64_t e = face_list ? (std::int64_t)face_list[t] : t;
+
+  // (uniform trip counts: every lane takes part in the shuffles)
+#pragma unroll
+  for (int c0 = 0; c0 < FPW * CHUNKS; c0 += 32) {
+    const int c = min(c0 + lane, FPW * CHUNKS - 1);
+    const int fc = c / CHUNKS, part = c - fc * CHUNKS;
+    const std::int64_t ef = __shfl_sync(0xffffffffu, e, fc * LPF);
+    if (c0 + lane < FPW * CHUNKS) cp_async16(tr + fc * PITCH + part * 2, P.trace + ef * (2 * CHUNKS) + part * 2);
+  }
+#pragma unroll
+  for (int c0 = 0; c0 < FPW * 5; c0 += 32) {
+    const int c = min(c0 + lane, FPW * 5 - 1);
+    const int fc = c / 5, part = c - fc * 5;
+    const std::int64_t ef = __shfl_sync(0xffffffffu, e, fc * LPF);
+    if (c0 + lane < FPW * 5) cp_async16(frs + fc * 10 + part * 2, P.face_frame + ef * 10 + part * 2);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const bool skip = !in_range || P.left_right[2 * e] < 0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  const double *fr = frs + f * 10;
+  double n[3], t1[3], t2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    n[d] = fr[d];
+    t1[d] = fr[3 + d];
+    t2[d] = fr[6 + d];
+  }
+  double wf[NVARS] = {0.0, 0.0, 0.0, 0.0, 0.0};  // weighted flux of this Gauss point in the face frame
+  if (q < QF && !skip) {
+    double uL[NVARS], uR[NVARS];
+#pragma unroll
+    for (int v = 0; v < NVARS; ++v) {
+      uL[v] = tr[f * PITCH + q * NVARS + v];
+      uR[v] = tr[f * PITCH + (QF + q) * NVARS + v];
+    }
+    auto rot = [&](double u[NVARS]) {
+      const double un = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
+      const double ut1 = u[1] * t1[0] + u[2] * t1[1] + u[3] * t1[2];
+      const double ut2 = u[1] * t2[0] + u[2] * t2[1] + u[3] * t2[2];
+      u[1] = un;
+      u[2] = ut1;
+      u[3] = ut2;
+    };
+    rot(uL);
+    rot(uR);
+    double fl[NVARS];
+    if (FLUX == FLUX_HLLC)
+      hllc_flux(uL, uR, sc.gamma, fl);
+    else
+      rusanov_flux(uL, uR, sc.gamma, fl);
+    const double wq = fr[9] * sc.face_w[q];
+#pragma unroll
+    for (int v = 0; v < NVARS; ++v) wf[v] = wq * fl[v];
+  }
+  // lane q = 0 accumulates point 0, 1, .. in order
+  double nf[NVARS];
+#pragma unroll
+  for (int v = 0; v < NVARS; ++v) {
+    nf[v] = wf[v];
+#pragma unroll
+    for (int qq = 1; qq < QF; ++qq) nf[v] += __shfl_sync(0xffffffffu, wf[v], (lane & ~(LPF - 1)) + qq);
+  }
+  __syncwarp();  // all lanes are done with the staged traces: reuse the area for the fluxes
+  if (q == 0) {
+    double *out = tr + f * NVARS;
+    out[0] = nf[0];
+    out[1] = nf[1] * n[0] + nf[2] * t1[0] + nf[3] * t2[0];
+    out[2] = nf[1] * n[1] + nf[2] * t1[1] + nf[3] * t2[1];
+    out[3] = nf[1] * n[2] + nf[2] * t1[2] + nf[3] * t2[2];
+    out[4] = nf[4];
+  }
+  __syncwarp();
+  for (int j = lane; j < ((FPW * NVARS + 31) / 32) * 32; j += 32) {
+    const int fc = min(j / NVARS, FPW - 1);
+    const std::int64_t ef = __shfl_sync(0xffffffffu, e, fc * LPF);
+    const int skip_f = __shfl_sync(0xffffffffu, (int)skip, fc * LPF);
+    if (j < FPW * NVARS && !skip_f) P.flux[ef * NVARS + (j - fc * NVARS)] = tr[j];
+  }
+}
+
 // K2.  One warp owns 32 faces, one thread one face.  A face's two traces are one contiguous 80 q_f-byte block and
 // its frame one 80-byte row, so a thread-per-face load touches 32 cache lines per instruction; instead the warp
 // copies its faces' blocks into shared memory with 16-byte cp.async (fully coalesced when the faces are
 // consecutive) and the threads read their rows from there (row pitch padded against bank conflicts).  The
 // fluxes go back the same way.
 template <int FLUX>
-__global__ void __launch_bounds__(64) flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+__global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces,
                                                   int pitch) {
   extern __shared__ __align__(16) double flux_smem[];
@@ -328,17 +459,45 @@ __global__ void axpy_stage_kernel(double *__restrict__ u_next, const double *__r
 
 }  // namespace
 
+template <int FLUX>
+static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
+                          cudaStream_t stream) {
+  static const bool per_point = [] {
+    const char *e = std::getenv("ZFVM_FLUX");
+    return e != nullptr && e[0] == 'p';
+  }();
+  if (!per_point) {  // one thread per face
+    const int block = 64, wpc = block / 32;
+    const int pitch = 2 * sc.q_f * NVARS + 2;  // doubles per staged face row: 16-byte aligned, 2-way bank conflicts at most
+    const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
+    const unsigned grid = (unsigned)((n_faces + block - 1) / block);
+    flux_face_kernel<FLUX><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    return;
+  }
+  auto go = [&](auto kern, int lanes_per_face) {
+    const int faces_per_block = 4 * (32 / lanes_per_face);
+    const unsigned grid = (unsigned)((n_faces + faces_per_block - 1) / faces_per_block);
+    kern<<<grid, 128, 0, stream>>>(P, sc, face_list, n_faces);
+  };
+  switch (sc.q_f) {  // edge rules: 1-3 points, triangle rules: 1, 3, 4, 6, 7 points
+    case 1: go(flux_kernel<FLUX, 1>, 1); break;
+    case 2: go(flux_kernel<FLUX, 2>, 2); break;
+    case 3: go(flux_kernel<FLUX, 3>, 4); break;
+    case 4: go(flux_kernel<FLUX, 4>, 4); break;
+    case 5: go(flux_kernel<FLUX, 5>, 8); break;
+    case 6: go(flux_kernel<FLUX, 6>, 8); break;
+    case 7: go(flux_kernel<FLUX, 7>, 8); break;
+    default: go(flux_kernel<FLUX, 8>, 8); break;
+  }
+}
+
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
                  cudaStream_t stream) {
   if (n_faces <= 0) return;
-  const int block = 64, wpc = block / 32;
-  const int pitch = 2 * sc.q_f * NVARS + 2;  // doubles per staged face row: 16-byte aligned, 2-way bank conflicts at most
-  const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
-  const unsigned grid = (unsigned)((n_faces + block - 1) / block);
   if (sc.flux == FLUX_HLLC)
-    flux_kernel<FLUX_HLLC><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    launch_flux_q<FLUX_HLLC>(P, sc, face_list, n_faces, stream);
   else
-    flux_kernel<FLUX_RUSANOV><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    launch_flux_q<FLUX_RUSANOV>(P, sc, face_list, n_faces, stream);
 }
 
 void launch_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream) {
