@@ -40,6 +40,8 @@
 
 namespace zfvm {
 
+constexpr int TILE_SLOT_TARGET = 4608;  // bytes of a ring slot aimed at (two central rows of the 3D order-3 scheme)
+
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
 struct TileTraits {
   static constexpr int F = ND + 1;
@@ -54,8 +56,9 @@ struct TileTraits {
   static constexpr int GEO_DOUBLES = F * ND + ND + 1 + N_MOM;
   static constexpr int GEO_BYTES = GEO_DOUBLES * TILE * 8 + F * TILE * 4 + TILE * 4;
   static constexpr int GEO_SECTION = (GEO_BYTES + 127) / 128 * 128;
-  static constexpr int SLOT_BYTES = LO_ST_BYTES > HI_ROW_BYTES ? LO_ST_BYTES : HI_ROW_BYTES;  // multiple of 256
-  static constexpr int R_HI = SLOT_BYTES / HI_ROW_BYTES;    // central rows per segment
+  static constexpr int R_FIT = TILE_SLOT_TARGET / HI_ROW_BYTES < 1 ? 1 : TILE_SLOT_TARGET / HI_ROW_BYTES;
+  static constexpr int R_HI = R_FIT > RM0 ? RM0 : R_FIT;    // central rows per segment
+  static constexpr int SLOT_BYTES = LO_ST_BYTES > R_HI * HI_ROW_BYTES ? LO_ST_BYTES : R_HI * HI_ROW_BYTES;  // multiple of 256
   static constexpr int N_HI = (RM0 + R_HI - 1) / R_HI;
   static constexpr int R_TAIL = RM0 - (N_HI - 1) * R_HI;
   static constexpr int N_LO = NS - 1;                       // one one-sided stencil per segment
@@ -63,7 +66,7 @@ struct TileTraits {
   static constexpr int N_GEO = (GEO_SECTION + SLOT_BYTES - 1) / SLOT_BYTES;
   static constexpr int GEO_TAIL_BYTES = GEO_SECTION - (N_GEO - 1) * SLOT_BYTES;
   static constexpr int N_SEG = N_LO + N_HI + N_GEO;
-  static constexpr int Q_STAGE = (QF % 2 == 0) ? 2 : QF;    // Gauss points staged per pass
+  static constexpr int Q_STAGE = 1;                         // Gauss points staged per pass (shared memory is what limits the warps per SM)
   static constexpr int CHUNK = Q_STAGE * NVARS;             // doubles per (cell, face) block written per pass
   static constexpr int STAGE_PITCH = CHUNK | 1;
   static constexpr int STAGE_BYTES = (TILE * STAGE_PITCH * 8 + 127) / 128 * 128;
@@ -81,6 +84,15 @@ struct TileCfg {
 };
 
 enum TilePhase : int { TP_TABLE_WAIT = 0, TP_LO = 1, TP_HI = 2, TP_TABLE_ISSUE = 3, TP_HYBRID = 4, TP_GEO_WAIT = 5, TP_TRACE = 6, TP_SEG_WAIT = 7, TP_TILES = 8, TP_COUNT = 9 };
+
+/// 1 / x from the hardware's 2^-23 approximation and two Newton steps (x: finite, normal, non-zero).
+ZFVM_DEVICE double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
 
 namespace ptx {
 ZFVM_DEVICE void cp_async8(void *dst_smem, const void *src) {
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(256, 1)
   extern __shared__ __align__(128) unsigned char smem_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *smem = smem_all + (size_t)warp * cfg.warp_bytes;
-  std::uint64_t *list_full = reinterpret_cast<std::uint64_t *>(smem);  // [2]
+  std::uint64_t *list_full = reinterpret_cast<std::uint64_t *>(smem);  // [1] (+1 unused)
   std::uint64_t *lidx_full = list_full + 2;                            // [1]
   std::uint64_t *seg_full = list_full + 3;                             // [n_slots]
   unsigned char *list_base = smem + cfg.s_list;
@@ -144,7 +156,6 @@ __global__ void __launch_bounds__(256, 1)
 
   if (lane == 0) {
     ptx::mbar_init(&list_full[0], 1);
-    ptx::mbar_init(&list_full[1], 1);
     ptx::mbar_init(&lidx_full[0], 1);
     for (int s = 0; s < NSLOT; ++s) ptx::mbar_init(&seg_full[s], 1);
     ptx::fence_barrier_init();
@@ -154,12 +165,10 @@ __global__ void __launch_bounds__(256, 1)
   const std::uint64_t pol = ptx::policy_evict_first();
 
   // ---- issue side (lane 0 only) ---------------------------------------------------------------------
-  auto issue_list = [&](int m) {  // n_list | meta | list of tile m -> list buffer m & 1
+  auto issue_list = [&](int m) {  // n_list | meta | list of tile m (one buffer: see the tile loop for its life time)
     if (lane == 0 && has_tile(m)) {
-      std::uint64_t *bar = &list_full[m & 1];
-      ptx::mbar_expect_tx(bar, (std::uint32_t)cfg.list_bytes);
-      ptx::bulk_g2s(list_base + (m & 1) * cfg.list_bytes, cfg.rec + tile_of(m) * cfg.rec_bytes, (std::uint32_t)cfg.list_bytes,
-                    bar, pol);
+      ptx::mbar_expect_tx(&list_full[0], (std::uint32_t)cfg.list_bytes);
+      ptx::bulk_g2s(list_base, cfg.rec + tile_of(m) * cfg.rec_bytes, (std::uint32_t)cfg.list_bytes, &list_full[0], pol);
     }
   };
   auto issue_lidx = [&](int m) {
@@ -210,8 +219,8 @@ __global__ void __launch_bounds__(256, 1)
   // copy the rows of tile m's list into the table (asynchronously)
   auto load_table = [&](int m) {
     if (!has_tile(m)) return;
-    const unsigned char *lb = list_base + (m & 1) * cfg.list_bytes;
-    ptx::mbar_wait(&list_full[m & 1], (m >> 1) & 1);
+    const unsigned char *lb = list_base;
+    ptx::mbar_wait(&list_full[0], m & 1);
     const int n_list = *reinterpret_cast<const int *>(lb);
     const std::int32_t *list = reinterpret_cast<const std::int32_t *>(lb + cfg.off_list);
 #pragma unroll 2
@@ -236,7 +245,11 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll 1
   for (int m = 0; has_tile(m); ++m) {
     mark(-1);
-    issue_list(m + 1);  // its buffer held tile m-1's list
+    // The list buffer holds tile m's part (its rows went into the table during tile m-1; only the meta words
+    // are still needed): read them, then let tile m+1's part overwrite the buffer while tile m is applied.
+    const std::uint64_t meta = reinterpret_cast<const std::uint64_t *>(list_base + TILE_OFF_META)[lane];
+    __syncwarp();
+    issue_list(m + 1);
     nxt_ptr = has_tile(m + 1) ? cfg.rec + tile_of(m + 1) * cfg.rec_bytes + cfg.off_wlo : nullptr;
     ptx::cp_async_wait_all();
     ptx::mbar_wait(&lidx_full[0], m & 1);
@@ -245,8 +258,6 @@ __global__ void __launch_bounds__(256, 1)
     const std::int64_t tile = tile_of(m);
     const std::int64_t cell = tile * TILE + lane;
     const bool active = cell < P.n_cells;
-    const std::uint64_t meta =
-        reinterpret_cast<const std::uint64_t *>(list_base + (m & 1) * cfg.list_bytes + TILE_OFF_META)[lane];
     const int kh_m = (int)((meta >> 56) & 0xF);
     const bool single_m = ((meta >> 60) & 1) != 0;
     const bool fast = __all_sync(0xffffffffu, kh_m == 0 && !single_m);
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(256, 1)
       } else {
         is_pow = pow(is_max, sc.exponent);
       }
-      return g / (sc.epsilon + is_pow);
+      return g * fast_rcp(sc.epsilon + is_pow);  // within an ulp or two of the quotient
     };
 
     // coefficients of the hybridised polynomial: constant | low-order part | high-order part
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(256, 1)
             for (int v = 0; v < NVARS; ++v) wsum[c][v] = fma(alpha_h, keep[c][v], wsum[c][v]);
         }
       }
-      const double inv_tot = 1.0 / al_sum;
+      const double inv_tot = fast_rcp(al_sum);
       // constant coefficient: q0 for every stencil but kh, whose value carries the correction:
       // sum_k w_k a0_k = (alpha_h a0h + (sum alpha - alpha_h) q0) / sum alpha
       double g_others = 0.0;
@@ -678,7 +689,7 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   c.rec_bytes = L.rec_bytes;
   c.rec = P.rec2;
   c.s_list = 128;
-  c.s_lidx = c.s_list + 2 * c.list_bytes;
+  c.s_lidx = c.s_list + c.list_bytes;
   c.s_table = c.s_lidx + c.lidx_bytes;
   c.s_stage = c.s_table + (L.cap * NVARS * 8 + 127) / 128 * 128;
   c.s_ring = c.s_stage + T::STAGE_BYTES;
