@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
 // [n][5] arrays (state, tendencies, fluxes) is then contiguous across the warp, and a face's flux row is read by
 // five adjacent lanes.  The face fluxes are gathered in the fixed order of the cell's face list (no atomics).
 template <int F>
-__global__ void __launch_bounds__(320) update_kernel(const DevicePlan P, const UpdateArgs A) {
+__global__ void __launch_bounds__(320, 6) update_kernel(const DevicePlan P, const UpdateArgs A) {
   constexpr int CELLS = 2 * TILE;
   __shared__ double s_un[CELLS * NVARS];
   const int cl = threadIdx.x / NVARS, v = threadIdx.x - cl * NVARS;  // cell within the block, variable
@@ -330,17 +330,32 @@ __global__ void __launch_bounds__(320) update_kernel(const DevicePlan P, const U
   if (active) {
     const std::int64_t tile = i / TILE;
     const int lane = (int)(i % TILE);
-    const double inv_vol = 1.0 / P.volume[i];
+    // all independent loads first (face references, then the four flux rows, the cell's own rows): the face
+    // gather is a two-level dependent chain and the kernel is latency bound otherwise
+    std::uint32_t fref[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) fref[k] = P.face_ref[(tile * F + k) * TILE + lane];
+    const double vol = P.volume[i];
+    const std::int64_t iv = i * NVARS + v;
+    double ub = 0.0, kp[MAX_RK_STAGES - 1];
+    if (A.u_next) ub = A.u_base[iv];
+#pragma unroll
+    for (int s = 0; s < MAX_RK_STAGES - 1; ++s)
+      kp[s] = (A.u_next && s < A.n_prev && A.coef_prev[s] != 0.0) ? A.k_prev[s][iv] : 0.0;
+    double fl[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      const bool use = (fref[k] & FREF_TRACE) != 0;
+      const std::int64_t e = use ? (std::int64_t)(fref[k] & FREF_EDGE_MASK) : 0;
+      fl[k] = P.flux[e * NVARS + v];
+      if (!use) fl[k] = 0.0;
+    }
+    const double inv_vol = 1.0 / vol;
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < F; ++k) {
-      const std::uint32_t fref = P.face_ref[(tile * F + k) * TILE + lane];
-      if (!(fref & FREF_TRACE)) continue;
-      const std::int64_t e = fref & FREF_EDGE_MASK;
-      const double fl = P.flux[e * NVARS + v];
-      t += ((fref & FREF_SIDE) ? fl : -fl) * inv_vol;
+      if (fref[k] & FREF_TRACE) t += ((fref[k] & FREF_SIDE) ? fl[k] : -fl[k]) * inv_vol;
     }
-    const std::int64_t iv = i * NVARS + v;
     if (A.has_source) t += P.source[iv];
     if (A.tendency) {
       if (A.accumulate)
@@ -351,10 +366,11 @@ __global__ void __launch_bounds__(320) update_kernel(const DevicePlan P, const U
     if (A.u_next) {
       // runge_kutta_sum: stages in index order, the stage just computed is the last one
       double dudt = 0.0;
-      for (int s = 0; s < A.n_prev; ++s)
-        if (A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * A.k_prev[s][iv];
+#pragma unroll
+      for (int s = 0; s < MAX_RK_STAGES - 1; ++s)
+        if (s < A.n_prev && A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * kp[s];
       if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
-      un = A.u_base[iv] + A.dt * dudt;
+      un = ub + A.dt * dudt;
       if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[iv];
       A.u_next[iv] = un;
     }
