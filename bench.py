@@ -67,9 +67,11 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        """Started before the warm-up (nvidia-smi needs ~0.1 s to come up); rows are time-stamped on arrival and
+        ``stop`` keeps those that fall inside the timed region."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -78,18 +80,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if t_begin <= t <= t_end]
+        window = "timed region"
+        if not rows:  # region shorter than the sampling period: take the samples closest to it
+            rows = [r for (t, r) in self.rows if t_begin - 0.25 <= t <= t_end + 0.25]
+            window = "timed region +- 0.25 s"
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
@@ -99,7 +107,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peak_gbs():
@@ -109,6 +117,20 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except (OSError, KeyError, ValueError):
         return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def measured_traffic(args, n_cells: int, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ``ncu --set full`` capture
+    of this very configuration (profiles/r01_k1_traffic.json), else null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")) as f:
+            t = json.load(f)
+        if world == 1 and t["n"] == args.n and t["order"] == args.order and t["cells"] == n_cells:
+            return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "bytes_per_cell": t["dram_bytes_per_launch"] / n_cells,
+                    "source": t["source"]}
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
 
 
 def rank_box(rank: int, n_ranks: int):
@@ -216,12 +238,13 @@ def run_b200(args):
             dist.barrier()
 
     # ---- device-resident timing --------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        rk.step(0.0, dt)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        rk.step(0.0, dt)
+    barrier()
+    t_begin = time.time()
     launches0 = ctx.counters()["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -230,7 +253,7 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     launches = ctx.counters()["launches"] - launches0
     if distributed:
         tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
@@ -263,8 +286,9 @@ def run_b200(args):
     ach_k1 = n_counted * b_k1 / t_k1 / 1e9
     t_stage = sum(kms) / max(kcnt[0], 1) * 1e-3
     roofline = {
-        "bound": "hbm", "kernel": "recon_kernel (K1: stencil-weight apply + CWENO-AO + traces)",
-        "achieved": ach_k1, "peak": peak, "unit": "GB/s", "frac": ach_k1 / peak, "traffic": None,
+        "bound": "hbm", "kernel": "recon_tile_kernel (K1: stencil-weight apply + CWENO-AO + traces)",
+        "achieved": ach_k1, "peak": peak, "unit": "GB/s", "frac": ach_k1 / peak,
+        "traffic": measured_traffic(args, int(n), world),
         "peak_source": peak_src, "algorithmic_bytes_per_cell": {"K1": b_k1, "K2": b_k2, "K3": b_k3, "stage": alg_bytes},
         "kernel_ms": {"K1_recon": kms[0] / max(kcnt[0], 1), "K2_flux": kms[1] / max(kcnt[1], 1),
                       "K3_update": kms[2] / max(kcnt[2], 1)},
