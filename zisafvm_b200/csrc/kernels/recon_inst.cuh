@@ -26,7 +26,7 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
   if (const char *e = std::getenv("ZFVM_TILE_SLOTS")) slots = std::max(2, std::min(13, std::atoi(e)));
   TileCfg cfg;
   if (!tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, 1 << 20, slots, cfg)) return 1;
-  int wpc = std::min(8, optin / cfg.warp_bytes);
+  int wpc = std::min(TILE_MAX_WARPS, optin / cfg.warp_bytes);
   if (const char *e = std::getenv("ZFVM_TILE_WARPS")) wpc = std::max(1, std::min(wpc, std::atoi(e)));
   if (wpc < 1) return 1;
   // spend what is left on deeper rings

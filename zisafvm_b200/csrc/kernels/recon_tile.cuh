@@ -40,6 +40,7 @@
 
 namespace zfvm {
 
+constexpr int TILE_MAX_WARPS = 8;       // warps per CTA the kernel is compiled for (register budget 65536 / (32 * TILE_MAX_WARPS))
 constexpr int TILE_SLOT_TARGET = 4608;  // bytes of a ring slot aimed at (two central rows of the 3D order-3 scheme)
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
@@ -114,7 +115,7 @@ ZFVM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" :::
 }  // namespace ptx
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF, typename LIDX>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     recon_tile_kernel(const __grid_constant__ ReconArgs args, const __grid_constant__ SchemeConst sc,
                       const __grid_constant__ TileCfg cfg) {
   using T = TileTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>;
