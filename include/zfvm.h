@@ -123,6 +123,9 @@ typedef struct zfvm_params {
    * supported (the equilibrium is refreshed every stage, local_reconstruction.hpp:87-100) */
   int steps_per_recompute;
   int keep_polynomials;      /* diagnostics: store every cell's WENO polynomial */
+  /* "flux-bc" (numerical_experiment.cpp:238-256 adds it to the FVM rate of change): 0 NoFluxBC, 1 FluxBC
+   * (include/zisa/boundary/flux_bc.hpp:13-52): on exterior faces the physical flux of the cell average leaves the cell */
+  int flux_bc;
 } zfvm_params;
 
 void zfvm_params_default(zfvm_params *p);

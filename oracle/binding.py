@@ -46,7 +46,7 @@ class StencilDesc(C.Structure):
 class OracleParams(C.Structure):
     _fields_ = [("recon_mode", C.c_int), ("linear_weights", C.c_double * 8), ("epsilon", C.c_double),
                 ("exponent", C.c_double), ("well_balanced", C.c_int), ("scaling", C.c_int), ("flux", C.c_int),
-                ("gamma", C.c_double), ("gas_constant", C.c_double), ("has_gravity", C.c_int)]
+                ("gamma", C.c_double), ("gas_constant", C.c_double), ("has_gravity", C.c_int), ("flux_bc", C.c_int)]
 
 
 _lib = None
@@ -141,6 +141,7 @@ class Oracle:
         p.flux = {"hllc": 0, "rusanov": 1}[params.flux]
         p.gamma, p.gas_constant = params.gamma, params.gas_constant
         p.has_gravity = int(params.gravity.kind != "none")
+        p.flux_bc = {"none": 0, "flux": 1}[getattr(params, "flux_bc", "none")]
         self._descs = (g, s, p)
         self.n_cells = grid.n_cells
         self._h = L.oracle_create(C.byref(g), C.byref(s), C.byref(p))

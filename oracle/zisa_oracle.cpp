@@ -303,6 +303,7 @@ struct Params {
   int flux = 0;     // 0 HLLC, 1 Rusanov (not in the reference)
   double gamma = 1.4, gas_constant = 1.0;
   int has_gravity = 0;
+  int flux_bc = 0;  // 0 NoFluxBC, 1 FluxBC (boundary/flux_bc.hpp:13-52)
 };
 
 struct Grid {
@@ -846,6 +847,25 @@ struct Oracle {
     std::vector<double> ff;
     flux_loop(tendency, ff);
     if (prm.has_gravity) gravity_source_loop(tendency);
+    if (prm.flux_bc) flux_bc_loop(tendency, state);
+  }
+
+  // FluxBC::compute, boundary/flux_bc.hpp:24-42: on every exterior face the physical flux of the adjacent cell's
+  // *average* state leaves the cell: tendency(i) -= |face| / |cell| * F(u_i) . n
+  void flux_bc_loop(double *tendency, const double *state) const {
+    for (i64 e = g.n_interior_edges; e < g.n_edges; ++e) {
+      const i64 i = g.left_right[2 * e];
+      const double *n = &g.face_normal[3 * e], *t1 = &g.face_t1[3 * e], *t2 = &g.face_t2[3 * e];
+      double u[NV], f[NV];
+      for (int v = 0; v < NV; ++v) u[v] = state[i * NV + v];
+      coord_transform(u, n, t1, t2);
+      euler_flux(u, eos.pressure(u), f);
+      inv_coord_transform(f, n, t1, t2);
+      double area = 0.0;
+      for (int q = 0; q < g.q_f; ++q) area += g.face_qw[(size_t)(e * g.q_f + q)];
+      const double c = area / g.volumes[i];
+      for (int v = 0; v < NV; ++v) tendency[i * NV + v] -= c * f[v];
+    }
   }
 
   void apply_bc(double *u) const {
@@ -966,6 +986,7 @@ struct oracle_params {
   int well_balanced, scaling, flux;
   double gamma, gas_constant;
   int has_gravity;
+  int flux_bc;
 };
 
 void *oracle_create(const oracle_grid_desc *gd, const oracle_stencil_desc *sd, const oracle_params *pp) {
@@ -1024,6 +1045,7 @@ void *oracle_create(const oracle_grid_desc *gd, const oracle_stencil_desc *sd, c
   p.gamma = pp->gamma;
   p.gas_constant = pp->gas_constant;
   p.has_gravity = pp->has_gravity;
+  p.flux_bc = pp->flux_bc;
   o->init();
   return o;
 }

@@ -39,6 +39,9 @@ CASES = {
     "polytrope_nowb": lambda: cases.polytrope_2d(n=36, order=3, well_balanced=False),
     "atmosphere_wb": lambda: cases.stellar_atmosphere_3d(n=7, order=3, well_balanced=True),
     "atmosphere_nowb": lambda: cases.stellar_atmosphere_3d(n=7, order=2, well_balanced=False),
+    # no ghost ring: the boundary is closed by FluxBC (boundary/flux_bc.hpp), stencils degrade towards the boundary
+    "vortex_fluxbc": lambda: cases.isentropic_vortex(n=24, order=3, ghost_ring_cells=0, flux_bc="flux"),
+    "blast_fluxbc": lambda: cases.blast_3d(n=6, order=3, kind="smooth", ghost_cubes=0, flux_bc="flux"),
 }
 
 

@@ -184,3 +184,26 @@ def test_frozen_bc_restores_ghost_rows():
         assert (out[i] == 100.0 * i + np.arange(5)).all()
     rest = np.setdiff1d(np.arange(n), ghost)
     assert np.array_equal(out[rest], u[rest])
+
+
+@pytest.mark.parametrize("maker", [lambda: cases.isentropic_vortex(n=10, ghost_ring_cells=0, flux_bc="flux"),
+                                   lambda: cases.blast_3d(n=3, kind="smooth", ghost_cubes=0, flux_bc="flux")],
+                         ids=["2d", "3d"])
+def test_flux_bc_closes_the_domain(maker):
+    """FluxBC (boundary/flux_bc.hpp:24-42; no test of its own in the reference): with the physical flux of the cell
+    average on every exterior face, a constant state has a zero residual in *every* cell of a domain without ghost ring
+    (interior faces: HLLC(u, u) = F(u), flux/hllc.cpp:10-26; the closed-surface sum of |face| n vanishes), and total
+    mass / energy change only through the boundary terms, which `flux_bc = none` lacks."""
+    case = maker()
+    st = case.ensure_stencils()
+    n = case.grid.n_cells
+    assert not case.grid.is_ghost.any()
+    u = np.tile(np.array([1.3, 0.4, -0.2, 0.3 if case.grid.n_dims == 3 else 0.0, 2.9]), (n, 1))
+    ora = Oracle(case.grid, st, case.params)
+    tend = ora.rate_of_change(u)
+    rho, p = 1.3, 0.4 * (2.9 - 0.5 * (0.4 ** 2 + 0.2 ** 2 + u[0, 3] ** 2) / 1.3)
+    scale = (np.sqrt(1.4 * p / rho) + 0.6) / case.grid.array("inradii").min() * np.abs(u[0]).max()
+    assert np.abs(tend).max() < 1e-12 * scale
+    case.params.flux_bc = "none"
+    open_tend = Oracle(case.grid, st, case.params).rate_of_change(u)
+    assert np.abs(open_tend).max() > 1e-3 * scale  # boundary cells see an unbalanced flux sum without it

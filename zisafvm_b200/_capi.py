@@ -38,6 +38,7 @@ class ZfvmParams(C.Structure):
         ("gravity_axis", C.c_double * 3),
         ("steps_per_recompute", C.c_int),
         ("keep_polynomials", C.c_int),
+        ("flux_bc", C.c_int),
     ]
 
 

@@ -64,12 +64,16 @@ def ghost_ring(grid: Grid, lo, hi, width):
 
 
 # ---- C1: 2D isentropic vortex ------------------------------------------------------------------------
-def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: int = 0, jitter: float = 0.15) -> Case:
+def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: int = 0, jitter: float = 0.15,
+                      ghost_ring_cells: int = 3, flux_bc: str = "none") -> Case:
+    """``ghost_ring_cells = 0, flux_bc = "flux"``: no ghost ring, the domain boundary is closed with ``FluxBC``
+    (boundary/flux_bc.hpp) -- the set-up of the reference's domains without a halo of frozen cells."""
     gamma = 1.4
     verts, vi = square_mesh(n, n, 0.0, 10.0, 0.0, 10.0, jitter=jitter, seed=seed)
     grid = Grid(2, verts, vi, QRDegrees(face_deg=3, volume_deg=3, moments_deg=4))
     h = 10.0 / n
-    grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0), (10.0, 10.0), 3.0 * h))
+    if ghost_ring_cells > 0:
+        grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0), (10.0, 10.0), ghost_ring_cells * h))
     beta = 5.0
 
     def ic(x):
@@ -83,8 +87,8 @@ def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: in
         rho = T ** (1.0 / (gamma - 1.0))
         return cvars_from_primitive(rho, vel, rho * T, gamma)
 
-    params = EulerParams(weno=WENO_PARAMS[f"2d_o{order}"], flux=flux, gamma=gamma)
-    return Case("isentropic_vortex", grid, params, cell_average(grid, ic), "ssp3", 0.4)
+    params = EulerParams(weno=WENO_PARAMS[f"2d_o{order}"], flux=flux, gamma=gamma, flux_bc=flux_bc)
+    return Case("isentropic_vortex", grid, params, cell_average(grid, ic), "ssp3", 0.4, frozen_bc=ghost_ring_cells > 0)
 
 
 # ---- C2: 2D well-balanced polytrope ------------------------------------------------------------------
@@ -155,7 +159,7 @@ def blast_3d_on_grid(grid: Grid, order: int = 3, kind: str = "blast", stencils=N
 
 # ---- C3: 3D Sod / blast --------------------------------------------------------------------------------
 def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, ghost_cubes: int = 2,
-             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None) -> Case:
+             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None, flux_bc: str = "none") -> Case:
     """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}."""
     gamma = 1.4
     gn = global_n or n
@@ -169,9 +173,9 @@ def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, gh
 
     ic = blast_ic(kind, gamma)
 
-    params = EulerParams(weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma)
+    params = EulerParams(weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma, flux_bc=flux_bc)
     method = "ssp2" if order == 2 else "ssp3"
-    return Case(f"{kind}_3d_o{order}", grid, params, cell_average(grid, ic), method, 0.4)
+    return Case(f"{kind}_3d_o{order}", grid, params, cell_average(grid, ic), method, 0.4, frozen_bc=ghost_cubes > 0)
 
 
 # ---- C4: 3D stellar atmosphere -----------------------------------------------------------------------------

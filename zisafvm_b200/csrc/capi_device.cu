@@ -225,7 +225,9 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
   launch_flux(ctx->plan, ctx->sc, nullptr, ctx->plan.n_interior_edges, ctx->stream);
   prof_mark(ctx, 1);
   prof_mark(ctx, 2);
-  launch_update(ctx->plan, ctx->n_dims, upd, ctx->stream);
+  UpdateArgs upd_bc = upd;
+  upd_bc.flux_bc_state = ctx->params.flux_bc ? state : nullptr;  // FluxBC is part of the rate of change
+  launch_update(ctx->plan, ctx->n_dims, upd_bc, ctx->stream);
   prof_mark(ctx, 2);
   ctx->launches += 2;
   ZFVM_CUDA(cudaGetLastError());
@@ -261,6 +263,7 @@ void zfvm_params_default(zfvm_params *p) {
   p->gas_constant = 1.0;
   p->gravity_kind = GRAVITY_NONE;
   p->steps_per_recompute = 1;
+  p->flux_bc = 0;
 }
 
 int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params, int device,

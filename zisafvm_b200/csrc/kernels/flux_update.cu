@@ -319,14 +319,15 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
 // K3.  One thread owns one (cell, variable) pair and a block two tiles of 32 cells: every access to the row-major
 // [n][5] arrays (state, tendencies, fluxes) is then contiguous across the warp, and a face's flux row is read by
 // five adjacent lanes.  The face fluxes are gathered in the fixed order of the cell's face list (no atomics).
-template <int F>
-__global__ void __launch_bounds__(320, 6) update_kernel(const DevicePlan P, const UpdateArgs A) {
+template <int F, bool FLUX_BC>
+__global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const DevicePlan P, const UpdateArgs A) {
   constexpr int CELLS = 2 * TILE;
   __shared__ double s_un[CELLS * NVARS];
   const int cl = threadIdx.x / NVARS, v = threadIdx.x - cl * NVARS;  // cell within the block, variable
   const std::int64_t i = (std::int64_t)blockIdx.x * CELLS + cl;
+  const std::int64_t iv = i * NVARS + v;
   const bool active = i < A.n_cells_update;
-  double un = 1.0;
+  double un = 1.0, t = 0.0, ub = 0.0, kp[MAX_RK_STAGES - 1];
   if (active) {
     const std::int64_t tile = i / TILE;
     const int lane = (int)(i % TILE);
@@ -336,8 +337,6 @@ __global__ void __launch_bounds__(320, 6) update_kernel(const DevicePlan P, cons
 #pragma unroll
     for (int k = 0; k < F; ++k) fref[k] = P.face_ref[(tile * F + k) * TILE + lane];
     const double vol = P.volume[i];
-    const std::int64_t iv = i * NVARS + v;
-    double ub = 0.0, kp[MAX_RK_STAGES - 1];
     if (A.u_next) ub = A.u_base[iv];
 #pragma unroll
     for (int s = 0; s < MAX_RK_STAGES - 1; ++s)
@@ -351,10 +350,35 @@ __global__ void __launch_bounds__(320, 6) update_kernel(const DevicePlan P, cons
       if (!use) fl[k] = 0.0;
     }
     const double inv_vol = 1.0 / vol;
-    double t = 0.0;
 #pragma unroll
     for (int k = 0; k < F; ++k) {
       if (fref[k] & FREF_TRACE) t += ((fref[k] & FREF_SIDE) ? fl[k] : -fl[k]) * inv_vol;
+    }
+    if constexpr (FLUX_BC) {
+      // FluxBC::compute (boundary/flux_bc.hpp:24-42): the cell's exterior faces, in face-list order; the cell is the
+      // left cell of an exterior face.  Rare (boundary cells only): every thread of the cell evaluates the 5-vector.
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        if (!(fref[k] & FREF_INTERIOR)) {
+          const std::int64_t e = fref[k] & FREF_EDGE_MASK;
+          const double *fr = P.face_frame + e * 10;
+          double u[NVARS];
+#pragma unroll
+          for (int w = 0; w < NVARS; ++w) u[w] = A.flux_bc_state[i * NVARS + w];
+          const double un_ = u[1] * fr[0] + u[2] * fr[1] + u[3] * fr[2];
+          const double ut1 = u[1] * fr[3] + u[2] * fr[4] + u[3] * fr[5];
+          const double ut2 = u[1] * fr[6] + u[2] * fr[7] + u[3] * fr[8];
+          const double p = (u[4] - 0.5 * (u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) / u[0]) * (A.gamma - 1.0);
+          const double vn = un_ / u[0];
+          const double f1 = vn * un_ + p, f2 = vn * ut1, f3 = vn * ut2;
+          double fv = un_;  // mass flux; the momentum components are rotated back (inv_coord_transform)
+          if (v == 1) fv = f1 * fr[0] + f2 * fr[3] + f3 * fr[6];
+          if (v == 2) fv = f1 * fr[1] + f2 * fr[4] + f3 * fr[7];
+          if (v == 3) fv = f1 * fr[2] + f2 * fr[5] + f3 * fr[8];
+          if (v == 4) fv = vn * (u[4] + p);
+          t -= fr[9] / vol * fv;
+        }
+      }
     }
     if (A.has_source) t += P.source[iv];
     if (A.tendency) {
@@ -363,17 +387,20 @@ __global__ void __launch_bounds__(320, 6) update_kernel(const DevicePlan P, cons
       else
         A.tendency[iv] = t;
     }
-    if (A.u_next) {
-      // runge_kutta_sum: stages in index order, the stage just computed is the last one
-      double dudt = 0.0;
+  }
+  // the fused stage update may overwrite the very rows FluxBC has just read (u_next aliases the stage's input state
+  // from the second stage on): all reads of the block's cells are done before any of them is updated
+  if constexpr (FLUX_BC) __syncthreads();
+  if (active && A.u_next) {
+    // runge_kutta_sum: stages in index order, the stage just computed is the last one
+    double dudt = 0.0;
 #pragma unroll
-      for (int s = 0; s < MAX_RK_STAGES - 1; ++s)
-        if (s < A.n_prev && A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * kp[s];
-      if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
-      un = ub + A.dt * dudt;
-      if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[iv];
-      A.u_next[iv] = un;
-    }
+    for (int s = 0; s < MAX_RK_STAGES - 1; ++s)
+      if (s < A.n_prev && A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * kp[s];
+    if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
+    un = ub + A.dt * dudt;
+    if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[iv];
+    A.u_next[iv] = un;
   }
   if (A.reduce_out) {  // LocalCFL + plausibility over the updated state (uniform branch)
     s_un[threadIdx.x] = un;
@@ -520,10 +547,18 @@ void launch_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStr
   if (A.n_cells_update <= 0) return;
   const int block = 2 * TILE * NVARS;
   const unsigned grid = (unsigned)((A.n_cells_update + 2 * TILE - 1) / (2 * TILE));
-  if (n_dims == 2)
-    update_kernel<3><<<grid, block, 0, stream>>>(P, A);
-  else
-    update_kernel<4><<<grid, block, 0, stream>>>(P, A);
+  const bool bc = A.flux_bc_state != nullptr;
+  if (n_dims == 2) {
+    if (bc)
+      update_kernel<3, true><<<grid, block, 0, stream>>>(P, A);
+    else
+      update_kernel<3, false><<<grid, block, 0, stream>>>(P, A);
+  } else {
+    if (bc)
+      update_kernel<4, true><<<grid, block, 0, stream>>>(P, A);
+    else
+      update_kernel<4, false><<<grid, block, 0, stream>>>(P, A);
+  }
 }
 
 void launch_cfl(const double *u, const double *inradius, std::int64_t n, double gamma, ReduceOut *out,

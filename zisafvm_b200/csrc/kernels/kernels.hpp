@@ -36,6 +36,8 @@ struct UpdateArgs {
   double coef_cur;
   double dt;
   const double *frozen;    // FrozenBC steady state (null: no boundary condition)
+  // FluxBC (boundary/flux_bc.hpp:24-42): exterior faces of the cell, evaluated on `state`; null = NoFluxBC
+  const double *flux_bc_state;
   // CFL / plausibility reduction over the updated state
   ReduceOut *reduce_out;
   const double *inradius;

@@ -51,6 +51,7 @@ class EulerParams:
     gas_constant: float = 1.0
     gravity: Gravity = field(default_factory=Gravity)
     keep_polynomials: bool = False
+    flux_bc: str = "none"  # "flux-bc": none | flux (FluxBC, boundary/flux_bc.hpp)
 
     def to_c(self) -> ZfvmParams:
         p = ZfvmParams()
@@ -75,6 +76,7 @@ class EulerParams:
             p.gravity_axis[k] = float(v)
         p.steps_per_recompute = 1
         p.keep_polynomials = int(self.keep_polynomials)
+        p.flux_bc = {"none": 0, "flux": 1}[self.flux_bc]
         return p
 
 
