@@ -195,8 +195,10 @@ def test_reconstruction_kernels_agree(maker, monkeypatch):
     out = {}
     for key, env in [("default", {}), ("few_ctas", {"ZFVM_STREAM_MAX_CTAS": "3"}), ("one_cta", {"ZFVM_STREAM_MAX_CTAS": "1"}),
                      ("one_warp", {"ZFVM_TILE_WARPS": "1", "ZFVM_STREAM_MAX_CTAS": "2"}),
+                     ("wide_index", {"ZFVM_TILE_MIN_CAP": "288"}),  # 16-bit list indices, larger table, fewer warps
+                     ("two_slots", {"ZFVM_TILE_SLOTS": "2", "ZFVM_STREAM_MAX_CTAS": "5"}),
                      ("stream", {"ZFVM_RECON": "stream"}), ("v1", {"ZFVM_RECON": "v1"})]:
-        for k in ("ZFVM_STREAM_MAX_CTAS", "ZFVM_RECON", "ZFVM_TILE_WARPS"):
+        for k in ("ZFVM_STREAM_MAX_CTAS", "ZFVM_RECON", "ZFVM_TILE_WARPS", "ZFVM_TILE_MIN_CAP", "ZFVM_TILE_SLOTS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -210,6 +212,8 @@ def test_reconstruction_kernels_agree(maker, monkeypatch):
     assert np.array_equal(out["default"], out["few_ctas"])
     assert np.array_equal(out["default"], out["one_cta"])
     assert np.array_equal(out["default"], out["one_warp"])
+    assert np.array_equal(out["default"], out["wide_index"])
+    assert np.array_equal(out["default"], out["two_slots"])
     scale = tendency_scales(case.u0, case.params.gamma, case.grid.array("inradii"))
     assert (np.abs(out["default"] - out["v1"]).max(axis=0) / scale).max() < 1e-12
     assert (np.abs(out["default"] - out["stream"]).max(axis=0) / scale).max() < 1e-12

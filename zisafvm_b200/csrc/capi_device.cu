@@ -401,6 +401,7 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       int cap = TILE;
       for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
       cap = (cap + 31) / 32 * 32;
+      if (const char *e = std::getenv("ZFVM_TILE_MIN_CAP")) cap = std::max(cap, (std::atoi(e) + 31) / 32 * 32);  // tests: 16-bit indices
       if (cap > 1024) use_tile = false;  // the shared-memory table would not fit; fall back to the older kernels
       P.rec2_cap = cap;
     }
@@ -409,7 +410,7 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       const TileRecLayout L = tile_rec_layout(sc, nd, D2, P.rec2_cap);
       P.rec2_bytes = L.rec_bytes;
       char *d_rec = nullptr;
-      if (dev_alloc(ctx, &d_rec, T * L.rec_bytes)) {
+      if (dev_alloc(ctx, &d_rec, T * L.rec_bytes + 65536)) {  // slack: the kernel may prefetch a little past the last record
         zfvm_destroy(ctx);
         return 1;
       }

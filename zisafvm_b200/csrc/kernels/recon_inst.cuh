@@ -32,6 +32,8 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
   // spend what is left on deeper rings
   if (!std::getenv("ZFVM_TILE_SLOTS")) tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, (optin / wpc) / 128 * 128, 13, cfg);
   cfg.prof = tile_prof_buffer();
+  cfg.l2_ahead = 0;
+  if (const char *e = std::getenv("ZFVM_TILE_L2_AHEAD")) cfg.l2_ahead = std::max(0, std::atoi(e));
   const int smem_bytes = cfg.warp_bytes * wpc;
   const char *e_ctas = std::getenv("ZFVM_STREAM_MAX_CTAS");
   const int max_ctas = e_ctas ? std::max(1, std::atoi(e_ctas)) : (1 << 30);

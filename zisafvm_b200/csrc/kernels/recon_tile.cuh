@@ -80,6 +80,7 @@ struct TileCfg {
   const char *rec;
   // shared memory of one warp
   int n_slots, s_list, s_lidx, s_table, s_ring, s_stage, warp_bytes;
+  int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off, -1 never used)
   int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
 };
@@ -108,6 +109,15 @@ ZFVM_DEVICE void bulk_g2s_if(bool pred, void *dst, const void *src, std::uint32_
       "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
       "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy), "r"((std::uint32_t)pred)
+      : "memory");
+}
+/// L2 prefetch of a global range (no shared-memory destination, no completion tracking), predicated like bulk_g2s_if.
+ZFVM_DEVICE void bulk_prefetch_l2_if(bool pred, const void *src, std::uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "@p cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src),
+      "r"(bytes), "r"((std::uint32_t)pred)
       : "memory");
 }
 ZFVM_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -192,6 +202,11 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     const int bytes = live ? cfg.seg_bytes[iss_s] : 0;
     ptx::bulk_g2s_if(live && lane == 0, ring + (size_t)slot * T::SLOT_BYTES, iss_ptr, (std::uint32_t)bytes, &seg_full[slot],
                      pol);
+    // the ring is short (shared memory): pull the bytes behind it towards L2 so that the next copies are L2 hits
+    if (cfg.l2_ahead > 0) {
+      const bool in_rec = iss_s + 1 < N_SEG;  // stay inside this record's W | geometry stream
+      ptx::bulk_prefetch_l2_if(live && in_rec && lane == 0, iss_ptr + bytes + cfg.l2_ahead, (std::uint32_t)T::SLOT_BYTES);
+    }
     const bool last = (iss_s == N_SEG - 1);
     iss_ptr = last ? nxt_ptr : (live ? iss_ptr + bytes : nullptr);
     nxt_ptr = last ? nullptr : nxt_ptr;
@@ -710,6 +725,7 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
     if (i == T::N_SEG - 1) bytes = T::GEO_TAIL_BYTES;
     c.seg_bytes[i] = bytes;
   }
+  c.l2_ahead = 0;
   c.prof = nullptr;
   return true;
 }
