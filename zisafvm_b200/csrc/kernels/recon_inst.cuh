@@ -42,10 +42,16 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     kern<<<grid, 32 * wpc, (size_t)smem_bytes, stream>>>(args, sc, cfg);
   };
-  if (args.plan.rec2_cap <= 256)
-    go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint8_t>);
-  else
-    go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint16_t>);
+  if (cfg.prof != nullptr) {  // ZFVM_TILE_PROF=1: instantiation with the phase timers
+    if (args.plan.rec2_cap <= 256)
+      go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint8_t, true>);
+    else
+      go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint16_t, true>);
+  } else if (args.plan.rec2_cap <= 256) {
+    go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint8_t, false>);
+  } else {
+    go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint16_t, false>);
+  }
   (void)sizeof(T);
   return 0;
 }

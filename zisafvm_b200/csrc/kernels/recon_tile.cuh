@@ -124,7 +124,7 @@ ZFVM_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "
 ZFVM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 }  // namespace ptx
 
-template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF, typename LIDX>
+template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF, typename LIDX, bool PROF>
 __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     recon_tile_kernel(const __grid_constant__ ReconArgs args, const __grid_constant__ SchemeConst sc,
                       const __grid_constant__ TileCfg cfg) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     return args.tile_list ? (std::int64_t)args.tile_list[idx] : idx;
   };
   if (!has_tile(0)) return;
-  const bool prof = cfg.prof != nullptr && first == 0;
+  const bool prof = PROF && cfg.prof != nullptr && first == 0;  // PROF = false: the timers compile away
   long long t_mark = 0, t_segwait = 0;
   auto mark = [&](int phase) {
     if (prof) {
@@ -255,6 +255,13 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
   load_table(0);
 
   const bool cweno = sc.recon_mode == RECON_CWENO_AO;
+  // write-out pattern of the trace staging buffer: element it * 32 + lane of a pass belongs to cell wo_owner, offset wo_j
+  int wo_owner[T::CHUNK], wo_j[T::CHUNK];
+#pragma unroll
+  for (int it = 0; it < T::CHUNK; ++it) {
+    wo_owner[it] = (it * TILE + lane) / T::CHUNK;
+    wo_j[it] = (it * TILE + lane) - wo_owner[it] * T::CHUNK;
+  }
   // one dump block per warp (TRACE_DUMP_BLOCKS of them are allocated): no two warps store to the same lines
   const std::uint32_t dump_blk = (std::uint32_t)(2 * P.n_interior_edges) + (std::uint32_t)(first % TRACE_DUMP_BLOCKS);
 
@@ -667,10 +674,8 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
         // coalesced write-out: consecutive lanes write consecutive doubles of a cell's block
 #pragma unroll
         for (int it = 0; it < T::CHUNK; ++it) {
-          const int idx = it * TILE + lane;
-          const int owner = idx / T::CHUNK, j = idx - owner * T::CHUNK;
-          const std::uint32_t b = __shfl_sync(0xffffffffu, blk, owner);
-          P.trace[(std::int64_t)b * (QF * NVARS) + q0 * NVARS + j] = stage[owner * T::STAGE_PITCH + j];
+          const std::uint32_t b = __shfl_sync(0xffffffffu, blk, wo_owner[it]);
+          P.trace[(std::int64_t)b * (QF * NVARS) + (q0 * NVARS + wo_j[it])] = stage[wo_owner[it] * T::STAGE_PITCH + wo_j[it]];
         }
         __syncwarp();  // the staging buffer is reused
       }

@@ -236,8 +236,10 @@ class CudaRungeKutta:
         check(lib.zfvm_rk_step(self.ctx._h, t, dt, cfl_number, C.byref(dtn), C.byref(bad)))
         return float(dtn.value), bool(bad.value)
 
-    def compute_step(self, u0: AllVariables, t: float, dt: float) -> AllVariables:
-        """``TimeIntegration::compute_step(u0, t, dt) -> u1`` with host buffers (H2D + D2H inside)."""
-        u1 = AllVariables(self.ctx.n_cells)
+    def compute_step(self, u0: AllVariables, t: float, dt: float, out: Optional[AllVariables] = None) -> AllVariables:
+        """``TimeIntegration::compute_step(u0, t, dt) -> u1`` with host buffers (H2D + D2H inside).  ``out`` lets the
+        caller hand in the result buffer (the reference's RungeKutta owns and swaps its buffers, runge_kutta.cpp:109-111);
+        pinned buffers are copied without staging."""
+        u1 = AllVariables(self.ctx.n_cells) if out is None else out
         check(lib.zfvm_rk_step_host(self.ctx._h, _capi.ptr_f64(u0.cvars), _capi.ptr_f64(u1.cvars), t, dt))
         return u1
