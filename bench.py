@@ -119,6 +119,12 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
+def workload_name(args, method: str) -> str:
+    """The same string in both arms (the driver pairs the lines by metric and config)."""
+    return (f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets per GPU, CWENO-AO order {args.order} "
+            f"{{3,2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell")
+
+
 def measured_traffic(args, n_cells: int, world: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ``ncu --set full`` capture
     of this very configuration (profiles/r01_k1_traffic.json), else null."""
@@ -178,8 +184,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D {args.kind}, CWENO-AO order {args.order}, HLLC, {case.method}; reference algorithm "
-                               f"restated on the CPU (oracle port; the reference binary cannot be built here)",
+        "config": {"workload": workload_name(args, case.method),
+                   "sample": sample + "; reference algorithm restated on the CPU with OpenMP on all host cores (oracle "
+                             "port: the reference binary cannot be built in this image, DESIGN.md section 4)",
                    "cells": int(case.grid.n_cells), "l2_flush": "state + weights larger than any cache"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -354,8 +361,7 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets per GPU, CWENO-AO order {args.order} "
-                            f"{{3,2,2,2,2}}, HLLC, {case.method}, FrozenBC ghost shell",
+                "workload": workload_name(args, case.method),
                 "cells_per_gpu": int(n), "counted_cells": int(total_counted), "stages_per_step": stages,
                 "device_bytes": int(dev_bytes), "setup_seconds": round(setup_s, 1),
                 "l2_flush": "inputs larger than L2 (weights + state >> 126 MB per stage)",
