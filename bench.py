@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("ZFVM_BENCH_N", "118")), help="cubes per direction per GPU")
     ap.add_argument("--order", type=int, default=3)
-    ap.add_argument("--kind", default="blast")
+    ap.add_argument("--kind", default="blast", help="blast | sod | smooth (3D, BASELINE configs 3/5); vortex2d (BASELINE "
+                    "config 1 scaled up: --n squares per direction x 2 triangles; single GPU, extra measurement)")
     ap.add_argument("--cpu-n", type=int, default=32, help="cubes per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -121,6 +122,9 @@ def measured_peak_gbs():
 
 def workload_name(args, method: str) -> str:
     """The same string in both arms (the driver pairs the lines by metric and config)."""
+    if args.kind == "vortex2d":
+        return (f"2D isentropic vortex on [0,10]^2, {args.n}^2 squares x 2 triangles, CWENO-AO order {args.order}, HLLC, "
+                f"{method}, FrozenBC ghost ring")
     return (f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets per GPU, CWENO-AO order {args.order} "
             f"{{3,2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell")
 
@@ -222,7 +226,10 @@ def run_b200(args):
         case, ctx = sub.case, sub.ctx
         n_counted = sub.n_counted
     else:
-        case = cases.blast_3d(n=args.n, order=args.order, kind=args.kind)
+        if args.kind == "vortex2d":
+            case = cases.isentropic_vortex(n=args.n, order=args.order)
+        else:
+            case = cases.blast_3d(n=args.n, order=args.order, kind=args.kind)
         st = case.ensure_stencils()
         ctx = z.CudaContext(case.grid, st, case.params, device=local_rank)
         n_counted = int((~case.grid.is_ghost).sum())
@@ -285,8 +292,9 @@ def run_b200(args):
     kms, kcnt = ctx.profile_read()
     ctx.profile(False)
     peak, peak_src = measured_peak_gbs()
-    D = {2: 4, 3: 10, 4: 20}[args.order]
-    b_k2 = 40.0 * D + 2.0 * (8.0 * (9 + 4 * case.grid.q_f) + 8.0)      # polynomial read + face data  (F/2 = 2)
+    nd = case.grid.n_dims
+    D = {2: 4, 3: 10, 4: 20}[args.order] if nd == 3 else {2: 3, 3: 6, 4: 10, 5: 15}[args.order]
+    b_k2 = 40.0 * D + ((nd + 1) / 2.0) * (8.0 * (9 + 4 * case.grid.q_f) + 8.0)   # polynomial read + face data (F/2 faces)
     b_k3 = 40.0 + 40.0 * (1.0 + {3: 2.0, 2: 1.5}[stages]) + 40.0        # tendency write + RK sum
     b_k1 = alg_bytes - b_k2 - b_k3
     t_k1 = kms[0] / max(kcnt[0], 1) * 1e-3
@@ -351,7 +359,7 @@ def run_b200(args):
                                   "tendency_l1": checksum}}
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline and not distributed:
+    if rank == 0 and not args.no_cpu_baseline and not distributed and args.kind != "vortex2d":
         v, ms, cores, sample, _ = cpu_reference_run(args, steps=2, warmup=1)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __g
   constexpr int LPF = QF <= 1 ? 1 : (QF <= 2 ? 2 : (QF <= 4 ? 4 : 8));  // lanes per face
   constexpr int FPW = 32 / LPF;                                          // faces per warp
   constexpr int CHUNKS = QF * NVARS;                                     // 16-byte chunks of a trace block [2][QF][5]
-  constexpr int PITCH = 2 * QF * NVARS + 2;                              // doubles per staged face row
+  constexpr int PITCH = 2 * ((QF * NVARS + 1) | 1);                      // doubles per staged face row (odd count of 16-byte units)
   __shared__ __align__(16) double flux_smem[4 * FPW * (PITCH + 10)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *tr = flux_smem + warp * FPW * (PITCH + 10);
@@ -511,7 +511,9 @@ static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std:
   }();
   if (!per_point) {  // one thread per face
     const int block = 64, wpc = block / 32;
-    const int pitch = 2 * sc.q_f * NVARS + 2;  // doubles per staged face row: 16-byte aligned, 2-way bank conflicts at most
+    // doubles per staged face row: even (16-byte cp.async) with an odd number of 16-byte units, so that the 64-bit
+    // reads of 32 consecutive rows spread over all banks (q_f = 3 would otherwise give a pitch of 32 doubles)
+    const int pitch = 2 * ((sc.q_f * NVARS + 1) | 1);
     const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
     const unsigned grid = (unsigned)((n_faces + block - 1) / block);
     flux_face_kernel<FLUX><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
