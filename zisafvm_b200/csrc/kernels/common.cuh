@@ -62,14 +62,60 @@ ZFVM_DEVICE double pressure_of(const double u[NVARS], double gamma) {
   return (u[4] - ekin) * (gamma - 1.0);
 }
 
+// Reciprocal and reciprocal square root from the hardware's 2^-23 approximations plus two Newton steps: full
+// double precision to within an ulp or two, at about a third of the FP64-pipe cost of the IEEE division /
+// square root sequences (which is what bounds the flux kernel).  Arguments here are densities, pressures and
+// wave-speed differences: finite, normal numbers; a non-positive argument of rsqrt yields NaN like sqrt would.
+ZFVM_DEVICE double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+ZFVM_DEVICE double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+/// x^(1/(gamma-1)) for the density of an isentropic state.  For the adiabatic indices in practical use the exponent
+/// is a half-integer (gamma = 2, 5/3, 3/2, 7/5, 4/3 -> 1, 3/2, 2, 5/2, 3): square root and multiplications instead of
+/// pow(), which is what the well-balanced reconstruction spends its time in (one evaluation per stencil member and
+/// Gauss point, each cell with its own (h, K)).  gamma is a kernel-uniform scalar: no divergence.
+ZFVM_DEVICE double pow_inv_gamma_minus_one(double x, double gamma) {
+  if (gamma == 2.0) return x;
+  const double e = 1.0 / (gamma - 1.0);
+  const double twice = 2.0 * e, r = rint(twice);
+  if (fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) {
+    const int n = (int)r;  // x^(n/2); odd n: x^((n+1)/2) / sqrt(x) with the Newton-refined reciprocal square root
+    double pw = (n & 1) ? x * fast_rsqrt(x) : 1.0;
+    for (int m = n >> 1; m > 0; --m) pw *= x;
+    return pw;
+  }
+  return pow(x, e);
+}
+
 /// Isentropic ideal-gas state at specific enthalpy h and entropy function K
-/// (ideal_gas_eos.hpp:162-168,188-191,208-215).
+/// (ideal_gas_eos.hpp:162-168,188-191,208-215): rho = ((gamma-1) h / (gamma K))^(1/(gamma-1)), p = K rho^gamma,
+/// E = p / (gamma-1).  rho^(gamma-1) is the base of that power, so p = K rho base needs no second pow().
 ZFVM_DEVICE void isentropic_state(double h, double K, double gamma, double &rho, double &E, double &p) {
-  double base = 1.0 / K * (gamma - 1.0) / gamma * h;
-  double exponent = 1.0 / (gamma - 1.0);
-  rho = (gamma == 2.0) ? base : pow(base, exponent);
-  p = K * ((gamma == 2.0) ? rho * rho : pow(rho, gamma));
+  const double base = 1.0 / K * (gamma - 1.0) / gamma * h;
+  rho = pow_inv_gamma_minus_one(base, gamma);
+  p = K * (rho * base);
   E = p / (gamma - 1.0);
+}
+/// Same state with the per-equilibrium constant c1 = (gamma-1) / (gamma K) and 1/(gamma-1) formed once by the caller:
+/// no division per point.
+ZFVM_DEVICE void isentropic_state_c(double h, double K, double c1, double gamma, double inv_gm1, double &rho, double &E,
+                                    double &p) {
+  const double base = c1 * h;
+  rho = pow_inv_gamma_minus_one(base, gamma);
+  p = K * (rho * base);
+  E = p * inv_gm1;
 }
 
 }  // namespace zfvm

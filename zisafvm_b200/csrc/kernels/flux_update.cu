@@ -18,26 +18,6 @@ namespace zfvm {
 
 namespace {
 
-// Reciprocal and reciprocal square root from the hardware's 2^-23 approximations plus two Newton steps: full
-// double precision to within an ulp or two, at about a third of the FP64-pipe cost of the IEEE division /
-// square root sequences (which is what bounds the flux kernel).  Arguments here are densities, pressures and
-// wave-speed differences: finite, normal numbers; a non-positive argument of rsqrt yields NaN like sqrt would.
-ZFVM_DEVICE double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(fma(-x, r, 1.0), r, r);
-  r = fma(fma(-x, r, 1.0), r, r);
-  return r;
-}
-ZFVM_DEVICE double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  return y;
-}
-
 // HLLCBatten::flux (flux/hllc.hpp:36-81,143-176).  1/rho and sqrt(rho_R/rho_L) come from rsqrt(rho_L), rsqrt(rho_R);
 // the sound speeds from rsqrt(gamma p); the remaining quotients from fast_rcp: 5 rsqrt + 4 rcp per Gauss point
 // instead of 21 divisions and 4 square roots.  Results differ from the operation-by-operation form by rounding only.

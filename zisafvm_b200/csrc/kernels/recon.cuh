@@ -56,6 +56,11 @@ struct PolyEval {
 struct LocalEq {
   double h_ref, K, phi_ref;
   bool found;
+  double c1 = 0.0, inv_gm1 = 0.0;  // (gamma-1) / (gamma K), 1 / (gamma-1): set by prepare()
+  ZFVM_DEVICE void prepare(double gamma) {
+    c1 = (gamma - 1.0) / (gamma * K);
+    inv_gm1 = 1.0 / (gamma - 1.0);
+  }
   ZFVM_DEVICE void at(double phi, double gamma, double &rho, double &E, double &p) const {
     if (!found) {
       rho = 0.0;
@@ -63,7 +68,7 @@ struct LocalEq {
       p = 0.0;
       return;
     }
-    isentropic_state(h_ref + phi_ref - phi, K, gamma, rho, E, p);
+    isentropic_state_c(h_ref + phi_ref - phi, K, c1, gamma, inv_gm1, rho, E, p);
   }
 };
 
@@ -101,6 +106,7 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
 
   auto f = [&](double h, double K, double &f0, double &f1) {
     LocalEq t{h, K, eq.phi_ref, true};
+    t.prepare(gamma);
     double rb, Eb;
     eq_cell_average(t, phi_own, sc, rb, Eb);
     f0 = rho_bar - rb;
@@ -150,6 +156,7 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
   eq.h_ref = ok ? h : h0;
   eq.K = ok ? K : K0;
   eq.found = ok;
+  eq.prepare(gamma);
   return eq;
 }
 

@@ -87,15 +87,6 @@ struct TileCfg {
 
 enum TilePhase : int { TP_TABLE_WAIT = 0, TP_LO = 1, TP_HI = 2, TP_TABLE_ISSUE = 3, TP_HYBRID = 4, TP_GEO_WAIT = 5, TP_TRACE = 6, TP_SEG_WAIT = 7, TP_TILES = 8, TP_COUNT = 9 };
 
-/// 1 / x from the hardware's 2^-23 approximation and two Newton steps (x: finite, normal, non-zero).
-ZFVM_DEVICE double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(fma(-x, r, 1.0), r, r);
-  r = fma(fma(-x, r, 1.0), r, r);
-  return r;
-}
-
 namespace ptx {
 ZFVM_DEVICE void cp_async8(void *dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
