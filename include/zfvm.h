@@ -124,8 +124,17 @@ typedef struct zfvm_params {
   int steps_per_recompute;
   int keep_polynomials;      /* diagnostics: store every cell's WENO polynomial */
   /* "flux-bc" (numerical_experiment.cpp:238-256 adds it to the FVM rate of change): 0 NoFluxBC, 1 FluxBC
-   * (include/zisa/boundary/flux_bc.hpp:13-52): on exterior faces the physical flux of the cell average leaves the cell */
+   * (include/zisa/boundary/flux_bc.hpp:13-52): on exterior faces the physical flux of the cell average leaves the cell,
+   * 2 EquilibriumFluxBC (include/zisa/boundary/equilibrium_flux_bc.hpp:18-75): the pressure of the cell's local
+   * isentropic equilibrium at the exterior face's Gauss points (needs a gravity model) */
   int flux_bc;
+  /* advected scalars: AllVariables::avars[n_cells][n_avars] (include/zisa/model/all_variables.hpp:31-35), each
+   * reconstructed on its own (LocalReconstruction::compute_tracer, local_reconstruction.hpp:127-147) and upwinded
+   * with the HLLC wave speeds (HLLCBatten::tracer_flux, flux/hllc.hpp:178-197).  At most 8. */
+  int n_avars;
+  /* Heating (include/zisa/model/heating.hpp:18-80): dE/dt += average(rho * heating_rate * [r0 <= |x| <= r1]);
+   * heating_rate == 0: no heating term */
+  double heating_rate, heating_r0, heating_r1;
 } zfvm_params;
 
 void zfvm_params_default(zfvm_params *p);
@@ -155,6 +164,13 @@ int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *stat
 int zfvm_rate_of_change_device(zfvm_ctx *ctx, double *tendency_dev, const double *state_dev, double t,
                                int accumulate);
 
+/* The same for AllVariables{cvars, avars} (n_avars > 0): the avars tendency is the tracer part of
+ * FluxLoop::compute_patch (fvm_loops/flux_loop.hpp:157-161,180-192); sources do not touch avars. */
+int zfvm_rate_of_change_av(zfvm_ctx *ctx, double *tendency_host, double *tendency_avars_host, const double *state_host,
+                           const double *state_avars_host, double t, int accumulate);
+int zfvm_rate_of_change_av_device(zfvm_ctx *ctx, double *tendency_dev, double *tendency_avars_dev,
+                                  const double *state_dev, const double *state_avars_dev, double t, int accumulate);
+
 /* TimeIntegration::compute_step for RungeKutta (src/zisa/ode/runge_kutta.cpp:87-143).
  * method: "forward_euler", "ssp2", "ssp3", "wicker", "rk4", "fehlberg" (make_tableau :145-213).
  * The state lives on the device between calls. */
@@ -162,16 +178,24 @@ int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method);
 int zfvm_upload_state(zfvm_ctx *ctx, const double *state_host);
 int zfvm_download_state(zfvm_ctx *ctx, double *state_host);
 double *zfvm_state_device(zfvm_ctx *ctx);
+/* resident advected scalars [n_cells][n_avars]; zfvm_rk_step advances them together with the state */
+int zfvm_upload_avars(zfvm_ctx *ctx, const double *avars_host);
+int zfvm_download_avars(zfvm_ctx *ctx, double *avars_host);
+double *zfvm_avars_device(zfvm_ctx *ctx);
 /* FrozenBC (src/zisa/boundary/frozen_boundary_condition.cpp:11-55): ghost rows are reset to
  * `steady_state_host` after every stage.  Pass NULL for NoBoundaryCondition. */
 int zfvm_set_frozen_bc(zfvm_ctx *ctx, const double *steady_state_host);
 int zfvm_apply_frozen_bc(zfvm_ctx *ctx, double *state_dev);
+/* FrozenBC on AllVariables: ghost rows of cvars and avars (frozen_boundary_condition.cpp:39-55 copies both) */
+int zfvm_set_frozen_bc_av(zfvm_ctx *ctx, const double *steady_state_host, const double *steady_avars_host);
 /* One RK step on the resident state.  If dt_next / not_plausible are non-NULL the CFL time step
  * cfl_number * min inradius/(|v|+a) (LocalCFL, model/local_cfl_condition_impl.hpp:25-40) and the
  * SanityCheckFor<Euler> flag of the new state come back with it (one 16-byte D2H copy). */
 int zfvm_rk_step(zfvm_ctx *ctx, double t, double dt, double cfl_number, double *dt_next, int *not_plausible);
 /* Same with host buffers: u0_host -> u1_host (one H2D + one D2H copy of the state). */
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double t, double dt);
+int zfvm_rk_step_host_av(zfvm_ctx *ctx, const double *u0_host, const double *a0_host, double *u1_host, double *a1_host,
+                         double t, double dt);
 /* LocalCFL on a device / the resident state */
 int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, double *dt, int *not_plausible);
 int zfvm_synchronize(zfvm_ctx *ctx);
@@ -194,6 +218,8 @@ int zfvm_comm_init(zfvm_ctx *ctx, const char id[128], int rank, int n_ranks);
 int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_rank, const int64_t *recv_begin,
                   const int64_t *recv_end, const int64_t *send_offset, const int32_t *send_index);
 int zfvm_halo_exchange(zfvm_ctx *ctx, double *state_dev); /* post + wait (HaloExchange::operator(), wait) */
+/* the same exchange for cvars and avars rows in one NCCL group (mpi_halo_exchange.cpp:178-201 exchanges both) */
+int zfvm_halo_exchange_av(zfvm_ctx *ctx, double *state_dev, double *avars_dev);
 int zfvm_allreduce_min(zfvm_ctx *ctx, double *value);     /* MPIAllReduce MIN (mpi_all_reduce.cpp:16-24) */
 
 #ifdef __cplusplus

@@ -81,6 +81,16 @@ def lib() -> C.CDLL:
         _lib.oracle_eos_hK_to_rhoE.argtypes = [C.c_double, C.c_double, C.c_double, dp, dp]
         _lib.oracle_local_equilibrium.argtypes = [C.c_double, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, dp, dp, dp]
         _lib.oracle_local_equilibrium.restype = C.c_int
+        _lib.oracle_set_tracers.argtypes = [C.c_void_p, C.c_int]
+        _lib.oracle_set_heating.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        _lib.oracle_set_flux_bc.argtypes = [C.c_void_p, C.c_int]
+        _lib.oracle_set_frozen_bc_av.argtypes = [C.c_void_p, dp, dp]
+        _lib.oracle_rate_of_change_av.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        _lib.oracle_tracer_polys.argtypes = [C.c_void_p, dp, C.c_int]
+        _lib.oracle_hllc_tracer_flux.argtypes = [C.c_double, dp, dp, C.c_double, C.c_double]
+        _lib.oracle_hllc_tracer_flux.restype = C.c_double
+        _lib.oracle_rk_step_av.argtypes = [C.c_void_p, C.c_char_p, dp, dp, dp, dp, C.c_double]
+        _lib.oracle_rk_step_av.restype = C.c_int
     return _lib
 
 
@@ -141,10 +151,15 @@ class Oracle:
         p.flux = {"hllc": 0, "rusanov": 1}[params.flux]
         p.gamma, p.gas_constant = params.gamma, params.gas_constant
         p.has_gravity = int(params.gravity.kind != "none")
-        p.flux_bc = {"none": 0, "flux": 1}[getattr(params, "flux_bc", "none")]
+        p.flux_bc = {"none": 0, "flux": 1, "equilibrium": 2}[getattr(params, "flux_bc", "none")]
         self._descs = (g, s, p)
         self.n_cells = grid.n_cells
         self._h = L.oracle_create(C.byref(g), C.byref(s), C.byref(p))
+        self.n_avars = int(getattr(params, "n_avars", 0))
+        L.oracle_set_tracers(self._h, self.n_avars)
+        heating = getattr(params, "heating", None)
+        if heating is not None:
+            L.oracle_set_heating(self._h, float(heating[0]), float(heating[1]), float(heating[2]))
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -191,11 +206,39 @@ class Oracle:
             raise ValueError(f"Unknown Butcher Tableau. [{method}]")
         return u1
 
+    # -- AllVariables{cvars, avars} (advected scalars) ----------------------------------
+    def set_frozen_bc_av(self, steady, steady_av):
+        lib().oracle_set_frozen_bc_av(self._h, _p(f64(steady)), _p(f64(steady_av)))
+
+    def rate_of_change_av(self, state, avars):
+        state, avars = f64(state), f64(avars)
+        t, ta = np.zeros_like(state), np.zeros_like(avars)
+        lib().oracle_rate_of_change_av(self._h, _p(t), _p(ta), _p(state), _p(avars))
+        return t, ta
+
+    def tracer_polys(self, n_coef):
+        out = np.zeros((self.n_cells, self.n_avars, n_coef))
+        lib().oracle_tracer_polys(self._h, _p(out), n_coef)
+        return out
+
+    def rk_step_av(self, method, u0, a0, dt):
+        u0, a0 = f64(u0), f64(a0)
+        u1, a1 = np.zeros_like(u0), np.zeros_like(a0)
+        rc = lib().oracle_rk_step_av(self._h, method.encode(), _p(u0), _p(a0), _p(u1), _p(a1), dt)
+        if rc:
+            raise ValueError(f"Unknown Butcher Tableau. [{method}]")
+        return u1, a1
+
     def cfl_dt(self, u, cfl_number):
         return lib().oracle_cfl_dt(self._h, _p(f64(u)), cfl_number)
 
     def eq_failures(self):
         return lib().oracle_eq_failures(self._h)
+
+
+def hllc_tracer_flux(gamma, uL, uR, mqL, mqR) -> float:
+    """HLLCBatten::tracer_flux (flux/hllc.hpp:178-197) with the speeds of HLLCBatten::flux for (uL, uR)."""
+    return lib().oracle_hllc_tracer_flux(gamma, _p(f64(uL)), _p(f64(uR)), float(mqL), float(mqR))
 
 
 def num_threads() -> int:

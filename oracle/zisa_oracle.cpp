@@ -303,7 +303,9 @@ struct Params {
   int flux = 0;     // 0 HLLC, 1 Rusanov (not in the reference)
   double gamma = 1.4, gas_constant = 1.0;
   int has_gravity = 0;
-  int flux_bc = 0;  // 0 NoFluxBC, 1 FluxBC (boundary/flux_bc.hpp:13-52)
+  int flux_bc = 0;  // 0 NoFluxBC, 1 FluxBC (boundary/flux_bc.hpp:13-52), 2 EquilibriumFluxBC (equilibrium_flux_bc.hpp:18-75)
+  int n_avars = 0;  // advected scalars, AllVariables::avars (all_variables.hpp:31-35)
+  double heating_rate = 0.0, heating_r0 = 0.0, heating_r1 = 0.0;  // make_heating_source, heating.hpp:54-80
 };
 
 struct Grid {
@@ -509,7 +511,8 @@ struct Oracle {
   std::vector<LocalEquilibrium> eq;   // [n_cells]
   std::vector<PointValues> pv_cell;   // [n_cells][q_c]
   std::vector<PointValues> pv_face;   // [n_cells][F][q_f]
-  std::vector<double> frozen;
+  std::vector<Poly<1>> scalar_polys;   // [n_cells][n_avars]  (LocalReconstruction::scalar_polys)
+  std::vector<double> frozen, frozen_av;
   std::vector<i32> ghost_index;
   bool has_frozen = false;
   int eq_failures = 0;
@@ -541,22 +544,70 @@ struct Oracle {
   }
 
   // eno_hybridize, hybrid_weno.cpp:110-128
-  Poly<NV> hybridize(const std::vector<Poly<NV>> &polys, const double *lw, int n_st) const {
+  template <int NVV>
+  Poly<NVV> hybridize(const std::vector<Poly<NVV>> &polys, const double *lw, int n_st) const {
     double nlw[8];
     double al_tot = 0.0;
     for (int k = 0; k < n_st; ++k) {
-      double beta[NV];
+      double beta[NVV];
       smoothness_indicator(polys[(size_t)k], beta);
       double IS = beta[0];
-      for (int v = 1; v < NV; ++v) IS = std::max(IS, beta[v]);
+      for (int v = 1; v < NVV; ++v) IS = std::max(IS, beta[v]);
       double al = lw[k] / (prm.epsilon + std::pow(IS, prm.exponent));
       nlw[k] = al;
       al_tot += al;
     }
     double zero = 0.0, xz[3] = {0, 0, 0};
-    Poly<NV> p(0, &zero, 1, xz, 1.0, 2);
+    Poly<NVV> p(0, &zero, 1, xz, 1.0, 2);
     for (int k = 0; k < n_st; ++k) poly_add_scaled(p, nlw[k] / al_tot, polys[(size_t)k]);
     return p;
+  }
+
+  // LocalReconstruction::compute_tracer (local_reconstruction.hpp:127-147) for cell i: every advected scalar is
+  // reconstructed on its own (no equilibrium, no scaling; its own smoothness indicators and non-linear weights)
+  // with the cell's stencils and LSQ solvers: rc.reconstruct(rhs_view, polys, q_component) ->
+  // compute_polys_impl (hybrid_weno.cpp:72-92) + CWENO_AO / WENO_AO for ScalarPoly (cweno_ao.cpp:24-34, weno_ao.cpp:26-36)
+  void reconstruct_tracers_cell(i64 i, const double *avars, std::vector<Poly<1>> &polys, std::vector<double> &rhs) {
+    const int ns = st.n_stencils, na = prm.n_avars;
+    const int n_st = st.n_family[i];
+    const i32 *l2g = st.l2g + i * st.l2g_stride;
+    for (int a = 0; a < na; ++a) {
+      const double q0 = avars[(size_t)l2g[0] * na + a];
+      polys.resize((size_t)n_st);
+      for (int k = 0; k < n_st; ++k) {
+        const int size = st.size[i * ns + k];
+        const i32 *loc = st.local + i * st.l2g_stride + st.local_off[k];
+        rhs.resize((size_t)std::max(size - 1, 1));
+        for (int ig = 0; ig < size - 1; ++ig) rhs[(size_t)ig] = avars[(size_t)l2g[loc[ig + 1]] * na + a] - q0;
+        polys[(size_t)k] = lsq[(size_t)(i * ns + k)].solve<1>(rhs.data(), g, i);
+        polys[(size_t)k].coeffs[0] = q0;
+      }
+      double lw[8];
+      if (n_st == 1 && st.order[i * ns] == 1) {
+        lw[0] = 1.0;
+      } else {
+        for (int k = 0; k < n_st; ++k) lw[k] = lin_w_full[(size_t)k];
+      }
+      if (prm.recon_mode == 0) {
+        const int k_high = st.k_high[i];
+        for (int k = 0; k < n_st; ++k)
+          if (k_high != k) poly_sub_scaled(polys[(size_t)k_high], lw[k], polys[(size_t)k]);
+        poly_div(polys[(size_t)k_high], lw[k_high]);
+      }
+      scalar_polys[(size_t)(i * na + a)] = hybridize(polys, lw, n_st);
+    }
+  }
+
+  void global_tracer_reconstruction(const double *avars) {
+    const i64 n = g.n_cells;
+    scalar_polys.resize((size_t)(n * prm.n_avars));
+#pragma omp parallel
+    {
+      std::vector<Poly<1>> polys;
+      std::vector<double> rhs;
+#pragma omp for schedule(static, 8)
+      for (i64 i = 0; i < n; ++i) reconstruct_tracers_cell(i, avars, polys, rhs);
+    }
   }
 
   // LocalReconstruction::compute for cell i (local_reconstruction.hpp:69-120)
@@ -672,7 +723,7 @@ struct Oracle {
     pf[4] = v * (u[4] + p);
   }
 
-  void hllc(const double *uL, const double *uR, double *nf) const {
+  void hllc(const double *uL, const double *uR, double *nf, double *speeds = nullptr) const {
     const double pL = eos.pressure(uL), aL = eos.sound_speed(uL);
     const double pR = eos.pressure(uR), aR = eos.sound_speed(uR);
     const double roe_ratio = std::sqrt(uR[0] / uL[0]);
@@ -688,6 +739,11 @@ struct Oracle {
     double sL = std::min(vL - aL, v_tilda - a_tilda);
     double sR = std::max(vR + aR, v_tilda + a_tilda);
     double s_star = (uR[1] * (sR - vR) - uL[1] * (sL - vL) + pL - pR) / (uR[0] * (sR - vR) - uL[0] * (sL - vL));
+    if (speeds) {
+      speeds[0] = sL;
+      speeds[1] = s_star;
+      speeds[2] = sR;
+    }
     const double *uK = (0.0 <= s_star ? uL : uR);
     const double pK = (0.0 <= s_star ? pL : pR);
     euler_flux(uK, pK, nf);
@@ -701,6 +757,27 @@ struct Oracle {
       nf[3] += sK * (cK * uK[3] - uK[3]);
       nf[4] += sK * (cK * (uK[4] + (s_star - vK) * (uK[0] * s_star + pK / (sK - vK))) - uK[4]);
     }
+  }
+
+  // HLLCBatten::tracer_flux, flux/hllc.hpp:178-197
+  static double hllc_tracer_flux(const double *uL, const double *uR, double mqL, double mqR, const double *speeds) {
+    const double sL = speeds[0], s_star = speeds[1], sR = speeds[2];
+    double mqK = (0.0 <= s_star ? mqL : mqR);
+    double vK = (0.0 <= s_star ? uL[1] / uL[0] : uR[1] / uR[0]);
+    double fK = mqK * vK;
+    if (sL < 0.0 && 0.0 < sR) {
+      double sK = (0.0 <= s_star ? sL : sR);
+      double cK = (sK - vK) / (sK - s_star);
+      return fK + sK * (cK * mqK - mqK);
+    }
+    return fK;
+  }
+  // Rusanov tracer flux: like the Rusanov flux itself not in the reference; same local Lax-Friedrichs form
+  double rusanov_tracer_flux(const double *uL, const double *uR, double mqL, double mqR) const {
+    const double aL = eos.sound_speed(uL), aR = eos.sound_speed(uR);
+    const double vL = uL[1] / uL[0], vR = uR[1] / uR[0];
+    const double lam = std::max(std::abs(vL) + aL, std::abs(vR) + aR);
+    return 0.5 * (mqL * vL + mqR * vR) - 0.5 * lam * (mqR - mqL);
   }
 
   // Not in the reference: defined by this project, parity is against this only.
@@ -739,8 +816,10 @@ struct Oracle {
 
   // FluxLoop::compute_patch, flux_loop.hpp:106-195.  The face fluxes are computed in parallel and
   // scattered serially in edge order (deviation: deterministic order instead of omp atomic).
-  void flux_loop(double *tendency, std::vector<double> &face_flux) {
+  void flux_loop(double *tendency, std::vector<double> &face_flux, double *tendency_av = nullptr) {
     const i64 EI = g.n_interior_edges;
+    const int na = tendency_av ? prm.n_avars : 0;
+    std::vector<double> face_qflux((size_t)(EI * std::max(na, 1)), 0.0);
     face_flux.assign((size_t)(EI * NV), 0.0);
     std::vector<std::uint8_t> active((size_t)EI, 0);
 #pragma omp parallel for schedule(static, 8)
@@ -751,6 +830,7 @@ struct Oracle {
       const double *n = &g.face_normal[3 * e], *t1 = &g.face_t1[3 * e], *t2 = &g.face_t2[3 * e];
       const int kL = local_face(iL, e), kR = local_face(iR, e);
       double nf[NV] = {0, 0, 0, 0, 0};
+      double qnf[16] = {0};
       for (int k = 0; k < g.q_f; ++k) {
         const double w = g.face_qw[(size_t)(e * g.q_f + k)];
         const double *x = &g.face_qp[(size_t)((e * g.q_f + k) * 3)];
@@ -759,15 +839,22 @@ struct Oracle {
         point_value(iR, x, prm.well_balanced ? &pv_face[(size_t)((iR * g.F + kR) * g.q_f + k)] : nullptr, uR);
         coord_transform(uL, n, t1, t2);
         coord_transform(uR, n, t1, t2);
-        double f[NV];
+        double f[NV], speeds[3] = {0, 0, 0};
         if (prm.flux == 0)
-          hllc(uL, uR, f);
+          hllc(uL, uR, f, speeds);
         else
           rusanov(uL, uR, f);
         for (int v = 0; v < NV; ++v) nf[v] += w * f[v];
+        for (int a = 0; a < na; ++a) {  // flux_loop.hpp:157-161
+          double qL, qR;
+          scalar_polys[(size_t)(iL * na + a)].eval(x, &qL);
+          scalar_polys[(size_t)(iR * na + a)].eval(x, &qR);
+          qnf[a] += w * (prm.flux == 0 ? hllc_tracer_flux(uL, uR, qL, qR, speeds) : rusanov_tracer_flux(uL, uR, qL, qR));
+        }
       }
       inv_coord_transform(nf, n, t1, t2);
       for (int v = 0; v < NV; ++v) face_flux[(size_t)(e * NV + v)] = nf[v];
+      for (int a = 0; a < na; ++a) face_qflux[(size_t)(e * na + a)] = qnf[a];
     }
     for (i64 e = 0; e < EI; ++e) {
       if (!active[(size_t)e]) continue;
@@ -777,6 +864,12 @@ struct Oracle {
         tendency[iL * NV + v] -= nfL;
         const double nfR = face_flux[(size_t)(e * NV + v)] / g.volumes[iR];
         tendency[iR * NV + v] += nfR;
+      }
+      for (int a = 0; a < na; ++a) {  // flux_loop.hpp:180-192
+        const double qfL = face_qflux[(size_t)(e * na + a)] / g.volumes[iL];
+        tendency_av[iL * na + a] -= qfL;
+        const double qfR = face_qflux[(size_t)(e * na + a)] / g.volumes[iR];
+        tendency_av[iR * na + a] += qfR;
       }
     }
   }
@@ -842,12 +935,61 @@ struct Oracle {
   }
 
   // Sum[FluxLoop, GravitySourceLoop]::compute (accumulating; ZeroRateOfChange is the caller's)
-  void rate_of_change(double *tendency, const double *state) {
+  void rate_of_change(double *tendency, const double *state, double *tendency_av = nullptr,
+                      const double *state_av = nullptr) {
     global_reconstruction(state);
+    if (prm.n_avars > 0 && state_av && tendency_av) global_tracer_reconstruction(state_av);
     std::vector<double> ff;
-    flux_loop(tendency, ff);
+    flux_loop(tendency, ff, (prm.n_avars > 0 && state_av) ? tendency_av : nullptr);
     if (prm.has_gravity) gravity_source_loop(tendency);
-    if (prm.flux_bc) flux_bc_loop(tendency, state);
+    if (prm.heating_rate != 0.0) heating_loop(tendency);
+    if (prm.flux_bc == 1) flux_bc_loop(tendency, state);
+    if (prm.flux_bc == 2) equilibrium_flux_bc_loop(tendency, state);
+  }
+
+  // Heating::compute, model/heating.hpp:30-44 with the rate of make_heating_source (:54-80):
+  // dudt(i, 4) += average(cell, rho(x) * epsilon * [r0 <= |x| <= r1]), rho = first component of rc(i)(x)
+  void heating_loop(double *tendency) {
+    const i64 n = g.n_cells;
+#pragma omp parallel for schedule(static, 8)
+    for (i64 i = 0; i < n; ++i) {
+      double acc = 0.0;
+      for (int q = 0; q < g.q_c; ++q) {
+        const double *x = &g.cell_qp[(size_t)((i * g.q_c + q) * 3)];
+        double u[NV];
+        point_value(i, x, prm.well_balanced ? &pv_cell[(size_t)(i * g.q_c + q)] : nullptr, u);
+        const double r = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        const double rate = prm.heating_rate * ((prm.heating_r0 <= r) && (r <= prm.heating_r1) ? 1.0 : 0.0);
+        const double f = u[0] * rate;
+        const double w = g.cell_qw[(size_t)(i * g.q_c + q)];
+        acc = (q == 0) ? w * f : acc + w * f;
+      }
+      tendency[i * NV + 4] += (1.0 * acc) / g.volumes[i];
+    }
+  }
+
+  // EquilibriumFluxBC::compute, boundary/equilibrium_flux_bc.hpp:37-63: per exterior face the local equilibrium of
+  // the adjacent cell is solved from its average (rho, E_int) and the flux of the (resting) equilibrium state at the
+  // face Gauss points, i.e. its pressure along the face normal, leaves the cell.
+  void equilibrium_flux_bc_loop(double *tendency, const double *state) const {
+    for (i64 e = g.n_interior_edges; e < g.n_edges; ++e) {
+      const i64 i = g.left_right[2 * e];
+      const double *n = &g.face_normal[3 * e], *t1 = &g.face_t1[3 * e], *t2 = &g.face_t2[3 * e];
+      LocalEquilibrium le;
+      le.solve(eos, g, i, state[i * NV], eos.internal_energy(&state[i * NV]));
+      double acc[NV] = {0, 0, 0, 0, 0};
+      for (int q = 0; q < g.q_f; ++q) {
+        double rho, E;
+        le.extrapolate(eos, g.phi_fqp[(size_t)(e * g.q_f + q)], rho, E);
+        double u[NV] = {rho, 0.0, 0.0, 0.0, E}, f[NV];
+        euler_flux(u, le.found ? eos.pressure(u) : 0.0, f);  // (reference: 0/0 when the solve failed)
+        if (!le.found) f[0] = f[2] = f[3] = f[4] = 0.0;
+        inv_coord_transform(f, n, t1, t2);
+        const double w = g.face_qw[(size_t)(e * g.q_f + q)];
+        for (int v = 0; v < NV; ++v) acc[v] = (q == 0) ? w * f[v] : acc[v] + w * f[v];
+      }
+      for (int v = 0; v < NV; ++v) tendency[i * NV + v] -= (1.0 * acc[v]) / g.volumes[i];
+    }
   }
 
   // FluxBC::compute, boundary/flux_bc.hpp:24-42: on every exterior face the physical flux of the adjacent cell's
@@ -872,6 +1014,13 @@ struct Oracle {
     if (!has_frozen) return;
     for (i32 i : ghost_index)
       for (int v = 0; v < NV; ++v) u[(size_t)i * NV + v] = frozen[(size_t)i * NV + v];
+  }
+
+  void apply_bc_av(double *a) const {  // FrozenBC::apply also resets avars (frozen_boundary_condition.cpp:39-55)
+    if (!has_frozen || frozen_av.empty()) return;
+    const int na = prm.n_avars;
+    for (i32 i : ghost_index)
+      for (int v = 0; v < na; ++v) a[(size_t)i * na + v] = frozen_av[(size_t)i * na + v];
   }
 
   double cfl_dt(const double *u, double cfl_number) const {
@@ -1123,6 +1272,67 @@ int oracle_rk_step(void *h, const char *method, const double *u0, double *u1, do
   }
   runge_kutta_sum(u1, u0, k, t.b, t.n, dt, n);
   o->apply_bc(u1);
+  return 0;
+}
+
+/* ---- extensions: advected scalars (a27), Heating, EquilibriumFluxBC -------------------------------- */
+void oracle_set_tracers(void *h, int n_avars) { ((Oracle *)h)->prm.n_avars = n_avars; }
+void oracle_set_heating(void *h, double rate, double r0, double r1) {
+  Oracle *o = (Oracle *)h;
+  o->prm.heating_rate = rate;
+  o->prm.heating_r0 = r0;
+  o->prm.heating_r1 = r1;
+}
+void oracle_set_flux_bc(void *h, int kind) { ((Oracle *)h)->prm.flux_bc = kind; }
+void oracle_set_frozen_bc_av(void *h, const double *steady, const double *steady_av) {
+  Oracle *o = (Oracle *)h;
+  oracle_set_frozen_bc(h, steady);
+  if (steady_av && o->prm.n_avars > 0)
+    o->frozen_av.assign(steady_av, steady_av + o->g.n_cells * o->prm.n_avars);
+  else
+    o->frozen_av.clear();
+}
+void oracle_rate_of_change_av(void *h, double *tendency, double *tendency_av, const double *state, const double *state_av) {
+  ((Oracle *)h)->rate_of_change(tendency, state, tendency_av, state_av);
+}
+/* scalar polynomial coefficients [n][n_avars][n_coef] after a rate_of_change_av */
+void oracle_tracer_polys(void *h, double *coeffs, int n_coef) {
+  Oracle *o = (Oracle *)h;
+  const int na = o->prm.n_avars;
+  for (int64_t i = 0; i < o->g.n_cells * na; ++i)
+    for (int c = 0; c < n_coef; ++c) coeffs[i * n_coef + c] = o->scalar_polys[(size_t)i].coeffs[c];
+}
+double oracle_hllc_tracer_flux(double gamma, const double *uL, const double *uR, double mqL, double mqR) {
+  Oracle o;
+  o.eos.gamma = gamma;
+  double nf[NV], speeds[3];
+  o.hllc(uL, uR, nf, speeds);
+  return Oracle::hllc_tracer_flux(uL, uR, mqL, mqR, speeds);
+}
+/* RungeKutta::compute_step on AllVariables{cvars, avars} */
+int oracle_rk_step_av(void *h, const char *method, const double *u0, const double *a0, double *u1, double *a1, double dt) {
+  Oracle *o = (Oracle *)h;
+  Tableau t;
+  if (!make_tableau(method, t)) return 1;
+  const int na = o->prm.n_avars;
+  const int64_t n = o->g.n_cells * NV, m = o->g.n_cells * na;
+  std::vector<std::vector<double>> k((size_t)t.n, std::vector<double>((size_t)n, 0.0));
+  std::vector<std::vector<double>> ka((size_t)t.n, std::vector<double>((size_t)m, 0.0));
+  std::vector<double> ux((size_t)n), ax((size_t)m);
+  o->rate_of_change(k[0].data(), u0, ka[0].data(), a0);
+  for (int stage = 1; stage < t.n; ++stage) {
+    runge_kutta_sum(ux.data(), u0, k, t.a[stage], t.n, dt, n);
+    runge_kutta_sum(ax.data(), a0, ka, t.a[stage], t.n, dt, m);
+    o->apply_bc(ux.data());
+    o->apply_bc_av(ax.data());
+    std::fill(k[(size_t)stage].begin(), k[(size_t)stage].end(), 0.0);
+    std::fill(ka[(size_t)stage].begin(), ka[(size_t)stage].end(), 0.0);
+    o->rate_of_change(k[(size_t)stage].data(), ux.data(), ka[(size_t)stage].data(), ax.data());
+  }
+  runge_kutta_sum(u1, u0, k, t.b, t.n, dt, n);
+  runge_kutta_sum(a1, a0, ka, t.b, t.n, dt, m);
+  o->apply_bc(u1);
+  o->apply_bc_av(a1);
   return 0;
 }
 

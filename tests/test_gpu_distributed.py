@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 N_PER_RANK, ORDER, KIND, STEPS, CFL = 6, 3, "smooth", 3, 0.4
+N_AVARS = 2  # advected scalars ride along: their halo rows travel in the same NCCL group
 
 
 def _free_port():
@@ -34,14 +35,15 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        run = zd.make_weak_scaling_case(rank, world, n=N_PER_RANK, order=ORDER, kind=KIND, device=rank)
+        run = zd.make_weak_scaling_case(rank, world, n=N_PER_RANK, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
         sub, case, ctx = run.sub, run.case, run.ctx
         n = sub.n_local
         rk = z.CudaRungeKutta(ctx, case.method)
-        z.FrozenBC(ctx, z.AllVariables(n, case.u0))
-        u0 = case.u0.copy()
+        z.FrozenBC(ctx, z.AllVariables(n, case.u0, case.a0))
+        u0, a0 = case.u0.copy(), case.a0.copy()
         u0[sub.n_owned:] = 1e300  # halo rows must come from the exchange, not from the upload
-        rk.upload(z.AllVariables(n, u0))
+        a0[sub.n_owned:] = 1e300
+        rk.upload(z.AllVariables(n, u0, a0))
         dt, bad = z.LocalCFL(ctx, CFL)()
         dts = [dt]
         for _ in range(STEPS):
@@ -49,7 +51,9 @@ def _worker(rank, world, port, out_dir):
             assert not bad
             dt = dt_next
             dts.append(dt)
-        u = rk.download().cvars
+        out = rk.download()
+        u = out.cvars
+        np.save(os.path.join(out_dir, f"a_{rank}.npy"), out.avars[: sub.n_owned])
         cnt = ctx.counters()
         assert cnt["tiles_interior"] > 0 and cnt["tiles_exterior"] > 0
         np.save(os.path.join(out_dir, f"u_{rank}.npy"), u[: sub.n_owned])
@@ -88,14 +92,15 @@ def test_two_gpu_run_matches_single_domain_oracle(tmp_path):
     g2 = 2
     grid.mask_ghost_cells((cx < g2) | (cx >= G[0] - g2) | (cy < g2) | (cy >= G[1] - g2) | (cz < g2) | (cz >= G[2] - g2))
     case = cases.blast_3d_on_grid(grid, order=ORDER, kind=KIND)
+    cases.with_tracers(case, N_AVARS, box=((0.0, 0.0, 0.0), tuple(float(g) * h for g in G)))
     st = case.ensure_stencils()
     ora = Oracle(grid, st, case.params)
-    ora.set_frozen_bc(case.u0)
-    u_ref = case.u0.copy()
+    ora.set_frozen_bc_av(case.u0, case.a0)
+    u_ref, a_ref = case.u0.copy(), case.a0.copy()
     dt = ora.cfl_dt(u_ref, CFL)
     dts = [dt]
     for _ in range(STEPS):
-        u_ref = ora.rk_step(case.method, u_ref, dt)
+        u_ref, a_ref = ora.rk_step_av(case.method, u_ref, a_ref, dt)
         dt = ora.cfl_dt(u_ref, CFL)
         dts.append(dt)
 
@@ -105,5 +110,8 @@ def test_two_gpu_run_matches_single_domain_oracle(tmp_path):
         gid = np.load(tmp_path / f"gid_{r}.npy")
         err = np.abs(u - u_ref[gid]).max(axis=0) / scale
         assert err.max() < 1e-11, (r, err)
+        a = np.load(tmp_path / f"a_{r}.npy")
+        err_a = np.abs(a - a_ref[gid]).max(axis=0) / np.abs(a_ref).max(axis=0)
+        assert err_a.max() < 1e-11, (r, err_a)
         # ncclMin of the local CFL steps == the global CFL step
         assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)

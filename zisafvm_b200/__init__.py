@@ -5,11 +5,12 @@ The package is a thin host mirror of the reference's operator interfaces over ``
 """
 from .grid import (Grid, HybridWENOParams, QRDegrees, StencilFamilies, StencilFamilyParams, WENO_PARAMS,
                    compute_stencil_families, cube_mesh, square_mesh)
+from ._capi import ZfvmError
 from .solver import (AllVariables, CudaContext, CudaEulerRateOfChange, CudaRungeKutta, EulerParams, FrozenBC, Gravity,
                      LocalCFL)
 
 __all__ = [
     "Grid", "HybridWENOParams", "QRDegrees", "StencilFamilies", "StencilFamilyParams", "WENO_PARAMS",
     "compute_stencil_families", "cube_mesh", "square_mesh", "AllVariables", "CudaContext", "CudaEulerRateOfChange",
-    "CudaRungeKutta", "EulerParams", "FrozenBC", "Gravity", "LocalCFL",
+    "CudaRungeKutta", "EulerParams", "FrozenBC", "Gravity", "LocalCFL", "ZfvmError",
 ]

@@ -39,6 +39,10 @@ class ZfvmParams(C.Structure):
         ("steps_per_recompute", C.c_int),
         ("keep_polynomials", C.c_int),
         ("flux_bc", C.c_int),
+        ("n_avars", C.c_int),
+        ("heating_rate", C.c_double),
+        ("heating_r0", C.c_double),
+        ("heating_r1", C.c_double),
     ]
 
 
@@ -108,6 +112,14 @@ _SIGNATURES = {
     "zfvm_profile_read": (C.c_int, [_vp, c_double_p, c_int64_p]),
     "zfvm_download_polynomials": (C.c_int, [_vp, c_double_p, c_double_p, C.POINTER(C.c_int)]),
     "zfvm_download_work": (C.c_int, [_vp, C.c_char_p, c_double_p, C.c_int64]),
+    "zfvm_rate_of_change_av": (C.c_int, [_vp, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int]),
+    "zfvm_rate_of_change_av_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int]),
+    "zfvm_upload_avars": (C.c_int, [_vp, c_double_p]),
+    "zfvm_download_avars": (C.c_int, [_vp, c_double_p]),
+    "zfvm_avars_device": (_vp, [_vp]),
+    "zfvm_set_frozen_bc_av": (C.c_int, [_vp, c_double_p, c_double_p]),
+    "zfvm_rk_step_host_av": (C.c_int, [_vp, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double]),
+    "zfvm_halo_exchange_av": (C.c_int, [_vp, _vp, _vp]),
     "zfvm_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "zfvm_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "zfvm_set_halo": (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_int), c_int64_p, c_int64_p, c_int64_p, c_int32_p]),

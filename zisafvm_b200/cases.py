@@ -25,6 +25,7 @@ class Case:
     cfl: float
     frozen_bc: bool = True
     stencils: object = None
+    a0: Optional[np.ndarray] = None   # [n_cells][n_avars] advected scalars (conserved form rho * q)
 
     def ensure_stencils(self):
         if self.stencils is None:
@@ -51,6 +52,27 @@ def cvars_from_primitive(rho, v, p, gamma):
     u[:, 1:4] = rho[:, None] * v
     u[:, 4] = p / (gamma - 1.0) + 0.5 * rho * np.sum(v * v, axis=1)
     return u
+
+
+def with_tracers(case: "Case", n_avars: int = 1, box=None) -> "Case":
+    """Adds advected scalars rho * q_a with smooth concentrations q_a (the reference's Rayleigh-Taylor set-up carries
+    one, src/zisa/experiments/rayleigh_taylor.cpp:26): cell averages of rho(x) q_a(x) with rho taken as the cell's
+    average density (a second-order accurate initial field, which is all the parity tests need)."""
+    c = case.grid.array("cell_centers")
+    if box is None:  # concentrations in coordinates relative to the grid's bounding box ...
+        lo, span = c.min(axis=0), np.maximum(c.max(axis=0) - c.min(axis=0), 1e-300)
+    else:            # ... or to a given box (lo, hi): sub-domains of one global mesh then carry the same field
+        lo, span = np.asarray(box[0], dtype=float), np.asarray(box[1], dtype=float) - np.asarray(box[0], dtype=float)
+    xi = (c - lo) / span
+    a0 = np.zeros((case.grid.n_cells, n_avars))
+    for a in range(n_avars):
+        q = 0.6 + 0.3 * np.sin((2.0 + a) * np.pi * xi[:, 0]) * np.cos((1.0 + a) * np.pi * xi[:, 1]) + 0.1 * a * xi[:, 2]
+        if a % 2 == 1:  # a discontinuous one as well: the non-linear weights must switch
+            q = np.where(xi[:, 0] + 0.5 * xi[:, 1] < 0.7, 1.0, 0.1) + 0.05 * xi[:, 1]
+        a0[:, a] = case.u0[:, 0] * q
+    case.a0 = a0
+    case.params.n_avars = n_avars
+    return case
 
 
 def ghost_ring(grid: Grid, lo, hi, width):
@@ -97,13 +119,14 @@ def polytrope_alpha(G=1.0, K=1.0):
 
 
 def polytrope_2d(n: int = 158, order: int = 3, well_balanced: bool = True, amplitude: float = 0.0,
-                 width: float = 0.05, seed: int = 0) -> Case:
+                 width: float = 0.05, seed: int = 0, ghost: bool = True, flux_bc: str = "none") -> Case:
     """gamma = 2 polytrope in hydrostatic equilibrium (src/zisa/experiments/polytrope.cpp:12-63)."""
     gamma = 2.0
     verts, vi = square_mesh(n, n, -0.6, 0.6, -0.6, 0.6, jitter=0.15, seed=seed)
     grid = Grid(2, verts, vi, QRDegrees(face_deg=3, volume_deg=3, moments_deg=4))
     c = grid.array("cell_centers")
-    grid.mask_ghost_cells(np.linalg.norm(c, axis=1) > 0.5)  # boundary_mask, polytrope.cpp:55-63
+    if ghost:
+        grid.mask_ghost_cells(np.linalg.norm(c, axis=1) > 0.5)  # boundary_mask, polytrope.cpp:55-63
     alpha = polytrope_alpha()
 
     def ic(x):
@@ -116,9 +139,9 @@ def polytrope_2d(n: int = 158, order: int = 3, well_balanced: bool = True, ampli
     params = EulerParams(
         weno=WENO_PARAMS[f"2d_o{order}"], gamma=gamma,
         well_balancing="isentropic" if well_balanced else "constant",
-        gravity=Gravity(kind="polytrope", params=(1.0, 1.0, 1.0), alignment="radial"),
+        gravity=Gravity(kind="polytrope", params=(1.0, 1.0, 1.0), alignment="radial"), flux_bc=flux_bc,
     )
-    return Case("polytrope_2d", grid, params, cell_average(grid, ic), "ssp3", 0.4)
+    return Case("polytrope_2d", grid, params, cell_average(grid, ic), "ssp3", 0.4, frozen_bc=ghost)
 
 
 def blast_ic(kind: str, gamma: float = 1.4):

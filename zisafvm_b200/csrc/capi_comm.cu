@@ -69,12 +69,17 @@ int load_nccl() {
 
 }  // namespace
 
-int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev) {
+int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev, double *avars_dev) {
   // the state must be complete on the compute stream before it is packed
   ZFVM_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
   ZFVM_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
   launch_pack_rows(ctx->send_buf, state_dev, ctx->send_index_dev, ctx->n_send, ctx->comm_stream);
   ctx->launches += 1;
+  const int na = (avars_dev && ctx->send_buf_a) ? ctx->n_avars : 0;  // avars rows travel in the same group
+  if (na > 0) {
+    launch_pack_rows_n(ctx->send_buf_a, avars_dev, ctx->send_index_dev, ctx->n_send, na, ctx->comm_stream);
+    ctx->launches += 1;
+  }
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   ZFVM_NCCL(g_nccl.GroupStart());
   for (const HaloPeer &p : ctx->peers) {
@@ -84,6 +89,12 @@ int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev) {
     if (p.send_end > p.send_begin)
       ZFVM_NCCL(g_nccl.Send(ctx->send_buf + p.send_begin * NVARS, (size_t)((p.send_end - p.send_begin) * NVARS),
                             ncclDouble, p.rank, comm, ctx->comm_stream));
+    if (na > 0 && p.recv_end > p.recv_begin)
+      ZFVM_NCCL(g_nccl.Recv(avars_dev + p.recv_begin * na, (size_t)((p.recv_end - p.recv_begin) * na), ncclDouble, p.rank,
+                            comm, ctx->comm_stream));
+    if (na > 0 && p.send_end > p.send_begin)
+      ZFVM_NCCL(g_nccl.Send(ctx->send_buf_a + p.send_begin * na, (size_t)((p.send_end - p.send_begin) * na), ncclDouble,
+                            p.rank, comm, ctx->comm_stream));
   }
   ZFVM_NCCL(g_nccl.GroupEnd());
   ZFVM_CUDA(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
@@ -148,6 +159,12 @@ int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_r
   ctx->allocations.push_back(p);
   ctx->send_buf = (double *)p;
   ctx->device_bytes += ctx->n_send * (int64_t)(NVARS * sizeof(double) + sizeof(int32_t));
+  if (ctx->n_avars > 0) {
+    ZFVM_CUDA(cudaMalloc(&p, (size_t)std::max<int64_t>(ctx->n_send, 1) * ctx->n_avars * sizeof(double)));
+    ctx->allocations.push_back(p);
+    ctx->send_buf_a = (double *)p;
+    ctx->device_bytes += ctx->n_send * (int64_t)(ctx->n_avars * sizeof(double));
+  }
 
   // tiles whose stencils reference no halo row can be reconstructed before the exchange completes
   std::vector<int32_t> ti, te;
@@ -175,7 +192,16 @@ int zfvm_halo_exchange(zfvm_ctx *ctx, double *state_dev) {
   if (ctx->n_ranks <= 1 || !ctx->nccl_comm) return 0;  // NoHaloExchange, halo_exchange.hpp:23-29
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   if (!state_dev) state_dev = ctx->u_cur;
-  if (zfvm_halo_post_internal(ctx, state_dev)) return 1;
+  if (zfvm_halo_post_internal(ctx, state_dev, nullptr)) return 1;
+  return zfvm_halo_wait_internal(ctx);
+}
+
+int zfvm_halo_exchange_av(zfvm_ctx *ctx, double *state_dev, double *avars_dev) {
+  if (ctx->n_ranks <= 1 || !ctx->nccl_comm) return 0;
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  if (!state_dev) state_dev = ctx->u_cur;
+  if (!avars_dev) avars_dev = ctx->a_cur;
+  if (zfvm_halo_post_internal(ctx, state_dev, avars_dev)) return 1;
   return zfvm_halo_wait_internal(ctx);
 }
 

@@ -184,11 +184,12 @@ bool make_tableau(const std::string &m, Tableau &t) {
 // update).  In a multi-rank context the halo exchange is posted first and the tiles whose stencils
 // touch no halo cell are reconstructed while it is in flight (flux_loop.hpp:96-104, with a correct
 // interior set, see SURVEY.md 5 "Distributed backend").
-int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd);
+int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const double *avars = nullptr,
+             const UpdateArgs *upd_av = nullptr);
 
 }  // namespace
 
-int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev);
+int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev, double *avars_dev);
 int zfvm_halo_wait_internal(zfvm_ctx *ctx);
 int zfvm_allreduce_min_internal(zfvm_ctx *ctx, double *dev_value);
 
@@ -202,11 +203,13 @@ void prof_mark(zfvm_ctx *ctx, int which) {
   ctx->prof_events[which].push_back(ev);
 }
 
-int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
+int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const double *avars, const UpdateArgs *upd_av) {
   int rc;
+  if (ctx->n_avars > 0 && (!avars || !upd_av))
+    return fail("this context carries advected scalars: use the *_av entry points (AllVariables has cvars and avars)");
   prof_mark(ctx, 0);
   if (ctx->n_ranks > 1 && ctx->nccl_comm) {
-    if (zfvm_halo_post_internal(ctx, const_cast<double *>(state))) return 1;
+    if (zfvm_halo_post_internal(ctx, const_cast<double *>(state), const_cast<double *>(avars))) return 1;
     rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_interior,
                       ctx->n_tiles_interior, ctx->stream);
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
@@ -227,11 +230,36 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd) {
   prof_mark(ctx, 2);
   UpdateArgs upd_bc = upd;
   upd_bc.flux_bc_state = ctx->params.flux_bc ? state : nullptr;  // FluxBC is part of the rate of change
-  launch_update(ctx->plan, ctx->n_dims, upd_bc, ctx->stream);
+  upd_bc.flux_bc_kind = ctx->params.flux_bc;
+  launch_update(ctx->plan, ctx->sc, upd_bc, ctx->stream);
   prof_mark(ctx, 2);
   ctx->launches += 2;
+  if (ctx->n_avars > 0) {
+    // advected scalars: T1 scalar reconstruction + traces (after the halo rows have arrived), T2 tracer face flux on
+    // the Euler traces K1 has just written, T3 gather / RK update of the avars rows
+    if (launch_tracer_recon(ctx->plan, ctx->sc, ctx->tracer_view, avars, ctx->tiles_needed, ctx->n_tiles_needed, ctx->stream))
+      return fail("no tracer reconstruction kernel is compiled for this scheme");
+    launch_tracer_flux(ctx->plan, ctx->sc, ctx->plan.n_interior_edges, ctx->stream);
+    launch_tracer_update(ctx->plan, ctx->n_dims, *upd_av, ctx->stream);
+    ctx->launches += 3;
+  }
   ZFVM_CUDA(cudaGetLastError());
   return 0;
+}
+
+// the avars half of a residual's update arguments: same tableau row, the avars buffers
+UpdateArgs avars_update_args(zfvm_ctx *ctx, const UpdateArgs &A) {
+  UpdateArgs B = A;
+  B.n_avars = ctx->n_avars;
+  B.has_source = 0;
+  B.reduce_out = nullptr;
+  B.flux_bc_state = nullptr;
+  B.tendency = nullptr;
+  B.u_next = nullptr;
+  B.u_base = nullptr;
+  B.frozen = nullptr;
+  for (int j = 0; j < MAX_RK_STAGES; ++j) B.k_prev[j] = nullptr;
+  return B;
 }
 
 UpdateArgs base_update_args(zfvm_ctx *ctx) {
@@ -279,6 +307,10 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     if (params->well_balanced && params->gravity_kind == GRAVITY_NONE)
       return fail("zfvm_create: isentropic well-balancing needs a gravity model");
     if (g.q_f > MAX_QF || g.q_c > MAX_QC) return fail("zfvm_create: quadrature rule too large");
+    if (params->n_avars < 0 || params->n_avars > MAX_AVARS) return fail("zfvm_create: n_avars must be in [0, 8]");
+    if (params->flux_bc < 0 || params->flux_bc > 2) return fail("zfvm_create: unknown flux_bc");
+    if (params->flux_bc == 2 && params->gravity_kind == GRAVITY_NONE)
+      return fail("zfvm_create: EquilibriumFluxBC needs a gravity model (equilibrium_flux_bc.hpp:18-35)");
     if (ns > MAX_STENCILS) return fail("zfvm_create: too many stencils");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
@@ -309,7 +341,13 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     sc.scaling = params->scaling;
     sc.flux = params->flux;
     sc.well_balanced = params->well_balanced;
-    sc.has_gravity = params->gravity_kind != GRAVITY_NONE;
+    // the cell-local source pass (GravitySourceLoop and / or Heating) runs when either term is present; without a
+    // gravity model its potential tables stay zero
+    sc.has_gravity = params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0;
+    sc.heating_rate = params->heating_rate;
+    sc.heating_r0 = params->heating_r0;
+    sc.heating_r1 = params->heating_r1;
+    ctx->n_avars = params->n_avars;
     sc.epsilon = params->epsilon;
     sc.exponent = params->exponent;
     sc.gamma = params->gamma;
@@ -425,6 +463,18 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
           b += sc.rows_max[k] * sc.ncoef[k] * TILE * 8;
         }
         lo_row0[0] = r;  // the central stencil's rows come last
+      }
+      {
+        TracerRecView &V = ctx->tracer_view;
+        V.tile_record = 1;
+        V.off_meta = TILE_OFF_META;
+        V.off_list = L.off_list;
+        V.off_lidx = L.off_lidx;
+        V.lidx_elem = L.lidx_elem;
+        for (int k = 0; k < ns; ++k) {
+          V.row0[k] = lo_row0[(size_t)k];
+          V.off_w[k] = (k == 0) ? L.off_whi : L.off_wlo + lo_w0[(size_t)k];
+        }
       }
       const int n_mom2 = std::max(D2 - 3, 0);
       const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / L.rec_bytes));
@@ -551,6 +601,15 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
         return 1;
       }
       P.rec = d_rec;
+      {
+        TracerRecView &V = ctx->tracer_view;
+        V.tile_record = 0;
+        V.off_meta = 0;
+        for (int k = 0; k < ns; ++k) {
+          V.off_sidx[k] = P.off_sidx[k];
+          V.off_w[k] = P.off_W[k];
+        }
+      }
       const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / P.rec_bytes));
       std::vector<char> h_rec((size_t)(chunk * P.rec_bytes));
       for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
@@ -650,7 +709,7 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       // tiles none of whose cells contributes a trace to the flux loop (ghost cells deeper than the l1 layer)
       // are not reconstructed at all -- unless the caller wants every cell's polynomial back
       ctx->tile_needed.assign((size_t)T, 1);
-      if (!params->keep_polynomials && params->gravity_kind == GRAVITY_NONE) {  // (the source loop visits every cell)
+      if (!params->keep_polynomials && !sc.has_gravity) {  // (the source loop visits every cell)
         for (std::int64_t t = 0; t < T; ++t) {
           bool any = false;
           for (std::int64_t a = t * F * TILE; a < (t + 1) * F * TILE && !any; ++a) any = (fref[(size_t)a] & FREF_TRACE) != 0;
@@ -777,6 +836,19 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       return 1;
     }
 
+    // advected scalars: traces, face fluxes, resident rows and host-entry work rows
+    P.n_avars = ctx->n_avars;
+    if (ctx->n_avars > 0) {
+      const std::int64_t na = ctx->n_avars;
+      if (dev_alloc(ctx, &P.qtrace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * na, true) ||
+          dev_alloc(ctx, &P.qflux, std::max<std::int64_t>(EI, 1) * na, true) || dev_alloc(ctx, &ctx->a_cur, n * na, true) ||
+          dev_alloc(ctx, &ctx->a_tmp, n * na, true) || dev_alloc(ctx, &ctx->tend_work_a, n * na, true) ||
+          dev_alloc(ctx, &ctx->state_work_a, n * na, true)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+    }
+
     // ---- algorithmic bytes per cell and stage -----------------------------------------
     {
       const double nc = (double)std::max<std::int64_t>(n_counted, 1);
@@ -863,6 +935,44 @@ int zfvm_rate_of_change_device(zfvm_ctx *ctx, double *tendency_dev, const double
   return residual(ctx, state_dev, A);
 }
 
+int zfvm_rate_of_change_av_device(zfvm_ctx *ctx, double *tendency_dev, double *tendency_avars_dev,
+                                  const double *state_dev, const double *state_avars_dev, double /*t*/, int accumulate) {
+  if (ctx->n_avars <= 0) return fail("zfvm_rate_of_change_av_device: the context was created with n_avars = 0");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  UpdateArgs A = base_update_args(ctx);
+  A.tendency = tendency_dev;
+  A.accumulate = accumulate;
+  UpdateArgs B = avars_update_args(ctx, A);
+  B.tendency = tendency_avars_dev;
+  return residual(ctx, state_dev, A, state_avars_dev, &B);
+}
+
+int zfvm_rate_of_change_av(zfvm_ctx *ctx, double *tendency_host, double *tendency_avars_host, const double *state_host,
+                           const double *state_avars_host, double t, int accumulate) {
+  if (ctx->n_avars <= 0) return fail("zfvm_rate_of_change_av: the context was created with n_avars = 0");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
+  const size_t bytes_a = (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double);
+  if (copy_h2d(ctx, ctx->state_work, state_host, bytes) || copy_h2d(ctx, ctx->state_work_a, state_avars_host, bytes_a)) return 1;
+  if (accumulate && (copy_h2d(ctx, ctx->tend_work, tendency_host, bytes) ||
+                     copy_h2d(ctx, ctx->tend_work_a, tendency_avars_host, bytes_a)))
+    return 1;
+  if (zfvm_rate_of_change_av_device(ctx, ctx->tend_work, ctx->tend_work_a, ctx->state_work, ctx->state_work_a, t, accumulate))
+    return 1;
+  if (ctx->n_ranks > 1) {
+    const size_t na = (size_t)ctx->n_avars;
+    for (auto &p : ctx->peers) {
+      const size_t off = (size_t)(p.recv_begin * NVARS), cnt = (size_t)((p.recv_end - p.recv_begin) * NVARS);
+      if (copy_d2h(ctx, const_cast<double *>(state_host) + off, ctx->state_work + off, cnt * sizeof(double))) return 1;
+      const size_t off_a = (size_t)p.recv_begin * na, cnt_a = (size_t)(p.recv_end - p.recv_begin) * na;
+      if (copy_d2h(ctx, const_cast<double *>(state_avars_host) + off_a, ctx->state_work_a + off_a, cnt_a * sizeof(double)))
+        return 1;
+    }
+  }
+  if (copy_d2h(ctx, tendency_avars_host, ctx->tend_work_a, bytes_a)) return 1;
+  return copy_d2h(ctx, tendency_host, ctx->tend_work, bytes);
+}
+
 int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
@@ -892,8 +1002,10 @@ int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method) {
     for (int j = 0; j < t.n; ++j) nk += (row[j] != 0.0);
   }
   ctx->n_k_avg = nk / t.n;
-  for (int s = 0; s + 1 < t.n; ++s)
+  for (int s = 0; s + 1 < t.n; ++s) {
     if (!ctx->k[s] && dev_alloc(ctx, &ctx->k[s], ctx->n_cells * NVARS, true)) return 1;
+    if (ctx->n_avars > 0 && !ctx->ka[s] && dev_alloc(ctx, &ctx->ka[s], ctx->n_cells * ctx->n_avars, true)) return 1;
+  }
   return 0;
 }
 
@@ -910,6 +1022,33 @@ int zfvm_download_state(zfvm_ctx *ctx, double *state_host) {
 }
 
 double *zfvm_state_device(zfvm_ctx *ctx) { return ctx->u_cur; }
+
+int zfvm_upload_avars(zfvm_ctx *ctx, const double *avars_host) {
+  if (ctx->n_avars <= 0) return fail("zfvm_upload_avars: the context was created with n_avars = 0");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  if (copy_h2d(ctx, ctx->a_cur, avars_host, (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double))) return 1;
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int zfvm_download_avars(zfvm_ctx *ctx, double *avars_host) {
+  if (ctx->n_avars <= 0) return fail("zfvm_download_avars: the context was created with n_avars = 0");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  return copy_d2h(ctx, avars_host, ctx->a_cur, (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double));
+}
+
+double *zfvm_avars_device(zfvm_ctx *ctx) { return ctx->a_cur; }
+
+int zfvm_set_frozen_bc_av(zfvm_ctx *ctx, const double *steady_state_host, const double *steady_avars_host) {
+  if (zfvm_set_frozen_bc(ctx, steady_state_host)) return 1;
+  ctx->frozen_a = nullptr;
+  if (!steady_state_host || !steady_avars_host || ctx->n_avars <= 0) return 0;
+  double *f = nullptr;
+  if (dev_alloc(ctx, &f, ctx->n_cells * ctx->n_avars)) return 1;
+  ZFVM_CUDA(cudaMemcpy(f, steady_avars_host, (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->frozen_a = f;
+  return 0;
+}
 
 int zfvm_set_frozen_bc(zfvm_ctx *ctx, const double *steady_state_host) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
@@ -965,9 +1104,20 @@ static int rk_step_impl(zfvm_ctx *ctx, double dt, bool reduce) {
     A.dt = dt;
     A.frozen = ctx->frozen;
     A.reduce_out = (reduce && s + 1 == S) ? ctx->reduce_dev : nullptr;
-    if (residual(ctx, in, A)) return 1;
+    if (ctx->n_avars > 0) {  // the avars rows take the same Butcher sum (runge_kutta.cpp:122-143 sums AllVariables)
+      UpdateArgs B = avars_update_args(ctx, A);
+      B.tendency = needed_later ? ctx->ka[s] : nullptr;
+      B.u_next = ctx->a_tmp;
+      B.u_base = ctx->a_cur;
+      for (int j = 0; j < s; ++j) B.k_prev[j] = ctx->ka[j];
+      B.frozen = ctx->frozen ? ctx->frozen_a : nullptr;
+      if (residual(ctx, in, A, (s == 0) ? ctx->a_cur : ctx->a_tmp, &B)) return 1;
+    } else if (residual(ctx, in, A)) {
+      return 1;
+    }
   }
   std::swap(ctx->u_cur, ctx->u_tmp);
+  std::swap(ctx->a_cur, ctx->a_tmp);
   return 0;
 }
 
@@ -991,6 +1141,18 @@ int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, dou
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
   if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes)) return 1;
   if (rk_step_impl(ctx, dt, false)) return 1;
+  return copy_d2h(ctx, u1_host, ctx->u_cur, bytes);
+}
+
+int zfvm_rk_step_host_av(zfvm_ctx *ctx, const double *u0_host, const double *a0_host, double *u1_host, double *a1_host,
+                         double /*t*/, double dt) {
+  if (ctx->n_avars <= 0) return fail("zfvm_rk_step_host_av: the context was created with n_avars = 0");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
+  const size_t bytes_a = (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double);
+  if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes) || copy_h2d(ctx, ctx->a_cur, a0_host, bytes_a)) return 1;
+  if (rk_step_impl(ctx, dt, false)) return 1;
+  if (copy_d2h(ctx, a1_host, ctx->a_cur, bytes_a)) return 1;
   return copy_d2h(ctx, u1_host, ctx->u_cur, bytes);
 }
 

@@ -37,6 +37,13 @@ struct zfvm_ctx {
   double *tend_work = nullptr;  // device tendency for the host entry point
   double *state_work = nullptr; // device state for the host entry point
   double *frozen = nullptr;
+  // advected scalars [n][n_avars]: resident values, RK buffers, host entry point work arrays, FrozenBC copy
+  int n_avars = 0;
+  double *a_cur = nullptr, *a_tmp = nullptr;
+  double *ka[zfvm::MAX_RK_STAGES] = {nullptr};
+  double *tend_work_a = nullptr, *state_work_a = nullptr, *frozen_a = nullptr;
+  double *send_buf_a = nullptr;
+  zfvm::TracerRecView tracer_view{};
   double *inradius = nullptr;
   std::int32_t *ghost_index = nullptr;
   std::int64_t n_ghost = 0;

@@ -23,6 +23,7 @@ constexpr int MAX_STENCILS = 6;
 constexpr int NVARS = 5;        // rho, m1, m2, m3, E  (euler_variables.hpp:30-36)
 constexpr int MAX_QF = 8;
 constexpr int MAX_QC = 16;
+constexpr int MAX_AVARS = 8;    // advected scalars per cell (AllVariables::avars)
 
 // face_ref bit layout
 constexpr std::uint32_t FREF_EDGE_MASK = 0x0FFFFFFFu;  // edge index
@@ -56,6 +57,7 @@ struct SchemeConst {
   double face_bary[MAX_QF][3];   // barycentric coordinates w.r.t. the left cell's face vertices
   double cell_w[MAX_QC];
   double cell_bary[MAX_QC][4];
+  double heating_rate, heating_r0, heating_r1;  // Heating (model/heating.hpp:54-80); rate 0: off
 };
 
 /// Raw device pointers of one context. Sizes in comments use n = n_cells, T = n_tiles, E = n_edges.
@@ -107,6 +109,10 @@ struct DevicePlan {
   double *poly_scale;                       // optional [n][5]
   int n_poly_coef;
   int *eq_fail;                             // counter of cells whose equilibrium solve failed
+  // advected scalars (tracers.cu): traces and face fluxes of the n_avars scalars; null when n_avars == 0
+  int n_avars;
+  double *qtrace;                           // [E_int][2][q_f][n_avars]
+  double *qflux;                            // [E_int][n_avars]
 };
 
 }  // namespace zfvm

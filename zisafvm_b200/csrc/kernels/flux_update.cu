@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "equilibrium.cuh"
 #include "kernels.hpp"
 
 namespace zfvm {
@@ -21,7 +22,9 @@ namespace {
 // HLLCBatten::flux (flux/hllc.hpp:36-81,143-176).  1/rho and sqrt(rho_R/rho_L) come from rsqrt(rho_L), rsqrt(rho_R);
 // the sound speeds from rsqrt(gamma p); the remaining quotients from fast_rcp: 5 rsqrt + 4 rcp per Gauss point
 // instead of 21 divisions and 4 square roots.  Results differ from the operation-by-operation form by rounding only.
-ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], double gamma, double nf[NVARS]) {
+template <bool SPEEDS = false>
+ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], double gamma, double nf[NVARS],
+                           double *speeds = nullptr) {
   const double rL = fast_rsqrt(uL[0]), rR = fast_rsqrt(uR[0]);
   const double iL = rL * rL, iR = rR * rR;
   const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (gamma - 1.0);
@@ -46,6 +49,11 @@ ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], doubl
   const double s_star =
       (uR[1] * (sR - vR) - uL[1] * (sL - vL) + pL - pR) * fast_rcp(uR[0] * (sR - vR) - uL[0] * (sL - vL));
 
+  if constexpr (SPEEDS) {  // for HLLCBatten::tracer_flux (hllc.hpp:178-197)
+    speeds[0] = sL;
+    speeds[1] = s_star;
+    speeds[2] = sR;
+  }
   const bool left = (0.0 <= s_star);
   double uK[NVARS];
 #pragma unroll
@@ -300,7 +308,8 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
 // [n][5] arrays (state, tendencies, fluxes) is then contiguous across the warp, and a face's flux row is read by
 // five adjacent lanes.  The face fluxes are gathered in the fixed order of the cell's face list (no atomics).
 template <int F, bool FLUX_BC>
-__global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const DevicePlan P, const UpdateArgs A) {
+__global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const DevicePlan P, const UpdateArgs A,
+                                                                      const __grid_constant__ SchemeConst sc) {
   constexpr int CELLS = 2 * TILE;
   __shared__ double s_un[CELLS * NVARS];
   const int cl = threadIdx.x / NVARS, v = threadIdx.x - cl * NVARS;  // cell within the block, variable
@@ -345,6 +354,24 @@ __global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const Devi
           double u[NVARS];
 #pragma unroll
           for (int w = 0; w < NVARS; ++w) u[w] = A.flux_bc_state[i * NVARS + w];
+          if (A.flux_bc_kind == 2) {
+            // EquilibriumFluxBC::compute (boundary/equilibrium_flux_bc.hpp:37-63): the cell's local equilibrium is solved
+            // from its average (rho, E_int); the flux of the resting equilibrium state at the face Gauss points is its
+            // pressure along the face normal (Euler::flux of (rho, 0, 0, 0, E), rotated back with inv_coord_transform)
+            if (v >= 1 && v <= 3) {
+              const double eint = u[4] - 0.5 * (u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) / u[0];
+              const LocalEq eq = solve_local_equilibrium(u[0], eint, P.phi_cqp + i * sc.q_c, sc);
+              double acc = 0.0;
+              for (int q = 0; q < sc.q_f; ++q) {
+                double r_, E_, p_;
+                eq.at(P.phi_fqp[e * sc.q_f + q], sc.gamma, r_, E_, p_);
+                const double wq = fr[9] * sc.face_w[q];
+                acc = (q == 0) ? wq * (p_ * fr[v - 1]) : acc + wq * (p_ * fr[v - 1]);
+              }
+              t -= acc / vol;
+            }
+            continue;
+          }
           const double un_ = u[1] * fr[0] + u[2] * fr[1] + u[3] * fr[2];
           const double ut1 = u[1] * fr[3] + u[2] * fr[4] + u[3] * fr[5];
           const double ut2 = u[1] * fr[6] + u[2] * fr[7] + u[3] * fr[8];
@@ -480,7 +507,179 @@ __global__ void axpy_stage_kernel(double *__restrict__ u_next, const double *__r
   u_next[t] = u_base[t] + dt * dudt;
 }
 
+// T2.  Tracer face flux (fvm_loops/flux_loop.hpp:157-161): one thread per interior face.  The wave speeds are those of
+// the face's HLLC evaluation on the same rotated traces (HLLCBatten::flux returns them, hllc.hpp:175); every scalar is
+// upwinded with HLLCBatten::tracer_flux (hllc.hpp:178-197).  Rusanov (not in the reference): the same local
+// Lax-Friedrichs form as the flux itself.
+template <int FLUX>
+__global__ void __launch_bounds__(128) tracer_flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                          std::int64_t n_faces) {
+  const std::int64_t e = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_faces || P.left_right[2 * e] < 0) return;
+  const int NA = P.n_avars;
+  const double *fr = P.face_frame + e * 10;
+  double n[3], t1[3], t2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    n[d] = fr[d];
+    t1[d] = fr[3 + d];
+    t2[d] = fr[6 + d];
+  }
+  const double area = fr[9];
+  double qnf[MAX_AVARS];
+#pragma unroll
+  for (int a = 0; a < MAX_AVARS; ++a) qnf[a] = 0.0;
+  const double *trL = P.trace + e * (2 * sc.q_f * NVARS);
+  const double *trR = trL + sc.q_f * NVARS;
+  const double *qL = P.qtrace + e * (2 * sc.q_f * NA);
+  const double *qR = qL + sc.q_f * NA;
+  for (int q = 0; q < sc.q_f; ++q) {
+    double uL[NVARS], uR[NVARS];
+#pragma unroll
+    for (int v = 0; v < NVARS; ++v) {
+      uL[v] = trL[q * NVARS + v];
+      uR[v] = trR[q * NVARS + v];
+    }
+    auto rot = [&](double u[NVARS]) {
+      const double un = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
+      const double ut1 = u[1] * t1[0] + u[2] * t1[1] + u[3] * t1[2];
+      const double ut2 = u[1] * t2[0] + u[2] * t2[1] + u[3] * t2[2];
+      u[1] = un;
+      u[2] = ut1;
+      u[3] = ut2;
+    };
+    rot(uL);
+    rot(uR);
+    const double wq = area * sc.face_w[q];
+    if (FLUX == FLUX_HLLC) {
+      double f[NVARS], sp[3];
+      hllc_flux<true>(uL, uR, sc.gamma, f, sp);
+      const double sL = sp[0], s_star = sp[1], sR = sp[2];
+      const bool left = (0.0 <= s_star);
+      const double vK = left ? uL[1] / uL[0] : uR[1] / uR[0];
+      const bool fan = (sL < 0.0 && 0.0 < sR);
+      const double sK = left ? sL : sR;
+      const double cK = (sK - vK) / (sK - s_star);
+#pragma unroll
+      for (int a = 0; a < MAX_AVARS; ++a) {
+        if (a < NA) {
+          const double mqK = left ? qL[q * NA + a] : qR[q * NA + a];
+          double fq = mqK * vK;
+          if (fan) fq = fq + sK * (cK * mqK - mqK);
+          qnf[a] += wq * fq;
+        }
+      }
+    } else {
+      const double iL = 1.0 / uL[0], iR = 1.0 / uR[0];
+      const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (sc.gamma - 1.0);
+      const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (sc.gamma - 1.0);
+      const double aL = sqrt(sc.gamma * pL * iL), aR = sqrt(sc.gamma * pR * iR);
+      const double vL = uL[1] * iL, vR = uR[1] * iR;
+      const double lam = fmax(fabs(vL) + aL, fabs(vR) + aR);
+#pragma unroll
+      for (int a = 0; a < MAX_AVARS; ++a) {
+        if (a < NA) {
+          const double mL = qL[q * NA + a], mR = qR[q * NA + a];
+          qnf[a] += wq * (0.5 * (mL * vL + mR * vR) - 0.5 * lam * (mR - mL));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < MAX_AVARS; ++a)
+    if (a < NA) P.qflux[e * NA + a] = qnf[a];
+}
+
+// T3.  One thread per (cell, scalar): atomic-free gather of the cell's tracer face fluxes (flux_loop.hpp:180-192),
+// fused Runge-Kutta sum and FrozenBC on the avars rows -- the avars half of K3 (no sources act on avars).
+template <int F>
+__global__ void __launch_bounds__(256) tracer_update_kernel(const DevicePlan P, const UpdateArgs A) {
+  const int NA = A.n_avars;
+  const std::int64_t idx = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= A.n_cells_update * NA) return;
+  const std::int64_t i = idx / NA;
+  const int a = (int)(idx - i * NA);
+  const std::int64_t tile = i / TILE;
+  const int lane = (int)(i % TILE);
+  const double inv_vol = 1.0 / P.volume[i];
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+    const std::uint32_t fref = P.face_ref[(tile * F + k) * TILE + lane];
+    if (fref & FREF_TRACE) {
+      const double fl = P.qflux[(std::int64_t)(fref & FREF_EDGE_MASK) * NA + a];
+      t += ((fref & FREF_SIDE) ? fl : -fl) * inv_vol;
+    }
+  }
+  if (A.tendency) {
+    if (A.accumulate)
+      A.tendency[idx] += t;
+    else
+      A.tendency[idx] = t;
+  }
+  if (A.u_next) {
+    double dudt = 0.0;
+    for (int s = 0; s < A.n_prev; ++s)
+      if (A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * A.k_prev[s][idx];
+    if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
+    double un = A.u_base[idx] + A.dt * dudt;
+    if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[idx];
+    A.u_next[idx] = un;
+  }
+}
+
+__global__ void frozen_bc_n_kernel(double *__restrict__ u, const double *__restrict__ frozen,
+                                   const std::int32_t *__restrict__ ghost_index, std::int64_t n_ghost, int row_len) {
+  const std::int64_t t = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_ghost * row_len) return;
+  const std::int64_t i = ghost_index[t / row_len];
+  u[i * row_len + t % row_len] = frozen[i * row_len + t % row_len];
+}
+
+__global__ void pack_rows_n_kernel(double *__restrict__ out, const double *__restrict__ state,
+                                   const std::int32_t *__restrict__ index, std::int64_t n_rows, int row_len) {
+  const std::int64_t t = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_rows * row_len) return;
+  out[t] = state[(std::int64_t)index[t / row_len] * row_len + t % row_len];
+}
+
 }  // namespace
+
+void launch_tracer_flux(const DevicePlan &P, const SchemeConst &sc, std::int64_t n_faces, cudaStream_t stream) {
+  if (n_faces <= 0 || P.n_avars <= 0) return;
+  const int block = 128;
+  const unsigned grid = (unsigned)((n_faces + block - 1) / block);
+  if (sc.flux == FLUX_HLLC)
+    tracer_flux_kernel<FLUX_HLLC><<<grid, block, 0, stream>>>(P, sc, n_faces);
+  else
+    tracer_flux_kernel<FLUX_RUSANOV><<<grid, block, 0, stream>>>(P, sc, n_faces);
+}
+
+void launch_tracer_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream) {
+  if (A.n_cells_update <= 0 || A.n_avars <= 0) return;
+  const int block = 256;
+  const unsigned grid = (unsigned)((A.n_cells_update * A.n_avars + block - 1) / block);
+  if (n_dims == 2)
+    tracer_update_kernel<3><<<grid, block, 0, stream>>>(P, A);
+  else
+    tracer_update_kernel<4><<<grid, block, 0, stream>>>(P, A);
+}
+
+void launch_frozen_bc_n(double *u, const double *frozen, const std::int32_t *ghost_index, std::int64_t n_ghost,
+                        int row_len, cudaStream_t stream) {
+  if (n_ghost <= 0 || row_len <= 0) return;
+  const int block = 256;
+  frozen_bc_n_kernel<<<(unsigned)((n_ghost * row_len + block - 1) / block), block, 0, stream>>>(u, frozen, ghost_index,
+                                                                                                 n_ghost, row_len);
+}
+
+void launch_pack_rows_n(double *out, const double *state, const std::int32_t *index, std::int64_t n_rows, int row_len,
+                        cudaStream_t stream) {
+  if (n_rows <= 0 || row_len <= 0) return;
+  const int block = 256;
+  pack_rows_n_kernel<<<(unsigned)((n_rows * row_len + block - 1) / block), block, 0, stream>>>(out, state, index, n_rows,
+                                                                                               row_len);
+}
 
 template <int FLUX>
 static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
@@ -525,21 +724,22 @@ void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t 
     launch_flux_q<FLUX_RUSANOV>(P, sc, face_list, n_faces, stream);
 }
 
-void launch_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream) {
+void launch_update(const DevicePlan &P, const SchemeConst &sc, const UpdateArgs &A, cudaStream_t stream) {
+  const int n_dims = sc.n_dims;
   if (A.n_cells_update <= 0) return;
   const int block = 2 * TILE * NVARS;
   const unsigned grid = (unsigned)((A.n_cells_update + 2 * TILE - 1) / (2 * TILE));
   const bool bc = A.flux_bc_state != nullptr;
   if (n_dims == 2) {
     if (bc)
-      update_kernel<3, true><<<grid, block, 0, stream>>>(P, A);
+      update_kernel<3, true><<<grid, block, 0, stream>>>(P, A, sc);
     else
-      update_kernel<3, false><<<grid, block, 0, stream>>>(P, A);
+      update_kernel<3, false><<<grid, block, 0, stream>>>(P, A, sc);
   } else {
     if (bc)
-      update_kernel<4, true><<<grid, block, 0, stream>>>(P, A);
+      update_kernel<4, true><<<grid, block, 0, stream>>>(P, A, sc);
     else
-      update_kernel<4, false><<<grid, block, 0, stream>>>(P, A);
+      update_kernel<4, false><<<grid, block, 0, stream>>>(P, A, sc);
   }
 }
 

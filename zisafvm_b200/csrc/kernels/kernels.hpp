@@ -38,6 +38,8 @@ struct UpdateArgs {
   const double *frozen;    // FrozenBC steady state (null: no boundary condition)
   // FluxBC (boundary/flux_bc.hpp:24-42): exterior faces of the cell, evaluated on `state`; null = NoFluxBC
   const double *flux_bc_state;
+  int flux_bc_kind;        // 1 FluxBC, 2 EquilibriumFluxBC (boundary/equilibrium_flux_bc.hpp:37-63)
+  int n_avars;             // launch_tracer_update only: row length of the avars arrays
   // CFL / plausibility reduction over the updated state
   ReduceOut *reduce_out;
   const double *inradius;
@@ -73,6 +75,16 @@ inline TileRecLayout tile_rec_layout(const SchemeConst &sc, int n_dims, int dof_
   return L;
 }
 
+/// Where the tracer reconstruction (tracers.cu) finds a cell's stencil members and weights: either record kind.
+struct TracerRecView {
+  int tile_record;             // 1: tile-kernel record (DevicePlan::rec2), 0: older record (DevicePlan::rec)
+  int off_meta;                // u64[32]
+  int off_list, off_lidx, lidx_elem;  // tile record: row list, local index rows [row][32] of u8 / u16
+  int row0[MAX_STENCILS];      // tile record: first index row of stencil k
+  int off_sidx[MAX_STENCILS];  // older record: i32[rows_max_k][32]
+  int off_w[MAX_STENCILS];     // W_k f64[rows_max_k][ncoef_k][32]
+};
+
 /// Phase timers of the tile kernel (ZFVM_TILE_PROF=1): device buffer of 16 counters, or null when profiling is off.
 unsigned long long *tile_prof_buffer();
 /// Copies the counters to the host and clears them; returns false when profiling is off.
@@ -87,7 +99,16 @@ int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int 
 
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
                  cudaStream_t stream);
-void launch_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream);
+void launch_update(const DevicePlan &P, const SchemeConst &sc, const UpdateArgs &A, cudaStream_t stream);
+/// Advected scalars: T1 scalar reconstruction + traces, T2 tracer face flux, T3 gather / RK update.
+int launch_tracer_recon(const DevicePlan &P, const SchemeConst &sc, const TracerRecView &view, const double *avars,
+                        const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
+void launch_tracer_flux(const DevicePlan &P, const SchemeConst &sc, std::int64_t n_faces, cudaStream_t stream);
+void launch_tracer_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream);
+void launch_pack_rows_n(double *out, const double *state, const std::int32_t *index, std::int64_t n_rows, int row_len,
+                        cudaStream_t stream);
+void launch_frozen_bc_n(double *u, const double *frozen, const std::int32_t *ghost_index, std::int64_t n_ghost,
+                        int row_len, cudaStream_t stream);
 void launch_cfl(const double *u, const double *inradius, std::int64_t n, double gamma, ReduceOut *out,
                 cudaStream_t stream);
 void launch_reset_reduce(ReduceOut *out, cudaStream_t stream);

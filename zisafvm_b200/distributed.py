@@ -311,7 +311,7 @@ class RankRun:
 
 
 def make_weak_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, kind: str = "blast", device: int = 0,
-                           group=None) -> RankRun:
+                           group=None, n_avars: int = 0) -> RankRun:
     """BASELINE config 5, weak scaling: every rank owns an ``n^3``-cube box of the lattice, NCCL halo exchange."""
     from . import cases
     from .grid import WENO_PARAMS
@@ -320,6 +320,8 @@ def make_weak_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, kind
     weno = WENO_PARAMS[f"3d_o{order}"]
     sub, h, G = box_subdomain(rank, n_ranks, n, weno.stencil_family_params, cases.blast_qr(order))
     case = cases.blast_3d_on_grid(sub.grid, order=order, kind=kind, stencils=sub.stencils)
+    if n_avars > 0:  # advected scalars as functions of the global position
+        cases.with_tracers(case, n_avars, box=((0.0, 0.0, 0.0), tuple(float(g) * h for g in G)))
     ctx = CudaContext(sub.grid, sub.stencils, case.params, device=device)
     connect(sub, ctx, group)
     return RankRun(sub, case, ctx, int(sub.counted.sum()))

@@ -51,7 +51,9 @@ class EulerParams:
     gas_constant: float = 1.0
     gravity: Gravity = field(default_factory=Gravity)
     keep_polynomials: bool = False
-    flux_bc: str = "none"  # "flux-bc": none | flux (FluxBC, boundary/flux_bc.hpp)
+    flux_bc: str = "none"  # "flux-bc": none | flux (FluxBC, boundary/flux_bc.hpp) | equilibrium (EquilibriumFluxBC)
+    n_avars: int = 0  # advected scalars, AllVariables::avars (all_variables.hpp:31-35)
+    heating: Optional[tuple] = None  # (rate, lower_boundary, upper_boundary) of "heating" (model/heating.hpp:54-80)
 
     def to_c(self) -> ZfvmParams:
         p = ZfvmParams()
@@ -76,16 +78,23 @@ class EulerParams:
             p.gravity_axis[k] = float(v)
         p.steps_per_recompute = 1
         p.keep_polynomials = int(self.keep_polynomials)
-        p.flux_bc = {"none": 0, "flux": 1}[self.flux_bc]
+        p.flux_bc = {"none": 0, "flux": 1, "equilibrium": 2}[self.flux_bc]
+        p.n_avars = int(self.n_avars)
+        if self.heating is not None:
+            p.heating_rate, p.heating_r0, p.heating_r1 = (float(x) for x in self.heating)
         return p
 
 
 class AllVariables:
-    """``zisa::AllVariables`` restricted to the conserved variables: ``cvars[n_cells][5]`` (host)."""
+    """``zisa::AllVariables`` (all_variables.hpp:31-35): ``cvars[n_cells][5]`` and ``avars[n_cells][n_avars]`` (host)."""
 
-    def __init__(self, n_cells: int, cvars: Optional[np.ndarray] = None):
+    def __init__(self, n_cells: int, cvars: Optional[np.ndarray] = None, avars: Optional[np.ndarray] = None, n_avars: int = 0):
         self.cvars = np.zeros((n_cells, 5)) if cvars is None else np.ascontiguousarray(cvars, dtype=np.float64)
         assert self.cvars.shape == (n_cells, 5)
+        if avars is None:
+            self.avars = np.zeros((n_cells, n_avars))
+        else:
+            self.avars = np.ascontiguousarray(avars, dtype=np.float64).reshape(n_cells, -1)
 
 
 class CudaContext:
@@ -100,6 +109,7 @@ class CudaContext:
         check(lib.zfvm_create(grid._h, stencils._h, C.byref(cp), device, C.byref(h)))
         self._h = h
         self.n_cells = grid.n_cells
+        self.n_avars = int(params.n_avars)
         if params.gravity.kind == "table":
             r, phi = params.gravity.table
             r = _capi.as_f64(r)
@@ -174,6 +184,12 @@ class CudaEulerRateOfChange:
     def compute(self, tendency: AllVariables, current_state: AllVariables, t: float = 0.0, accumulate: bool = True):
         """``RateOfChange::compute``: ``tendency += rate(current_state)`` (host buffers)."""
         assert tendency.cvars.flags.c_contiguous and current_state.cvars.flags.c_contiguous
+        if self.ctx.n_avars > 0:
+            assert tendency.avars.shape == current_state.avars.shape == (self.ctx.n_cells, self.ctx.n_avars)
+            check(lib.zfvm_rate_of_change_av(self.ctx._h, _capi.ptr_f64(tendency.cvars), _capi.ptr_f64(tendency.avars),
+                                             _capi.ptr_f64(current_state.cvars), _capi.ptr_f64(current_state.avars),
+                                             float(t), int(accumulate)))
+            return
         check(lib.zfvm_rate_of_change(self.ctx._h, _capi.ptr_f64(tendency.cvars), _capi.ptr_f64(current_state.cvars),
                                       float(t), int(accumulate)))
 
@@ -190,7 +206,11 @@ class FrozenBC:
     def __init__(self, ctx: CudaContext, steady_state: AllVariables):
         self.ctx = ctx
         s = _capi.as_f64(steady_state.cvars)
-        check(lib.zfvm_set_frozen_bc(ctx._h, _capi.ptr_f64(s)))
+        if ctx.n_avars > 0:
+            a = _capi.as_f64(steady_state.avars)
+            check(lib.zfvm_set_frozen_bc_av(ctx._h, _capi.ptr_f64(s), _capi.ptr_f64(a)))
+        else:
+            check(lib.zfvm_set_frozen_bc(ctx._h, _capi.ptr_f64(s)))
 
     def apply_device(self, state_ptr: int):
         check(lib.zfvm_apply_frozen_bc(self.ctx._h, state_ptr))
@@ -220,10 +240,14 @@ class CudaRungeKutta:
 
     def upload(self, u0: AllVariables):
         check(lib.zfvm_upload_state(self.ctx._h, _capi.ptr_f64(u0.cvars)))
+        if self.ctx.n_avars > 0:
+            check(lib.zfvm_upload_avars(self.ctx._h, _capi.ptr_f64(u0.avars)))
 
     def download(self, out: Optional[AllVariables] = None) -> AllVariables:
-        out = out or AllVariables(self.ctx.n_cells)
+        out = out or AllVariables(self.ctx.n_cells, n_avars=self.ctx.n_avars)
         check(lib.zfvm_download_state(self.ctx._h, _capi.ptr_f64(out.cvars)))
+        if self.ctx.n_avars > 0:
+            check(lib.zfvm_download_avars(self.ctx._h, _capi.ptr_f64(out.avars)))
         return out
 
     def step(self, t: float, dt: float, cfl_number: Optional[float] = None):
@@ -240,6 +264,10 @@ class CudaRungeKutta:
         """``TimeIntegration::compute_step(u0, t, dt) -> u1`` with host buffers (H2D + D2H inside).  ``out`` lets the
         caller hand in the result buffer (the reference's RungeKutta owns and swaps its buffers, runge_kutta.cpp:109-111);
         pinned buffers are copied without staging."""
-        u1 = AllVariables(self.ctx.n_cells) if out is None else out
+        u1 = AllVariables(self.ctx.n_cells, n_avars=self.ctx.n_avars) if out is None else out
+        if self.ctx.n_avars > 0:
+            check(lib.zfvm_rk_step_host_av(self.ctx._h, _capi.ptr_f64(u0.cvars), _capi.ptr_f64(u0.avars),
+                                           _capi.ptr_f64(u1.cvars), _capi.ptr_f64(u1.avars), t, dt))
+            return u1
         check(lib.zfvm_rk_step_host(self.ctx._h, _capi.ptr_f64(u0.cvars), _capi.ptr_f64(u1.cvars), t, dt))
         return u1
