@@ -31,6 +31,11 @@ def test_oracle_reproduces_golden(name):
     assert (np.abs(g["tendency"] - now["tendency"]).max(axis=0) / sc_t).max() < 1e-13
     sc_u = state_scales(case.u0, case.params.gamma)
     assert (np.abs(g["u3"] - now["u3"]).max(axis=0) / sc_u).max() < 1e-13
+    if "a0" in g:
+        assert np.array_equal(g["a0"], now["a0"])
+        sa = np.abs(g["a0"]).max(axis=0)
+        assert (np.abs(g["a3"] - now["a3"]).max(axis=0) / sa).max() < 1e-13
+        assert (np.abs(g["tendency_a"] - now["tendency_a"]).max(axis=0) / (sa * sc_t[0] / sc_u[0])).max() < 1e-13
 
 
 @pytest.mark.gpu
@@ -43,17 +48,24 @@ def test_cuda_matches_golden(name):
     st = case.ensure_stencils()
     n = case.grid.n_cells
     ctx = z.CudaContext(case.grid, st, case.params)
-    tend = z.AllVariables(n)
-    z.CudaEulerRateOfChange(ctx).compute(tend, z.AllVariables(n, g["u0"]), accumulate=False)
+    a0 = g["a0"] if "a0" in g else None
+    na = 0 if a0 is None else a0.shape[1]
+    tend = z.AllVariables(n, n_avars=na)
+    z.CudaEulerRateOfChange(ctx).compute(tend, z.AllVariables(n, g["u0"], a0), accumulate=False)
     sc_t = tendency_scales(case.u0, case.params.gamma, case.grid.array("inradii"))
     assert (np.abs(tend.cvars - g["tendency"]).max(axis=0) / sc_t).max() < 1e-12
     rk = z.CudaRungeKutta(ctx, case.method)
-    z.FrozenBC(ctx, z.AllVariables(n, g["u0"]))
-    rk.upload(z.AllVariables(n, g["u0"]))
+    if case.frozen_bc:
+        z.FrozenBC(ctx, z.AllVariables(n, g["u0"], a0))
+    rk.upload(z.AllVariables(n, g["u0"], a0))
     for _ in range(3):
         rk.step(0.0, float(g["dt"]))
-    u3 = rk.download().cvars
+    out = rk.download()
     sc_u = state_scales(case.u0, case.params.gamma)
     vs = active_vars(case.grid.n_dims)
-    assert (np.abs(u3 - g["u3"]).max(axis=0) / sc_u)[vs].max() < 1e-11
+    assert (np.abs(out.cvars - g["u3"]).max(axis=0) / sc_u)[vs].max() < 1e-11
+    if a0 is not None:
+        sa = np.abs(a0).max(axis=0)
+        assert (np.abs(tend.avars - g["tendency_a"]).max(axis=0) / (sa * sc_t[0] / sc_u[0])).max() < 1e-12
+        assert (np.abs(out.avars - g["a3"]).max(axis=0) / sa).max() < 1e-11
     ctx.close()

@@ -344,6 +344,11 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     // the cell-local source pass (GravitySourceLoop and / or Heating) runs when either term is present; without a
     // gravity model its potential tables stay zero
     sc.has_gravity = params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0;
+    {
+      sc.eos_pow_e = 1.0 / (params->gamma - 1.0);
+      const double twice = 2.0 * sc.eos_pow_e, r = std::rint(twice);
+      sc.eos_pow_n = (std::fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) ? (int)r : 0;
+    }
     sc.heating_rate = params->heating_rate;
     sc.heating_r0 = params->heating_r0;
     sc.heating_r1 = params->heating_r1;

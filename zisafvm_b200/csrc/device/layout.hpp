@@ -58,6 +58,10 @@ struct SchemeConst {
   double cell_w[MAX_QC];
   double cell_bary[MAX_QC][4];
   double heating_rate, heating_r0, heating_r1;  // Heating (model/heating.hpp:54-80); rate 0: off
+  // isentropic EOS power x^(1/(gamma-1)): eos_pow_n = 2/(gamma-1) when that is an integer in [2, 8] (square-root and
+  // multiplication forms), else 0 -> pow(x, eos_pow_e)
+  int eos_pow_n;
+  double eos_pow_e;
 };
 
 /// Raw device pointers of one context. Sizes in comments use n = n_cells, T = n_tiles, E = n_edges.

@@ -85,35 +85,29 @@ ZFVM_DEVICE double fast_rsqrt(double x) {
 /// x^(1/(gamma-1)) for the density of an isentropic state.  For the adiabatic indices in practical use the exponent
 /// is a half-integer (gamma = 2, 5/3, 3/2, 7/5, 4/3 -> 1, 3/2, 2, 5/2, 3): square root and multiplications instead of
 /// pow(), which is what the well-balanced reconstruction spends its time in (one evaluation per stencil member and
-/// Gauss point, each cell with its own (h, K)).  gamma is a kernel-uniform scalar: no divergence.
-ZFVM_DEVICE double pow_inv_gamma_minus_one(double x, double gamma) {
-  if (gamma == 2.0) return x;
-  const double e = 1.0 / (gamma - 1.0);
-  const double twice = 2.0 * e, r = rint(twice);
-  if (fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) {
-    const int n = (int)r;  // x^(n/2); odd n: x^((n+1)/2) / sqrt(x) with the Newton-refined reciprocal square root
-    double pw = (n & 1) ? x * fast_rsqrt(x) : 1.0;
-    for (int m = n >> 1; m > 0; --m) pw *= x;
-    return pw;
-  }
-  return pow(x, e);
+/// Gauss point, each cell with its own (h, K)).  The host classifies gamma once (SchemeConst::eos_pow_n =
+/// 2 / (gamma - 1) when that is an integer in [2, 8], else 0): kernel-uniform predicates over straight-line code, no
+/// per-point division, rounding test or counted loop.  Multiplication order: ((x rsqrt(x)) x) x .. / (x x) x ..
+ZFVM_DEVICE double pow_inv_gamma_minus_one(double x, const SchemeConst &sc) {
+  const int n = sc.eos_pow_n;  // x^(n/2)
+  if (n == 2) return x;        // gamma = 2
+  if (n == 0) return pow(x, sc.eos_pow_e);
+  double pw = x;
+  if (n & 1) pw = (x * fast_rsqrt(x)) * x;
+  if (n >= 4) pw *= x;
+  if (n >= 6) pw *= x;
+  if (n >= 8) pw *= x;
+  return pw;
 }
 
 /// Isentropic ideal-gas state at specific enthalpy h and entropy function K
 /// (ideal_gas_eos.hpp:162-168,188-191,208-215): rho = ((gamma-1) h / (gamma K))^(1/(gamma-1)), p = K rho^gamma,
 /// E = p / (gamma-1).  rho^(gamma-1) is the base of that power, so p = K rho base needs no second pow().
-ZFVM_DEVICE void isentropic_state(double h, double K, double gamma, double &rho, double &E, double &p) {
-  const double base = 1.0 / K * (gamma - 1.0) / gamma * h;
-  rho = pow_inv_gamma_minus_one(base, gamma);
-  p = K * (rho * base);
-  E = p / (gamma - 1.0);
-}
-/// Same state with the per-equilibrium constant c1 = (gamma-1) / (gamma K) and 1/(gamma-1) formed once by the caller:
-/// no division per point.
-ZFVM_DEVICE void isentropic_state_c(double h, double K, double c1, double gamma, double inv_gm1, double &rho, double &E,
-                                    double &p) {
+/// c1 = (gamma-1) / (gamma K) and 1/(gamma-1) are formed once per equilibrium by the caller: no division per point.
+ZFVM_DEVICE void isentropic_state_c(double h, double K, double c1, const SchemeConst &sc, double inv_gm1, double &rho,
+                                    double &E, double &p) {
   const double base = c1 * h;
-  rho = pow_inv_gamma_minus_one(base, gamma);
+  rho = pow_inv_gamma_minus_one(base, sc);
   p = K * (rho * base);
   E = p * inv_gm1;
 }

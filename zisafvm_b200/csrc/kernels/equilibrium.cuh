@@ -14,16 +14,66 @@ struct LocalEq {
     c1 = (gamma - 1.0) / (gamma * K);
     inv_gm1 = 1.0 / (gamma - 1.0);
   }
-  ZFVM_DEVICE void at(double phi, double gamma, double &rho, double &E, double &p) const {
+  ZFVM_DEVICE void at(double phi, const SchemeConst &sc, double &rho, double &E, double &p) const {
     if (!found) {
       rho = 0.0;
       E = 0.0;
       p = 0.0;
       return;
     }
-    isentropic_state_c(h_ref + phi_ref - phi, K, c1, gamma, inv_gm1, rho, E, p);
+    isentropic_state_c(h_ref + phi_ref - phi, K, c1, sc, inv_gm1, rho, E, p);
   }
 };
+
+/// Cell averages of N isentropic equilibria (h_n, K_n, same reference potential) over a cell whose Gauss-point
+/// potentials are `phi` (AoS row), accumulated point 0 first (quadrature.hpp:43-48).  The kernel is bound by the
+/// latency of the dependent rsqrt / Newton / multiply chain of one state evaluation, so independent evaluations are
+/// issued together: the N equilibria of a finite-difference Jacobian and CH Gauss points at a time.  Every value is
+/// formed by the same operations as in the one-at-a-time form (bit-identical results).
+template <int N, int CH>
+ZFVM_DEVICE void eq_cell_average_multi(const double h_ref[N], const double K[N], double phi_ref,
+                                       const double *__restrict__ phi, const SchemeConst &sc, double rho_bar[N],
+                                       double E_bar[N]) {
+  const double gamma = sc.gamma, inv_gm1 = 1.0 / (gamma - 1.0);
+  double c1[N], hp[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    c1[n] = (gamma - 1.0) / (gamma * K[n]);
+    hp[n] = h_ref[n] + phi_ref;
+    rho_bar[n] = 0.0;
+    E_bar[n] = 0.0;
+  }
+  int q = 0;
+  for (; q + CH <= sc.q_c; q += CH) {
+    double r[CH][N], E[CH][N], ph[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) ph[j] = phi[q + j];
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double p;
+        isentropic_state_c(hp[n] - ph[j], K[n], c1[n], sc, inv_gm1, r[j][n], E[j][n], p);
+      }
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        rho_bar[n] = fma(sc.cell_w[q + j], r[j][n], rho_bar[n]);
+        E_bar[n] = fma(sc.cell_w[q + j], E[j][n], E_bar[n]);
+      }
+  }
+  for (; q < sc.q_c; ++q) {
+    const double ph = phi[q];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      double r, E, p;
+      isentropic_state_c(hp[n] - ph, K[n], c1[n], sc, inv_gm1, r, E, p);
+      rho_bar[n] = fma(sc.cell_w[q], r, rho_bar[n]);
+      E_bar[n] = fma(sc.cell_w[q], E, E_bar[n]);
+    }
+  }
+}
 
 /// cell average of the equilibrium over a cell whose Gauss-point potentials are `phi` (AoS row)
 ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ phi, const SchemeConst &sc,
@@ -33,14 +83,31 @@ ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ p
     E_bar = 0.0;
     return;
   }
-  double r, E, p;
-  eq.at(phi[0], sc.gamma, r, E, p);
-  rho_bar = sc.cell_w[0] * r;
-  E_bar = sc.cell_w[0] * E;
-  for (int q = 1; q < sc.q_c; ++q) {
-    eq.at(phi[q], sc.gamma, r, E, p);
-    rho_bar += sc.cell_w[q] * r;
-    E_bar += sc.cell_w[q] * E;
+  const double hp = eq.h_ref + eq.phi_ref;
+  constexpr int CH = 4;
+  rho_bar = 0.0;
+  E_bar = 0.0;
+  int q = 0;
+  for (; q + CH <= sc.q_c; q += CH) {
+    double r[CH], E[CH], ph[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) ph[j] = phi[q + j];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      double p;
+      isentropic_state_c(hp - ph[j], eq.K, eq.c1, sc, eq.inv_gm1, r[j], E[j], p);
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      rho_bar = fma(sc.cell_w[q + j], r[j], rho_bar);
+      E_bar = fma(sc.cell_w[q + j], E[j], E_bar);
+    }
+  }
+  for (; q < sc.q_c; ++q) {
+    double r, E, p;
+    isentropic_state_c(hp - phi[q], eq.K, eq.c1, sc, eq.inv_gm1, r, E, p);
+    rho_bar = fma(sc.cell_w[q], r, rho_bar);
+    E_bar = fma(sc.cell_w[q], E, E_bar);
   }
 }
 
@@ -74,13 +141,15 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
   bool ok = true;
   while (!(fabs(dx0) <= atol_h && fabs(dx1) <= atol_K) && iter < 20) {
     double eps_h = 1e-6 * fabs(h), eps_K = 1e-6 * fabs(K);
-    double fp0, fp1, fm0, fm1;
-    f(h + 0.5 * eps_h, K, fp0, fp1);
-    f(h - 0.5 * eps_h, K, fm0, fm1);
-    const double d00 = (fp0 - fm0) / eps_h, d01 = (fp1 - fm1) / eps_h;  // df0 = d f / d h
-    f(h, K + 0.5 * eps_K, fp0, fp1);
-    f(h, K - 0.5 * eps_K, fm0, fm1);
-    const double d10 = (fp0 - fm0) / eps_K, d11 = (fp1 - fm1) / eps_K;  // df1 = d f / d K
+    // the four states of the central differences, evaluated together (independent dependency chains)
+    const double hs[4] = {h + 0.5 * eps_h, h - 0.5 * eps_h, h, h};
+    const double Ks[4] = {K, K, K + 0.5 * eps_K, K - 0.5 * eps_K};
+    double rb4[4], Eb4[4];
+    eq_cell_average_multi<4, 2>(hs, Ks, eq.phi_ref, phi_own, sc, rb4, Eb4);
+    const double d00 = ((rho_bar - rb4[0]) - (rho_bar - rb4[1])) / eps_h;  // df0 = d f / d h
+    const double d01 = ((E_bar - Eb4[0]) - (E_bar - Eb4[1])) / eps_h;
+    const double d10 = ((rho_bar - rb4[2]) - (rho_bar - rb4[3])) / eps_K;  // df1 = d f / d K
+    const double d11 = ((E_bar - Eb4[2]) - (E_bar - Eb4[3])) / eps_K;
     const double inv_det = 1.0 / (d00 * d11 - d01 * d10);
     dx0 = inv_det * (d11 * f0 - d10 * f1);
     dx1 = inv_det * (-d01 * f0 + d00 * f1);

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const Devi
               double acc = 0.0;
               for (int q = 0; q < sc.q_f; ++q) {
                 double r_, E_, p_;
-                eq.at(P.phi_fqp[e * sc.q_f + q], sc.gamma, r_, E_, p_);
+                eq.at(P.phi_fqp[e * sc.q_f + q], sc, r_, E_, p_);
                 const double wq = fr[9] * sc.face_w[q];
                 acc = (q == 0) ? wq * (p_ * fr[v - 1]) : acc + wq * (p_ * fr[v - 1]);
               }

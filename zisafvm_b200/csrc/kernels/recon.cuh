@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
       double bg_rho = 0.0, bg_E = 0.0;
       if (WB) {
         double p_eq;
-        eq.at(P.phi_fqp[e * sc.q_f + q], sc.gamma, bg_rho, bg_E, p_eq);
+        eq.at(P.phi_fqp[e * sc.q_f + q], sc, bg_rho, bg_E, p_eq);
         const double wq = area * sc.face_w[q];
         if (q == 0) {
 #pragma unroll
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
         double rho_full = du[0];
         if (WB) {
           double br, bE, bp;
-          eq.at(P.phi_cqp[ci * sc.q_c + q], sc.gamma, br, bE, bp);
+          eq.at(P.phi_cqp[ci * sc.q_c + q], sc, br, bE, bp);
           rho_full += br;
         }
         const double r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
