@@ -28,3 +28,7 @@ def run(name, case, steps=5):
 run("atmosphere 3D o3 WB (gamma 5/3)", cases.stellar_atmosphere_3d(n=40, order=3, well_balanced=True))
 run("atmosphere 3D o3 no WB, gravity", cases.stellar_atmosphere_3d(n=40, order=3, well_balanced=False))
 run("polytrope 2D o3 WB (gamma 2)", cases.polytrope_2d(n=600, order=3, well_balanced=True))
+if os.environ.get("WB_O4", "1") == "1":
+    # BASELINE config 4 itself (order 4, well-balanced) and its plain counterpart
+    run("atmosphere 3D o4 WB (C4)", cases.stellar_atmosphere_3d(n=32, order=4, well_balanced=True), steps=3)
+    run("smooth 3D o4, no gravity", cases.blast_3d(n=32, order=4, kind="smooth"), steps=3)

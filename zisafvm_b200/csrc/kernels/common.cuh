@@ -88,26 +88,39 @@ ZFVM_DEVICE double fast_rsqrt(double x) {
 /// Gauss point, each cell with its own (h, K)).  The host classifies gamma once (SchemeConst::eos_pow_n =
 /// 2 / (gamma - 1) when that is an integer in [2, 8], else 0): kernel-uniform predicates over straight-line code, no
 /// per-point division, rounding test or counted loop.  Multiplication order: ((x rsqrt(x)) x) x .. / (x x) x ..
+/// POWN > 0: the exponent n/2 is a compile-time constant (the well-balanced kernels are instantiated for gamma = 2,
+/// 5/3, 7/5: n = 2, 3, 5); POWN == 0: decided at run time from sc.eos_pow_n.
+template <int POWN = 0>
 ZFVM_DEVICE double pow_inv_gamma_minus_one(double x, const SchemeConst &sc) {
-  const int n = sc.eos_pow_n;  // x^(n/2)
-  if (n == 2) return x;        // gamma = 2
-  if (n == 0) return pow(x, sc.eos_pow_e);
-  double pw = x;
-  if (n & 1) pw = (x * fast_rsqrt(x)) * x;
-  if (n >= 4) pw *= x;
-  if (n >= 6) pw *= x;
-  if (n >= 8) pw *= x;
-  return pw;
+  if constexpr (POWN > 0) {
+    double pw = x;
+    if constexpr ((POWN & 1) != 0) pw = (x * fast_rsqrt(x)) * x;
+    if constexpr (POWN >= 4) pw *= x;
+    if constexpr (POWN >= 6) pw *= x;
+    if constexpr (POWN >= 8) pw *= x;
+    return pw;
+  } else {
+    const int n = sc.eos_pow_n;  // x^(n/2)
+    if (n == 2) return x;        // gamma = 2
+    if (n == 0) return pow(x, sc.eos_pow_e);
+    double pw = x;
+    if (n & 1) pw = (x * fast_rsqrt(x)) * x;
+    if (n >= 4) pw *= x;
+    if (n >= 6) pw *= x;
+    if (n >= 8) pw *= x;
+    return pw;
+  }
 }
 
 /// Isentropic ideal-gas state at specific enthalpy h and entropy function K
 /// (ideal_gas_eos.hpp:162-168,188-191,208-215): rho = ((gamma-1) h / (gamma K))^(1/(gamma-1)), p = K rho^gamma,
 /// E = p / (gamma-1).  rho^(gamma-1) is the base of that power, so p = K rho base needs no second pow().
 /// c1 = (gamma-1) / (gamma K) and 1/(gamma-1) are formed once per equilibrium by the caller: no division per point.
+template <int POWN = 0>
 ZFVM_DEVICE void isentropic_state_c(double h, double K, double c1, const SchemeConst &sc, double inv_gm1, double &rho,
                                     double &E, double &p) {
   const double base = c1 * h;
-  rho = pow_inv_gamma_minus_one(base, sc);
+  rho = pow_inv_gamma_minus_one<POWN>(base, sc);
   p = K * (rho * base);
   E = p * inv_gm1;
 }

@@ -14,6 +14,7 @@ struct LocalEq {
     c1 = (gamma - 1.0) / (gamma * K);
     inv_gm1 = 1.0 / (gamma - 1.0);
   }
+  template <int POWN = 0>
   ZFVM_DEVICE void at(double phi, const SchemeConst &sc, double &rho, double &E, double &p) const {
     if (!found) {
       rho = 0.0;
@@ -21,7 +22,7 @@ struct LocalEq {
       p = 0.0;
       return;
     }
-    isentropic_state_c(h_ref + phi_ref - phi, K, c1, sc, inv_gm1, rho, E, p);
+    isentropic_state_c<POWN>(h_ref + phi_ref - phi, K, c1, sc, inv_gm1, rho, E, p);
   }
 };
 
@@ -30,7 +31,7 @@ struct LocalEq {
 /// latency of the dependent rsqrt / Newton / multiply chain of one state evaluation, so independent evaluations are
 /// issued together: the N equilibria of a finite-difference Jacobian and CH Gauss points at a time.  Every value is
 /// formed by the same operations as in the one-at-a-time form (bit-identical results).
-template <int N, int CH>
+template <int N, int CH, int POWN = 0>
 ZFVM_DEVICE void eq_cell_average_multi(const double h_ref[N], const double K[N], double phi_ref,
                                        const double *__restrict__ phi, const SchemeConst &sc, double rho_bar[N],
                                        double E_bar[N]) {
@@ -53,7 +54,7 @@ ZFVM_DEVICE void eq_cell_average_multi(const double h_ref[N], const double K[N],
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         double p;
-        isentropic_state_c(hp[n] - ph[j], K[n], c1[n], sc, inv_gm1, r[j][n], E[j][n], p);
+        isentropic_state_c<POWN>(hp[n] - ph[j], K[n], c1[n], sc, inv_gm1, r[j][n], E[j][n], p);
       }
 #pragma unroll
     for (int j = 0; j < CH; ++j)
@@ -68,7 +69,7 @@ ZFVM_DEVICE void eq_cell_average_multi(const double h_ref[N], const double K[N],
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       double r, E, p;
-      isentropic_state_c(hp[n] - ph, K[n], c1[n], sc, inv_gm1, r, E, p);
+      isentropic_state_c<POWN>(hp[n] - ph, K[n], c1[n], sc, inv_gm1, r, E, p);
       rho_bar[n] = fma(sc.cell_w[q], r, rho_bar[n]);
       E_bar[n] = fma(sc.cell_w[q], E, E_bar[n]);
     }
@@ -76,6 +77,7 @@ ZFVM_DEVICE void eq_cell_average_multi(const double h_ref[N], const double K[N],
 }
 
 /// cell average of the equilibrium over a cell whose Gauss-point potentials are `phi` (AoS row)
+template <int POWN = 0>
 ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ phi, const SchemeConst &sc,
                                  double &rho_bar, double &E_bar) {
   if (!eq.found) {
@@ -95,7 +97,7 @@ ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ p
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       double p;
-      isentropic_state_c(hp - ph[j], eq.K, eq.c1, sc, eq.inv_gm1, r[j], E[j], p);
+      isentropic_state_c<POWN>(hp - ph[j], eq.K, eq.c1, sc, eq.inv_gm1, r[j], E[j], p);
     }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -105,7 +107,7 @@ ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ p
   }
   for (; q < sc.q_c; ++q) {
     double r, E, p;
-    isentropic_state_c(hp - phi[q], eq.K, eq.c1, sc, eq.inv_gm1, r, E, p);
+    isentropic_state_c<POWN>(hp - phi[q], eq.K, eq.c1, sc, eq.inv_gm1, r, E, p);
     rho_bar = fma(sc.cell_w[q], r, rho_bar);
     E_bar = fma(sc.cell_w[q], E, E_bar);
   }
@@ -113,6 +115,7 @@ ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ p
 
 /// quasi_newton (quasi_newton.hpp:12-50) on f(theta) = rhoE_bar - avg_cell rhoE_eq(theta) with
 /// the central-difference Jacobian of local_equilibrium_impl.hpp:64-86.
+template <int POWN = 0>
 ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const double *__restrict__ phi_own,
                                             const SchemeConst &sc) {
   const double gamma = sc.gamma;
@@ -128,7 +131,7 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
     LocalEq t{h, K, eq.phi_ref, true};
     t.prepare(gamma);
     double rb, Eb;
-    eq_cell_average(t, phi_own, sc, rb, Eb);
+    eq_cell_average<POWN>(t, phi_own, sc, rb, Eb);
     f0 = rho_bar - rb;
     f1 = E_bar - Eb;
   };
@@ -145,7 +148,7 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
     const double hs[4] = {h + 0.5 * eps_h, h - 0.5 * eps_h, h, h};
     const double Ks[4] = {K, K, K + 0.5 * eps_K, K - 0.5 * eps_K};
     double rb4[4], Eb4[4];
-    eq_cell_average_multi<4, 2>(hs, Ks, eq.phi_ref, phi_own, sc, rb4, Eb4);
+    eq_cell_average_multi<4, 2, POWN>(hs, Ks, eq.phi_ref, phi_own, sc, rb4, Eb4);
     const double d00 = ((rho_bar - rb4[0]) - (rho_bar - rb4[1])) / eps_h;  // df0 = d f / d h
     const double d01 = ((E_bar - Eb4[0]) - (E_bar - Eb4[1])) / eps_h;
     const double d10 = ((rho_bar - rb4[2]) - (rho_bar - rb4[3])) / eps_K;  // df1 = d f / d K

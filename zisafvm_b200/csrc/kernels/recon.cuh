@@ -52,7 +52,7 @@ struct PolyEval {
   }
 };
 
-template <int ND, int DEG_HI, int DEG_LO, int NS, int VARIANT>
+template <int ND, int DEG_HI, int DEG_LO, int NS, int VARIANT, int POWN = 0>
 __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ ReconArgs args,
                                                     const __grid_constant__ SchemeConst sc) {
   constexpr int F = ND + 1;
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
   double eq0_rho = 0.0, eq0_E = 0.0;
   if (WB) {
     const double *phi_own = P.phi_cqp + ci * sc.q_c;
-    eq = solve_local_equilibrium(u0[0], eint0, phi_own, sc);
+    eq = solve_local_equilibrium<POWN>(u0[0], eint0, phi_own, sc);
     if (!eq.found && active) atomicAdd(P.eq_fail, 1);
-    eq_cell_average(eq, phi_own, sc, eq0_rho, eq0_E);
+    eq_cell_average<POWN>(eq, phi_own, sc, eq0_rho, eq0_E);
   }
 
   // u_local(0) after equilibrium subtraction and scaling (local_reconstruction.hpp:109-116)
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
         for (int v = 0; v < NVARS; ++v) rhs[v] = args.state[g * NVARS + v];
         if (WB) {
           double rb, Eb;
-          eq_cell_average(eq, P.phi_cqp + g * sc.q_c, sc, rb, Eb);
+          eq_cell_average<POWN>(eq, P.phi_cqp + g * sc.q_c, sc, rb, Eb);
           rhs[0] -= rb;
           rhs[4] -= Eb;
         }
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
       double bg_rho = 0.0, bg_E = 0.0;
       if (WB) {
         double p_eq;
-        eq.at(P.phi_fqp[e * sc.q_f + q], sc, bg_rho, bg_E, p_eq);
+        eq.template at<POWN>(P.phi_fqp[e * sc.q_f + q], sc, bg_rho, bg_E, p_eq);
         const double wq = area * sc.face_w[q];
         if (q == 0) {
 #pragma unroll
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
         double rho_full = du[0];
         if (WB) {
           double br, bE, bp;
-          eq.at(P.phi_cqp[ci * sc.q_c + q], sc, br, bE, bp);
+          eq.template at<POWN>(P.phi_cqp[ci * sc.q_c + q], sc, br, bE, bp);
           rho_full += br;
         }
         const double r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);

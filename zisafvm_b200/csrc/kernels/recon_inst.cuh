@@ -109,9 +109,15 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
   }
   const int block = 128;  // 4 tiles per CTA
   const unsigned grid = (unsigned)((n_tiles + 3) / 4);
-  if (sc.well_balanced)
-    recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED><<<grid, block, 0, stream>>>(args, sc);
-  else if (sc.has_gravity)
+  if (sc.well_balanced) {
+    // the isentropic EOS power x^(n/2) as a compile-time constant for gamma = 2, 5/3, 7/5 (n = 2, 3, 5)
+    switch (sc.eos_pow_n) {
+      case 2: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 2><<<grid, block, 0, stream>>>(args, sc); break;
+      case 3: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 3><<<grid, block, 0, stream>>>(args, sc); break;
+      case 5: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 5><<<grid, block, 0, stream>>>(args, sc); break;
+      default: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 0><<<grid, block, 0, stream>>>(args, sc); break;
+    }
+  } else if (sc.has_gravity)
     recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_GRAVITY><<<grid, block, 0, stream>>>(args, sc);
   else
     recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_PLAIN><<<grid, block, 0, stream>>>(args, sc);
