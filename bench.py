@@ -49,7 +49,10 @@ def parse_args():
     ap.add_argument("--n", type=int, default=int(os.environ.get("ZFVM_BENCH_N", "118")), help="cubes per direction per GPU")
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--kind", default="blast", help="blast | sod | smooth (3D, BASELINE configs 3/5); vortex2d (BASELINE "
-                    "config 1 scaled up: --n squares per direction x 2 triangles; single GPU, extra measurement)")
+                    "config 1 scaled up: --n squares per direction x 2 triangles; single GPU, extra measurement); "
+                    "atmosphere (BASELINE config 4: 3D well-balanced stellar atmosphere, --order 3 or 4; single GPU); "
+                    "polytrope2d (BASELINE config 2 scaled up; single GPU)")
+    ap.add_argument("--avars", type=int, default=0, help="advected scalars carried along (extra measurement; BASELINE configs have 0)")
     ap.add_argument("--cpu-n", type=int, default=32, help="cubes per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -122,11 +125,34 @@ def measured_peak_gbs():
 
 def workload_name(args, method: str) -> str:
     """The same string in both arms (the driver pairs the lines by metric and config)."""
+    extra = f", {args.avars} advected scalar(s)" if args.avars else ""
     if args.kind == "vortex2d":
         return (f"2D isentropic vortex on [0,10]^2, {args.n}^2 squares x 2 triangles, CWENO-AO order {args.order}, HLLC, "
-                f"{method}, FrozenBC ghost ring")
+                f"{method}, FrozenBC ghost ring" + extra)
+    if args.kind == "atmosphere":
+        return (f"3D well-balanced stellar atmosphere (gamma 5/3, point-mass gravity, isentropic equilibrium) on [-1,1]^3, "
+                f"{args.n}^3 cubes x 6 Kuhn tets, CWENO-AO order {args.order}, HLLC, {method}, FrozenBC ghost shell" + extra)
+    if args.kind == "polytrope2d":
+        return (f"2D well-balanced polytrope (gamma 2) on [-0.6,0.6]^2, {args.n}^2 squares x 2 triangles, CWENO-AO order "
+                f"{args.order}, HLLC, {method}, FrozenBC for r > 0.5" + extra)
     return (f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets per GPU, CWENO-AO order {args.order} "
-            f"{{3,2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell")
+            f"{{3,2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell" + extra)
+
+
+def make_case(args, n: int):
+    from zisafvm_b200 import cases
+
+    if args.kind == "vortex2d":
+        case = cases.isentropic_vortex(n=n, order=args.order)
+    elif args.kind == "atmosphere":
+        case = cases.stellar_atmosphere_3d(n=n, order=args.order, well_balanced=True)
+    elif args.kind == "polytrope2d":
+        case = cases.polytrope_2d(n=n, order=args.order, well_balanced=True)
+    else:
+        case = cases.blast_3d(n=n, order=args.order, kind=args.kind)
+    if args.avars > 0:
+        cases.with_tracers(case, args.avars)
+    return case
 
 
 def measured_traffic(args, n_cells: int, world: int):
@@ -157,22 +183,30 @@ def cpu_reference_run(args, steps: int, warmup: int):
     from oracle import binding as ob
     from zisafvm_b200 import cases
 
-    case = cases.blast_3d(n=args.cpu_n, order=args.order, kind=args.kind)
+    cpu_n = args.cpu_n if args.kind not in ("vortex2d", "polytrope2d") else min(args.n, 8 * args.cpu_n)
+    case = make_case(args, cpu_n)
     st = case.ensure_stencils()
-    ora = ob.Oracle(case.grid, st, case.params)
-    ora.set_frozen_bc(case.u0)
+    tables = cases.gravity_tables(case.grid, case.params.gravity) if case.params.gravity.kind != "none" else None
+    ora = ob.Oracle(case.grid, st, case.params, tables)
     n_int = int((~case.grid.is_ghost).sum())
     stages = {"ssp3": 3, "ssp2": 2}[case.method]
     dt = ora.cfl_dt(case.u0, case.cfl)
-    u = case.u0
+    if case.a0 is not None:
+        ora.set_frozen_bc_av(case.u0, case.a0)
+        state = (case.u0, case.a0)
+        step = lambda s: ora.rk_step_av(case.method, s[0], s[1], dt)  # noqa: E731
+    else:
+        ora.set_frozen_bc(case.u0)
+        state = case.u0
+        step = lambda s: ora.rk_step(case.method, s, dt)  # noqa: E731
     for _ in range(warmup):
-        u = ora.rk_step(case.method, u, dt)
+        state = step(state)
     t0 = time.perf_counter()
     for _ in range(steps):
-        u = ora.rk_step(case.method, u, dt)
+        state = step(state)
     el = time.perf_counter() - t0
     value = n_int * stages * steps / el
-    sample = (f"{case.grid.n_cells} tets ({args.cpu_n}^3 cubes x 6) of the same 3D {args.kind} order-{args.order} workload, "
+    sample = (f"{case.grid.n_cells} cells ({cpu_n} per direction) of the same {args.kind} order-{args.order} workload, "
               f"{steps} {case.method} steps")
     return value, el / steps * 1e3, ob.num_threads(), sample, case
 
@@ -222,22 +256,20 @@ def run_b200(args):
     if distributed:
         from zisafvm_b200 import distributed as zd
 
-        sub = zd.make_weak_scaling_case(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank)
+        sub = zd.make_weak_scaling_case(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank,
+                                        n_avars=args.avars)
         case, ctx = sub.case, sub.ctx
         n_counted = sub.n_counted
     else:
-        if args.kind == "vortex2d":
-            case = cases.isentropic_vortex(n=args.n, order=args.order)
-        else:
-            case = cases.blast_3d(n=args.n, order=args.order, kind=args.kind)
+        case = make_case(args, args.n)
         st = case.ensure_stencils()
         ctx = z.CudaContext(case.grid, st, case.params, device=local_rank)
         n_counted = int((~case.grid.is_ghost).sum())
     n = case.grid.n_cells
     rk = z.CudaRungeKutta(ctx, case.method)
-    z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+    z.FrozenBC(ctx, z.AllVariables(n, case.u0, case.a0))
     stages = {"ssp3": 3, "ssp2": 2}[case.method]
-    rk.upload(z.AllVariables(n, case.u0))
+    rk.upload(z.AllVariables(n, case.u0, case.a0))
     dt_next, bad = z.LocalCFL(ctx, case.cfl)()
     dt = 0.5 * dt_next
     setup_s = time.perf_counter() - t_setup
@@ -300,13 +332,16 @@ def run_b200(args):
     t_k1 = kms[0] / max(kcnt[0], 1) * 1e-3
     ach_k1 = n_counted * b_k1 / t_k1 / 1e9
     t_stage = sum(kms) / max(kcnt[0], 1) * 1e-3
+    k1_name = ("recon_tile_kernel" if case.params.gravity.kind == "none" and case.params.heating is None
+               else "recon_kernel (thread per cell: + equilibrium / gravity source)")
     roofline = {
-        "bound": "hbm", "kernel": "recon_tile_kernel (K1: stencil-weight apply + CWENO-AO + traces)",
+        "bound": "hbm", "kernel": k1_name + " (K1: stencil-weight apply + CWENO-AO + traces)",
         "achieved": ach_k1, "peak": peak, "unit": "GB/s", "frac": ach_k1 / peak,
         "traffic": measured_traffic(args, int(n), world),
         "peak_source": peak_src, "algorithmic_bytes_per_cell": {"K1": b_k1, "K2": b_k2, "K3": b_k3, "stage": alg_bytes},
         "kernel_ms": {"K1_recon": kms[0] / max(kcnt[0], 1), "K2_flux": kms[1] / max(kcnt[1], 1),
-                      "K3_update": kms[2] / max(kcnt[2], 1)},
+                      "K3_update": kms[2] / max(kcnt[2], 1),
+                      "T_tracers": (kms[3] / max(kcnt[3], 1)) if len(kms) > 3 and kcnt[3] else None},
         "stage": {"achieved": n_counted * alg_bytes / t_stage / 1e9, "frac": n_counted * alg_bytes / t_stage / 1e9 / peak},
     }
 
@@ -316,8 +351,11 @@ def run_b200(args):
         roc = z.CudaEulerRateOfChange(ctx)
         h_state = torch.from_numpy(case.u0.copy()).pin_memory()
         h_tend = torch.zeros_like(h_state).pin_memory()
-        s_av = z.AllVariables(n, h_state.numpy())
-        t_av = z.AllVariables(n, h_tend.numpy())
+        na = args.avars
+        h_a = torch.from_numpy(case.a0.copy()).pin_memory() if na else None
+        h_ta = torch.zeros_like(h_a).pin_memory() if na else None
+        s_av = z.AllVariables(n, h_state.numpy(), h_a.numpy() if na else None)
+        t_av = z.AllVariables(n, h_tend.numpy(), h_ta.numpy() if na else None)
         calls = max(3, min(3 * args.steps, 9))
         for _ in range(2):
             roc.compute(t_av, s_av, 0.0, accumulate=False)
@@ -335,8 +373,8 @@ def run_b200(args):
         roc_value = total_counted * calls / el
         # TimeIntegration::compute_step with host buffers (one H2D of u0 + one D2H of u1 per time step): the boundary
         # SURVEY.md 8b recommends so that the stages of a step do not cross PCIe
-        u_av = z.AllVariables(n, h_state.numpy())
-        o_av = z.AllVariables(n, h_tend.numpy())
+        u_av = z.AllVariables(n, h_state.numpy(), h_a.numpy() if na else None)
+        o_av = z.AllVariables(n, h_tend.numpy(), h_ta.numpy() if na else None)
         rk.compute_step(u_av, 0.0, dt, out=o_av)
         barrier()
         t0 = time.perf_counter()
@@ -349,17 +387,17 @@ def run_b200(args):
             tm = torch.tensor([el2], device="cuda", dtype=torch.float64)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             el2 = float(tm.item())
-        e2e = {"value": total_counted * stages * reps / el2, "unit": UNIT, "h2d_bytes_per_step": int(n * 40),
-               "d2h_bytes_per_step": int(n * 40),
+        e2e = {"value": total_counted * stages * reps / el2, "unit": UNIT, "h2d_bytes_per_step": int(n * (40 + 8 * na)),
+               "d2h_bytes_per_step": int(n * (40 + 8 * na)),
                "call": "zfvm_rk_step_host (TimeIntegration::compute_step), pinned host buffers, per time step",
                "steps": reps, "state_l1": float(np.abs(o_av.cvars).sum()),
                "rate_of_change": {"value": roc_value, "call": "zfvm_rate_of_change (RateOfChange::compute), pinned host "
                                   "buffers, one H2D + one D2H per stage", "calls": calls,
-                                  "h2d_bytes_per_call": int(n * 40), "d2h_bytes_per_call": int(n * 40),
+                                  "h2d_bytes_per_call": int(n * (40 + 8 * na)), "d2h_bytes_per_call": int(n * (40 + 8 * na)),
                                   "tendency_l1": checksum}}
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline and not distributed and args.kind != "vortex2d":
+    if rank == 0 and not args.no_cpu_baseline and not distributed:
         v, ms, cores, sample, _ = cpu_reference_run(args, steps=2, warmup=1)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 

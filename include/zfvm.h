@@ -203,6 +203,8 @@ int zfvm_synchronize(zfvm_ctx *ctx);
  * residual evaluation while enabled; read returns the summed milliseconds and the launch counts */
 int zfvm_profile_enable(zfvm_ctx *ctx, int enable);
 int zfvm_profile_read(zfvm_ctx *ctx, double ms[3], int64_t counts[3]);
+/* the same for the advected-scalar kernels (T1 reconstruction + T2 flux + T3 update, one event pair per residual) */
+int zfvm_profile_read_tracers(zfvm_ctx *ctx, double *ms, int64_t *count);
 /* counters: [0] kernels launched since creation, [1] cells whose equilibrium solve failed */
 int zfvm_counters(zfvm_ctx *ctx, int64_t counters[4]);
 /* diagnostics (keep_polynomials): [n_cells][n_coef][5] coefficients in the scaled basis, [n_cells][5] scales */

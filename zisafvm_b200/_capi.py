@@ -110,6 +110,7 @@ _SIGNATURES = {
     "zfvm_counters": (C.c_int, [_vp, c_int64_p]),
     "zfvm_profile_enable": (C.c_int, [_vp, C.c_int]),
     "zfvm_profile_read": (C.c_int, [_vp, c_double_p, c_int64_p]),
+    "zfvm_profile_read_tracers": (C.c_int, [_vp, c_double_p, c_int64_p]),
     "zfvm_download_polynomials": (C.c_int, [_vp, c_double_p, c_double_p, C.POINTER(C.c_int)]),
     "zfvm_download_work": (C.c_int, [_vp, C.c_char_p, c_double_p, C.c_int64]),
     "zfvm_rate_of_change_av": (C.c_int, [_vp, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int]),

@@ -58,7 +58,7 @@ struct zfvm_ctx {
 
   // optional per-kernel timing (cudaEvent pairs around K1 / K2 / K3), see zfvm_profile_*
   bool prof_enabled = false;
-  std::vector<cudaEvent_t> prof_events[3];
+  std::vector<cudaEvent_t> prof_events[4];  // K1, K2, K3, tracer kernels (T1 + T2 + T3)
 
   // pinned staging chunks for copies from / to pageable caller memory
   void *stage[2] = {nullptr, nullptr};

@@ -215,7 +215,11 @@ __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __g
 // copies its faces' blocks into shared memory with 16-byte cp.async (fully coalesced when the faces are
 // consecutive) and the threads read their rows from there (row pitch padded against bank conflicts).  The
 // fluxes go back the same way.
-template <int FLUX>
+// With TRACERS the kernel also upwinds the advected scalars (fvm_loops/flux_loop.hpp:157-161): the wave speeds are
+// those of the face's HLLC evaluation on the same rotated traces (HLLCBatten::flux returns them, hllc.hpp:175), every
+// scalar goes through HLLCBatten::tracer_flux (hllc.hpp:178-197) -- Rusanov (not in the reference): the same local
+// Lax-Friedrichs form as the flux itself -- and the quadrature sums go to qflux[e][n_avars].
+template <int FLUX, bool TRACERS>
 __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces,
                                                   int pitch) {
@@ -257,6 +261,12 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
   double nf[NVARS] = {0.0, 0.0, 0.0, 0.0, 0.0};
   const double *trL = tr + lane * pitch;
   const double *trR = trL + sc.q_f * NVARS;
+  const int NA = TRACERS ? P.n_avars : 0;
+  double qnf[TRACERS ? MAX_AVARS : 1];
+#pragma unroll
+  for (int a = 0; a < (TRACERS ? MAX_AVARS : 1); ++a) qnf[a] = 0.0;
+  const double *qL = TRACERS ? P.qtrace + e * (2 * sc.q_f * NA) : nullptr;
+  const double *qR = TRACERS ? qL + sc.q_f * NA : nullptr;
   if (!skip) {
     for (int q = 0; q < sc.q_f; ++q) {
       double uL[NVARS], uR[NVARS];
@@ -275,14 +285,52 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
       };
       rot(uL);
       rot(uR);
-      double f[NVARS];
+      double f[NVARS], sp[3] = {0.0, 0.0, 0.0};
       if (FLUX == FLUX_HLLC)
-        hllc_flux(uL, uR, sc.gamma, f);
+        hllc_flux<TRACERS>(uL, uR, sc.gamma, f, sp);
       else
         rusanov_flux(uL, uR, sc.gamma, f);
       const double wq = area * sc.face_w[q];
 #pragma unroll
       for (int v = 0; v < NVARS; ++v) nf[v] += wq * f[v];
+      if constexpr (TRACERS) {
+        if (FLUX == FLUX_HLLC) {
+          const double sL = sp[0], s_star = sp[1], sR = sp[2];
+          const bool left = (0.0 <= s_star);
+          const double vK = left ? uL[1] / uL[0] : uR[1] / uR[0];
+          const bool fan = (sL < 0.0 && 0.0 < sR);
+          const double sK = left ? sL : sR;
+          const double cK = (sK - vK) / (sK - s_star);
+#pragma unroll
+          for (int a = 0; a < MAX_AVARS; ++a) {
+            if (a < NA) {
+              const double mqK = left ? qL[q * NA + a] : qR[q * NA + a];
+              double fq = mqK * vK;
+              if (fan) fq = fq + sK * (cK * mqK - mqK);
+              qnf[a] += wq * fq;
+            }
+          }
+        } else {
+          const double iL = 1.0 / uL[0], iR = 1.0 / uR[0];
+          const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (sc.gamma - 1.0);
+          const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (sc.gamma - 1.0);
+          const double aL = sqrt(sc.gamma * pL * iL), aR = sqrt(sc.gamma * pR * iR);
+          const double vL = uL[1] * iL, vR = uR[1] * iR;
+          const double lam = fmax(fabs(vL) + aL, fabs(vR) + aR);
+#pragma unroll
+          for (int a = 0; a < MAX_AVARS; ++a) {
+            if (a < NA) {
+              const double mL = qL[q * NA + a], mR = qR[q * NA + a];
+              qnf[a] += wq * (0.5 * (mL * vL + mR * vR) - 0.5 * lam * (mR - mL));
+            }
+          }
+        }
+      }
+    }
+    if constexpr (TRACERS) {
+#pragma unroll
+      for (int a = 0; a < MAX_AVARS; ++a)
+        if (a < NA) P.qflux[e * NA + a] = qnf[a];
     }
   }
   const double fx = nf[1] * n[0] + nf[2] * t1[0] + nf[3] * t2[0];
@@ -507,89 +555,6 @@ __global__ void axpy_stage_kernel(double *__restrict__ u_next, const double *__r
   u_next[t] = u_base[t] + dt * dudt;
 }
 
-// T2.  Tracer face flux (fvm_loops/flux_loop.hpp:157-161): one thread per interior face.  The wave speeds are those of
-// the face's HLLC evaluation on the same rotated traces (HLLCBatten::flux returns them, hllc.hpp:175); every scalar is
-// upwinded with HLLCBatten::tracer_flux (hllc.hpp:178-197).  Rusanov (not in the reference): the same local
-// Lax-Friedrichs form as the flux itself.
-template <int FLUX>
-__global__ void __launch_bounds__(128) tracer_flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
-                                                          std::int64_t n_faces) {
-  const std::int64_t e = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_faces || P.left_right[2 * e] < 0) return;
-  const int NA = P.n_avars;
-  const double *fr = P.face_frame + e * 10;
-  double n[3], t1[3], t2[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    n[d] = fr[d];
-    t1[d] = fr[3 + d];
-    t2[d] = fr[6 + d];
-  }
-  const double area = fr[9];
-  double qnf[MAX_AVARS];
-#pragma unroll
-  for (int a = 0; a < MAX_AVARS; ++a) qnf[a] = 0.0;
-  const double *trL = P.trace + e * (2 * sc.q_f * NVARS);
-  const double *trR = trL + sc.q_f * NVARS;
-  const double *qL = P.qtrace + e * (2 * sc.q_f * NA);
-  const double *qR = qL + sc.q_f * NA;
-  for (int q = 0; q < sc.q_f; ++q) {
-    double uL[NVARS], uR[NVARS];
-#pragma unroll
-    for (int v = 0; v < NVARS; ++v) {
-      uL[v] = trL[q * NVARS + v];
-      uR[v] = trR[q * NVARS + v];
-    }
-    auto rot = [&](double u[NVARS]) {
-      const double un = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
-      const double ut1 = u[1] * t1[0] + u[2] * t1[1] + u[3] * t1[2];
-      const double ut2 = u[1] * t2[0] + u[2] * t2[1] + u[3] * t2[2];
-      u[1] = un;
-      u[2] = ut1;
-      u[3] = ut2;
-    };
-    rot(uL);
-    rot(uR);
-    const double wq = area * sc.face_w[q];
-    if (FLUX == FLUX_HLLC) {
-      double f[NVARS], sp[3];
-      hllc_flux<true>(uL, uR, sc.gamma, f, sp);
-      const double sL = sp[0], s_star = sp[1], sR = sp[2];
-      const bool left = (0.0 <= s_star);
-      const double vK = left ? uL[1] / uL[0] : uR[1] / uR[0];
-      const bool fan = (sL < 0.0 && 0.0 < sR);
-      const double sK = left ? sL : sR;
-      const double cK = (sK - vK) / (sK - s_star);
-#pragma unroll
-      for (int a = 0; a < MAX_AVARS; ++a) {
-        if (a < NA) {
-          const double mqK = left ? qL[q * NA + a] : qR[q * NA + a];
-          double fq = mqK * vK;
-          if (fan) fq = fq + sK * (cK * mqK - mqK);
-          qnf[a] += wq * fq;
-        }
-      }
-    } else {
-      const double iL = 1.0 / uL[0], iR = 1.0 / uR[0];
-      const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (sc.gamma - 1.0);
-      const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (sc.gamma - 1.0);
-      const double aL = sqrt(sc.gamma * pL * iL), aR = sqrt(sc.gamma * pR * iR);
-      const double vL = uL[1] * iL, vR = uR[1] * iR;
-      const double lam = fmax(fabs(vL) + aL, fabs(vR) + aR);
-#pragma unroll
-      for (int a = 0; a < MAX_AVARS; ++a) {
-        if (a < NA) {
-          const double mL = qL[q * NA + a], mR = qR[q * NA + a];
-          qnf[a] += wq * (0.5 * (mL * vL + mR * vR) - 0.5 * lam * (mR - mL));
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < MAX_AVARS; ++a)
-    if (a < NA) P.qflux[e * NA + a] = qnf[a];
-}
-
 // T3.  One thread per (cell, scalar): atomic-free gather of the cell's tracer face fluxes (flux_loop.hpp:180-192),
 // fused Runge-Kutta sum and FrozenBC on the avars rows -- the avars half of K3 (no sources act on avars).
 template <int F>
@@ -645,16 +610,6 @@ __global__ void pack_rows_n_kernel(double *__restrict__ out, const double *__res
 
 }  // namespace
 
-void launch_tracer_flux(const DevicePlan &P, const SchemeConst &sc, std::int64_t n_faces, cudaStream_t stream) {
-  if (n_faces <= 0 || P.n_avars <= 0) return;
-  const int block = 128;
-  const unsigned grid = (unsigned)((n_faces + block - 1) / block);
-  if (sc.flux == FLUX_HLLC)
-    tracer_flux_kernel<FLUX_HLLC><<<grid, block, 0, stream>>>(P, sc, n_faces);
-  else
-    tracer_flux_kernel<FLUX_RUSANOV><<<grid, block, 0, stream>>>(P, sc, n_faces);
-}
-
 void launch_tracer_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream) {
   if (A.n_cells_update <= 0 || A.n_avars <= 0) return;
   const int block = 256;
@@ -688,14 +643,17 @@ static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std:
     const char *e = std::getenv("ZFVM_FLUX");
     return e != nullptr && e[0] == 'p';
   }();
-  if (!per_point) {  // one thread per face
+  if (!per_point || P.n_avars > 0) {  // one thread per face (the only variant that carries advected scalars)
     const int block = 64, wpc = block / 32;
     // doubles per staged face row: even (16-byte cp.async) with an odd number of 16-byte units, so that the 64-bit
     // reads of 32 consecutive rows spread over all banks (q_f = 3 would otherwise give a pitch of 32 doubles)
     const int pitch = 2 * ((sc.q_f * NVARS + 1) | 1);
     const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
     const unsigned grid = (unsigned)((n_faces + block - 1) / block);
-    flux_face_kernel<FLUX><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    if (P.n_avars > 0)
+      flux_face_kernel<FLUX, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    else
+      flux_face_kernel<FLUX, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
     return;
   }
   auto go = [&](auto kern, int lanes_per_face) {

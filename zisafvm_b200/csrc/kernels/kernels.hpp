@@ -100,10 +100,10 @@ int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int 
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
                  cudaStream_t stream);
 void launch_update(const DevicePlan &P, const SchemeConst &sc, const UpdateArgs &A, cudaStream_t stream);
-/// Advected scalars: T1 scalar reconstruction + traces, T2 tracer face flux, T3 gather / RK update.
-int launch_tracer_recon(const DevicePlan &P, const SchemeConst &sc, const TracerRecView &view, const double *avars,
-                        const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
-void launch_tracer_flux(const DevicePlan &P, const SchemeConst &sc, std::int64_t n_faces, cudaStream_t stream);
+/// Advected scalars: T1 scalar reconstruction + traces, T3 gather / RK update; the tracer face flux
+/// is evaluated by launch_flux (K2) when the plan carries scalars (it needs the face's HLLC wave speeds).
+int launch_tracer_recon(const DevicePlan &P, const SchemeConst &sc, const TracerRecView &view, int deg_hi, int deg_lo,
+                        const double *avars, const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
 void launch_tracer_update(const DevicePlan &P, int n_dims, const UpdateArgs &A, cudaStream_t stream);
 void launch_pack_rows_n(double *out, const double *state, const std::int32_t *index, std::int64_t n_rows, int row_len,
                         cudaStream_t stream);

@@ -145,7 +145,13 @@ class CudaContext:
         ms = (C.c_double * 3)()
         cnt = (C.c_int64 * 3)()
         check(lib.zfvm_profile_read(self._h, ms, cnt))
-        return [float(x) for x in ms], [int(x) for x in cnt]
+        out_ms, out_cnt = [float(x) for x in ms], [int(x) for x in cnt]
+        if self.n_avars > 0:  # fourth entry: the advected-scalar kernels (T1 + T2 + T3)
+            tms, tcnt = C.c_double(), C.c_int64()
+            check(lib.zfvm_profile_read_tracers(self._h, C.byref(tms), C.byref(tcnt)))
+            out_ms.append(float(tms.value))
+            out_cnt.append(int(tcnt.value))
+        return out_ms, out_cnt
 
     def stream(self) -> int:
         return int(lib.zfvm_stream(self._h) or 0)
