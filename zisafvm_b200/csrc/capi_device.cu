@@ -223,6 +223,7 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     ctx->launches += 1;
   }
+  if (ctx->sc.well_balanced) ctx->launches += (ctx->n_ranks > 1 && ctx->nccl_comm) ? 4 : 2;  // E1 + E2 per K1 launch
   prof_mark(ctx, 0);
   if (ctx->n_avars > 0) {
     // advected scalars, T1: scalar reconstruction + traces (after the halo rows have arrived, before the face kernel,
@@ -846,6 +847,19 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       return 1;
     }
 
+    // well-balanced runs: equilibrium parameters per cell and equilibrium averages per (cell, stencil row)
+    if (sc.well_balanced) {
+      int r = 0;
+      for (int k = 0; k < ns; ++k) {
+        P.eq_row0[k] = r;
+        r += sc.rows_max[k];
+      }
+      P.eq_rows = r;
+      if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)r * 2 * TILE, true)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+    }
     // advected scalars: traces, face fluxes, resident rows and host-entry work rows
     P.n_avars = ctx->n_avars;
     if (ctx->n_avars > 0) {

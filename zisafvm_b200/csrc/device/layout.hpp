@@ -113,6 +113,12 @@ struct DevicePlan {
   double *poly_scale;                       // optional [n][5]
   int n_poly_coef;
   int *eq_fail;                             // counter of cells whose equilibrium solve failed
+  // well-balanced runs: per-cell local equilibrium (h_ref, K, phi_ref, found) and its cell averages over every
+  // stencil member, written by the two equilibrium kernels (equilibrium.cuh) ahead of the reconstruction
+  double *eq_par;                           // [n][4]
+  double *eq_avg;                           // [T][eq_rows][2][32]: (rho_bar, E_bar) of stencil row r = row0_k + j
+  int eq_rows;                              // sum_k rows_max_k
+  int eq_row0[MAX_STENCILS];
   // advected scalars (tracers.cu): traces and face fluxes of the n_avars scalars; null when n_avars == 0
   int n_avars;
   double *qtrace;                           // [E_int][2][q_f][n_avars]

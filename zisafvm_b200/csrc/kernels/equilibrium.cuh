@@ -185,4 +185,65 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
   return eq;
 }
 
+
+/// E1.  One thread per cell: the local equilibrium of the cell's average state (LocalEquilibrium::solve,
+/// local_equilibrium_impl.hpp:34-94) -> eq_par[cell] = (h_ref, K, phi_ref, found).  Kept out of the reconstruction
+/// kernel: the Newton iteration needs few registers and no stencil data, so it runs at full occupancy here.
+template <int POWN>
+__global__ void __launch_bounds__(256) eq_solve_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                       const double *__restrict__ state,
+                                                       const std::int32_t *__restrict__ tile_list, std::int64_t n_tiles) {
+  const std::int64_t t = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles * TILE) return;
+  const std::int64_t tw = t / TILE;
+  const std::int64_t i = (tile_list ? (std::int64_t)tile_list[tw] : tw) * TILE + (t - tw * TILE);
+  if (i >= P.n_cells) return;
+  const double *u = state + i * NVARS;
+  const double rho = u[0];
+  const double eint = u[4] - 0.5 * (u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) / rho;
+  const LocalEq eq = solve_local_equilibrium<POWN>(rho, eint, P.phi_cqp + i * sc.q_c, sc);
+  if (!eq.found) atomicAdd(P.eq_fail, 1);
+  double *out = P.eq_par + i * 4;
+  out[0] = eq.h_ref;
+  out[1] = eq.K;
+  out[2] = eq.phi_ref;
+  out[3] = eq.found ? 1.0 : 0.0;
+}
+
+/// E2.  One thread per (cell, stencil row): the cell average of cell i's equilibrium over stencil member g
+/// (LocalEquilibrium::extrapolate(cell), local_reconstruction.hpp:109-113) -> eq_avg[tile][row][2][lane].  These are
+/// the bulk of the equilibrium evaluations (rows x q_c per cell); one per thread, they fill the FP64 pipe instead of
+/// serialising inside the register-bound reconstruction kernel.  A warp owns one row of a tile: the member index and
+/// the outputs are contiguous across lanes, the member's potentials are a gathered 8 q_c-byte row.
+template <int POWN>
+__global__ void __launch_bounds__(256) eq_member_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                        const std::int32_t *__restrict__ tile_list, std::int64_t n_tiles) {
+  const int lane = threadIdx.x & 31;
+  const std::int64_t w = (std::int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_tiles * P.eq_rows) return;
+  const std::int64_t tw = w / P.eq_rows;
+  const int row = (int)(w - tw * P.eq_rows);
+  const std::int64_t tile = tile_list ? (std::int64_t)tile_list[tw] : tw;
+  int k = 0;
+#pragma unroll
+  for (int kk = 1; kk < MAX_STENCILS; ++kk)
+    if (kk < sc.n_stencils && row >= P.eq_row0[kk]) k = kk;
+  const int j = row - P.eq_row0[k];
+  const std::int64_t cell = tile * TILE + lane;
+  const bool active = cell < P.n_cells;
+  const std::uint64_t meta = active ? P.meta_of(tile)[lane] : 0ull;
+  const int rows = (int)((meta >> (8 * k)) & 0xFF);
+  double rb = 0.0, Eb = 0.0;
+  if (j < rows) {
+    const std::int64_t g = P.sidx_of(tile, k)[(std::int64_t)j * TILE + lane];
+    const double *par = P.eq_par + cell * 4;
+    LocalEq eq{par[0], par[1], par[2], par[3] != 0.0};
+    eq.prepare(sc.gamma);
+    eq_cell_average<POWN>(eq, P.phi_cqp + g * sc.q_c, sc, rb, Eb);
+  }
+  double *out = P.eq_avg + ((tile * P.eq_rows + row) * 2) * TILE + lane;
+  out[0] = rb;
+  out[TILE] = Eb;
+}
+
 }  // namespace zfvm

@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
   LocalEq eq{0.0, 1.0, 0.0, false};
   double eq0_rho = 0.0, eq0_E = 0.0;
   if (WB) {
+    // the cell's local equilibrium comes from eq_solve_kernel (E1), its averages over the stencil members from
+    // eq_member_kernel (E2); only the cell's own average and point values are evaluated here
     const double *phi_own = P.phi_cqp + ci * sc.q_c;
-    eq = solve_local_equilibrium<POWN>(u0[0], eint0, phi_own, sc);
-    if (!eq.found && active) atomicAdd(P.eq_fail, 1);
+    const double *par = P.eq_par + ci * 4;
+    eq = LocalEq{par[0], par[1], par[2], par[3] != 0.0};
+    eq.prepare(sc.gamma);
     eq_cell_average<POWN>(eq, phi_own, sc, eq0_rho, eq0_E);
   }
 
@@ -144,10 +147,9 @@ __global__ void __launch_bounds__(128) recon_kernel(const __grid_constant__ Reco
 #pragma unroll
         for (int v = 0; v < NVARS; ++v) rhs[v] = args.state[g * NVARS + v];
         if (WB) {
-          double rb, Eb;
-          eq_cell_average<POWN>(eq, P.phi_cqp + g * sc.q_c, sc, rb, Eb);
-          rhs[0] -= rb;
-          rhs[4] -= Eb;
+          const double *av = P.eq_avg + ((tile * P.eq_rows + P.eq_row0[k] + j) * 2) * TILE + lane;
+          rhs[0] -= ld_stream(av);
+          rhs[4] -= ld_stream(av + TILE);
         }
 #pragma unroll
         for (int v = 0; v < NVARS; ++v) rhs[v] = rhs[v] * inv_scale[v] - q0s[v];

@@ -22,6 +22,27 @@ int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int 
   return 1;
 }
 
+template <int POWN>
+void launch_eq_solve(const DevicePlan &plan, const SchemeConst &sc, const double *state, const std::int32_t *tile_list,
+                     std::int64_t n_tiles, unsigned grid, cudaStream_t stream) {
+  eq_solve_kernel<POWN><<<grid, 256, 0, stream>>>(plan, sc, state, tile_list, n_tiles);
+}
+template <int POWN>
+void launch_eq_member(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
+                      unsigned grid, cudaStream_t stream) {
+  eq_member_kernel<POWN><<<grid, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
+}
+#define ZFVM_EQ_INST(POWN)                                                                                          \
+  template void launch_eq_solve<POWN>(const DevicePlan &, const SchemeConst &, const double *, const std::int32_t *,    \
+                                      std::int64_t, unsigned, cudaStream_t);                                            \
+  template void launch_eq_member<POWN>(const DevicePlan &, const SchemeConst &, const std::int32_t *, std::int64_t,     \
+                                       unsigned, cudaStream_t);
+ZFVM_EQ_INST(0)
+ZFVM_EQ_INST(2)
+ZFVM_EQ_INST(3)
+ZFVM_EQ_INST(5)
+#undef ZFVM_EQ_INST
+
 namespace {
 unsigned long long *g_tile_prof = nullptr;
 bool g_tile_prof_init = false;

@@ -59,6 +59,14 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
 /// The tile kernel keeps (dof - 1) x 5 accumulators of the central stencil in registers: compiled up to 9 coefficients.
 constexpr bool tile_kernel_enabled(int nd, int deg_hi) { return dof_of(deg_hi, nd) - 1 <= 9; }
 
+/// The two equilibrium kernels are independent of dimension and degrees: one definition (recon_dispatch.cu).
+template <int POWN>
+void launch_eq_solve(const DevicePlan &plan, const SchemeConst &sc, const double *state, const std::int32_t *tile_list,
+                     std::int64_t n_tiles, unsigned grid, cudaStream_t stream);
+template <int POWN>
+void launch_eq_member(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
+                      unsigned grid, cudaStream_t stream);
+
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO>
 int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const double *state,
                           const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream) {
@@ -110,13 +118,23 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
   const int block = 128;  // 4 tiles per CTA
   const unsigned grid = (unsigned)((n_tiles + 3) / 4);
   if (sc.well_balanced) {
-    // the isentropic EOS power x^(n/2) as a compile-time constant for gamma = 2, 5/3, 7/5 (n = 2, 3, 5)
+    // E1 (equilibrium solve per cell) and E2 (its averages over every stencil member) run ahead of the reconstruction;
+    // the isentropic EOS power x^(n/2) is a compile-time constant for gamma = 2, 5/3, 7/5 (n = 2, 3, 5)
+    const unsigned g1 = (unsigned)((n_tiles * TILE + 255) / 256);
+    const unsigned g2 = (unsigned)((n_tiles * plan.eq_rows + 7) / 8);
+#define ZFVM_WB_LAUNCH(POWN)                                                                              \
+  {                                                                                                       \
+    launch_eq_solve<POWN>(plan, sc, state, tile_list, n_tiles, g1, stream);                                                 \
+    launch_eq_member<POWN>(plan, sc, tile_list, n_tiles, g2, stream);                                     \
+    recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, POWN><<<grid, block, 0, stream>>>(args, sc);   \
+  }
     switch (sc.eos_pow_n) {
-      case 2: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 2><<<grid, block, 0, stream>>>(args, sc); break;
-      case 3: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 3><<<grid, block, 0, stream>>>(args, sc); break;
-      case 5: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 5><<<grid, block, 0, stream>>>(args, sc); break;
-      default: recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_WELL_BALANCED, 0><<<grid, block, 0, stream>>>(args, sc); break;
+      case 2: ZFVM_WB_LAUNCH(2) break;
+      case 3: ZFVM_WB_LAUNCH(3) break;
+      case 5: ZFVM_WB_LAUNCH(5) break;
+      default: ZFVM_WB_LAUNCH(0) break;
     }
+#undef ZFVM_WB_LAUNCH
   } else if (sc.has_gravity)
     recon_kernel<ND, DEG_HI, DEG_LO, NS, RV_GRAVITY><<<grid, block, 0, stream>>>(args, sc);
   else
