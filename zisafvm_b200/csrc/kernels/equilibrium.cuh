@@ -90,10 +90,20 @@ ZFVM_DEVICE void eq_cell_average(const LocalEq &eq, const double *__restrict__ p
   rho_bar = 0.0;
   E_bar = 0.0;
   int q = 0;
+  const bool vec = (sc.q_c & 1) == 0;  // rows of an even number of doubles are 16-byte aligned: 128-bit loads
   for (; q + CH <= sc.q_c; q += CH) {
     double r[CH], E[CH], ph[CH];
+    if (vec) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) ph[j] = phi[q + j];
+      for (int j = 0; j < CH; j += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(phi + q + j);
+        ph[j] = v.x;
+        ph[j + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) ph[j] = phi[q + j];
+    }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       double p;

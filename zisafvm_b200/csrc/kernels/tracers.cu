@@ -31,7 +31,7 @@ struct TracerArgs {
 // one-sided stencils of degree DEG_LO): the NS * CLO + NHI coefficients of a scalar's stencil polynomials live in
 // registers.  Stencil *sizes* stay run-time (ragged stencils next to boundaries, rows_max from the scheme).
 template <int ND, int DEG_HI, int DEG_LO, int NS>
-__global__ void __launch_bounds__(128) tracer_recon_kernel(const __grid_constant__ TracerArgs args,
+__global__ void __launch_bounds__(128, 4) tracer_recon_kernel(const __grid_constant__ TracerArgs args,
                                                            const __grid_constant__ SchemeConst sc) {
   constexpr int F = ND + 1;
   constexpr int D = dof_of(DEG_HI, ND);
