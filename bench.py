@@ -53,6 +53,9 @@ def parse_args():
                     "atmosphere (BASELINE config 4: 3D well-balanced stellar atmosphere, --order 3 or 4; single GPU); "
                     "polytrope2d (BASELINE config 2 scaled up; single GPU)")
     ap.add_argument("--avars", type=int, default=0, help="advected scalars carried along (extra measurement; BASELINE configs have 0)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank owns an n^3 box of a lattice (default, the driver's scaling run); strong = "
+                         "ONE global n^3 mesh cut into N chunks of the Hilbert curve (the reference's SFC partition path)")
     ap.add_argument("--cpu-n", type=int, default=32, help="cubes per direction of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -135,7 +138,8 @@ def workload_name(args, method: str) -> str:
     if args.kind == "polytrope2d":
         return (f"2D well-balanced polytrope (gamma 2) on [-0.6,0.6]^2, {args.n}^2 squares x 2 triangles, CWENO-AO order "
                 f"{args.order}, HLLC, {method}, FrozenBC for r > 0.5" + extra)
-    return (f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets per GPU, CWENO-AO order {args.order} "
+    per = "in total" if (args.scaling == "strong" and args.gpus > 1) else "per GPU"
+    return (f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets {per}, CWENO-AO order {args.order} "
             f"{{3,2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell" + extra)
 
 
@@ -256,8 +260,8 @@ def run_b200(args):
     if distributed:
         from zisafvm_b200 import distributed as zd
 
-        sub = zd.make_weak_scaling_case(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank,
-                                        n_avars=args.avars)
+        maker = zd.make_strong_scaling_case if args.scaling == "strong" else zd.make_weak_scaling_case
+        sub = maker(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank, n_avars=args.avars)
         case, ctx = sub.case, sub.ctx
         n_counted = sub.n_counted
     else:
@@ -404,10 +408,13 @@ def run_b200(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": args.scaling if distributed else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": workload_name(args, case.method),
+                "workload": workload_name(args, case.method) + (
+                    f"; ONE global mesh of {args.n}^3 cubes cut into {world} chunks of the Hilbert curve (SFC partition)"
+                    if distributed and args.scaling == "strong" else ""),
                 "cells_per_gpu": int(n), "counted_cells": int(total_counted), "stages_per_step": stages,
                 "device_bytes": int(dev_bytes), "setup_seconds": round(setup_s, 1),
                 "l2_flush": "inputs larger than L2 (weights + state >> 126 MB per stage)",

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 N_PER_RANK, ORDER, KIND, STEPS, CFL = 6, 3, "smooth", 3, 0.4
+N_SFC = 8    # cubes per direction of the global mesh of the SFC-partition test
 N_AVARS = 2  # advected scalars ride along: their halo rows travel in the same NCCL group
 
 
@@ -23,7 +24,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, partition="lattice"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch
@@ -35,7 +36,10 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        run = zd.make_weak_scaling_case(rank, world, n=N_PER_RANK, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
+        if partition == "sfc":  # one global mesh, contiguous chunks of the Hilbert curve (the reference's shipped path)
+            run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
+        else:
+            run = zd.make_weak_scaling_case(rank, world, n=N_PER_RANK, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
         sub, case, ctx = run.sub, run.case, run.ctx
         n = sub.n_local
         rk = z.CudaRungeKutta(ctx, case.method)
@@ -115,3 +119,42 @@ def test_two_gpu_run_matches_single_domain_oracle(tmp_path):
         assert err_a.max() < 1e-11, (r, err_a)
         # ncclMin of the local CFL steps == the global CFL step
         assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)
+
+
+def test_two_gpu_sfc_partition_matches_single_domain_oracle(tmp_path):
+    """The same check for the reference's shipped partition: the Hilbert-ordered global mesh cut into two contiguous
+    chunks of the curve (ragged partition boundary, halo rows grouped per owner)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle.binding import Oracle
+    from zisafvm_b200 import cases
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "sfc"), nprocs=world, join=True)
+
+    case = cases.with_tracers(cases.blast_3d(n=N_SFC, order=ORDER, kind=KIND), N_AVARS)
+    st = case.ensure_stencils()
+    ora = Oracle(case.grid, st, case.params)
+    ora.set_frozen_bc_av(case.u0, case.a0)
+    u_ref, a_ref = case.u0.copy(), case.a0.copy()
+    dt = ora.cfl_dt(u_ref, CFL)
+    dts = [dt]
+    for _ in range(STEPS):
+        u_ref, a_ref = ora.rk_step_av(case.method, u_ref, a_ref, dt)
+        dt = ora.cfl_dt(u_ref, CFL)
+        dts.append(dt)
+    scale = np.abs(u_ref).max(axis=0)
+    seen = np.zeros(case.grid.n_cells, dtype=bool)
+    for r in range(world):
+        u = np.load(tmp_path / f"u_{r}.npy")
+        a = np.load(tmp_path / f"a_{r}.npy")
+        gid = np.load(tmp_path / f"gid_{r}.npy")
+        seen[gid] = True
+        assert (np.abs(u - u_ref[gid]).max(axis=0) / scale).max() < 1e-11, r
+        assert (np.abs(a - a_ref[gid]).max(axis=0) / np.abs(a_ref).max(axis=0)).max() < 1e-11, r
+        assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)
+    assert seen.all()

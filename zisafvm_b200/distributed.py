@@ -325,3 +325,28 @@ def make_weak_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, kind
     ctx = CudaContext(sub.grid, sub.stencils, case.params, device=device)
     connect(sub, ctx, group)
     return RankRun(sub, case, ctx, int(sub.counted.sum()))
+
+
+def make_strong_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, kind: str = "blast", device: int = 0,
+                             group=None, n_avars: int = 0) -> RankRun:
+    """BASELINE config 5, strong scaling: ONE global ``n^3``-cube mesh (the single-GPU workload), Hilbert-ordered and cut
+    into ``n_ranks`` contiguous chunks of the space-filling curve -- the reference's shipped partition path
+    (``compute_partitioned_grid_by_sfc``, src/zisa/grid/domain_decomposition.cpp:577-609) -- each rank extracting its
+    sub-grid, halo and stencils from the global mesh (``extract_subgrid`` / ``extract_stencils``, :300-326,412-447)."""
+    from . import cases
+    from .solver import CudaContext
+
+    g_case = cases.blast_3d(n=n, order=order, kind=kind)
+    if n_avars > 0:
+        cases.with_tracers(g_case, n_avars)
+    g = g_case.grid
+    n_cells = g.n_cells
+    part = partition_by_sfc(n_cells, n_ranks)
+    sub = extract_subdomain(g.n_dims, g.array("vertices").copy(), g.array("vertex_indices").copy(), part, np.arange(n_cells),
+                            rank, n_ranks, g.qr, g_case.params.weno.stencil_family_params, physical_ghost=g.is_ghost.copy())
+    exchange_requests(sub, group)
+    case = cases.Case(g_case.name, sub.grid, g_case.params, g_case.u0[sub.global_index].copy(), g_case.method, g_case.cfl,
+                      stencils=sub.stencils, a0=None if g_case.a0 is None else g_case.a0[sub.global_index].copy())
+    ctx = CudaContext(sub.grid, sub.stencils, case.params, device=device)
+    connect(sub, ctx, group)
+    return RankRun(sub, case, ctx, int(sub.counted.sum()))
