@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round-1 closing run: tests, smoke, bench line, well-balanced bench lines (through gpurun, repository root).
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_main.json 2> gpurun_out/bench_main.err
+python bench.py --kind atmosphere --order 4 --n 56 --steps 5 --warmup 3 --cpu-n 12 > gpurun_out/bench_c4_o4.json 2> gpurun_out/bench_c4_o4.err
+python bench.py --kind atmosphere --order 3 --n 64 --steps 5 --warmup 3 --cpu-n 16 > gpurun_out/bench_atm_o3.json 2> gpurun_out/bench_atm_o3.err
+python bench.py --kind polytrope2d --order 3 --n 600 --steps 5 --warmup 3 --cpu-n 20 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
+python bench.py --kind vortex2d --order 3 --n 158 --steps 20 --warmup 5 --cpu-n 20 > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err
+for f in main c4_o4 atm_o3 c2 c1; do python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/bench_$f.json").read().strip().splitlines()[-1])
+    print("$f", "%.4g" % d["value"], {k: (round(v, 3) if v else v) for k, v in d["roofline"]["kernel_ms"].items()}, "K1 frac %.3f stage frac %.3f" % (d["roofline"]["frac"], d["roofline"]["stage"]["frac"]), "e2e %.4g" % d["e2e"]["value"], "cpu %.4g" % (d["cpu_baseline"] or {"value": 0})["value"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+except Exception as e:
+    print("$f failed", e); print(open("gpurun_out/bench_$f.err").read()[-800:])
+PY
+done
