@@ -38,6 +38,10 @@ def test_params_struct_layout_matches_header():
     assert p.recon_mode == 0 and list(p.linear_weights)[:2] == [100.0, 1.0]
     assert p.epsilon == 1e-10 and p.exponent == 4.0 and p.gamma == 1.4 and p.steps_per_recompute == 1
     assert p.keep_polynomials == 0 and p.flux == 0 and p.scaling == 1
+    # the fields behind flux_bc (appended later): defaults are "off"
+    assert p.flux_bc == 0 and p.n_avars == 0 and p.heating_rate == 0.0 and p.heating_r0 == 0.0 and p.heating_r1 == 0.0
+    p.n_avars, p.heating_r1 = 3, 0.75  # and they are the last fields: sizeof agrees with the header's layout
+    assert C.sizeof(_capi.ZfvmParams) == _capi.ZfvmParams.heating_r1.offset + 8
 
 
 def test_no_cpu_fallback_without_a_device():
