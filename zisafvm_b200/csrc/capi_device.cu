@@ -224,6 +224,7 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
     ctx->launches += 1;
   }
   if (ctx->sc.well_balanced) ctx->launches += (ctx->n_ranks > 1 && ctx->nccl_comm) ? 4 : 2;  // E1 + E2 per K1 launch
+  else if (ctx->sc.has_gravity && ctx->plan.rec2) ctx->launches += (ctx->n_ranks > 1 && ctx->nccl_comm) ? 2 : 1;  // S1
   prof_mark(ctx, 0);
   if (ctx->n_avars > 0) {
     // advected scalars, T1: scalar reconstruction + traces (after the halo rows have arrived, before the face kernel,
@@ -420,7 +421,12 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     {
       const char *e_recon = std::getenv("ZFVM_RECON");
       const bool other = e_recon && (e_recon[0] == 'v' || e_recon[0] == 's');
-      use_tile = !other && !sc.well_balanced && !sc.has_gravity && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
+      // (gravity / heating without well-balancing: the tile kernel stores the polynomial, source_kernel evaluates the
+      // cell-local source terms from it; ZFVM_SOURCE=v1 keeps those runs on the thread-per-cell kernel)
+      const char *e_src = std::getenv("ZFVM_SOURCE");
+      const bool source_v1 = e_src && e_src[0] == 'v';
+      use_tile = !other && !sc.well_balanced && !(sc.has_gravity && source_v1) && ns >= 2 &&
+                 recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
     }
     if (use_tile) {
       // distinct cells read by a tile's stencils
@@ -806,7 +812,7 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     }
     P.eq_fail = ctx->eq_fail_dev;
     P.n_poly_coef = D;
-    if (params->keep_polynomials) {
+    if (params->keep_polynomials || (P.rec2 != nullptr && sc.has_gravity)) {  // diagnostics, or the hand-over to source_kernel
       if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
         zfvm_destroy(ctx);
         return 1;

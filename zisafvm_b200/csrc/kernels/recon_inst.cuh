@@ -6,6 +6,7 @@
 #include "recon.cuh"
 #include "recon_stream.cuh"
 #include "recon_tile.cuh"
+#include "source.cuh"
 
 #include <cstdlib>
 
@@ -86,6 +87,11 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
       } else {
         if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream);
         if (sc.q_f == 4) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 4>(args, sc, n_tiles, stream);
+      }
+      // cell-local source terms (gravity without well-balancing, heating) from the polynomial the tile kernel stored
+      if (rc == 0 && sc.has_gravity && !sc.well_balanced) {
+        if (plan.poly == nullptr) return 1;
+        source_kernel<ND, DEG_HI, false, 0><<<(unsigned)((n_tiles + 3) / 4), 128, 0, stream>>>(args, sc);
       }
       return rc;
     }
