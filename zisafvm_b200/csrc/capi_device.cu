@@ -223,8 +223,11 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     ctx->launches += 1;
   }
-  if (ctx->sc.well_balanced) ctx->launches += (ctx->n_ranks > 1 && ctx->nccl_comm) ? 4 : 2;  // E1 + E2 per K1 launch
-  else if (ctx->sc.has_gravity && ctx->plan.rec2) ctx->launches += (ctx->n_ranks > 1 && ctx->nccl_comm) ? 2 : 1;  // S1
+  {
+    const int k1_launches = (ctx->n_ranks > 1 && ctx->nccl_comm) ? 2 : 1;
+    if (ctx->sc.well_balanced) ctx->launches += k1_launches * (ctx->plan.rec2 ? 4 : 2);  // E1, E2 (+ E3, S1 with tile records)
+    else if (ctx->sc.has_gravity && ctx->plan.rec2) ctx->launches += k1_launches;        // S1
+  }
   prof_mark(ctx, 0);
   if (ctx->n_avars > 0) {
     // advected scalars, T1: scalar reconstruction + traces (after the halo rows have arrived, before the face kernel,
@@ -425,8 +428,7 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
       // cell-local source terms from it; ZFVM_SOURCE=v1 keeps those runs on the thread-per-cell kernel)
       const char *e_src = std::getenv("ZFVM_SOURCE");
       const bool source_v1 = e_src && e_src[0] == 'v';
-      use_tile = !other && !sc.well_balanced && !(sc.has_gravity && source_v1) && ns >= 2 &&
-                 recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
+      use_tile = !other && !(sc.has_gravity && source_v1) && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
     }
     if (use_tile) {
       // distinct cells read by a tile's stencils
@@ -470,6 +472,9 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
         return 1;
       }
       P.rec2 = d_rec;
+      P.rec2_off_list = L.off_list;
+      P.rec2_off_lidx = L.off_lidx;
+      P.rec2_lidx_elem = L.lidx_elem;
       std::vector<int> lo_row0((size_t)ns, 0), lo_w0((size_t)ns, 0);  // row / byte offsets of the one-sided stencils
       {
         int r = 0, b = 0;
@@ -812,7 +817,13 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     }
     P.eq_fail = ctx->eq_fail_dev;
     P.n_poly_coef = D;
-    if (params->keep_polynomials || (P.rec2 != nullptr && sc.has_gravity)) {  // diagnostics, or the hand-over to source_kernel
+    if (P.rec2 != nullptr && sc.has_gravity) {  // the tile kernel hands the polynomial to source_kernel
+      if (dev_alloc(ctx, &P.poly_tile, T * (std::int64_t)(D + 1) * NVARS * TILE, true)) {
+        zfvm_destroy(ctx);
+        return 1;
+      }
+    }
+    if (params->keep_polynomials) {
       if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
         zfvm_destroy(ctx);
         return 1;
@@ -860,8 +871,9 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
         P.eq_row0[k] = r;
         r += sc.rows_max[k];
       }
-      P.eq_rows = r;
-      if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)r * 2 * TILE, true)) {
+      P.eq_rows = P.rec2 ? r + 1 : r;  // tile records: rows in lidx order plus one row for the cell itself
+      if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)P.eq_rows * 2 * TILE, true) ||
+          (P.rec2 && dev_alloc(ctx, &P.eq_bg, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * 2, true))) {
         zfvm_destroy(ctx);
         return 1;
       }

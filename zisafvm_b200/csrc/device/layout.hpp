@@ -111,14 +111,17 @@ struct DevicePlan {
   }
   double *poly;                             // optional diagnostics [n][n_poly_coef][5]; may be null
   double *poly_scale;                       // optional [n][5]
+  double *poly_tile;                        // tile kernel -> source_kernel hand-over [T][D + 1][5][32]; may be null
   int n_poly_coef;
   int *eq_fail;                             // counter of cells whose equilibrium solve failed
   // well-balanced runs: per-cell local equilibrium (h_ref, K, phi_ref, found) and its cell averages over every
   // stencil member, written by the two equilibrium kernels (equilibrium.cuh) ahead of the reconstruction
   double *eq_par;                           // [n][4]
   double *eq_avg;                           // [T][eq_rows][2][32]: (rho_bar, E_bar) of stencil row r = row0_k + j
-  int eq_rows;                              // sum_k rows_max_k
-  int eq_row0[MAX_STENCILS];
+  int eq_rows;                              // sum_k rows_max_k (+ 1 with tile records: the last row is the cell itself)
+  int eq_row0[MAX_STENCILS];                // older records: first row of stencil k (tile records: lidx row order)
+  double *eq_bg;                            // tile records: [E_int][2][q_f][2] equilibrium (rho, E) at the face Gauss points
+  int rec2_off_list, rec2_off_lidx, rec2_lidx_elem;  // where a tile record keeps its row list and local indices
   // advected scalars (tracers.cu): traces and face fluxes of the n_avars scalars; null when n_avars == 0
   int n_avars;
   double *qtrace;                           // [E_int][2][q_f][n_avars]

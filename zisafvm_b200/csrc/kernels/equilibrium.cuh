@@ -256,4 +256,67 @@ __global__ void __launch_bounds__(256) eq_member_kernel(const DevicePlan P, cons
   out[TILE] = Eb;
 }
 
+
+/// E2 for tile records (recon_tile.cuh): rows in lidx order (the one-sided stencils' rows, then the central stencil's),
+/// members through the tile's row list, and one more row for the cell itself.  Padded rows of ragged stencils point
+/// at the cell itself and get the cell's own average, which makes their rhs vanish like in the plain scheme.
+template <int POWN>
+__global__ void __launch_bounds__(256) eq_member_tile_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                             const std::int32_t *__restrict__ tile_list,
+                                                             std::int64_t n_tiles) {
+  const int lane = threadIdx.x & 31;
+  const std::int64_t w = (std::int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_tiles * P.eq_rows) return;
+  const std::int64_t tw = w / P.eq_rows;
+  const int row = (int)(w - tw * P.eq_rows);
+  const std::int64_t tile = tile_list ? (std::int64_t)tile_list[tw] : tw;
+  const std::int64_t cell = tile * TILE + lane;
+  const std::int64_t ci = cell < P.n_cells ? cell : P.n_cells - 1;
+  const char *rec = P.rec2 + tile * P.rec2_bytes;
+  std::int64_t g = ci;
+  if (row < P.eq_rows - 1) {
+    const char *lrow = rec + P.rec2_off_lidx + (std::size_t)row * TILE * P.rec2_lidx_elem;
+    const int li = (P.rec2_lidx_elem == 1) ? (int)reinterpret_cast<const std::uint8_t *>(lrow)[lane]
+                                           : (int)reinterpret_cast<const std::uint16_t *>(lrow)[lane];
+    g = reinterpret_cast<const std::int32_t *>(rec + P.rec2_off_list)[li];
+  }
+  const double *par = P.eq_par + ci * 4;
+  LocalEq eq{par[0], par[1], par[2], par[3] != 0.0};
+  eq.prepare(sc.gamma);
+  double rb, Eb;
+  eq_cell_average<POWN>(eq, P.phi_cqp + g * sc.q_c, sc, rb, Eb);
+  double *out = P.eq_avg + ((tile * P.eq_rows + row) * 2) * TILE + lane;
+  out[0] = rb;
+  out[TILE] = Eb;
+}
+
+/// E3 (tile records).  One thread per (cell, face): the cell's equilibrium (rho, E) at the face's Gauss points
+/// (LocalReconstruction::background, local_reconstruction.hpp:157-163; the FewPointsCache entries of the face points)
+/// -> eq_bg[e][side][q][2], laid out like the trace array; the face-flux kernel adds it to the traces it reads.
+template <int POWN>
+__global__ void __launch_bounds__(256) eq_face_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                      const std::int32_t *__restrict__ tile_list, std::int64_t n_tiles) {
+  const int F = sc.n_dims + 1;
+  const int lane = threadIdx.x & 31;
+  const std::int64_t w = (std::int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_tiles * F) return;
+  const std::int64_t tw = w / F;
+  const int k = (int)(w - tw * F);
+  const std::int64_t tile = tile_list ? (std::int64_t)tile_list[tw] : tw;
+  const std::int64_t cell = tile * TILE + lane;
+  const std::int64_t ci = cell < P.n_cells ? cell : P.n_cells - 1;
+  const std::uint32_t fref = cell < P.n_cells ? P.face_ref[(tile * F + k) * TILE + lane] : 0u;
+  if (!(fref & FREF_TRACE)) return;
+  const std::int64_t e = fref & FREF_EDGE_MASK;
+  const int side = (fref & FREF_SIDE) ? 1 : 0;
+  const double *par = P.eq_par + ci * 4;
+  LocalEq eq{par[0], par[1], par[2], par[3] != 0.0};
+  eq.prepare(sc.gamma);
+  for (int q = 0; q < sc.q_f; ++q) {
+    double r, E, p;
+    eq.template at<POWN>(P.phi_fqp[e * sc.q_f + q], sc, r, E, p);
+    *reinterpret_cast<double2 *>(P.eq_bg + ((e * 2 + side) * sc.q_f + q) * 2) = make_double2(r, E);
+  }
+}
+
 }  // namespace zfvm

@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __g
 // those of the face's HLLC evaluation on the same rotated traces (HLLCBatten::flux returns them, hllc.hpp:175), every
 // scalar goes through HLLCBatten::tracer_flux (hllc.hpp:178-197) -- Rusanov (not in the reference): the same local
 // Lax-Friedrichs form as the flux itself -- and the quadrature sums go to qflux[e][n_avars].
-template <int FLUX, bool TRACERS>
+// With WBBG (well-balanced runs on the tile kernel) the staged traces are those of the perturbation: the equilibrium
+// background (rho, E) of either side at the Gauss point (eq_bg, written by eq_face_kernel) is added first.
+template <int FLUX, bool TRACERS, bool WBBG>
 __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces,
                                                   int pitch) {
@@ -274,6 +276,14 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
       for (int v = 0; v < NVARS; ++v) {
         uL[v] = trL[q * NVARS + v];
         uR[v] = trR[q * NVARS + v];
+      }
+      if constexpr (WBBG) {
+        const double2 bL = *reinterpret_cast<const double2 *>(P.eq_bg + ((e * 2 + 0) * sc.q_f + q) * 2);
+        const double2 bR = *reinterpret_cast<const double2 *>(P.eq_bg + ((e * 2 + 1) * sc.q_f + q) * 2);
+        uL[0] = bL.x + uL[0];
+        uL[4] = bL.y + uL[4];
+        uR[0] = bR.x + uR[0];
+        uR[4] = bR.y + uR[4];
       }
       auto rot = [&](double u[NVARS]) {
         const double un = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
@@ -643,17 +653,25 @@ static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std:
     const char *e = std::getenv("ZFVM_FLUX");
     return e != nullptr && e[0] == 'p';
   }();
-  if (!per_point || P.n_avars > 0) {  // one thread per face (the only variant that carries advected scalars)
+  if (!per_point || P.n_avars > 0 || P.eq_bg != nullptr) {  // one thread per face (the only variant with scalars / WB background)
     const int block = 64, wpc = block / 32;
     // doubles per staged face row: even (16-byte cp.async) with an odd number of 16-byte units, so that the 64-bit
     // reads of 32 consecutive rows spread over all banks (q_f = 3 would otherwise give a pitch of 32 doubles)
     const int pitch = 2 * ((sc.q_f * NVARS + 1) | 1);
     const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
     const unsigned grid = (unsigned)((n_faces + block - 1) / block);
-    if (P.n_avars > 0)
-      flux_face_kernel<FLUX, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
-    else
-      flux_face_kernel<FLUX, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    const bool bg = P.eq_bg != nullptr;
+    if (P.n_avars > 0) {
+      if (bg)
+        flux_face_kernel<FLUX, true, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+      else
+        flux_face_kernel<FLUX, true, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    } else {
+      if (bg)
+        flux_face_kernel<FLUX, false, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+      else
+        flux_face_kernel<FLUX, false, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+    }
     return;
   }
   auto go = [&](auto kern, int lanes_per_face) {

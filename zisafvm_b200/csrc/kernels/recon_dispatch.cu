@@ -32,11 +32,20 @@ void launch_eq_member(const DevicePlan &plan, const SchemeConst &sc, const std::
                       unsigned grid, cudaStream_t stream) {
   eq_member_kernel<POWN><<<grid, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
 }
+template <int POWN>
+void launch_eq_tile(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
+                    cudaStream_t stream) {
+  const unsigned g2 = (unsigned)((n_tiles * plan.eq_rows + 7) / 8);
+  const unsigned g3 = (unsigned)((n_tiles * (sc.n_dims + 1) + 7) / 8);
+  eq_member_tile_kernel<POWN><<<g2, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
+  eq_face_kernel<POWN><<<g3, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
+}
 #define ZFVM_EQ_INST(POWN)                                                                                          \
   template void launch_eq_solve<POWN>(const DevicePlan &, const SchemeConst &, const double *, const std::int32_t *,    \
                                       std::int64_t, unsigned, cudaStream_t);                                            \
   template void launch_eq_member<POWN>(const DevicePlan &, const SchemeConst &, const std::int32_t *, std::int64_t,     \
-                                       unsigned, cudaStream_t);
+                                       unsigned, cudaStream_t);                                                         \
+  template void launch_eq_tile<POWN>(const DevicePlan &, const SchemeConst &, const std::int32_t *, std::int64_t, cudaStream_t);
 ZFVM_EQ_INST(0)
 ZFVM_EQ_INST(2)
 ZFVM_EQ_INST(3)

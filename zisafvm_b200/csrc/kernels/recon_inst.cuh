@@ -16,7 +16,7 @@ namespace zfvm {
 constexpr bool tile_kernel_qf(int nd, int q_f) { return nd == 2 ? (q_f == 2 || q_f == 3) : (q_f == 3 || q_f == 4); }
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
-int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_tiles, cudaStream_t stream) {
+int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_tiles, cudaStream_t stream, bool wb = false) {
   using T = TileTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>;
   int dev = 0, optin = 0, n_sm = 0;
   cudaGetDevice(&dev);
@@ -43,7 +43,12 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     kern<<<grid, 32 * wpc, (size_t)smem_bytes, stream>>>(args, sc, cfg);
   };
-  if (cfg.prof != nullptr) {  // ZFVM_TILE_PROF=1: instantiation with the phase timers
+  if (wb) {  // well-balanced: equilibrium tables in, background added to the traces (no phase-timer instantiation)
+    if (args.plan.rec2_cap <= 256)
+      go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint8_t, false, true>);
+    else
+      go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint16_t, false, true>);
+  } else if (cfg.prof != nullptr) {  // ZFVM_TILE_PROF=1: instantiation with the phase timers
     if (args.plan.rec2_cap <= 256)
       go(recon_tile_kernel<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF, std::uint8_t, true>);
     else
@@ -68,6 +73,11 @@ template <int POWN>
 void launch_eq_member(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
                       unsigned grid, cudaStream_t stream);
 
+/// E2 + E3 for tile records (members through the tile's row list; equilibrium at the face Gauss points).
+template <int POWN>
+void launch_eq_tile(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
+                    cudaStream_t stream);
+
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO>
 int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const double *state,
                           const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream) {
@@ -81,17 +91,37 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
     // tile kernel (recon_tile.cuh): used whenever the context carries tile records (zfvm_create decides)
     if (plan.rec2 != nullptr) {
       int rc = 1;
-      if constexpr (ND == 2) {
-        if (sc.q_f == 2) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 2>(args, sc, n_tiles, stream);
-        if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream);
-      } else {
-        if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream);
-        if (sc.q_f == 4) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 4>(args, sc, n_tiles, stream);
+      const bool wb = sc.well_balanced != 0;
+      if (wb) {  // E1 equilibrium solve, E2 its averages over the stencil members, E3 its values at the face points
+        const unsigned g1 = (unsigned)((n_tiles * TILE + 255) / 256);
+        switch (sc.eos_pow_n) {
+          case 2: launch_eq_solve<2>(plan, sc, state, tile_list, n_tiles, g1, stream); launch_eq_tile<2>(plan, sc, tile_list, n_tiles, stream); break;
+          case 3: launch_eq_solve<3>(plan, sc, state, tile_list, n_tiles, g1, stream); launch_eq_tile<3>(plan, sc, tile_list, n_tiles, stream); break;
+          case 5: launch_eq_solve<5>(plan, sc, state, tile_list, n_tiles, g1, stream); launch_eq_tile<5>(plan, sc, tile_list, n_tiles, stream); break;
+          default: launch_eq_solve<0>(plan, sc, state, tile_list, n_tiles, g1, stream); launch_eq_tile<0>(plan, sc, tile_list, n_tiles, stream); break;
+        }
       }
-      // cell-local source terms (gravity without well-balancing, heating) from the polynomial the tile kernel stored
-      if (rc == 0 && sc.has_gravity && !sc.well_balanced) {
-        if (plan.poly == nullptr) return 1;
-        source_kernel<ND, DEG_HI, false, 0><<<(unsigned)((n_tiles + 3) / 4), 128, 0, stream>>>(args, sc);
+      if constexpr (ND == 2) {
+        if (sc.q_f == 2) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 2>(args, sc, n_tiles, stream, wb);
+        if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream, wb);
+      } else {
+        if (sc.q_f == 3) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 3>(args, sc, n_tiles, stream, wb);
+        if (sc.q_f == 4) rc = launch_tile<ND, DEG_HI, DEG_LO, NS, RM0, RLO, 4>(args, sc, n_tiles, stream, wb);
+      }
+      // cell-local source terms (gravity, heating) from the polynomial the tile kernel stored
+      if (rc == 0 && sc.has_gravity) {
+        if (plan.poly_tile == nullptr) return 1;
+        const unsigned gs = (unsigned)((n_tiles + 3) / 4);
+        if (!wb) {
+          source_kernel<ND, DEG_HI, false, 0><<<gs, 128, 0, stream>>>(args, sc);
+        } else {
+          switch (sc.eos_pow_n) {
+            case 2: source_kernel<ND, DEG_HI, true, 2><<<gs, 128, 0, stream>>>(args, sc); break;
+            case 3: source_kernel<ND, DEG_HI, true, 3><<<gs, 128, 0, stream>>>(args, sc); break;
+            case 5: source_kernel<ND, DEG_HI, true, 5><<<gs, 128, 0, stream>>>(args, sc); break;
+            default: source_kernel<ND, DEG_HI, true, 0><<<gs, 128, 0, stream>>>(args, sc); break;
+          }
+        }
       }
       return rc;
     }

@@ -115,7 +115,12 @@ ZFVM_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "
 ZFVM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 }  // namespace ptx
 
-template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF, typename LIDX, bool PROF>
+// WB (well-balanced runs): the equilibrium kernels (equilibrium.cuh: E1, E2, E3) have written, per tile, the cell
+// averages of each cell's local equilibrium over its stencil members in lidx row order plus one row for the cell
+// itself (eq_avg): the rhs subtracts them (local_reconstruction.hpp:109-116).  The traces written here are those of
+// the perturbation; the equilibrium background at the face Gauss points (local_reconstruction.hpp:149-163) is added by
+// the face-flux kernel from E3's table (eq_bg).
+template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF, typename LIDX, bool PROF, bool WB = false>
 __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     recon_tile_kernel(const __grid_constant__ ReconArgs args, const __grid_constant__ SchemeConst sc,
                       const __grid_constant__ TileCfg cfg) {
@@ -270,6 +275,14 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     __syncwarp();  // the table of tile m is complete and visible to the whole warp
     mark(TP_TABLE_WAIT);
     const std::int64_t tile = tile_of(m);
+    if constexpr (WB) {
+      // the next tile's equilibrium rows (one contiguous block E2 has just written) are pulled towards L2 a whole
+      // tile ahead: load_rhs reads them with plain loads one stencil ahead, which hides an L2 hit but not HBM
+      const bool nxt = has_tile(m + 1);
+      const std::int64_t tn = nxt ? tile_of(m + 1) : tile;
+      const std::uint32_t bytes = (std::uint32_t)(P.eq_rows * 2 * TILE * 8);
+      ptx::bulk_prefetch_l2_if(nxt && lane == 0, P.eq_avg + tn * P.eq_rows * 2 * TILE, bytes);
+    }
     const std::int64_t cell = tile * TILE + lane;
     const bool active = cell < P.n_cells;
     const int kh_m = (int)((meta >> 56) & 0xF);
@@ -297,14 +310,28 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
       inv_scale[0] = 1.0 / scale[0];
       inv_scale[1] = inv_scale[2] = inv_scale[3] = 1.0 / scale[1];
       inv_scale[4] = 1.0 / scale[4];
+      if constexpr (WB) {  // the cell's own equilibrium average: row ROWS of the tile's eq_avg block
+        const double *e0 = P.eq_avg + ((tile * P.eq_rows + T::ROWS) * 2) * TILE + lane;
+        u0[0] -= e0[0];
+        u0[4] -= e0[TILE];
+      }
 #pragma unroll
       for (int v = 0; v < NVARS; ++v) q0s[v] = u0[v] * inv_scale[v];
     }
+    const double *eq_rows_tile = WB ? P.eq_avg + (tile * P.eq_rows * 2) * TILE + lane : nullptr;
     // rhs of stencil row `row` (rows numbered as in lidx): u_local(j) - u_local(0), local_reconstruction.hpp:109-116
     auto load_rhs = [&](int row, double rhs[NVARS]) {
       const double *t = table + (int)lidx[row * TILE] * NVARS;
+      if constexpr (WB) {
+        const double *ea = eq_rows_tile + row * 2 * TILE;
+        rhs[0] = fma(t[0] - ea[0], inv_scale[0], -q0s[0]);
+        rhs[4] = fma(t[4] - ea[TILE], inv_scale[4], -q0s[4]);
 #pragma unroll
-      for (int v = 0; v < NVARS; ++v) rhs[v] = fma(t[v], inv_scale[v], -q0s[v]);
+        for (int v = 1; v < 4; ++v) rhs[v] = fma(t[v], inv_scale[v], -q0s[v]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) rhs[v] = fma(t[v], inv_scale[v], -q0s[v]);
+      }
     };
     auto nonlinear_weight = [&](double is_max, double g) {  // alpha = g / (eps + IS^p), hybrid_weno.cpp:117-119
       double is_pow;
@@ -564,6 +591,15 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
 #pragma unroll
       for (int v = 0; v < NVARS; ++v) P.poly_scale[cell * NVARS + v] = scale[v];
     }
+    if (P.poly_tile != nullptr) {  // hand-over to source_kernel: [tile][D + 1][5][32], coefficients then scales
+      double *pt = P.poly_tile + tile * ((D + 1) * NVARS * TILE) + lane;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) pt[(i * NVARS + v) * TILE] = coef_at(i, v);
+#pragma unroll
+      for (int v = 0; v < NVARS; ++v) pt[(D * NVARS + v) * TILE] = scale[v];
+    }
     // fold the characteristic scale into the coefficients: delta(x) = scale * p(x)
 #pragma unroll
     for (int i = 0; i < D; ++i)
@@ -658,7 +694,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
             double s = c0[v];
 #pragma unroll
             for (int i = 1; i < D; ++i) s = fma(coef_at(i, v), mono[i], s);
-            stage[lane * T::STAGE_PITCH + qq * NVARS + v] = s;
+            stage[lane * T::STAGE_PITCH + qq * NVARS + v] = s;  // WB: the perturbation; K2 adds the background
           }
         }
         __syncwarp();

@@ -6,7 +6,8 @@
 //   Heating                               model/heating.hpp:30-44                      dE/dt += avg_cell rho(x) rate(x)
 //
 // One warp owns a tile, one thread a cell; the same arithmetic as the source part of recon.cuh, with the polynomial
-// read back (D x 5 coefficients in the scaled basis + the 5 scales) instead of being live in registers.
+// read back (D x 5 coefficients in the scaled basis + the 5 scales, tile-interleaved: DevicePlan::poly_tile) instead of
+// being live in registers.
 #pragma once
 #include "common.cuh"
 #include "equilibrium.cuh"
@@ -31,13 +32,14 @@ __global__ void __launch_bounds__(128) source_kernel(const __grid_constant__ Rec
   // hybridised polynomial, scale folded in: delta(x) = scale * p(x)
   double coef[D][NVARS];
   {
+    const double *pt = P.poly_tile + tile * ((D + 1) * NVARS * TILE) + lane;  // [tile][D + 1][5][32]
     double scale[NVARS];
 #pragma unroll
-    for (int v = 0; v < NVARS; ++v) scale[v] = P.poly_scale[ci * NVARS + v];
+    for (int v = 0; v < NVARS; ++v) scale[v] = ld_stream(pt + (D * NVARS + v) * TILE);
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
-      for (int v = 0; v < NVARS; ++v) coef[i][v] = P.poly[(ci * P.n_poly_coef + i) * NVARS + v] * scale[v];
+      for (int v = 0; v < NVARS; ++v) coef[i][v] = ld_stream(pt + (i * NVARS + v) * TILE) * scale[v];
   }
   double vt[F][3];
 #pragma unroll
