@@ -36,7 +36,9 @@ def _worker(rank, world, port, out_dir, partition="lattice"):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        if partition == "sfc":  # one global mesh, contiguous chunks of the Hilbert curve (the reference's shipped path)
+        if partition == "sfc_wb":  # the same partition for a well-balanced run with gravity (equilibrium kernels per tile list)
+            run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind="atmosphere", device=rank, n_avars=N_AVARS)
+        elif partition == "sfc":  # one global mesh, contiguous chunks of the Hilbert curve (the reference's shipped path)
             run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
         else:
             run = zd.make_weak_scaling_case(rank, world, n=N_PER_RANK, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
@@ -158,3 +160,42 @@ def test_two_gpu_sfc_partition_matches_single_domain_oracle(tmp_path):
         assert (np.abs(a - a_ref[gid]).max(axis=0) / np.abs(a_ref).max(axis=0)).max() < 1e-11, r
         assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)
     assert seen.all()
+
+
+def test_two_gpu_well_balanced_matches_single_domain_oracle(tmp_path):
+    """Well-balanced atmosphere with gravity on two GPUs (SFC partition): the equilibrium kernels, the tile kernel and the
+    source kernel run per tile list (interior tiles while the halo is in flight, the rest after it)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle.binding import Oracle
+    from zisafvm_b200 import cases
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "sfc_wb"), nprocs=world, join=True)
+
+    case = cases.with_tracers(cases.stellar_atmosphere_3d(n=N_SFC, order=ORDER, well_balanced=True), N_AVARS)
+    st = case.ensure_stencils()
+    ora = Oracle(case.grid, st, case.params, cases.gravity_tables(case.grid, case.params.gravity))
+    ora.set_frozen_bc_av(case.u0, case.a0)
+    u_ref, a_ref = case.u0.copy(), case.a0.copy()
+    dt = ora.cfl_dt(u_ref, CFL)
+    dts = [dt]
+    for _ in range(STEPS):
+        u_ref, a_ref = ora.rk_step_av(case.method, u_ref, a_ref, dt)
+        dt = ora.cfl_dt(u_ref, CFL)
+        dts.append(dt)
+    gamma = case.params.gamma
+    p = (gamma - 1.0) * case.u0[:, 4]
+    ra = (case.u0[:, 0] * np.sqrt(gamma * p / case.u0[:, 0])).max()   # acoustic momentum scale (the momenta are ~ 0)
+    scale = np.array([case.u0[:, 0].max(), ra, ra, ra, case.u0[:, 4].max()])
+    for r in range(world):
+        u = np.load(tmp_path / f"u_{r}.npy")
+        a = np.load(tmp_path / f"a_{r}.npy")
+        gid = np.load(tmp_path / f"gid_{r}.npy")
+        assert (np.abs(u - u_ref[gid]).max(axis=0) / scale).max() < 1e-11, r
+        assert (np.abs(a - a_ref[gid]).max(axis=0) / np.abs(a_ref).max(axis=0)).max() < 1e-11, r
+        assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)

@@ -336,7 +336,10 @@ def make_strong_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, ki
     from . import cases
     from .solver import CudaContext
 
-    g_case = cases.blast_3d(n=n, order=order, kind=kind)
+    if kind == "atmosphere":  # well-balanced stellar atmosphere (BASELINE config 4 shape): gravity tables per sub-grid
+        g_case = cases.stellar_atmosphere_3d(n=n, order=order, well_balanced=True)
+    else:
+        g_case = cases.blast_3d(n=n, order=order, kind=kind)
     if n_avars > 0:
         cases.with_tracers(g_case, n_avars)
     g = g_case.grid
