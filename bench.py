@@ -336,8 +336,10 @@ def run_b200(args):
     t_k1 = kms[0] / max(kcnt[0], 1) * 1e-3
     ach_k1 = n_counted * b_k1 / t_k1 / 1e9
     t_stage = sum(kms) / max(kcnt[0], 1) * 1e-3
-    k1_name = ("recon_tile_kernel" if case.params.gravity.kind == "none" and case.params.heating is None
-               else "recon_kernel (thread per cell: + equilibrium / gravity source)")
+    tile_capable = (nd == 2 and args.order <= 4) or (nd == 3 and args.order <= 3)
+    recon_name = "recon_tile_kernel" if tile_capable else "recon_kernel (thread per cell)"
+    k1_name = (recon_name if case.params.gravity.kind == "none" and case.params.heating is None
+               else "equilibrium kernels (well-balanced runs) + " + recon_name + (" + source_kernel" if tile_capable else ""))
     roofline = {
         "bound": "hbm", "kernel": k1_name + " (K1: stencil-weight apply + CWENO-AO + traces)",
         "achieved": ach_k1, "peak": peak, "unit": "GB/s", "frac": ach_k1 / peak,

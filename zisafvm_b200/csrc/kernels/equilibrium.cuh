@@ -290,6 +290,46 @@ __global__ void __launch_bounds__(256) eq_member_tile_kernel(const DevicePlan P,
   out[TILE] = Eb;
 }
 
+/// E2 for tile records, shared-memory form: one CTA per tile.  The potentials of the tile's distinct stencil members
+/// (the record's row list, 125-250 cells) are staged in shared memory once -- contiguous 8 q_c-byte rows -- and every
+/// (cell, row) pair then reads its member's row through the record's local index: no gathered global loads (which
+/// bound the one-warp-per-row form at 84 % L1 throughput), the FP64 pipe is what is left.
+template <int POWN>
+__global__ void __launch_bounds__(256) eq_member_tile_smem_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                                  const std::int32_t *__restrict__ tile_list,
+                                                                  std::int64_t n_tiles) {
+  extern __shared__ __align__(16) double eq_phi_s[];  // [n_list][q_c]
+  const std::int64_t tile = tile_list ? (std::int64_t)tile_list[blockIdx.x] : (std::int64_t)blockIdx.x;
+  const char *rec = P.rec2 + tile * P.rec2_bytes;
+  const int n_list = *reinterpret_cast<const int *>(rec);
+  const std::int32_t *list = reinterpret_cast<const std::int32_t *>(rec + P.rec2_off_list);
+  const int q_c = sc.q_c;
+  for (int idx = threadIdx.x; idx < n_list * q_c; idx += blockDim.x) {
+    const int row = idx / q_c;
+    eq_phi_s[idx] = P.phi_cqp[(std::int64_t)list[row] * q_c + (idx - row * q_c)];
+  }
+  __syncthreads();
+  for (int pair = threadIdx.x; pair < P.eq_rows * TILE; pair += blockDim.x) {
+    const int row = pair / TILE, lane = pair - row * TILE;
+    const std::int64_t cell = tile * TILE + lane;
+    const std::int64_t ci = cell < P.n_cells ? cell : P.n_cells - 1;
+    int li = lane;  // the last row: the cell itself (list[0..31] are the tile's own cells)
+    if (row < P.eq_rows - 1) {
+      const char *lrow = rec + P.rec2_off_lidx + (std::size_t)row * TILE * P.rec2_lidx_elem;
+      li = (P.rec2_lidx_elem == 1) ? (int)reinterpret_cast<const std::uint8_t *>(lrow)[lane]
+                                   : (int)reinterpret_cast<const std::uint16_t *>(lrow)[lane];
+    }
+    const double *par = P.eq_par + ci * 4;
+    LocalEq eq{par[0], par[1], par[2], par[3] != 0.0};
+    eq.prepare(sc.gamma);
+    double rb, Eb;
+    eq_cell_average<POWN>(eq, eq_phi_s + li * q_c, sc, rb, Eb);
+    double *out = P.eq_avg + ((tile * P.eq_rows + row) * 2) * TILE + lane;
+    out[0] = rb;
+    out[TILE] = Eb;
+  }
+}
+
 /// E3 (tile records).  One thread per (cell, face): the cell's equilibrium (rho, E) at the face's Gauss points
 /// (LocalReconstruction::background, local_reconstruction.hpp:157-163; the FewPointsCache entries of the face points)
 /// -> eq_bg[e][side][q][2], laid out like the trace array; the face-flux kernel adds it to the traces it reads.

@@ -37,7 +37,15 @@ void launch_eq_tile(const DevicePlan &plan, const SchemeConst &sc, const std::in
                     cudaStream_t stream) {
   const unsigned g2 = (unsigned)((n_tiles * plan.eq_rows + 7) / 8);
   const unsigned g3 = (unsigned)((n_tiles * (sc.n_dims + 1) + 7) / 8);
-  eq_member_tile_kernel<POWN><<<g2, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
+  const size_t smem = (size_t)plan.rec2_cap * sc.q_c * sizeof(double);  // potentials of the tile's row list
+  static const bool e2_v1 = [] {
+    const char *e = std::getenv("ZFVM_EQ_MEMBER");
+    return e != nullptr && e[0] == 'v';
+  }();
+  if (smem <= 48 * 1024 && !e2_v1)
+    eq_member_tile_smem_kernel<POWN><<<(unsigned)n_tiles, 256, smem, stream>>>(plan, sc, tile_list, n_tiles);
+  else
+    eq_member_tile_kernel<POWN><<<g2, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
   eq_face_kernel<POWN><<<g3, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
 }
 #define ZFVM_EQ_INST(POWN)                                                                                          \
