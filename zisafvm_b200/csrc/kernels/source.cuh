@@ -16,7 +16,7 @@
 namespace zfvm {
 
 template <int ND, int DEG_HI, bool WB, int POWN>
-__global__ void __launch_bounds__(128) source_kernel(const __grid_constant__ ReconArgs args,
+__global__ void __launch_bounds__(128, 3) source_kernel(const __grid_constant__ ReconArgs args,
                                                      const __grid_constant__ SchemeConst sc) {
   constexpr int F = ND + 1;
   constexpr int D = dof_of(DEG_HI, ND);
