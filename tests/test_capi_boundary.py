@@ -74,3 +74,23 @@ def test_unknown_tableau_is_rejected_like_the_reference():
     ora = ob.Oracle(case.grid, case.ensure_stencils(), case.params)
     with pytest.raises(ValueError, match="Unknown Butcher Tableau"):
         ora.rk_step("heun17", case.u0, 1e-3)
+
+
+def test_scheme_parameters_reach_the_c_struct():
+    """EulerParams.to_c(): the host mirror fills the zfvm_params fields of the rows that widen the path."""
+    from zisafvm_b200.grid import WENO_PARAMS
+
+    p = z.EulerParams(weno=WENO_PARAMS["3d_o3"], flux_bc="equilibrium", n_avars=2, heating=(0.3, 0.4, 0.8),
+                      well_balancing="isentropic", gravity=z.Gravity(kind="point_mass", params=(-1.0, 1.0))).to_c()
+    assert p.flux_bc == 2 and p.n_avars == 2 and p.well_balanced == 1 and p.gravity_kind == 2
+    assert (p.heating_rate, p.heating_r0, p.heating_r1) == (0.3, 0.4, 0.8)
+    q = z.EulerParams(weno=WENO_PARAMS["2d_o3"]).to_c()
+    assert q.flux_bc == 0 and q.n_avars == 0 and q.heating_rate == 0.0
+
+
+def test_all_variables_carries_avars():
+    a = z.AllVariables(4, n_avars=2)
+    assert a.cvars.shape == (4, 5) and a.avars.shape == (4, 2)
+    b = z.AllVariables(3, np.ones((3, 5)), np.arange(3.0))
+    assert b.avars.shape == (3, 1) and b.avars.flags.c_contiguous
+    assert z.AllVariables(3).avars.shape == (3, 0)
