@@ -38,6 +38,8 @@ struct Selector {
 
   bool cell_inside(const Region &region, i32 cand) const {
     if (region.kind == 0) return true;
+    // any quadrature point or the centre inside (stencil.cpp:192-215): the tests are independent, the cheap one first
+    if (region.is_inside(g.center(cand))) return true;
     const int F = g.max_neighbours;
     Vec3 v[4];
     for (int k = 0; k < F; ++k) v[k] = g.vertex(cand, k);
@@ -47,7 +49,7 @@ struct Selector {
       if (F == 4) x = x + v[3] * lam[3];
       if (region.is_inside(x)) return true;
     }
-    return region.is_inside(g.center(cand));
+    return false;
   }
 
   void candidates(std::vector<i32> &cands, i32 i_center, int n_points, const Region &region) const {
@@ -70,8 +72,22 @@ struct Selector {
   void region_stencil(std::vector<i32> &cands, i32 i_center, int n_points, const Region &region) const {
     candidates(cands, i_center, n_points, region);
     Vec3 xc = g.center(i_center);
-    auto closer = [&](i32 a, i32 b) { return norm(g.center(a) - xc) < norm(g.center(b) - xc); };
-    std::sort(cands.begin(), cands.end(), closer);
+    // sorted by distance of the centres (stencil.cpp:240-250); the distances are formed once per candidate, the
+    // comparisons (and so the permutation std::sort produces) are the ones of the comparator on the cell indices
+    struct Keyed {
+      double d;
+      i32 c;
+    };
+    Keyed keyed[512];
+    const size_t m = cands.size();
+    if (m > 512) {
+      auto closer = [&](i32 a, i32 b) { return norm(g.center(a) - xc) < norm(g.center(b) - xc); };
+      std::sort(cands.begin(), cands.end(), closer);
+    } else {
+      for (size_t a = 0; a < m; ++a) keyed[a] = Keyed{norm(g.center(cands[a]) - xc), cands[a]};
+      std::sort(keyed, keyed + m, [](const Keyed &a, const Keyed &b) { return a.d < b.d; });
+      for (size_t a = 0; a < m; ++a) cands[a] = keyed[a].c;
+    }
     if ((int)cands.size() > n_points) cands.resize((size_t)n_points);
   }
 
