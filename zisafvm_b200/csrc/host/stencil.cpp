@@ -57,6 +57,10 @@ struct Selector {
     const size_t max_points = (size_t)5 * n_points;
     cands.clear();
     cands.push_back(i_center);
+    // cells already found outside the region are met again as neighbours of later candidates: the (pure) membership
+    // test is not repeated for them
+    i32 rejected[256];
+    int n_rejected = 0;
     for (size_t p = 0; p < max_points; ++p) {
       if (p >= cands.size()) break;
       i32 j = cands[p];
@@ -64,7 +68,11 @@ struct Selector {
         i32 cand = g.neighbours[(i64)j * F + k];
         if (cand == INVALID) continue;
         if (std::find(cands.begin(), cands.end(), cand) != cands.end()) continue;
-        if (cell_inside(region, cand)) cands.push_back(cand);
+        if (std::find(rejected, rejected + n_rejected, cand) != rejected + n_rejected) continue;
+        if (cell_inside(region, cand))
+          cands.push_back(cand);
+        else if (n_rejected < 256)
+          rejected[n_rejected++] = cand;
       }
     }
   }
