@@ -57,22 +57,28 @@ struct Selector {
     const size_t max_points = (size_t)5 * n_points;
     cands.clear();
     cands.push_back(i_center);
-    // cells already found outside the region are met again as neighbours of later candidates: the (pure) membership
-    // test is not repeated for them
-    i32 rejected[256];
-    int n_rejected = 0;
+    // "seen" = already a candidate, or already found outside the region (the membership test is pure: it is not repeated
+    // for a cell met again as the neighbour of a later candidate).  Per-thread stamp array instead of linear searches.
+    static thread_local std::vector<std::uint32_t> stamp;
+    static thread_local std::uint32_t epoch = 0;
+    if (stamp.size() != (size_t)g.n_cells) {
+      stamp.assign((size_t)g.n_cells, 0u);
+      epoch = 0;
+    }
+    if (++epoch == 0) {  // wrapped around
+      std::fill(stamp.begin(), stamp.end(), 0u);
+      epoch = 1;
+    }
+    stamp[(size_t)i_center] = epoch;
     for (size_t p = 0; p < max_points; ++p) {
       if (p >= cands.size()) break;
       i32 j = cands[p];
       for (int k = 0; k < F; ++k) {
         i32 cand = g.neighbours[(i64)j * F + k];
         if (cand == INVALID) continue;
-        if (std::find(cands.begin(), cands.end(), cand) != cands.end()) continue;
-        if (std::find(rejected, rejected + n_rejected, cand) != rejected + n_rejected) continue;
-        if (cell_inside(region, cand))
-          cands.push_back(cand);
-        else if (n_rejected < 256)
-          rejected[n_rejected++] = cand;
+        if (stamp[(size_t)cand] == epoch) continue;
+        stamp[(size_t)cand] = epoch;
+        if (cell_inside(region, cand)) cands.push_back(cand);
       }
     }
   }
