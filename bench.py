@@ -26,9 +26,11 @@ import time
 
 # torchrun pins OMP_NUM_THREADS=1; the host precompute (stencils, pseudo-inverses) is OpenMP code, so give every
 # rank its share of the host cores before any OpenMP runtime is loaded
+# (the reference arm runs on rank 0 alone and takes all host cores at every N)
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     _lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(_lws, 1)))
+    _ref = "reference" in sys.argv[1:] or any(a.startswith("--impl=reference") for a in sys.argv[1:])
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // (1 if _ref else max(_lws, 1))))
 
 import numpy as np
 
@@ -56,7 +58,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = every rank owns an n^3 box of a lattice (default, the driver's scaling run); strong = "
                          "ONE global n^3 mesh cut into N chunks of the Hilbert curve (the reference's SFC partition path)")
-    ap.add_argument("--cpu-n", type=int, default=32, help="cubes per direction of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=0, help="cubes (squares) per direction of the bounded CPU sample; 0 = "
+                    "chosen from the requested steps so that the CPU run stays within about a minute")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -182,12 +185,25 @@ def rank_box(rank: int, n_ranks: int):
     return (px, py, pz), (rank % px, (rank // px) % py, rank // (px * py))
 
 
+def cpu_sample_n(args, total_steps: int) -> int:
+    """Cubes (squares) per direction of the bounded CPU sample: as large as ~60 s of oracle time allow for
+    ``total_steps`` steps at a conservative 0.1 M cell-updates/s per host core (3D order 3; 2D is ~2x faster)."""
+    if args.cpu_n > 0:
+        return args.cpu_n if args.kind not in ("vortex2d", "polytrope2d") else min(args.n, args.cpu_n)
+    cores = os.cpu_count() or 8
+    budget_updates = 60.0 * 0.1e6 * cores * (0.3 if args.order >= 4 else 1.0) * (0.4 if args.kind == "atmosphere" else 1.0)
+    cells = budget_updates / (3.0 * max(total_steps, 1))
+    if args.kind in ("vortex2d", "polytrope2d"):
+        return int(max(32, min(args.n, (cells / 2.0) ** 0.5)))
+    return int(max(16, min(args.n, 64, (cells / 6.0) ** (1.0 / 3.0))))
+
+
 def cpu_reference_run(args, steps: int, warmup: int):
     """The reference algorithm (CPU oracle port, OpenMP on all host cores) on a bounded sample of the workload."""
     from oracle import binding as ob
     from zisafvm_b200 import cases
 
-    cpu_n = args.cpu_n if args.kind not in ("vortex2d", "polytrope2d") else min(args.n, 8 * args.cpu_n)
+    cpu_n = cpu_sample_n(args, steps + warmup)
     case = make_case(args, cpu_n)
     st = case.ensure_stencils()
     tables = cases.gravity_tables(case.grid, case.params.gravity) if case.params.gravity.kind != "none" else None
@@ -210,31 +226,91 @@ def cpu_reference_run(args, steps: int, warmup: int):
         state = step(state)
     el = time.perf_counter() - t0
     value = n_int * stages * steps / el
-    sample = (f"{case.grid.n_cells} cells ({cpu_n} per direction) of the same {args.kind} order-{args.order} workload, "
-              f"{steps} {case.method} steps")
+    shape = f"{cpu_n}^2 squares x 2 triangles" if case.grid.n_dims == 2 else f"{cpu_n}^3 cubes x 6 Kuhn tets"
+    sample = (f"{shape} = {case.grid.n_cells} cells of the same {args.kind} order-{args.order} workload, "
+              f"{steps} {case.method} steps after {warmup} warm-up steps")
     return value, el / steps * 1e3, ob.num_threads(), sample, case
 
 
 def run_reference(args):
+    """The reference's own algorithm for the path on the host cores (oracle port: the reference cannot be compiled in this
+    image).  Rank 0 alone runs it, with all host cores, for exactly --steps / --warmup steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     value, ms, cores, sample, case = cpu_reference_run(args, steps, warmup)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, case.method),
+        "config": {"workload": workload_name(args, case.method) + f" [CPU arm: bounded sample of it, {sample}]",
                    "sample": sample + "; reference algorithm restated on the CPU with OpenMP on all host cores (oracle "
-                             "port: the reference binary cannot be built in this image, DESIGN.md section 4)",
+                             "port: the reference binary cannot be built in this image, DESIGN.md section 4); the metric "
+                             "is per cell and stage, so the sample size does not enter it beyond cache effects (the sample's "
+                             "working set is far larger than the host caches)",
                    "cells": int(case.grid.n_cells), "l2_flush": "state + weights larger than any cache"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out))
+
+
+def multi_gpu_parity_check(args, rank: int, world: int, local_rank: int):
+    """N > 1: before anything is timed, a small run on the reference's own partition (ONE Hilbert-ordered mesh cut into
+    `world` contiguous chunks, halo rows by NCCL send / recv, interior tiles overlapped with the exchange, ncclMin for dt)
+    is compared on rank 0 with the single-domain CPU oracle on the same mesh: three steps, CFL-driven dt."""
+    import torch.distributed as dist
+
+    import zisafvm_b200 as z
+    from zisafvm_b200 import cases
+    from zisafvm_b200 import distributed as zd
+
+    n_small, kind, steps, cfl = 10, "smooth", 3, 0.4
+    order = args.order if args.order in (2, 3) else 3
+    run = zd.make_strong_scaling_case(rank, world, n=n_small, order=order, kind=kind, device=local_rank)
+    sub, case, ctx = run.sub, run.case, run.ctx
+    n = sub.n_local
+    rk = z.CudaRungeKutta(ctx, case.method)
+    z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+    u0 = case.u0.copy()
+    u0[sub.n_owned:] = 1e300  # halo rows must come from the exchange
+    rk.upload(z.AllVariables(n, u0))
+    dt, bad = z.LocalCFL(ctx, cfl)()
+    dts = [dt]
+    for _ in range(steps):
+        dt, bad = rk.step(0.0, dt, cfl)
+        dts.append(dt)
+    u = rk.download().cvars[: sub.n_owned]
+    gid = sub.global_index[: sub.n_owned]
+    ctx.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, (gid, u, dts))
+    if rank != 0:
+        return None
+    from oracle.binding import Oracle
+
+    g_case = cases.blast_3d(n=n_small, order=order, kind=kind)
+    ora = Oracle(g_case.grid, g_case.ensure_stencils(), g_case.params)
+    ora.set_frozen_bc(g_case.u0)
+    u_ref = g_case.u0.copy()
+    d = ora.cfl_dt(u_ref, cfl)
+    dts_ref = [d]
+    for _ in range(steps):
+        u_ref = ora.rk_step(g_case.method, u_ref, d)
+        d = ora.cfl_dt(u_ref, cfl)
+        dts_ref.append(d)
+    scale = np.abs(u_ref).max(axis=0)
+    max_rel, max_dt, seen = 0.0, 0.0, 0
+    for gid_r, u_r, dts_r in parts:
+        max_rel = max(max_rel, float((np.abs(u_r - u_ref[gid_r]).max(axis=0) / scale).max()))
+        max_dt = max(max_dt, float(np.abs(np.array(dts_r) / np.array(dts_ref) - 1.0).max()))
+        seen += gid_r.size
+    return {"max_rel": max_rel, "max_rel_dt": max_dt, "tolerance": 1e-11, "ok": bool(max_rel <= 1e-11 and max_dt <= 1e-11),
+            "case": f"3D {kind}, {n_small}^3 cubes x 6 tets, order {order}, SFC partition into {world} chunks, {steps} "
+                    f"{g_case.method} steps with LocalCFL dt (ncclMin), vs the single-domain CPU oracle",
+            "cells_compared": int(seen), "cells_total": int(g_case.grid.n_cells)}
 
 
 def run_b200(args):
@@ -255,6 +331,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         if world != args.gpus:
             raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+
+    parity_check = multi_gpu_parity_check(args, rank, world, local_rank) if distributed else None
 
     t_setup = time.perf_counter()
     if distributed:
@@ -425,6 +503,8 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "state_plausible": bool(state_ok),
         }
+        if parity_check is not None:
+            out["parity_check"] = parity_check
         print(json.dumps(out))
     ctx.close()
     if distributed:

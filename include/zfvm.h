@@ -219,7 +219,13 @@ int zfvm_nccl_unique_id(char id_out[128]);
 int zfvm_comm_init(zfvm_ctx *ctx, const char id[128], int rank, int n_ranks);
 int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_rank, const int64_t *recv_begin,
                   const int64_t *recv_end, const int64_t *send_offset, const int32_t *send_index);
-int zfvm_halo_exchange(zfvm_ctx *ctx, double *state_dev); /* post + wait (HaloExchange::operator(), wait) */
+/* HaloExchange::operator()(AllVariables&) and HaloExchange::wait() (include/zisa/parallelization/halo_exchange.hpp:11-21;
+ * MPIHaloExchange::exchange / wait, mpi_halo_exchange.cpp:178-201): post packs and starts the NCCL group on the context's
+ * communication stream and returns; wait orders every later kernel of the context behind the transfer.  state_dev NULL:
+ * the resident state; avars_dev NULL with n_avars > 0: the resident scalars. */
+int zfvm_halo_post(zfvm_ctx *ctx, double *state_dev, double *avars_dev);
+int zfvm_halo_wait(zfvm_ctx *ctx);
+int zfvm_halo_exchange(zfvm_ctx *ctx, double *state_dev); /* post + wait in one call */
 /* the same exchange for cvars and avars rows in one NCCL group (mpi_halo_exchange.cpp:178-201 exchanges both) */
 int zfvm_halo_exchange_av(zfvm_ctx *ctx, double *state_dev, double *avars_dev);
 int zfvm_allreduce_min(zfvm_ctx *ctx, double *value);     /* MPIAllReduce MIN (mpi_all_reduce.cpp:16-24) */

@@ -1,0 +1,133 @@
+"""GPU parity at the sizes and step counts SURVEY.md 8d names for the BASELINE configurations (the small cases of
+test_gpu_parity.py never fill a 256-entry tile list, never wrap the per-warp TMA ring thousands of times and never skip
+tiles): C1 at its own size for 100 steps and C3 (order 3 and order 2) at 64^3 / 48^3 cubes for 20 steps against the CPU
+oracle, with the time-step sequence of the oracle's LocalCFL; and the bench grid itself (118^3 x 6 = 9 858 192
+tetrahedra), which the oracle cannot follow in seconds, through size-independent properties plus an oracle comparison
+of a sub-domain cut out of it (same cells, same stencils, same weights)."""
+import numpy as np
+import pytest
+
+import zisafvm_b200 as z
+from zisafvm_b200 import cases
+
+from util import active_vars, rel_err, rel_l1, tendency_scales
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_against_oracle(case, n_steps):
+    from oracle.binding import Oracle
+
+    st = case.ensure_stencils()
+    n = case.grid.n_cells
+    ctx = z.CudaContext(case.grid, st, case.params)
+    ora = Oracle(case.grid, st, case.params)
+    rk = z.CudaRungeKutta(ctx, case.method)
+    z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+    ora.set_frozen_bc(case.u0)
+    rk.upload(z.AllVariables(n, case.u0))
+    u_ref = case.u0.copy()
+    dt = ora.cfl_dt(u_ref, case.cfl)
+    for _ in range(n_steps):
+        dt_next, bad = rk.step(0.0, dt, case.cfl)
+        assert not bad
+        u_ref = ora.rk_step(case.method, u_ref, dt)
+        dt_ref = ora.cfl_dt(u_ref, case.cfl)
+        assert abs(dt_next - dt_ref) <= 1e-11 * dt_ref
+        dt = dt_ref
+    u = rk.download().cvars
+    cnt = ctx.counters()
+    ctx.close()
+    return u, u_ref, cnt
+
+
+def test_c1_vortex_49928_triangles_100_steps():
+    """BASELINE config 1 at its own size (158^2 squares x 2 triangles, CWENO-AO order 3, HLLC, SSP3, CFL 0.4)."""
+    case = cases.isentropic_vortex(n=158, order=3)
+    assert case.grid.n_cells == 49928
+    u, u_ref, _ = _run_against_oracle(case, 100)
+    vs = active_vars(2)
+    assert rel_err(u, u_ref)[vs].max() < 1e-11, rel_err(u, u_ref)
+    assert rel_l1(u, u_ref, case.grid.array("volumes"))[vs].max() < 1e-11
+    gh = case.grid.is_ghost
+    assert np.array_equal(u[gh], case.u0[gh])
+
+
+@pytest.mark.parametrize("order,n,kind", [(3, 64, "blast"), (2, 48, "sod")], ids=["o3_n64_blast", "o2_n48_sod"])
+def test_c3_twenty_steps(order, n, kind):
+    """BASELINE config 3 shape at 1.57 M (order 3) / 0.66 M (order 2) tetrahedra for 20 steps: tiles with up to 256 list
+    entries, every warp of the persistent kernel walks ~170 tiles, ghost tiles are skipped (tile_needed)."""
+    case = cases.blast_3d(n=n, order=order, kind=kind)
+    u, u_ref, _ = _run_against_oracle(case, 20)
+    assert rel_err(u, u_ref).max() < 1e-11, rel_err(u, u_ref)
+    assert rel_l1(u, u_ref, case.grid.array("volumes")).max() < 1e-11
+    gh = case.grid.is_ghost
+    assert np.array_equal(u[gh], case.u0[gh])
+
+
+def test_bench_grid_properties_and_subdomain_parity():
+    """The bench configuration itself (118^3 x 6 tets, order 3).  (a) conservation, (b) free stream, (c) bit
+    reproducibility on the full grid; (d) a block of consecutive cells of the Hilbert curve plus everything their
+    stencils and their face neighbours' stencils read is cut out (zfvm_stencils_extract keeps members and order), the
+    oracle evaluates the residual on that sub-grid with the same state, and the full-grid CUDA residual of the block's
+    cells must agree to 1e-12 of the flux scale."""
+    from oracle.binding import Oracle
+
+    case = cases.blast_3d(n=118, order=3, kind="blast")
+    g = case.grid
+    assert g.n_cells == 9858192
+    st = case.ensure_stencils()
+    n = g.n_cells
+    ctx = z.CudaContext(g, st, case.params)
+    roc = z.CudaEulerRateOfChange(ctx)
+    # one step first so that the state is not piecewise constant any more
+    rk = z.CudaRungeKutta(ctx, "ssp3")
+    z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+    rk.upload(z.AllVariables(n, case.u0))
+    dt, bad = z.LocalCFL(ctx, 0.4)()
+    rk.step(0.0, dt)
+    u = rk.download().cvars
+    a, b = z.AllVariables(n), z.AllVariables(n)
+    roc.compute(a, z.AllVariables(n, u), accumulate=False)
+    roc.compute(b, z.AllVariables(n, u), accumulate=False)
+    assert np.array_equal(a.cvars, b.cvars)                                     # (c)
+    vol = g.array("volumes")
+    inr = g.array("inradii")
+    total = (a.cvars * vol[:, None]).sum(axis=0)
+    gross = (np.abs(a.cvars) * vol[:, None]).sum(axis=0)
+    scale = tendency_scales(u, case.params.gamma, inr)
+    assert np.all(np.abs(total) <= 1e-12 * np.maximum(gross, 1e-6 * scale * vol.sum())), (total, gross)   # (a)
+    uc = np.tile(np.array([1.3, 0.4, -0.2, 0.3, 2.9]), (n, 1))
+    roc.compute(b, z.AllVariables(n, uc), accumulate=False)
+    interior = ~g.is_ghost
+    sc_c = tendency_scales(uc, case.params.gamma, inr)
+    assert (np.abs(b.cvars[interior]).max(axis=0) / sc_c).max() < 1e-12        # (b)
+    ctx.close()
+
+    # (d) sub-domain: 20 000 consecutive cells of the curve around the blast front, cut out with the partitioner's own
+    # extraction (owned = the block; halo = what its stencils and its face neighbours' stencils read)
+    from zisafvm_b200 import distributed as zd
+
+    cc = g.array("cell_centers")
+    r = np.linalg.norm(cc - 0.5, axis=1)
+    i0 = int(np.flatnonzero((r < 0.12) & interior)[0]) // 32 * 32
+    block = np.arange(i0, min(i0 + 20000, n))
+    h = 1.0 / 118
+    lo, hi = cc[block].min(axis=0) - 8 * h, cc[block].max(axis=0) + 8 * h
+    src = np.flatnonzero(((cc >= lo) & (cc <= hi)).all(axis=1))
+    in_block = (src >= block[0]) & (src <= block[-1])
+    vi = g.array("vertex_indices")[src]
+    used, inv = np.unique(vi.ravel(), return_inverse=True)
+    sub = zd.extract_subdomain(3, g.array("vertices")[used].copy(), inv.reshape(vi.shape).astype(np.int32),
+                               np.where(in_block, 0, 1).astype(np.int32), src, 0, 2, cases.blast_qr(3),
+                               case.params.weno.stencil_family_params, physical_ghost=g.is_ghost[src].copy())
+    assert sub.n_owned == block.size and np.array_equal(sub.global_index[: sub.n_owned], block)
+    # the extraction recomputes the stencils on the cut: they must be the full grid's (same geometry, same search)
+    for i_loc in range(0, sub.n_owned, 997):
+        for k in range(5):
+            assert np.array_equal(sub.global_index[sub.stencils.stencil(i_loc, k)], st.stencil(int(block[i_loc]), k))
+    ora = Oracle(sub.grid, sub.stencils, case.params)
+    ref = ora.rate_of_change(u[sub.global_index])
+    sel = interior[block]
+    err = np.abs(a.cvars[block][sel] - ref[: sub.n_owned][sel]).max(axis=0) / scale
+    assert err.max() < 1e-12, err

@@ -10,6 +10,7 @@ import pytest
 
 import zisafvm_b200 as z
 from zisafvm_b200 import cases
+from zisafvm_b200.grid import WENO_PARAMS
 
 from util import active_vars, rel_err, rel_l1, state_scales, tendency_scales
 
@@ -42,6 +43,43 @@ CASES = {
     # no ghost ring: the boundary is closed by FluxBC (boundary/flux_bc.hpp), stencils degrade towards the boundary
     "vortex_fluxbc": lambda: cases.isentropic_vortex(n=24, order=3, ghost_ring_cells=0, flux_bc="flux"),
     "blast_fluxbc": lambda: cases.blast_3d(n=6, order=3, kind="smooth", ghost_cubes=0, flux_bc="flux"),
+    # WENO_AO::reconstruct (src/zisa/reconstruction/weno_ao.cpp:14-24): no CWENO correction, tile kernel
+    "vortex_o3_weno_ao": lambda: cases.isentropic_vortex(n=30, order=3, reconstruction="WENO-AO"),
+    "vortex_o4_weno_ao": lambda: cases.isentropic_vortex(n=30, order=4, reconstruction="WENO-AO"),
+    "blast_o3_weno_ao": lambda: cases.blast_3d(n=6, order=3, kind="blast", reconstruction="WENO-AO"),
+    "smooth3d_o2_weno_ao": lambda: cases.blast_3d(n=6, order=2, kind="smooth", reconstruction="WENO-AO"),
+    # UnityScaling (model/characteristic_scale.hpp:35-46)
+    "vortex_o3_unity": lambda: cases.isentropic_vortex(n=30, order=3, scaling="unity"),
+    "blast_o3_unity": lambda: cases.blast_3d(n=6, order=3, kind="blast", scaling="unity"),
+    "atmosphere_wb_unity": lambda: cases.stellar_atmosphere_3d(n=6, order=3, well_balanced=True, scaling="unity"),
+    # the other Butcher tableaux of make_tableau (src/zisa/ode/runge_kutta.cpp:145-213): stages with zero
+    # coefficients (wicker, fehlberg b_1 = 0), four and six stages
+    "vortex_forward_euler": lambda: cases.isentropic_vortex(n=24, order=3, method="forward_euler"),
+    "vortex_ssp2": lambda: cases.isentropic_vortex(n=24, order=3, method="ssp2"),
+    "vortex_wicker": lambda: cases.isentropic_vortex(n=24, order=3, method="wicker"),
+    "vortex_rk4": lambda: cases.isentropic_vortex(n=24, order=3, method="rk4"),
+    "vortex_fehlberg": lambda: cases.isentropic_vortex(n=24, order=3, method="fehlberg"),
+    "smooth3d_rk4": lambda: cases.blast_3d(n=6, order=3, kind="smooth", method="rk4"),
+    # gravity models: ConstantGravity with AxialAlignment (gravity_impl.hpp:13-20, gravity_decl.hpp:97-120) and the
+    # tabulated RadialGravity (gravity_decl.hpp:312-338, math/linear_interpolation.hpp:14-45)
+    "constant_gravity_wb": lambda: cases.constant_gravity_2d(n=30, order=3, well_balanced=True),
+    "constant_gravity_nowb": lambda: cases.constant_gravity_2d(n=30, order=3, well_balanced=False),
+    "constant_gravity_x_axis": lambda: cases.constant_gravity_2d(n=24, order=2, well_balanced=True, axis=(1.0, 0.0, 0.0)),
+    "atmosphere_table_wb": lambda: cases.stellar_atmosphere_3d(n=6, order=3, well_balanced=True, gravity="table"),
+    "atmosphere_table_nowb": lambda: cases.stellar_atmosphere_3d(n=6, order=2, well_balanced=False, gravity="table"),
+    # stencil families of the reference's own reconstruction tests (generic kernel, kernels/recon_generic.cu):
+    # six stencils with two central ones (test/zisa/unit_test/reconstruction/cweno_ao.cpp:144-160), lone stencils and
+    # first order (weno_ao.cpp:47-55), a wider central stencil (weno_ao.cpp:57-62), weight 10 (cweno_ao.cpp:59-63)
+    "smooth3d_six_stencils": lambda: cases.blast_3d(n=8, order=4, kind="smooth", weno=WENO_PARAMS["3d_o4_six"]),
+    "smooth3d_six_stencils_o3": lambda: cases.blast_3d(n=8, order=4, kind="smooth", weno=WENO_PARAMS["3d_o4_six_o3"]),
+    "smooth3d_six_weno_ao": lambda: cases.blast_3d(n=8, order=4, kind="smooth", weno=WENO_PARAMS["3d_o4_six"],
+                                                   reconstruction="WENO-AO"),
+    "vortex_first_order": lambda: cases.isentropic_vortex(n=24, order=3, weno=WENO_PARAMS["2d_o1_c"]),
+    "vortex_lone_o2_biased": lambda: cases.isentropic_vortex(n=24, order=3, weno=WENO_PARAMS["2d_o2_b"], reconstruction="WENO-AO"),
+    "vortex_lone_o3_central": lambda: cases.isentropic_vortex(n=24, order=3, weno=WENO_PARAMS["2d_o3_c"]),
+    "vortex_lone_o4_central": lambda: cases.isentropic_vortex(n=24, order=4, weno=WENO_PARAMS["2d_o4_c"], reconstruction="WENO-AO"),
+    "vortex_o3_wide_central": lambda: cases.isentropic_vortex(n=24, order=3, weno=WENO_PARAMS["2d_o3_wide"], reconstruction="WENO-AO"),
+    "vortex_o4_weight10": lambda: cases.isentropic_vortex(n=24, order=4, weno=WENO_PARAMS["2d_o4_w10"]),
 }
 
 

@@ -93,6 +93,26 @@ def test_cweno_ao_convergence_3d_order4():
     assert 3.7 <= r <= 4.5, r
 
 
+def test_cweno_ao_convergence_3d_six_stencils():
+    """The reference's own 3D parameter sets (cweno_ao.cpp:144-160): six stencils, two of them central,
+    {4,2,2,2,2,2} / {c,c,b,b,b,b} / overfit {4,4,2.5,..} / weights {100,10,1,1,1,1}: rate in [3.7, 4.5]; and
+    {4,3,3,3,3,3}, whose third-order one-sided stencils leave the pre-asymptotic range later on these coarse synthetic
+    grids (the rate between 10 and 20 cubes per direction overshoots: lower bound only)."""
+    r = rate(3, (10, 20), 3, z.WENO_PARAMS["3d_o4_six"], "CWENO-AO", 3)
+    assert 3.7 <= r <= 4.5, r
+    r = rate(3, (10, 20), 3, z.WENO_PARAMS["3d_o4_six_o3"], "CWENO-AO", 3)
+    assert 3.7 <= r, r
+
+
+@pytest.mark.parametrize("key,mode,interval", [("2d_o1_c", "WENO-AO", (0.8, 1.15)), ("2d_o2_b", "WENO-AO", (1.8, 2.2)),
+                                               ("2d_o3_c", "WENO-AO", (2.8, 3.25)), ("2d_o4_c", "WENO-AO", (3.8, 4.4)),
+                                               ("2d_o3_wide", "WENO-AO", (2.9, 3.3))])
+def test_weno_ao_lone_stencils_2d(key, mode, interval):
+    """weno_ao.cpp:47-62: families of one stencil (first order included) and the wider central stencil."""
+    r = rate(2, (24, 48), 4, z.WENO_PARAMS[key], mode, 5)
+    assert interval[0] - 0.05 <= r <= interval[1] + 0.2, r
+
+
 @pytest.mark.parametrize("nd,key,mode", [(2, "2d_o3", "CWENO-AO"), (2, "2d_o4", "CWENO-AO"), (2, "2d_o3", "WENO-AO"),
                                          (3, "3d_o3", "CWENO-AO"), (3, "3d_o2", "CWENO-AO")])
 def test_non_oscillatory_at_a_jump(nd, key, mode):

@@ -124,6 +124,8 @@ _SIGNATURES = {
     "zfvm_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "zfvm_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "zfvm_set_halo": (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_int), c_int64_p, c_int64_p, c_int64_p, c_int32_p]),
+    "zfvm_halo_post": (C.c_int, [_vp, _vp, _vp]),
+    "zfvm_halo_wait": (C.c_int, [_vp]),
     "zfvm_halo_exchange": (C.c_int, [_vp, _vp]),
     "zfvm_allreduce_min": (C.c_int, [_vp, c_double_p]),
 }

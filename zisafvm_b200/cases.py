@@ -11,7 +11,8 @@ from typing import Callable, Optional
 
 import numpy as np
 
-from .grid import Grid, QRDegrees, WENO_PARAMS, compute_stencil_families, cube_mesh, square_mesh
+from .grid import (Grid, HybridWENOParams, QRDegrees, WENO_PARAMS, compute_stencil_families, cube_mesh,
+                   square_mesh)
 from .solver import EulerParams, Gravity
 
 
@@ -87,7 +88,8 @@ def ghost_ring(grid: Grid, lo, hi, width):
 
 # ---- C1: 2D isentropic vortex ------------------------------------------------------------------------
 def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: int = 0, jitter: float = 0.15,
-                      ghost_ring_cells: int = 3, flux_bc: str = "none") -> Case:
+                      ghost_ring_cells: int = 3, flux_bc: str = "none", reconstruction: str = "CWENO-AO",
+                      scaling: str = "euler", method: str = "ssp3", weno: Optional[HybridWENOParams] = None) -> Case:
     """``ghost_ring_cells = 0, flux_bc = "flux"``: no ghost ring, the domain boundary is closed with ``FluxBC``
     (boundary/flux_bc.hpp) -- the set-up of the reference's domains without a halo of frozen cells."""
     gamma = 1.4
@@ -109,8 +111,9 @@ def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: in
         rho = T ** (1.0 / (gamma - 1.0))
         return cvars_from_primitive(rho, vel, rho * T, gamma)
 
-    params = EulerParams(weno=WENO_PARAMS[f"2d_o{order}"], flux=flux, gamma=gamma, flux_bc=flux_bc)
-    return Case("isentropic_vortex", grid, params, cell_average(grid, ic), "ssp3", 0.4, frozen_bc=ghost_ring_cells > 0)
+    params = EulerParams(weno=weno or WENO_PARAMS[f"2d_o{order}"], flux=flux, gamma=gamma, flux_bc=flux_bc,
+                         reconstruction=reconstruction, scaling=scaling)
+    return Case("isentropic_vortex", grid, params, cell_average(grid, ic), method, 0.4, frozen_bc=ghost_ring_cells > 0)
 
 
 # ---- C2: 2D well-balanced polytrope ------------------------------------------------------------------
@@ -182,7 +185,9 @@ def blast_3d_on_grid(grid: Grid, order: int = 3, kind: str = "blast", stencils=N
 
 # ---- C3: 3D Sod / blast --------------------------------------------------------------------------------
 def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, ghost_cubes: int = 2,
-             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None, flux_bc: str = "none") -> Case:
+             hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None, flux_bc: str = "none",
+             reconstruction: str = "CWENO-AO", scaling: str = "euler", method: Optional[str] = None,
+             weno: Optional[HybridWENOParams] = None) -> Case:
     """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}."""
     gamma = 1.4
     gn = global_n or n
@@ -196,14 +201,15 @@ def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, gh
 
     ic = blast_ic(kind, gamma)
 
-    params = EulerParams(weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma, flux_bc=flux_bc)
-    method = "ssp2" if order == 2 else "ssp3"
+    params = EulerParams(weno=weno or WENO_PARAMS[f"3d_o{order}"], gamma=gamma, flux_bc=flux_bc,
+                         reconstruction=reconstruction, scaling=scaling)
+    method = method or ("ssp2" if order == 2 else "ssp3")
     return Case(f"{kind}_3d_o{order}", grid, params, cell_average(grid, ic), method, 0.4, frozen_bc=ghost_cubes > 0)
 
 
 # ---- C4: 3D stellar atmosphere -----------------------------------------------------------------------------
 def stellar_atmosphere_3d(n: int = 12, order: int = 3, well_balanced: bool = True, amplitude: float = 1e-3,
-                          seed: int = 0) -> Case:
+                          seed: int = 0, gravity: str = "point_mass", scaling: str = "euler") -> Case:
     """Isentropic hydrostatic atmosphere in a softened point-mass potential, gamma = 5/3 ideal gas,
     plus a pressure perturbation.  Orders 2 and 3 have compiled 3D kernels."""
     gamma = 5.0 / 3.0
@@ -223,12 +229,47 @@ def stellar_atmosphere_3d(n: int = 12, order: int = 3, well_balanced: bool = Tru
         p = K * rho ** gamma * (1.0 + amplitude * np.exp(-((r / 0.3) ** 2)))
         return cvars_from_primitive(rho, np.zeros((x.shape[0], 3)), p, gamma)
 
+    if gravity == "table":
+        # the same potential as a RadialGravity table (gravity_decl.hpp:312-338, piecewise linear in r): fine enough that
+        # the hydrostatic state above stays a near-equilibrium of the tabulated potential
+        radii = np.linspace(0.0, 2.0, 4001)
+        grav = Gravity(kind="table", alignment="radial", table=(radii, GM / (X + radii)))
+    else:
+        grav = Gravity(kind="point_mass", params=(GM, X), alignment="radial")
     params = EulerParams(
-        weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma,
-        well_balancing="isentropic" if well_balanced else "constant",
-        gravity=Gravity(kind="point_mass", params=(GM, X), alignment="radial"),
+        weno=WENO_PARAMS[f"3d_o{order}"], gamma=gamma, scaling=scaling,
+        well_balancing="isentropic" if well_balanced else "constant", gravity=grav,
     )
     return Case("stellar_atmosphere_3d", grid, params, cell_average(grid, ic), "ssp3", 0.4)
+
+
+def constant_gravity_2d(n: int = 32, order: int = 3, well_balanced: bool = True, amplitude: float = 1e-3,
+                        seed: int = 0, axis=(0.0, 1.0, 0.0)) -> Case:
+    """Isentropic hydrostatic layer in a constant gravitational field along ``axis`` (``ConstantGravityAxial``,
+    gravity_impl.hpp:13-20 with ``AxialAlignment``, gravity_decl.hpp:97-120): phi = g (x . axis), gamma = 1.4,
+    plus a Gaussian pressure perturbation.  The set-up of the reference's Rayleigh-Taylor / gaussian-bump experiments
+    without the tracer."""
+    gamma, g_acc = 1.4, 1.0
+    verts, vi = square_mesh(n, n, 0.0, 1.0, 0.0, 1.0, jitter=0.15, seed=seed)
+    grid = Grid(2, verts, vi, QRDegrees(face_deg=3, volume_deg=3, moments_deg=4))
+    grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0), (1.0, 1.0), 3.0 / n))
+    ax = np.asarray(axis, dtype=float)
+    h0, K = 3.0, 1.0
+
+    def ic(x):
+        phi = g_acc * (x @ ax)
+        hh = h0 - phi
+        rho = ((gamma - 1.0) / (gamma * K) * hh) ** (1.0 / (gamma - 1.0))
+        r2 = (x[:, 0] - 0.5) ** 2 + (x[:, 1] - 0.5) ** 2
+        p = K * rho ** gamma * (1.0 + amplitude * np.exp(-r2 / 0.05 ** 2))
+        return cvars_from_primitive(rho, np.zeros((x.shape[0], 3)), p, gamma)
+
+    params = EulerParams(
+        weno=WENO_PARAMS[f"2d_o{order}"], gamma=gamma,
+        well_balancing="isentropic" if well_balanced else "constant",
+        gravity=Gravity(kind="constant", params=(g_acc,), alignment="axial", axis=tuple(axis)),
+    )
+    return Case("constant_gravity_2d", grid, params, cell_average(grid, ic), "ssp3", 0.4)
 
 
 def gravity_tables(grid: Grid, gravity: Gravity):
@@ -245,6 +286,12 @@ def gravity_tables(grid: Grid, gravity: Gravity):
             alpha = np.sqrt(2.0 * np.pi * G / K)
             ce = alpha * (chi + np.finfo(float).tiny)
             return -2.0 * K * rhoC * np.sin(ce) / ce, -2.0 * K * rhoC * ((np.cos(ce) - np.sin(ce) / ce) / ce) * alpha
+        if kind == "table":  # NonUniformLinearInterpolation (math/linear_interpolation.hpp:14-45)
+            pts, val = (np.asarray(a, dtype=float) for a in gravity.table)
+            i = np.searchsorted(pts, chi, side="left")      # std::lower_bound
+            i = np.minimum(np.where(i == 0, 0, i - 1), pts.size - 2)
+            a = (chi - pts[i]) / (pts[i + 1] - pts[i])
+            return (1 - a) * val[i] + a * val[i + 1], (val[i + 1] - val[i]) / (pts[i + 1] - pts[i])
         raise ValueError(kind)
 
     def at(x):

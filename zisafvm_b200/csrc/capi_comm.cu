@@ -111,6 +111,40 @@ int zfvm_allreduce_min_internal(zfvm_ctx *ctx, double *dev_value) {
   return 0;
 }
 
+// min of the CFL quotient and max of the plausibility flag in one group (ReduceOut: double, int)
+int zfvm_allreduce_verdict_internal(zfvm_ctx *ctx) {
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  ZFVM_NCCL(g_nccl.GroupStart());
+  ZFVM_NCCL(g_nccl.AllReduce(&ctx->reduce_dev->min_dx_over_ev, &ctx->reduce_dev->min_dx_over_ev, 1, ncclDouble, ncclMin, comm,
+                             ctx->stream));
+  ZFVM_NCCL(g_nccl.AllReduce(&ctx->reduce_dev->not_plausible, &ctx->reduce_dev->not_plausible, 1, ncclInt, ncclMax, comm,
+                             ctx->stream));
+  ZFVM_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+void zfvm_comm_destroy_internal(zfvm_ctx *ctx) {
+  if (ctx->nccl_comm && g_nccl.CommDestroy) {
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+  }
+  ctx->nccl_comm = nullptr;
+}
+
+namespace {
+template <class T>
+void release_registered(zfvm_ctx *ctx, T *&ptr) {
+  if (!ptr) return;
+  for (size_t a = 0; a < ctx->allocations.size(); ++a)
+    if (ctx->allocations[a] == (void *)ptr) {
+      ctx->allocations.erase(ctx->allocations.begin() + (std::ptrdiff_t)a);
+      break;
+    }
+  cudaFree((void *)ptr);
+  ptr = nullptr;
+}
+}  // namespace
+
 extern "C" {
 
 int zfvm_nccl_unique_id(char id_out[128]) {
@@ -127,6 +161,7 @@ int zfvm_comm_init(zfvm_ctx *ctx, const char id_in[128], int rank, int n_ranks) 
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   ncclUniqueId id;
   std::memcpy(&id, id_in, sizeof(id));
+  zfvm_comm_destroy_internal(ctx);  // a second call replaces the communicator
   ncclComm_t comm;
   ZFVM_NCCL(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
   ctx->nccl_comm = comm;
@@ -149,6 +184,14 @@ int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_r
   ctx->n_send = n_peers > 0 ? send_offset[n_peers] : 0;
   for (int64_t r = 0; r < ctx->n_send; ++r)
     if (send_index[r] < 0 || send_index[r] >= n_owned) return fail("zfvm_set_halo: only owned rows can be sent");
+  // a second call replaces the plan: the previous buffers are released, not kept until zfvm_destroy
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  release_registered(ctx, ctx->send_index_dev);
+  release_registered(ctx, ctx->send_buf);
+  release_registered(ctx, ctx->send_buf_a);
+  release_registered(ctx, ctx->tiles_interior);
+  release_registered(ctx, ctx->tiles_exterior);
   void *p = nullptr;
   ZFVM_CUDA(cudaMalloc(&p, (size_t)std::max<int64_t>(ctx->n_send, 1) * sizeof(int32_t)));
   ctx->allocations.push_back(p);
@@ -186,6 +229,26 @@ int zfvm_set_halo(zfvm_ctx *ctx, int64_t n_owned, int n_peers, const int *peer_r
   ctx->tiles_exterior = (int32_t *)p;
   if (!te.empty()) ZFVM_CUDA(cudaMemcpy(p, te.data(), te.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   return 0;
+}
+
+// HaloExchange::operator() and HaloExchange::wait() as the reference declares them
+// (include/zisa/parallelization/halo_exchange.hpp:11-21): post returns immediately, the transfer runs on the context's
+// communication stream; wait makes the compute stream (every later kernel of this context) wait for it.
+int zfvm_halo_post(zfvm_ctx *ctx, double *state_dev, double *avars_dev) {
+  if (ctx->n_ranks <= 1 || !ctx->nccl_comm) return 0;  // NoHaloExchange, halo_exchange.hpp:23-29
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  if (!state_dev) state_dev = ctx->u_cur;
+  if (ctx->n_avars > 0 && !avars_dev) avars_dev = ctx->a_cur;
+  ctx->halo_posted = true;
+  return zfvm_halo_post_internal(ctx, state_dev, ctx->n_avars > 0 ? avars_dev : nullptr);
+}
+
+int zfvm_halo_wait(zfvm_ctx *ctx) {
+  if (ctx->n_ranks <= 1 || !ctx->nccl_comm) return 0;
+  if (!ctx->halo_posted) return fail("zfvm_halo_wait: no exchange has been posted");
+  ZFVM_CUDA(cudaSetDevice(ctx->device));
+  ctx->halo_posted = false;
+  return zfvm_halo_wait_internal(ctx);
 }
 
 int zfvm_halo_exchange(zfvm_ctx *ctx, double *state_dev) {

@@ -25,6 +25,17 @@ int dev_alloc(zfvm_ctx *ctx, T **ptr, std::int64_t count, bool zero = false) {
   return 0;
 }
 
+/// Frees a buffer that dev_alloc registered (setters that are called again replace their buffers).
+template <class T>
+void dev_release(zfvm_ctx *ctx, T *&ptr, std::int64_t count) {
+  if (!ptr) return;
+  auto it = std::find(ctx->allocations.begin(), ctx->allocations.end(), (void *)ptr);
+  if (it != ctx->allocations.end()) ctx->allocations.erase(it);
+  cudaFree((void *)ptr);
+  ctx->device_bytes -= (std::int64_t)((size_t)std::max<std::int64_t>(count, 1) * sizeof(T));
+  ptr = nullptr;
+}
+
 template <class T>
 int dev_upload(zfvm_ctx *ctx, const T **ptr, const std::vector<T> &host) {
   T *p = nullptr;
@@ -192,11 +203,19 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
 int zfvm_halo_post_internal(zfvm_ctx *ctx, double *state_dev, double *avars_dev);
 int zfvm_halo_wait_internal(zfvm_ctx *ctx);
 int zfvm_allreduce_min_internal(zfvm_ctx *ctx, double *dev_value);
+int zfvm_allreduce_verdict_internal(zfvm_ctx *ctx);
+void zfvm_comm_destroy_internal(zfvm_ctx *ctx);
 
 namespace {
 
+int run_recon(zfvm_ctx *ctx, const double *state, const std::int32_t *tiles, std::int64_t n_tiles) {
+  if (ctx->generic) return launch_recon_generic(ctx->plan, ctx->sc, state, tiles, n_tiles, ctx->stream);
+  return launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, tiles, n_tiles, ctx->stream);
+}
+
 void prof_mark(zfvm_ctx *ctx, int which) {
   if (!ctx->prof_enabled) return;
+  if (ctx->prof_events[which].size() >= 2 * 16384) return;  // bounded: profiling left on keeps the first 16 k residuals
   cudaEvent_t ev;
   cudaEventCreate(&ev);
   cudaEventRecord(ev, ctx->stream);
@@ -210,16 +229,14 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
   prof_mark(ctx, 0);
   if (ctx->n_ranks > 1 && ctx->nccl_comm) {
     if (zfvm_halo_post_internal(ctx, const_cast<double *>(state), const_cast<double *>(avars))) return 1;
-    rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_interior,
-                      ctx->n_tiles_interior, ctx->stream);
+    rc = run_recon(ctx, state, ctx->tiles_interior, ctx->n_tiles_interior);
+    if (zfvm_halo_wait_internal(ctx)) return 1;  // (also when rc != 0: the posted group must complete)
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
-    if (zfvm_halo_wait_internal(ctx)) return 1;
-    launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_exterior, ctx->n_tiles_exterior,
-                 ctx->stream);
+    rc = run_recon(ctx, state, ctx->tiles_exterior, ctx->n_tiles_exterior);
+    if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     ctx->launches += 2;
   } else {
-    rc = launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, ctx->tiles_needed, ctx->n_tiles_needed,
-                      ctx->stream);
+    rc = run_recon(ctx, state, ctx->tiles_needed, ctx->n_tiles_needed);
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     ctx->launches += 1;
   }
@@ -233,9 +250,11 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
     // advected scalars, T1: scalar reconstruction + traces (after the halo rows have arrived, before the face kernel,
     // which upwinds them with the wave speeds of its HLLC evaluation)
     prof_mark(ctx, 3);
-    if (launch_tracer_recon(ctx->plan, ctx->sc, ctx->tracer_view, ctx->deg_hi, ctx->deg_lo, avars, ctx->tiles_needed,
-                            ctx->n_tiles_needed, ctx->stream))
-      return fail("no tracer reconstruction kernel is compiled for this scheme");
+    const int trc = ctx->generic ? launch_tracer_recon_generic(ctx->plan, ctx->sc, avars, ctx->tiles_needed,
+                                                               ctx->n_tiles_needed, ctx->stream)
+                                 : launch_tracer_recon(ctx->plan, ctx->sc, ctx->tracer_view, ctx->deg_hi, ctx->deg_lo, avars,
+                                                       ctx->tiles_needed, ctx->n_tiles_needed, ctx->stream);
+    if (trc) return fail("no tracer reconstruction kernel is compiled for this scheme");
     prof_mark(ctx, 3);
     ctx->launches += 1;
   }
@@ -304,13 +323,15 @@ void zfvm_params_default(zfvm_params *p) {
   p->flux_bc = 0;
 }
 
+static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params);
+
 int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params, int device,
                 zfvm_ctx **out) {
   zfvm_ctx *ctx = nullptr;
   try {
     const HostGrid &g = grid->g;
     const HostStencils &S = stencils->s;
-    const int nd = g.n_dims, F = g.max_neighbours, ns = S.n_stencils;
+    const int ns = S.n_stencils;
     if (S.n_cells != g.n_cells) return fail("zfvm_create: stencils do not belong to this grid");
     if (params->steps_per_recompute != 1)
       return fail("zfvm_create: only steps_per_recompute == 1 is supported (local_reconstruction.hpp:87-100)");
@@ -329,589 +350,602 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
 
     ctx = new zfvm_ctx();
     ctx->device = device;
-    ctx->params = *params;
-    ctx->n_dims = nd;
-    ctx->n_cells = g.n_cells;
-    ctx->n_owned = g.n_cells;
-    const std::int64_t n = g.n_cells, T = (n + TILE - 1) / TILE, E = g.n_edges, EI = g.n_interior_edges;
-    ctx->n_tiles = T;
-    ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
-    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
-    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
-
-    // ---- scheme constants ------------------------------------------------------------------
-    SchemeConst &sc = ctx->sc;
-    std::memset(&sc, 0, sizeof(sc));
-    sc.n_dims = nd;
-    sc.n_stencils = ns;
-    sc.q_f = g.q_f;
-    sc.q_c = g.q_c;
-    sc.recon_mode = params->recon_mode;
-    sc.scaling = params->scaling;
-    sc.flux = params->flux;
-    sc.well_balanced = params->well_balanced;
-    // the cell-local source pass (GravitySourceLoop and / or Heating) runs when either term is present; without a
-    // gravity model its potential tables stay zero
-    sc.has_gravity = params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0;
-    {
-      sc.eos_pow_e = 1.0 / (params->gamma - 1.0);
-      const double twice = 2.0 * sc.eos_pow_e, r = std::rint(twice);
-      sc.eos_pow_n = (std::fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) ? (int)r : 0;
-    }
-    sc.heating_rate = params->heating_rate;
-    sc.heating_r0 = params->heating_r0;
-    sc.heating_r1 = params->heating_r1;
-    ctx->n_avars = params->n_avars;
-    sc.epsilon = params->epsilon;
-    sc.exponent = params->exponent;
-    sc.gamma = params->gamma;
-    ctx->deg_hi = S.params.orders[0] - 1;
-    ctx->deg_lo = 0;
-    for (int k = 1; k < ns; ++k) ctx->deg_lo = std::max(ctx->deg_lo, S.params.orders[(size_t)k] - 1);
-    if (ctx->deg_lo > ctx->deg_hi)
-      return fail("zfvm_create: the first stencil must have the highest order (all reference parameter sets do)");
-    if (ns == 1) ctx->deg_lo = std::min(ctx->deg_hi, 1);
-    if ((nd == 2 && ctx->deg_hi >= 5) || (nd == 3 && ctx->deg_hi >= 4))
-      return fail("zfvm_create: LSQ matrices exist up to order 5 in 2D and 4 in 3D (lsq_solver.cpp:288,399)");
-    if (g.n_moments < poly_dof(ctx->deg_hi, nd))
-      return fail("zfvm_create: grid moments_deg is lower than the polynomial degree");
-    double wsum = 0.0;
-    for (int k = 0; k < ns; ++k) wsum += params->linear_weights[k];
-    for (int k = 0; k < ns; ++k) {
-      sc.lin_w[k] = params->linear_weights[k] / wsum;  // hybrid_weno.cpp:26-31
-      sc.rows_max[k] = S.max_size[(size_t)k] - 1;
-      sc.ncoef[k] = poly_dof(k == 0 ? ctx->deg_hi : ctx->deg_lo, nd) - 1;
-    }
-    for (int q = 0; q < g.q_f; ++q) {
-      sc.face_w[q] = g.face_rule.weights[(size_t)q];
-      for (int b = 0; b < g.face_rule.n_bary; ++b) sc.face_bary[q][b] = g.face_rule.bary[(size_t)(q * g.face_rule.n_bary + b)];
-    }
-    for (int q = 0; q < g.q_c; ++q) {
-      sc.cell_w[q] = g.cell_rule.weights[(size_t)q];
-      for (int b = 0; b < g.cell_rule.n_bary; ++b) sc.cell_bary[q][b] = g.cell_rule.bary[(size_t)(q * g.cell_rule.n_bary + b)];
-    }
-
-    DevicePlan &P = ctx->plan;
-    std::memset(&P, 0, sizeof(P));
-    P.n_cells = n;
-    P.n_tiles = T;
-    P.n_edges = E;
-    P.n_interior_edges = EI;
-
-    // ---- tile records (meta | sidx_k | W_k), built and uploaded in chunks of tiles -------------------
-    ctx->tile_max_ref.assign((size_t)T, 0);
-    for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
-    double bytes_W = 0.0, bytes_idx = 0.0, bytes_m = 0.0;
-    std::int64_t n_counted = 0;
-    {
-      int off = TILE * (int)sizeof(std::uint64_t);
-      for (int k = 0; k < ns; ++k) {
-        P.off_sidx[k] = off;
-        off += sc.rows_max[k] * TILE * (int)sizeof(std::int32_t);
-      }
-      P.hdr_bytes = off;
-      for (int k = 0; k < ns; ++k) {
-        P.off_W[k] = off;
-        off += sc.rows_max[k] * sc.ncoef[k] * TILE * (int)sizeof(double);
-      }
-      P.rec_bytes = off;  // every section is a multiple of 128 bytes
-    }
-    // ---- tile kernel records (kernels/recon_tile.cuh): header | one-sided W | central W | geometry ----------
-    // Built instead of the records above whenever the tile kernel is compiled for the scheme (plain Euler,
-    // no gravity terms inside K1); ZFVM_RECON=v1|stream keeps the older kernels for comparisons.
-    bool use_tile = false;
-    {
-      const char *e_recon = std::getenv("ZFVM_RECON");
-      const bool other = e_recon && (e_recon[0] == 'v' || e_recon[0] == 's');
-      // (gravity / heating without well-balancing: the tile kernel stores the polynomial, source_kernel evaluates the
-      // cell-local source terms from it; ZFVM_SOURCE=v1 keeps those runs on the thread-per-cell kernel)
-      const char *e_src = std::getenv("ZFVM_SOURCE");
-      const bool source_v1 = e_src && e_src[0] == 'v';
-      use_tile = !other && !(sc.has_gravity && source_v1) && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
-    }
-    if (use_tile) {
-      // distinct cells read by a tile's stencils
-      std::vector<std::int32_t> n_union((size_t)T, 0);
-#pragma omp parallel
-      {
-        std::vector<std::int32_t> seen;
-#pragma omp for schedule(dynamic, 64)
-        for (std::int64_t t = 0; t < T; ++t) {
-          seen.clear();
-          for (int lane = 0; lane < TILE; ++lane) {
-            const std::int64_t i = t * TILE + lane;
-            seen.push_back((std::int32_t)std::min(i, n - 1));
-            if (i >= n) continue;
-            for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
-              if (S.order[(size_t)(i * ns + k)] <= 1) continue;
-              const int size = S.size[(size_t)(i * ns + k)];
-              for (int j = 1; j < size; ++j) seen.push_back(S.global(i, k, j));
-            }
-          }
-          std::sort(seen.begin(), seen.end());
-          // the own cells occupy 32 list entries even when the last tile repeats the last cell
-          const std::int64_t n_own_distinct = std::min<std::int64_t>(TILE, n - t * TILE);
-          n_union[(size_t)t] = (std::int32_t)((std::unique(seen.begin(), seen.end()) - seen.begin()) + (TILE - n_own_distinct));
-        }
-      }
-      int cap = TILE;
-      for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
-      cap = (cap + 31) / 32 * 32;
-      if (const char *e = std::getenv("ZFVM_TILE_MIN_CAP")) cap = std::max(cap, (std::atoi(e) + 31) / 32 * 32);  // tests: 16-bit indices
-      if (cap > 1024) use_tile = false;  // the shared-memory table would not fit; fall back to the older kernels
-      P.rec2_cap = cap;
-    }
-    if (use_tile) {
-      const int D2 = poly_dof(ctx->deg_hi, nd);
-      const TileRecLayout L = tile_rec_layout(sc, nd, D2, P.rec2_cap);
-      P.rec2_bytes = L.rec_bytes;
-      char *d_rec = nullptr;
-      if (dev_alloc(ctx, &d_rec, T * L.rec_bytes + 65536)) {  // slack: the kernel may prefetch a little past the last record
-        zfvm_destroy(ctx);
-        return 1;
-      }
-      P.rec2 = d_rec;
-      P.rec2_off_list = L.off_list;
-      P.rec2_off_lidx = L.off_lidx;
-      P.rec2_lidx_elem = L.lidx_elem;
-      std::vector<int> lo_row0((size_t)ns, 0), lo_w0((size_t)ns, 0);  // row / byte offsets of the one-sided stencils
-      {
-        int r = 0, b = 0;
-        for (int k = 1; k < ns; ++k) {
-          lo_row0[(size_t)k] = r;
-          lo_w0[(size_t)k] = b;
-          r += sc.rows_max[k];
-          b += sc.rows_max[k] * sc.ncoef[k] * TILE * 8;
-        }
-        lo_row0[0] = r;  // the central stencil's rows come last
-      }
-      {
-        TracerRecView &V = ctx->tracer_view;
-        V.tile_record = 1;
-        V.off_meta = TILE_OFF_META;
-        V.off_list = L.off_list;
-        V.off_lidx = L.off_lidx;
-        V.lidx_elem = L.lidx_elem;
-        for (int k = 0; k < ns; ++k) {
-          V.row0[k] = lo_row0[(size_t)k];
-          V.off_w[k] = (k == 0) ? L.off_whi : L.off_wlo + lo_w0[(size_t)k];
-        }
-      }
-      const int n_mom2 = std::max(D2 - 3, 0);
-      const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / L.rec_bytes));
-      std::vector<char> h_rec((size_t)(chunk * L.rec_bytes));
-      for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
-        const std::int64_t t1 = std::min(T, t0 + chunk);
-        std::memset(h_rec.data(), 0, h_rec.size());
-#pragma omp parallel
-        {
-          std::vector<double> A, W;
-          std::vector<std::pair<std::int32_t, std::int32_t>> map;  // (global, local), sorted by global
-          std::vector<std::int32_t> refs;
-#pragma omp for schedule(dynamic, 8)
-          for (std::int64_t t = t0; t < t1; ++t) {
-            char *rec = h_rec.data() + (size_t)((t - t0) * L.rec_bytes);
-            std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec + TILE_OFF_META);
-            std::int32_t *list = reinterpret_cast<std::int32_t *>(rec + L.off_list);
-            unsigned char *lidx = reinterpret_cast<unsigned char *>(rec + L.off_lidx);
-            auto put_lidx = [&](int row, int lane_, int value) {
-              if (L.lidx_elem == 1)
-                lidx[(size_t)row * TILE + lane_] = (unsigned char)value;
-              else
-                reinterpret_cast<std::uint16_t *>(lidx)[(size_t)row * TILE + lane_] = (std::uint16_t)value;
-            };
-            std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
-            // pass 1: the row list (own cells first, then the other stencil members in ascending order)
-            refs.clear();
-            for (int lane = 0; lane < TILE; ++lane) {
-              const std::int64_t i = t * TILE + lane;
-              list[lane] = (std::int32_t)std::min(i, n - 1);
-              if (i >= n) continue;
-              for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
-                if (S.order[(size_t)(i * ns + k)] <= 1) continue;
-                const int size = S.size[(size_t)(i * ns + k)];
-                for (int j = 1; j < size; ++j) refs.push_back(S.global(i, k, j));
-              }
-            }
-            std::sort(refs.begin(), refs.end());
-            refs.erase(std::unique(refs.begin(), refs.end()), refs.end());
-            map.clear();
-            const std::int32_t own_lo = (std::int32_t)(t * TILE), own_hi = (std::int32_t)std::min<std::int64_t>(n, (t + 1) * TILE);
-            int n_list = TILE;
-            for (std::int32_t gidx : refs) {
-              if (gidx >= own_lo && gidx < own_hi) {
-                map.emplace_back(gidx, gidx - own_lo);
-              } else {
-                list[n_list] = gidx;
-                map.emplace_back(gidx, n_list++);
-              }
-              tile_mx = std::max(tile_mx, gidx);
-            }
-            *reinterpret_cast<std::int32_t *>(rec) = n_list;
-            auto local_of = [&](std::int32_t gidx) {
-              auto it = std::lower_bound(map.begin(), map.end(), std::make_pair(gidx, (std::int32_t)-1));
-              return (int)it->second;
-            };
-            // pass 2: per cell meta, local indices, weights, geometry
-            double *geo = reinterpret_cast<double *>(rec + L.off_geo);
-            std::uint32_t *gref = reinterpret_cast<std::uint32_t *>(rec + L.off_geo + (size_t)L.geo_doubles * TILE * 8);
-            for (int lane = 0; lane < TILE; ++lane) {
-              const std::int64_t i = t * TILE + lane;
-              std::uint64_t m = 0;
-              for (int k = 0; k < ns; ++k) {
-                const int RM = sc.rows_max[k], NC = sc.ncoef[k];
-                const int row0 = lo_row0[(size_t)k];
-                for (int j = 0; j < RM; ++j) put_lidx(row0 + j, lane, lane);  // padded rows: rhs == 0
-                if (i >= n || k >= S.n_family[(size_t)i]) continue;
-                const int order = S.order[(size_t)(i * ns + k)];
-                if (order <= 1) continue;
-                int rows, cols;
-                stencil_matrix(A, rows, cols, g, S, i, k);
-                if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
-                W.resize((size_t)(rows * cols));
-                pseudo_inverse(A.data(), rows, cols, W.data());
-                for (int j = 0; j < rows; ++j) put_lidx(row0 + j, lane, local_of(S.global(i, k, j + 1)));
-                double *w = reinterpret_cast<double *>(rec + (k == 0 ? L.off_whi : L.off_wlo + lo_w0[(size_t)k])) + lane;
-                for (int j = 0; j < rows; ++j)
-                  for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
-                m |= ((std::uint64_t)rows) << (8 * k);
-              }
-              if (i < n) {
-                m |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
-                if (S.n_family[(size_t)i] == 1) m |= 1ull << 60;
-              }
-              meta[lane] = m;
-              // geometry: vtx[F][nd] | centre[nd] | 1/len | moments | face_ref u32[F] | face slots (byte k: face k)
-              const std::int64_t ic = std::min(i, n - 1);
-              for (int k = 0; k < F; ++k) {
-                const Vec3 v = g.vertex(ic, k);
-                for (int d = 0; d < nd; ++d) geo[(size_t)((k * nd + d) * TILE + lane)] = v[d];
-              }
-              for (int d = 0; d < nd; ++d) geo[(size_t)((F * nd + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * ic + d)];
-              geo[(size_t)((F * nd + nd) * TILE + lane)] = 1.0 / g.characteristic_length[(size_t)ic];
-              for (int mm = 0; mm < n_mom2; ++mm)
-                geo[(size_t)((F * nd + nd + 1 + mm) * TILE + lane)] = g.moments[(size_t)(ic * g.n_moments + 3 + mm)];
-              std::uint32_t slots_all = 0;
-              for (int k = 0; k < F; ++k) {
-                std::uint32_t r = 0;
-                if (i < n) {
-                  const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
-                  const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
-                  r = (std::uint32_t)e & FREF_EDGE_MASK;
-                  if (iL != (std::int32_t)i) r |= FREF_SIDE;
-                  if (iR != INVALID) {
-                    r |= FREF_INTERIOR;
-                    const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
-                    if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
-                  }
-                  slots_all |= ((std::uint32_t)g.face_vertex_slots[(size_t)(i * F + k)] & 0xFFu) << (8 * k);
-                }
-                gref[(size_t)(k * TILE + lane)] = r;
-              }
-              gref[(size_t)(F * TILE + lane)] = slots_all;
-            }
-            ctx->tile_max_ref[(size_t)t] = tile_mx;
-          }
-        }
-        ZFVM_CUDA(cudaMemcpy(d_rec + t0 * L.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * L.rec_bytes), cudaMemcpyHostToDevice));
-      }
-    } else {
-      char *d_rec = nullptr;
-      if (dev_alloc(ctx, &d_rec, T * P.rec_bytes)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-      P.rec = d_rec;
-      {
-        TracerRecView &V = ctx->tracer_view;
-        V.tile_record = 0;
-        V.off_meta = 0;
-        for (int k = 0; k < ns; ++k) {
-          V.off_sidx[k] = P.off_sidx[k];
-          V.off_w[k] = P.off_W[k];
-        }
-      }
-      const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / P.rec_bytes));
-      std::vector<char> h_rec((size_t)(chunk * P.rec_bytes));
-      for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
-        const std::int64_t t1 = std::min(T, t0 + chunk);
-        std::memset(h_rec.data(), 0, h_rec.size());
-#pragma omp parallel
-        {
-          std::vector<double> A, W;
-#pragma omp for schedule(dynamic, 8)
-          for (std::int64_t t = t0; t < t1; ++t) {
-            char *rec = h_rec.data() + (size_t)((t - t0) * P.rec_bytes);
-            std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec);
-            std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
-            for (int lane = 0; lane < TILE; ++lane) {
-              const std::int64_t i = t * TILE + lane;
-              const std::int64_t ic = std::min(i, n - 1);
-              std::uint64_t m = 0;
-              for (int k = 0; k < ns; ++k) {
-                const int RM = sc.rows_max[k], NC = sc.ncoef[k];
-                std::int32_t *si = reinterpret_cast<std::int32_t *>(rec + P.off_sidx[k]) + lane;
-                for (int j = 0; j < RM; ++j) si[(size_t)j * TILE] = (std::int32_t)ic;  // padded rows: rhs == 0
-                if (i >= n || k >= S.n_family[(size_t)i]) continue;
-                const int order = S.order[(size_t)(i * ns + k)];
-                if (order <= 1) continue;
-                int rows, cols;
-                stencil_matrix(A, rows, cols, g, S, i, k);
-                if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
-                W.resize((size_t)(rows * cols));
-                pseudo_inverse(A.data(), rows, cols, W.data());
-                for (int j = 0; j < rows; ++j) {
-                  si[(size_t)j * TILE] = S.global(i, k, j + 1);
-                  tile_mx = std::max(tile_mx, si[(size_t)j * TILE]);
-                }
-                double *w = reinterpret_cast<double *>(rec + P.off_W[k]) + lane;
-                for (int j = 0; j < rows; ++j)
-                  for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
-                m |= ((std::uint64_t)rows) << (8 * k);
-              }
-              if (i < n) {
-                m |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
-                if (S.n_family[(size_t)i] == 1) m |= 1ull << 60;
-              }
-              meta[lane] = m;
-            }
-            ctx->tile_max_ref[(size_t)t] = tile_mx;
-          }
-        }
-        ZFVM_CUDA(cudaMemcpy(d_rec + t0 * P.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * P.rec_bytes), cudaMemcpyHostToDevice));
-      }
-    }
-    for (std::int64_t i = 0; i < n; ++i) {
-      if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
-        ++n_counted;
-        bytes_m += S.l2g_size[(size_t)i];
-        for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
-          const int order = S.order[(size_t)(i * ns + k)], size = S.size[(size_t)(i * ns + k)];
-          if (order > 1) bytes_W += 8.0 * (size - 1) * (poly_dof(order - 1, nd) - 1);
-          bytes_idx += 4.0 * (size - 1);
-        }
-      }
-    }
-
-    // ---- geometry -----------------------------------------------------------------------------
-    const int D = poly_dof(ctx->deg_hi, nd);
-    P.n_mom = std::max(D - 3, 0);
-    {
-      std::vector<double> vtx((size_t)(T * F * 3 * TILE), 0.0), center((size_t)(T * 3 * TILE), 0.0),
-          inv_len((size_t)(T * TILE), 1.0), volume((size_t)(T * TILE), 1.0),
-          mom((size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
-      std::vector<std::uint32_t> fref((size_t)(T * F * TILE), 0u);
-      std::vector<std::uint8_t> fslots((size_t)(T * F * TILE), 0);
-#pragma omp parallel for schedule(static)
-      for (std::int64_t i = 0; i < n; ++i) {
-        const std::int64_t t = i / TILE;
-        const int lane = (int)(i % TILE);
-        for (int k = 0; k < F; ++k) {
-          const Vec3 v = g.vertex(i, k);
-          for (int d = 0; d < 3; ++d) vtx[(size_t)(((t * F + k) * 3 + d) * TILE + lane)] = v[d];
-          const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
-          const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
-          std::uint32_t r = (std::uint32_t)e & FREF_EDGE_MASK;
-          if (iL != (std::int32_t)i) r |= FREF_SIDE;
-          if (iR != INVALID) {
-            r |= FREF_INTERIOR;
-            const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
-            if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
-          }
-          fref[(size_t)((t * F + k) * TILE + lane)] = r;
-          fslots[(size_t)((t * F + k) * TILE + lane)] = g.face_vertex_slots[(size_t)(i * F + k)];
-        }
-        for (int d = 0; d < 3; ++d) center[(size_t)((t * 3 + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * i + d)];
-        inv_len[(size_t)i] = 1.0 / g.characteristic_length[(size_t)i];
-        volume[(size_t)i] = g.volumes[(size_t)i];
-        for (int m = 0; m < P.n_mom; ++m)
-          mom[(size_t)((t * P.n_mom + m) * TILE + lane)] = g.moments[(size_t)(i * g.n_moments + 3 + m)];
-      }
-      // tiles none of whose cells contributes a trace to the flux loop (ghost cells deeper than the l1 layer)
-      // are not reconstructed at all -- unless the caller wants every cell's polynomial back
-      ctx->tile_needed.assign((size_t)T, 1);
-      if (!params->keep_polynomials && !sc.has_gravity) {  // (the source loop visits every cell)
-        for (std::int64_t t = 0; t < T; ++t) {
-          bool any = false;
-          for (std::int64_t a = t * F * TILE; a < (t + 1) * F * TILE && !any; ++a) any = (fref[(size_t)a] & FREF_TRACE) != 0;
-          ctx->tile_needed[(size_t)t] = any ? 1 : 0;
-        }
-      }
-      if (E > (std::int64_t)FREF_EDGE_MASK) {
-        zfvm_destroy(ctx);
-        return fail("zfvm_create: too many faces for the packed face reference");
-      }
-      if (dev_upload(ctx, &P.vtx, vtx) || dev_upload(ctx, &P.center, center) || dev_upload(ctx, &P.inv_len, inv_len) ||
-          dev_upload(ctx, &P.volume, volume) || dev_upload(ctx, &P.moments, mom) || dev_upload(ctx, &P.face_ref, fref) ||
-          dev_upload(ctx, &P.face_slots, fslots) || dev_upload(ctx, &P.cell_flags, g.cell_flags)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-      const double *inr = nullptr;
-      if (dev_upload(ctx, &inr, g.inradii)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-      ctx->inradius = const_cast<double *>(inr);
-    }
-    // ---- faces ----------------------------------------------------------------------------------
-    {
-      std::vector<std::int32_t> lr((size_t)(2 * E));
-      std::vector<double> frame((size_t)(10 * E));
-#pragma omp parallel for schedule(static)
-      for (std::int64_t e = 0; e < E; ++e) {
-        std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
-        bool skip = (iR == INVALID);
-        if (!skip) skip = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
-        lr[(size_t)(2 * e)] = skip ? -1 : iL;
-        lr[(size_t)(2 * e + 1)] = iR;
-        for (int d = 0; d < 3; ++d) {
-          frame[(size_t)(10 * e + d)] = g.face_normal[(size_t)(3 * e + d)];
-          frame[(size_t)(10 * e + 3 + d)] = g.face_t1[(size_t)(3 * e + d)];
-          frame[(size_t)(10 * e + 6 + d)] = g.face_t2[(size_t)(3 * e + d)];
-        }
-        frame[(size_t)(10 * e + 9)] = g.face_area[(size_t)e];
-      }
-      if (dev_upload(ctx, &P.left_right, lr) || dev_upload(ctx, &P.face_frame, frame)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-    }
-    // ---- gravity ----------------------------------------------------------------------------------
-    if (sc.has_gravity) {
-      double *a = nullptr, *b = nullptr, *c = nullptr;
-      if (dev_alloc(ctx, &a, n * g.q_c, true) || dev_alloc(ctx, &b, n * g.q_c * 3, true) ||
-          dev_alloc(ctx, &c, E * g.q_f, true)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-      P.phi_cqp = a;
-      P.gradphi_cqp = b;
-      P.phi_fqp = c;
-      if (params->gravity_kind >= GRAVITY_CONSTANT && params->gravity_kind <= GRAVITY_POLYTROPE) {
-        GravityModel gm;
-        gm.kind = params->gravity_kind;
-        gm.alignment = params->gravity_alignment;
-        for (int q = 0; q < 4; ++q) gm.p[q] = params->gravity_p[q];
-        if (gm.kind == GRAVITY_POINT_MASS && params->gravity_p[2] != 0.0) {
-          // PointMassGravity(G, M, X): GM = G * M
-          gm.p[0] = params->gravity_p[0] * params->gravity_p[1];
-          gm.p[1] = params->gravity_p[2];
-        }
-        for (int d = 0; d < 3; ++d) gm.axis[d] = params->gravity_axis[d];
-        std::vector<double> h_a, h_b, h_c;
-        tabulate_gravity(gm, g, h_a, h_b, h_c);
-        ZFVM_CUDA(cudaMemcpy(a, h_a.data(), h_a.size() * sizeof(double), cudaMemcpyHostToDevice));
-        ZFVM_CUDA(cudaMemcpy(b, h_b.data(), h_b.size() * sizeof(double), cudaMemcpyHostToDevice));
-        ZFVM_CUDA(cudaMemcpy(c, h_c.data(), h_c.size() * sizeof(double), cudaMemcpyHostToDevice));
-      }
-    }
-    // ---- work arrays ------------------------------------------------------------------------------
-    // (+ dump blocks for the tile kernel's branch-free trace write-out)
-    if (dev_alloc(ctx, &P.trace, (std::max<std::int64_t>(EI, 1) + TRACE_DUMP_BLOCKS / 2) * 2 * g.q_f * NVARS, true) ||
-        dev_alloc(ctx, &P.flux, std::max<std::int64_t>(EI, 1) * NVARS, true) || dev_alloc(ctx, &P.source, n * NVARS, true) ||
-        dev_alloc(ctx, &ctx->eq_fail_dev, 1, true) || dev_alloc(ctx, &ctx->reduce_dev, 1, true)) {
+    // every failure below leaves through this one place: zfvm_destroy releases whatever had been allocated
+    if (create_impl(ctx, grid, stencils, params)) {
       zfvm_destroy(ctx);
       return 1;
     }
-    P.eq_fail = ctx->eq_fail_dev;
-    P.n_poly_coef = D;
-    if (P.rec2 != nullptr && sc.has_gravity) {  // the tile kernel hands the polynomial to source_kernel
-      if (dev_alloc(ctx, &P.poly_tile, T * (std::int64_t)(D + 1) * NVARS * TILE, true)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-    }
-    if (params->keep_polynomials) {
-      if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-    }
-    {
-      std::vector<std::int32_t> tl;
-      for (std::int64_t t = 0; t < T; ++t)
-        if (ctx->tile_needed[(size_t)t]) tl.push_back((std::int32_t)t);
-      ctx->n_tiles_needed = (std::int64_t)tl.size();
-      if (ctx->n_tiles_needed < T) {
-        const std::int32_t *p = nullptr;
-        if (dev_upload(ctx, &p, tl)) {
-          zfvm_destroy(ctx);
-          return 1;
-        }
-        ctx->tiles_needed = const_cast<std::int32_t *>(p);
-      }
-    }
-    ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));
-    // ghost cells (FrozenBC::count_ghost_cells)
-    {
-      std::vector<std::int32_t> gi;
-      for (std::int64_t i = 0; i < n; ++i)
-        if (g.cell_flags[(size_t)i] & FLAG_GHOST) gi.push_back((std::int32_t)i);
-      ctx->n_ghost = (std::int64_t)gi.size();
-      const std::int32_t *p = nullptr;
-      if (dev_upload(ctx, &p, gi)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-      ctx->ghost_index = const_cast<std::int32_t *>(p);
-    }
-    // resident state / RK buffers
-    if (dev_alloc(ctx, &ctx->u_cur, n * NVARS, true) || dev_alloc(ctx, &ctx->u_tmp, n * NVARS, true) ||
-        dev_alloc(ctx, &ctx->tend_work, n * NVARS, true) || dev_alloc(ctx, &ctx->state_work, n * NVARS, true)) {
-      zfvm_destroy(ctx);
-      return 1;
-    }
-
-    // well-balanced runs: equilibrium parameters per cell and equilibrium averages per (cell, stencil row)
-    if (sc.well_balanced) {
-      int r = 0;
-      for (int k = 0; k < ns; ++k) {
-        P.eq_row0[k] = r;
-        r += sc.rows_max[k];
-      }
-      P.eq_rows = P.rec2 ? r + 1 : r;  // tile records: rows in lidx order plus one row for the cell itself
-      if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)P.eq_rows * 2 * TILE, true) ||
-          (P.rec2 && dev_alloc(ctx, &P.eq_bg, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * 2, true))) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-    }
-    // advected scalars: traces, face fluxes, resident rows and host-entry work rows
-    P.n_avars = ctx->n_avars;
-    if (ctx->n_avars > 0) {
-      const std::int64_t na = ctx->n_avars;
-      if (dev_alloc(ctx, &P.qtrace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * na, true) ||
-          dev_alloc(ctx, &P.qflux, std::max<std::int64_t>(EI, 1) * na, true) || dev_alloc(ctx, &ctx->a_cur, n * na, true) ||
-          dev_alloc(ctx, &ctx->a_tmp, n * na, true) || dev_alloc(ctx, &ctx->tend_work_a, n * na, true) ||
-          dev_alloc(ctx, &ctx->state_work_a, n * na, true)) {
-        zfvm_destroy(ctx);
-        return 1;
-      }
-    }
-
-    // ---- algorithmic bytes per cell and stage -----------------------------------------
-    {
-      const double nc = (double)std::max<std::int64_t>(n_counted, 1);
-      const double B_W = bytes_W / nc, B_idx = bytes_idx / nc + 4.0 * bytes_m / nc, m = bytes_m / nc;
-      const double B_state = 80.0, B_poly = 2.0 * 40.0 * D;
-      const double B_cell = 8.0 * (3 + 1 + 1 + D + 5) + (sc.has_gravity ? 8.0 * 4 * g.q_c : 0.0);
-      const double B_face = (F / 2.0) * (8.0 * (9 + 4 * g.q_f) + 8.0);
-      const double B_wb = sc.well_balanced ? 8.0 * (2 * m + 4.0 * (g.q_c + F * g.q_f)) : 0.0;
-      ctx->algorithmic_bytes = B_W + B_idx + B_state + B_poly + B_cell + B_face + B_wb;  // + B_rk added per tableau
-    }
-    if (zfvm_set_time_integration(ctx, "ssp3")) {
-      zfvm_destroy(ctx);
-      return 1;
-    }
-    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
   } catch (const std::exception &e) {
     if (ctx) zfvm_destroy(ctx);
     return fail(std::string("zfvm_create: ") + e.what());
   }
+}
+
+// The body of zfvm_create once the arguments are validated and the device is selected; any non-zero return is followed
+// by zfvm_destroy(ctx) in the caller (allocations are registered in ctx->allocations as they are made).
+static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params) {
+  const HostGrid &g = grid->g;
+  const HostStencils &S = stencils->s;
+  const int nd = g.n_dims, F = g.max_neighbours, ns = S.n_stencils;
+  ctx->params = *params;
+  ctx->n_dims = nd;
+  ctx->n_cells = g.n_cells;
+  ctx->n_owned = g.n_cells;
+  const std::int64_t n = g.n_cells, T = (n + TILE - 1) / TILE, E = g.n_edges, EI = g.n_interior_edges;
+  ctx->n_tiles = T;
+  ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+  ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+
+  // ---- scheme constants ------------------------------------------------------------------
+  SchemeConst &sc = ctx->sc;
+  std::memset(&sc, 0, sizeof(sc));
+  sc.n_dims = nd;
+  sc.n_stencils = ns;
+  sc.q_f = g.q_f;
+  sc.q_c = g.q_c;
+  sc.recon_mode = params->recon_mode;
+  sc.scaling = params->scaling;
+  sc.flux = params->flux;
+  sc.well_balanced = params->well_balanced;
+  // the cell-local source pass (GravitySourceLoop and / or Heating) runs when either term is present; without a
+  // gravity model its potential tables stay zero
+  sc.has_gravity = params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0;
+  {
+    sc.eos_pow_e = 1.0 / (params->gamma - 1.0);
+    const double twice = 2.0 * sc.eos_pow_e, r = std::rint(twice);
+    sc.eos_pow_n = (std::fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) ? (int)r : 0;
+  }
+  sc.heating_rate = params->heating_rate;
+  sc.heating_r0 = params->heating_r0;
+  sc.heating_r1 = params->heating_r1;
+  ctx->n_avars = params->n_avars;
+  sc.epsilon = params->epsilon;
+  sc.exponent = params->exponent;
+  sc.gamma = params->gamma;
+  // Families the specialised kernels (tile / thread-per-cell with compile-time degrees) are built for: the shape of
+  // every parameter set the reference's experiments use -- one leading stencil of the highest order followed by
+  // n_dims + 1 stencils of order 2.  Anything else the reference's JSON can describe (first-order families, several
+  // central stencils, one-sided stencils of order 3, a lone stencil; test/.../weno_ao.cpp:47-55, cweno_ao.cpp:144-160)
+  // runs the generic kernel (kernels/recon_generic.cu), where every stencil keeps its own coefficient count.
+  ctx->deg_hi = 0;
+  for (int k = 0; k < ns; ++k) ctx->deg_hi = std::max(ctx->deg_hi, S.params.orders[(size_t)k] - 1);
+  ctx->deg_lo = 0;
+  for (int k = 1; k < ns; ++k) ctx->deg_lo = std::max(ctx->deg_lo, S.params.orders[(size_t)k] - 1);
+  bool specialised = (ns == nd + 2) && S.params.orders[0] >= 2 && S.params.orders[0] - 1 == ctx->deg_hi;
+  for (int k = 1; k < ns; ++k) specialised = specialised && S.params.orders[(size_t)k] == 2;
+  if (const char *e = std::getenv("ZFVM_RECON")) specialised = specialised && e[0] != 'g';  // tests: ZFVM_RECON=generic
+  ctx->generic = !specialised;
+  if ((nd == 2 && ctx->deg_hi >= 5) || (nd == 3 && ctx->deg_hi >= 4))
+    return fail("zfvm_create: LSQ matrices exist up to order 5 in 2D and 4 in 3D (lsq_solver.cpp:288,399)");
+  if (g.n_moments < poly_dof(ctx->deg_hi, nd))
+    return fail("zfvm_create: grid moments_deg is lower than the polynomial degree");
+  double wsum = 0.0;
+  for (int k = 0; k < ns; ++k) wsum += params->linear_weights[k];
+  for (int k = 0; k < ns; ++k) {
+    sc.lin_w[k] = params->linear_weights[k] / wsum;  // hybrid_weno.cpp:26-31
+    sc.rows_max[k] = S.max_size[(size_t)k] - 1;
+    if (sc.rows_max[k] > 255)
+      return fail("zfvm_create: a stencil may have at most 256 cells (8-bit row counts in the tile meta word)");
+    sc.ncoef[k] = ctx->generic ? poly_dof(S.params.orders[(size_t)k] - 1, nd) - 1
+                               : poly_dof(k == 0 ? ctx->deg_hi : ctx->deg_lo, nd) - 1;
+  }
+  // probe the dispatch now: a family no kernel is compiled for must fail here, not in the first residual evaluation
+  // (in a multi-rank run that would be after the NCCL group has been posted)
+  if (ctx->generic && !recon_generic_supported(sc, poly_dof(ctx->deg_hi, nd)))
+    return fail("zfvm_create: no reconstruction kernel for this stencil family (at most 6 stencils, order <= 5 in 2D / 4 in 3D)");
+  for (int q = 0; q < g.q_f; ++q) {
+    sc.face_w[q] = g.face_rule.weights[(size_t)q];
+    for (int b = 0; b < g.face_rule.n_bary; ++b) sc.face_bary[q][b] = g.face_rule.bary[(size_t)(q * g.face_rule.n_bary + b)];
+  }
+  for (int q = 0; q < g.q_c; ++q) {
+    sc.cell_w[q] = g.cell_rule.weights[(size_t)q];
+    for (int b = 0; b < g.cell_rule.n_bary; ++b) sc.cell_bary[q][b] = g.cell_rule.bary[(size_t)(q * g.cell_rule.n_bary + b)];
+  }
+
+  DevicePlan &P = ctx->plan;
+  std::memset(&P, 0, sizeof(P));
+  P.n_cells = n;
+  P.n_tiles = T;
+  P.n_edges = E;
+  P.n_interior_edges = EI;
+
+  // ---- tile records (meta | sidx_k | W_k), built and uploaded in chunks of tiles -------------------
+  ctx->tile_max_ref.assign((size_t)T, 0);
+  for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
+  double bytes_W = 0.0, bytes_idx = 0.0, bytes_m = 0.0;
+  std::int64_t n_counted = 0;
+  {
+    int off = TILE * (int)sizeof(std::uint64_t);
+    for (int k = 0; k < ns; ++k) {
+      P.off_sidx[k] = off;
+      off += sc.rows_max[k] * TILE * (int)sizeof(std::int32_t);
+    }
+    P.hdr_bytes = off;
+    for (int k = 0; k < ns; ++k) {
+      P.off_W[k] = off;
+      off += sc.rows_max[k] * sc.ncoef[k] * TILE * (int)sizeof(double);
+    }
+    P.rec_bytes = off;  // every section is a multiple of 128 bytes
+  }
+  // ---- tile kernel records (kernels/recon_tile.cuh): header | one-sided W | central W | geometry ----------
+  // Built instead of the records above whenever the tile kernel is compiled for the scheme (plain Euler,
+  // no gravity terms inside K1); ZFVM_RECON=v1|stream keeps the older kernels for comparisons.
+  bool use_tile = false;
+  {
+    const char *e_recon = std::getenv("ZFVM_RECON");
+    const bool other = e_recon && (e_recon[0] == 'v' || e_recon[0] == 's');
+    // (gravity / heating without well-balancing: the tile kernel stores the polynomial, source_kernel evaluates the
+    // cell-local source terms from it; ZFVM_SOURCE=v1 keeps those runs on the thread-per-cell kernel)
+    const char *e_src = std::getenv("ZFVM_SOURCE");
+    const bool source_v1 = e_src && e_src[0] == 'v';
+    use_tile = !ctx->generic && !other && !(sc.has_gravity && source_v1) && ns >= 2 &&
+               recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
+  }
+  if (use_tile) {
+    // distinct cells read by a tile's stencils
+    std::vector<std::int32_t> n_union((size_t)T, 0);
+#pragma omp parallel
+    {
+      std::vector<std::int32_t> seen;
+#pragma omp for schedule(dynamic, 64)
+      for (std::int64_t t = 0; t < T; ++t) {
+        seen.clear();
+        for (int lane = 0; lane < TILE; ++lane) {
+          const std::int64_t i = t * TILE + lane;
+          seen.push_back((std::int32_t)std::min(i, n - 1));
+          if (i >= n) continue;
+          for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+            if (S.order[(size_t)(i * ns + k)] <= 1) continue;
+            const int size = S.size[(size_t)(i * ns + k)];
+            for (int j = 1; j < size; ++j) seen.push_back(S.global(i, k, j));
+          }
+        }
+        std::sort(seen.begin(), seen.end());
+        // the own cells occupy 32 list entries even when the last tile repeats the last cell
+        const std::int64_t n_own_distinct = std::min<std::int64_t>(TILE, n - t * TILE);
+        n_union[(size_t)t] = (std::int32_t)((std::unique(seen.begin(), seen.end()) - seen.begin()) + (TILE - n_own_distinct));
+      }
+    }
+    int cap = TILE;
+    for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
+    cap = (cap + 31) / 32 * 32;
+    if (const char *e = std::getenv("ZFVM_TILE_MIN_CAP")) cap = std::max(cap, (std::atoi(e) + 31) / 32 * 32);  // tests: 16-bit indices
+    if (cap > 1024) use_tile = false;  // the shared-memory table would not fit; fall back to the older kernels
+    P.rec2_cap = cap;
+  }
+  if (use_tile) {
+    const int D2 = poly_dof(ctx->deg_hi, nd);
+    const TileRecLayout L = tile_rec_layout(sc, nd, D2, P.rec2_cap);
+    P.rec2_bytes = L.rec_bytes;
+    char *d_rec = nullptr;
+    if (dev_alloc(ctx, &d_rec, T * L.rec_bytes + 65536)) {  // slack: the kernel may prefetch a little past the last record
+              return 1;
+    }
+    P.rec2 = d_rec;
+    P.rec2_off_list = L.off_list;
+    P.rec2_off_lidx = L.off_lidx;
+    P.rec2_lidx_elem = L.lidx_elem;
+    std::vector<int> lo_row0((size_t)ns, 0), lo_w0((size_t)ns, 0);  // row / byte offsets of the one-sided stencils
+    {
+      int r = 0, b = 0;
+      for (int k = 1; k < ns; ++k) {
+        lo_row0[(size_t)k] = r;
+        lo_w0[(size_t)k] = b;
+        r += sc.rows_max[k];
+        b += sc.rows_max[k] * sc.ncoef[k] * TILE * 8;
+      }
+      lo_row0[0] = r;  // the central stencil's rows come last
+    }
+    {
+      TracerRecView &V = ctx->tracer_view;
+      V.tile_record = 1;
+      V.off_meta = TILE_OFF_META;
+      V.off_list = L.off_list;
+      V.off_lidx = L.off_lidx;
+      V.lidx_elem = L.lidx_elem;
+      for (int k = 0; k < ns; ++k) {
+        V.row0[k] = lo_row0[(size_t)k];
+        V.off_w[k] = (k == 0) ? L.off_whi : L.off_wlo + lo_w0[(size_t)k];
+      }
+    }
+    const int n_mom2 = std::max(D2 - 3, 0);
+    const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / L.rec_bytes));
+    std::vector<char> h_rec((size_t)(chunk * L.rec_bytes));
+    for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
+      const std::int64_t t1 = std::min(T, t0 + chunk);
+      std::memset(h_rec.data(), 0, h_rec.size());
+#pragma omp parallel
+      {
+        std::vector<double> A, W;
+        std::vector<std::pair<std::int32_t, std::int32_t>> map;  // (global, local), sorted by global
+        std::vector<std::int32_t> refs;
+#pragma omp for schedule(dynamic, 8)
+        for (std::int64_t t = t0; t < t1; ++t) {
+          char *rec = h_rec.data() + (size_t)((t - t0) * L.rec_bytes);
+          std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec + TILE_OFF_META);
+          std::int32_t *list = reinterpret_cast<std::int32_t *>(rec + L.off_list);
+          unsigned char *lidx = reinterpret_cast<unsigned char *>(rec + L.off_lidx);
+          auto put_lidx = [&](int row, int lane_, int value) {
+            if (L.lidx_elem == 1)
+              lidx[(size_t)row * TILE + lane_] = (unsigned char)value;
+            else
+              reinterpret_cast<std::uint16_t *>(lidx)[(size_t)row * TILE + lane_] = (std::uint16_t)value;
+          };
+          std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
+          // pass 1: the row list (own cells first, then the other stencil members in ascending order)
+          refs.clear();
+          for (int lane = 0; lane < TILE; ++lane) {
+            const std::int64_t i = t * TILE + lane;
+            list[lane] = (std::int32_t)std::min(i, n - 1);
+            if (i >= n) continue;
+            for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+              if (S.order[(size_t)(i * ns + k)] <= 1) continue;
+              const int size = S.size[(size_t)(i * ns + k)];
+              for (int j = 1; j < size; ++j) refs.push_back(S.global(i, k, j));
+            }
+          }
+          std::sort(refs.begin(), refs.end());
+          refs.erase(std::unique(refs.begin(), refs.end()), refs.end());
+          map.clear();
+          const std::int32_t own_lo = (std::int32_t)(t * TILE), own_hi = (std::int32_t)std::min<std::int64_t>(n, (t + 1) * TILE);
+          int n_list = TILE;
+          for (std::int32_t gidx : refs) {
+            if (gidx >= own_lo && gidx < own_hi) {
+              map.emplace_back(gidx, gidx - own_lo);
+            } else {
+              list[n_list] = gidx;
+              map.emplace_back(gidx, n_list++);
+            }
+            tile_mx = std::max(tile_mx, gidx);
+          }
+          *reinterpret_cast<std::int32_t *>(rec) = n_list;
+          auto local_of = [&](std::int32_t gidx) {
+            auto it = std::lower_bound(map.begin(), map.end(), std::make_pair(gidx, (std::int32_t)-1));
+            return (int)it->second;
+          };
+          // pass 2: per cell meta, local indices, weights, geometry
+          double *geo = reinterpret_cast<double *>(rec + L.off_geo);
+          std::uint32_t *gref = reinterpret_cast<std::uint32_t *>(rec + L.off_geo + (size_t)L.geo_doubles * TILE * 8);
+          for (int lane = 0; lane < TILE; ++lane) {
+            const std::int64_t i = t * TILE + lane;
+            std::uint64_t m = 0;
+            for (int k = 0; k < ns; ++k) {
+              const int RM = sc.rows_max[k], NC = sc.ncoef[k];
+              const int row0 = lo_row0[(size_t)k];
+              for (int j = 0; j < RM; ++j) put_lidx(row0 + j, lane, lane);  // padded rows: rhs == 0
+              if (i >= n || k >= S.n_family[(size_t)i]) continue;
+              const int order = S.order[(size_t)(i * ns + k)];
+              if (order <= 1) continue;
+              int rows, cols;
+              stencil_matrix(A, rows, cols, g, S, i, k);
+              if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
+              W.resize((size_t)(rows * cols));
+              pseudo_inverse(A.data(), rows, cols, W.data());
+              for (int j = 0; j < rows; ++j) put_lidx(row0 + j, lane, local_of(S.global(i, k, j + 1)));
+              double *w = reinterpret_cast<double *>(rec + (k == 0 ? L.off_whi : L.off_wlo + lo_w0[(size_t)k])) + lane;
+              for (int j = 0; j < rows; ++j)
+                for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+              m |= ((std::uint64_t)rows) << (8 * k);
+            }
+            if (i < n) {
+              m |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
+              if (S.n_family[(size_t)i] == 1) m |= 1ull << 60;
+            }
+            meta[lane] = m;
+            // geometry: vtx[F][nd] | centre[nd] | 1/len | moments | face_ref u32[F] | face slots (byte k: face k)
+            const std::int64_t ic = std::min(i, n - 1);
+            for (int k = 0; k < F; ++k) {
+              const Vec3 v = g.vertex(ic, k);
+              for (int d = 0; d < nd; ++d) geo[(size_t)((k * nd + d) * TILE + lane)] = v[d];
+            }
+            for (int d = 0; d < nd; ++d) geo[(size_t)((F * nd + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * ic + d)];
+            geo[(size_t)((F * nd + nd) * TILE + lane)] = 1.0 / g.characteristic_length[(size_t)ic];
+            for (int mm = 0; mm < n_mom2; ++mm)
+              geo[(size_t)((F * nd + nd + 1 + mm) * TILE + lane)] = g.moments[(size_t)(ic * g.n_moments + 3 + mm)];
+            std::uint32_t slots_all = 0;
+            for (int k = 0; k < F; ++k) {
+              std::uint32_t r = 0;
+              if (i < n) {
+                const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
+                const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+                r = (std::uint32_t)e & FREF_EDGE_MASK;
+                if (iL != (std::int32_t)i) r |= FREF_SIDE;
+                if (iR != INVALID) {
+                  r |= FREF_INTERIOR;
+                  const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+                  if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
+                }
+                slots_all |= ((std::uint32_t)g.face_vertex_slots[(size_t)(i * F + k)] & 0xFFu) << (8 * k);
+              }
+              gref[(size_t)(k * TILE + lane)] = r;
+            }
+            gref[(size_t)(F * TILE + lane)] = slots_all;
+          }
+          ctx->tile_max_ref[(size_t)t] = tile_mx;
+        }
+      }
+      ZFVM_CUDA(cudaMemcpy(d_rec + t0 * L.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * L.rec_bytes), cudaMemcpyHostToDevice));
+    }
+  } else {
+    char *d_rec = nullptr;
+    if (dev_alloc(ctx, &d_rec, T * P.rec_bytes)) {
+      return 1;
+    }
+    P.rec = d_rec;
+    {
+      TracerRecView &V = ctx->tracer_view;
+      V.tile_record = 0;
+      V.off_meta = 0;
+      for (int k = 0; k < ns; ++k) {
+        V.off_sidx[k] = P.off_sidx[k];
+        V.off_w[k] = P.off_W[k];
+      }
+    }
+    const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / P.rec_bytes));
+    std::vector<char> h_rec((size_t)(chunk * P.rec_bytes));
+    for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
+      const std::int64_t t1 = std::min(T, t0 + chunk);
+      std::memset(h_rec.data(), 0, h_rec.size());
+#pragma omp parallel
+      {
+        std::vector<double> A, W;
+#pragma omp for schedule(dynamic, 8)
+        for (std::int64_t t = t0; t < t1; ++t) {
+          char *rec = h_rec.data() + (size_t)((t - t0) * P.rec_bytes);
+          std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec);
+          std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
+          for (int lane = 0; lane < TILE; ++lane) {
+            const std::int64_t i = t * TILE + lane;
+            const std::int64_t ic = std::min(i, n - 1);
+            std::uint64_t m = 0;
+            for (int k = 0; k < ns; ++k) {
+              const int RM = sc.rows_max[k], NC = sc.ncoef[k];
+              std::int32_t *si = reinterpret_cast<std::int32_t *>(rec + P.off_sidx[k]) + lane;
+              for (int j = 0; j < RM; ++j) si[(size_t)j * TILE] = (std::int32_t)ic;  // padded rows: rhs == 0
+              if (i >= n || k >= S.n_family[(size_t)i]) continue;
+              const int order = S.order[(size_t)(i * ns + k)];
+              if (order <= 1) continue;
+              int rows, cols;
+              stencil_matrix(A, rows, cols, g, S, i, k);
+              if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
+              W.resize((size_t)(rows * cols));
+              pseudo_inverse(A.data(), rows, cols, W.data());
+              for (int j = 0; j < rows; ++j) {
+                si[(size_t)j * TILE] = S.global(i, k, j + 1);
+                tile_mx = std::max(tile_mx, si[(size_t)j * TILE]);
+              }
+              double *w = reinterpret_cast<double *>(rec + P.off_W[k]) + lane;
+              for (int j = 0; j < rows; ++j)
+                for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+              m |= ((std::uint64_t)rows) << (8 * k);
+            }
+            if (i < n) {
+              m |= ((std::uint64_t)(S.k_high[(size_t)i] & 0xF)) << 56;
+              if (S.n_family[(size_t)i] == 1) m |= 1ull << 60;
+            }
+            meta[lane] = m;
+          }
+          ctx->tile_max_ref[(size_t)t] = tile_mx;
+        }
+      }
+      ZFVM_CUDA(cudaMemcpy(d_rec + t0 * P.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * P.rec_bytes), cudaMemcpyHostToDevice));
+    }
+  }
+  for (std::int64_t i = 0; i < n; ++i) {
+    if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
+      ++n_counted;
+      bytes_m += S.l2g_size[(size_t)i];
+      for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+        const int order = S.order[(size_t)(i * ns + k)], size = S.size[(size_t)(i * ns + k)];
+        if (order > 1) bytes_W += 8.0 * (size - 1) * (poly_dof(order - 1, nd) - 1);
+        bytes_idx += 4.0 * (size - 1);
+      }
+    }
+  }
+
+  // ---- geometry -----------------------------------------------------------------------------
+  const int D = poly_dof(ctx->deg_hi, nd);
+  P.n_mom = std::max(D - 3, 0);
+  {
+    std::vector<double> vtx((size_t)(T * F * 3 * TILE), 0.0), center((size_t)(T * 3 * TILE), 0.0),
+        inv_len((size_t)(T * TILE), 1.0), volume((size_t)(T * TILE), 1.0),
+        mom((size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
+    std::vector<std::uint32_t> fref((size_t)(T * F * TILE), 0u);
+    std::vector<std::uint8_t> fslots((size_t)(T * F * TILE), 0);
+#pragma omp parallel for schedule(static)
+    for (std::int64_t i = 0; i < n; ++i) {
+      const std::int64_t t = i / TILE;
+      const int lane = (int)(i % TILE);
+      for (int k = 0; k < F; ++k) {
+        const Vec3 v = g.vertex(i, k);
+        for (int d = 0; d < 3; ++d) vtx[(size_t)(((t * F + k) * 3 + d) * TILE + lane)] = v[d];
+        const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
+        const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+        std::uint32_t r = (std::uint32_t)e & FREF_EDGE_MASK;
+        if (iL != (std::int32_t)i) r |= FREF_SIDE;
+        if (iR != INVALID) {
+          r |= FREF_INTERIOR;
+          const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+          if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
+        }
+        fref[(size_t)((t * F + k) * TILE + lane)] = r;
+        fslots[(size_t)((t * F + k) * TILE + lane)] = g.face_vertex_slots[(size_t)(i * F + k)];
+      }
+      for (int d = 0; d < 3; ++d) center[(size_t)((t * 3 + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * i + d)];
+      inv_len[(size_t)i] = 1.0 / g.characteristic_length[(size_t)i];
+      volume[(size_t)i] = g.volumes[(size_t)i];
+      for (int m = 0; m < P.n_mom; ++m)
+        mom[(size_t)((t * P.n_mom + m) * TILE + lane)] = g.moments[(size_t)(i * g.n_moments + 3 + m)];
+    }
+    // tiles none of whose cells contributes a trace to the flux loop (ghost cells deeper than the l1 layer)
+    // are not reconstructed at all -- unless the caller wants every cell's polynomial back
+    ctx->tile_needed.assign((size_t)T, 1);
+    if (!params->keep_polynomials && !sc.has_gravity) {  // (the source loop visits every cell)
+      for (std::int64_t t = 0; t < T; ++t) {
+        bool any = false;
+        for (std::int64_t a = t * F * TILE; a < (t + 1) * F * TILE && !any; ++a) any = (fref[(size_t)a] & FREF_TRACE) != 0;
+        ctx->tile_needed[(size_t)t] = any ? 1 : 0;
+      }
+    }
+    if (E > (std::int64_t)FREF_EDGE_MASK) {
+      return fail("zfvm_create: too many faces for the packed face reference");
+    }
+    if (dev_upload(ctx, &P.vtx, vtx) || dev_upload(ctx, &P.center, center) || dev_upload(ctx, &P.inv_len, inv_len) ||
+        dev_upload(ctx, &P.volume, volume) || dev_upload(ctx, &P.moments, mom) || dev_upload(ctx, &P.face_ref, fref) ||
+        dev_upload(ctx, &P.face_slots, fslots) || dev_upload(ctx, &P.cell_flags, g.cell_flags)) {
+      return 1;
+    }
+    const double *inr = nullptr;
+    if (dev_upload(ctx, &inr, g.inradii)) {
+      return 1;
+    }
+    ctx->inradius = const_cast<double *>(inr);
+  }
+  // ---- faces ----------------------------------------------------------------------------------
+  {
+    std::vector<std::int32_t> lr((size_t)(2 * E));
+    std::vector<double> frame((size_t)(10 * E));
+#pragma omp parallel for schedule(static)
+    for (std::int64_t e = 0; e < E; ++e) {
+      std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+      bool skip = (iR == INVALID);
+      if (!skip) skip = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+      lr[(size_t)(2 * e)] = skip ? -1 : iL;
+      lr[(size_t)(2 * e + 1)] = iR;
+      for (int d = 0; d < 3; ++d) {
+        frame[(size_t)(10 * e + d)] = g.face_normal[(size_t)(3 * e + d)];
+        frame[(size_t)(10 * e + 3 + d)] = g.face_t1[(size_t)(3 * e + d)];
+        frame[(size_t)(10 * e + 6 + d)] = g.face_t2[(size_t)(3 * e + d)];
+      }
+      frame[(size_t)(10 * e + 9)] = g.face_area[(size_t)e];
+    }
+    if (dev_upload(ctx, &P.left_right, lr) || dev_upload(ctx, &P.face_frame, frame)) {
+      return 1;
+    }
+  }
+  // ---- gravity ----------------------------------------------------------------------------------
+  if (sc.has_gravity) {
+    double *a = nullptr, *b = nullptr, *c = nullptr;
+    if (dev_alloc(ctx, &a, n * g.q_c, true) || dev_alloc(ctx, &b, n * g.q_c * 3, true) ||
+        dev_alloc(ctx, &c, E * g.q_f, true)) {
+      return 1;
+    }
+    P.phi_cqp = a;
+    P.gradphi_cqp = b;
+    P.phi_fqp = c;
+    if (params->gravity_kind >= GRAVITY_CONSTANT && params->gravity_kind <= GRAVITY_POLYTROPE) {
+      GravityModel gm;
+      gm.kind = params->gravity_kind;
+      gm.alignment = params->gravity_alignment;
+      for (int q = 0; q < 4; ++q) gm.p[q] = params->gravity_p[q];
+      if (gm.kind == GRAVITY_POINT_MASS && params->gravity_p[2] != 0.0) {
+        // PointMassGravity(G, M, X): GM = G * M
+        gm.p[0] = params->gravity_p[0] * params->gravity_p[1];
+        gm.p[1] = params->gravity_p[2];
+      }
+      for (int d = 0; d < 3; ++d) gm.axis[d] = params->gravity_axis[d];
+      std::vector<double> h_a, h_b, h_c;
+      tabulate_gravity(gm, g, h_a, h_b, h_c);
+      ZFVM_CUDA(cudaMemcpy(a, h_a.data(), h_a.size() * sizeof(double), cudaMemcpyHostToDevice));
+      ZFVM_CUDA(cudaMemcpy(b, h_b.data(), h_b.size() * sizeof(double), cudaMemcpyHostToDevice));
+      ZFVM_CUDA(cudaMemcpy(c, h_c.data(), h_c.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  // ---- work arrays ------------------------------------------------------------------------------
+  // (+ dump blocks for the tile kernel's branch-free trace write-out)
+  if (dev_alloc(ctx, &P.trace, (std::max<std::int64_t>(EI, 1) + TRACE_DUMP_BLOCKS / 2) * 2 * g.q_f * NVARS, true) ||
+      dev_alloc(ctx, &P.flux, std::max<std::int64_t>(EI, 1) * NVARS, true) || dev_alloc(ctx, &P.source, n * NVARS, true) ||
+      dev_alloc(ctx, &ctx->eq_fail_dev, 1, true) || dev_alloc(ctx, &ctx->reduce_dev, 1, true)) {
+    return 1;
+    }
+  P.eq_fail = ctx->eq_fail_dev;
+  P.n_poly_coef = D;
+  if (P.rec2 != nullptr && sc.has_gravity) {  // the tile kernel hands the polynomial to source_kernel
+    if (dev_alloc(ctx, &P.poly_tile, T * (std::int64_t)(D + 1) * NVARS * TILE, true)) {
+      return 1;
+    }
+  }
+  if (params->keep_polynomials) {
+    if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
+      return 1;
+    }
+  }
+  {
+    std::vector<std::int32_t> tl;
+    for (std::int64_t t = 0; t < T; ++t)
+      if (ctx->tile_needed[(size_t)t]) tl.push_back((std::int32_t)t);
+    ctx->n_tiles_needed = (std::int64_t)tl.size();
+    if (ctx->n_tiles_needed < T) {
+      const std::int32_t *p = nullptr;
+      if (dev_upload(ctx, &p, tl)) {
+        return 1;
+    }
+      ctx->tiles_needed = const_cast<std::int32_t *>(p);
+    }
+  }
+  ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));
+  // ghost cells (FrozenBC::count_ghost_cells)
+  {
+    std::vector<std::int32_t> gi;
+    for (std::int64_t i = 0; i < n; ++i)
+      if (g.cell_flags[(size_t)i] & FLAG_GHOST) gi.push_back((std::int32_t)i);
+    ctx->n_ghost = (std::int64_t)gi.size();
+    const std::int32_t *p = nullptr;
+    if (dev_upload(ctx, &p, gi)) {
+      return 1;
+    }
+    ctx->ghost_index = const_cast<std::int32_t *>(p);
+  }
+  // resident state / RK buffers
+  if (dev_alloc(ctx, &ctx->u_cur, n * NVARS, true) || dev_alloc(ctx, &ctx->u_tmp, n * NVARS, true) ||
+      dev_alloc(ctx, &ctx->tend_work, n * NVARS, true) || dev_alloc(ctx, &ctx->state_work, n * NVARS, true)) {
+    return 1;
+    }
+
+  // well-balanced runs: equilibrium parameters per cell and equilibrium averages per (cell, stencil row)
+  if (sc.well_balanced) {
+    int r = 0;
+    for (int k = 0; k < ns; ++k) {
+      P.eq_row0[k] = r;
+      r += sc.rows_max[k];
+    }
+    P.eq_rows = P.rec2 ? r + 1 : r;  // tile records: rows in lidx order plus one row for the cell itself
+    if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)P.eq_rows * 2 * TILE, true) ||
+        (P.rec2 && dev_alloc(ctx, &P.eq_bg, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * 2, true))) {
+      return 1;
+    }
+  }
+  // advected scalars: traces, face fluxes, resident rows and host-entry work rows
+  P.n_avars = ctx->n_avars;
+  if (ctx->n_avars > 0) {
+    const std::int64_t na = ctx->n_avars;
+    if (dev_alloc(ctx, &P.qtrace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * na, true) ||
+        dev_alloc(ctx, &P.qflux, std::max<std::int64_t>(EI, 1) * na, true) || dev_alloc(ctx, &ctx->a_cur, n * na, true) ||
+        dev_alloc(ctx, &ctx->a_tmp, n * na, true) || dev_alloc(ctx, &ctx->tend_work_a, n * na, true) ||
+        dev_alloc(ctx, &ctx->state_work_a, n * na, true)) {
+      return 1;
+    }
+  }
+
+  // ---- algorithmic bytes per cell and stage -----------------------------------------
+  {
+    const double nc = (double)std::max<std::int64_t>(n_counted, 1);
+    const double B_W = bytes_W / nc, B_idx = bytes_idx / nc + 4.0 * bytes_m / nc, m = bytes_m / nc;
+    const double B_state = 80.0, B_poly = 2.0 * 40.0 * D;
+    const double B_cell = 8.0 * (3 + 1 + 1 + D + 5) + (sc.has_gravity ? 8.0 * 4 * g.q_c : 0.0);
+    const double B_face = (F / 2.0) * (8.0 * (9 + 4 * g.q_f) + 8.0);
+    const double B_wb = sc.well_balanced ? 8.0 * (2 * m + 4.0 * (g.q_c + F * g.q_f)) : 0.0;
+    ctx->algorithmic_bytes = B_W + B_idx + B_state + B_poly + B_cell + B_face + B_wb;  // + B_rk added per tableau
+  }
+  if (zfvm_set_time_integration(ctx, "ssp3")) {
+    return 1;
+    }
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 void zfvm_destroy(zfvm_ctx *ctx) {
@@ -921,6 +955,11 @@ void zfvm_destroy(zfvm_ctx *ctx) {
   for (int b = 0; b < 2; ++b) {
     if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
     if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
+  }
+  zfvm_comm_destroy_internal(ctx);
+  for (auto &v : ctx->prof_events) {
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
   }
   for (void *p : ctx->allocations) cudaFree(p);
   if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
@@ -1083,12 +1122,14 @@ double *zfvm_avars_device(zfvm_ctx *ctx) { return ctx->a_cur; }
 
 int zfvm_set_frozen_bc_av(zfvm_ctx *ctx, const double *steady_state_host, const double *steady_avars_host) {
   if (zfvm_set_frozen_bc(ctx, steady_state_host)) return 1;
-  ctx->frozen_a = nullptr;
-  if (!steady_state_host || !steady_avars_host || ctx->n_avars <= 0) return 0;
-  double *f = nullptr;
-  if (dev_alloc(ctx, &f, ctx->n_cells * ctx->n_avars)) return 1;
-  ZFVM_CUDA(cudaMemcpy(f, steady_avars_host, (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double), cudaMemcpyHostToDevice));
-  ctx->frozen_a = f;
+  if (!steady_state_host || !steady_avars_host || ctx->n_avars <= 0) {
+    ctx->frozen_a = nullptr;
+    return 0;
+  }
+  if (!ctx->frozen_a_buf && dev_alloc(ctx, &ctx->frozen_a_buf, ctx->n_cells * ctx->n_avars)) return 1;  // reused by later calls
+  ZFVM_CUDA(cudaMemcpy(ctx->frozen_a_buf, steady_avars_host, (size_t)(ctx->n_cells * ctx->n_avars) * sizeof(double),
+                       cudaMemcpyHostToDevice));
+  ctx->frozen_a = ctx->frozen_a_buf;
   return 0;
 }
 
@@ -1098,10 +1139,11 @@ int zfvm_set_frozen_bc(zfvm_ctx *ctx, const double *steady_state_host) {
     ctx->frozen = nullptr;
     return 0;
   }
-  double *f = nullptr;
-  if (dev_alloc(ctx, &f, ctx->n_cells * NVARS)) return 1;
-  ZFVM_CUDA(cudaMemcpy(f, steady_state_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double), cudaMemcpyHostToDevice));
-  ctx->frozen = f;
+  if (!ctx->frozen_buf && dev_alloc(ctx, &ctx->frozen_buf, ctx->n_cells * NVARS)) return 1;  // reused by later calls
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));  // a step that still reads the previous steady state
+  ZFVM_CUDA(cudaMemcpy(ctx->frozen_buf, steady_state_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double),
+                       cudaMemcpyHostToDevice));
+  ctx->frozen = ctx->frozen_buf;
   return 0;
 }
 
@@ -1169,7 +1211,9 @@ int zfvm_rk_step(zfvm_ctx *ctx, double /*t*/, double dt, double cfl_number, doub
   const bool reduce = (dt_next != nullptr) || (not_plausible != nullptr);
   if (rk_step_impl(ctx, dt, reduce)) return 1;
   if (reduce) {
-    if (ctx->n_ranks > 1 && ctx->nccl_comm && zfvm_allreduce_min_internal(ctx, &ctx->reduce_dev->min_dx_over_ev)) return 1;
+    // every rank gets the same verdict: min of the CFL quotient, max of the plausibility flag (the reference aborts the
+    // whole MPI job through LOG_ERR when one rank sees a bad state)
+    if (ctx->n_ranks > 1 && ctx->nccl_comm && zfvm_allreduce_verdict_internal(ctx)) return 1;
     ZFVM_CUDA(cudaMemcpyAsync(ctx->reduce_host, ctx->reduce_dev, sizeof(ReduceOut), cudaMemcpyDeviceToHost, ctx->stream));
     ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (dt_next) *dt_next = cfl_number * ctx->reduce_host->min_dx_over_ev;
@@ -1207,7 +1251,7 @@ int zfvm_cfl_dt(zfvm_ctx *ctx, const double *state_dev, double cfl_number, doubl
   launch_cfl(state_dev, ctx->inradius, ctx->n_ranks > 1 ? ctx->n_owned : ctx->n_cells, ctx->sc.gamma, ctx->reduce_dev,
              ctx->stream);
   ctx->launches += 2;
-  if (ctx->n_ranks > 1 && ctx->nccl_comm && zfvm_allreduce_min_internal(ctx, &ctx->reduce_dev->min_dx_over_ev)) return 1;
+  if (ctx->n_ranks > 1 && ctx->nccl_comm && zfvm_allreduce_verdict_internal(ctx)) return 1;
   ZFVM_CUDA(cudaMemcpyAsync(ctx->reduce_host, ctx->reduce_dev, sizeof(ReduceOut), cudaMemcpyDeviceToHost, ctx->stream));
   ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (dt) *dt = cfl_number * ctx->reduce_host->min_dx_over_ev;

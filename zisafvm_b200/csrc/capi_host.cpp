@@ -181,6 +181,9 @@ int zfvm_stencils_compute(const zfvm_grid *grid, int n_stencils, const int *orde
       p.biases.push_back(biases[k] == 'b' ? 1 : 0);
       p.overfit_factors.push_back(overfit_factors[k]);
       if (orders[k] < 1) return fail("zfvm_stencils_compute: a non-positive convergence order?");
+      if (!(overfit_factors[k] >= 1.0)) return fail("zfvm_stencils_compute: overfit factors must be >= 1");
+      if (required_stencil_size(orders[k] - 1, overfit_factors[k], grid->g.n_dims) > 256)
+        return fail("zfvm_stencils_compute: a stencil of more than 256 cells (order / overfit factor too large)");
       if (poly_dof(orders[k] - 1, grid->g.n_dims) > grid->g.n_moments && orders[k] > 2)
         return fail("zfvm_stencils_compute: moments_deg of the grid is lower than the polynomial degree");
     }

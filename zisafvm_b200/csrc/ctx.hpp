@@ -25,6 +25,7 @@ struct zfvm_ctx {
   zfvm::DevicePlan plan{};
   zfvm_params params{};
   int n_dims = 0, deg_hi = 0, deg_lo = 0;
+  bool generic = false;  // stencil family outside the specialised kernels' shape: kernels/recon_generic.cu
   std::int64_t n_cells = 0, n_tiles = 0;
   std::vector<void *> allocations;
   std::int64_t device_bytes = 0;
@@ -36,7 +37,8 @@ struct zfvm_ctx {
   double *k[zfvm::MAX_RK_STAGES] = {nullptr};
   double *tend_work = nullptr;  // device tendency for the host entry point
   double *state_work = nullptr; // device state for the host entry point
-  double *frozen = nullptr;
+  double *frozen = nullptr;      // FrozenBC steady state in use (null: NoBoundaryCondition)
+  double *frozen_buf = nullptr, *frozen_a_buf = nullptr;  // its storage, kept and reused across zfvm_set_frozen_bc calls
   // advected scalars [n][n_avars]: resident values, RK buffers, host entry point work arrays, FrozenBC copy
   int n_avars = 0;
   double *a_cur = nullptr, *a_tmp = nullptr;
@@ -67,6 +69,7 @@ struct zfvm_ctx {
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, n_ranks = 1;
+  bool halo_posted = false;  // zfvm_halo_post without its zfvm_halo_wait yet
   std::int64_t n_owned = 0;
   std::vector<HaloPeer> peers;
   std::int32_t *send_index_dev = nullptr;

@@ -450,9 +450,9 @@ void stencil_matrix(std::vector<double> &A, int &rows, int &cols, const HostGrid
                     i64 i, int k) {
   const int size = s.size[(size_t)(i * s.n_stencils + k)];
   const int order = s.order[(size_t)(i * s.n_stencils + k)];
-  i32 glob[128];
-  for (int j = 0; j < size; ++j) glob[j] = s.global(i, k, j);
-  assemble_weno_ao_matrix(A, rows, cols, g, glob, size, order);
+  i32 glob[256];  // zfvm_stencils_compute rejects families whose stencils need more than 256 cells
+  for (int j = 0; j < size && j < 256; ++j) glob[j] = s.global(i, k, j);
+  assemble_weno_ao_matrix(A, rows, cols, g, glob, std::min(size, 256), order);
 }
 
 bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, const i32 *local_to_src,

@@ -97,6 +97,13 @@ bool recon_tile_compiled(const SchemeConst &sc, int deg_hi, int deg_lo);
 int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int deg_lo, const double *state,
                  const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
 
+/// Generic reconstruction (recon_generic.cu): any stencil family up to MAX_STENCILS stencils, per-stencil orders.
+bool recon_generic_supported(const SchemeConst &sc, int n_poly_coef);
+int launch_recon_generic(const DevicePlan &plan, const SchemeConst &sc, const double *state,
+                         const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
+int launch_tracer_recon_generic(const DevicePlan &P, const SchemeConst &sc, const double *avars,
+                                const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
+
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
                  cudaStream_t stream);
 void launch_update(const DevicePlan &P, const SchemeConst &sc, const UpdateArgs &A, cudaStream_t stream);

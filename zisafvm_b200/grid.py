@@ -140,6 +140,19 @@ WENO_PARAMS = {
                               [100.0, 1.0, 1.0, 1.0, 1.0]),
     "3d_o4": HybridWENOParams(StencilFamilyParams([4, 2, 2, 2, 2], "cbbbb", [3.0, 2.0, 2.0, 2.0, 2.0]),
                               [100.0, 1.0, 1.0, 1.0, 1.0]),
+    # parameter sets of the reference's own reconstruction tests
+    # test/zisa/unit_test/reconstruction/cweno_ao.cpp:144-160: six stencils, two of them central
+    "3d_o4_six": HybridWENOParams(StencilFamilyParams([4, 2, 2, 2, 2, 2], "ccbbbb", [4.0, 4.0, 2.5, 2.5, 2.5, 2.5]),
+                                  [100.0, 10.0, 1.0, 1.0, 1.0, 1.0]),
+    "3d_o4_six_o3": HybridWENOParams(StencilFamilyParams([4, 3, 3, 3, 3, 3], "ccbbbb", [4.0, 4.0, 2.5, 2.5, 2.5, 2.5]),
+                                     [100.0, 10.0, 1.0, 1.0, 1.0, 1.0]),
+    # test/zisa/unit_test/reconstruction/weno_ao.cpp:47-62: lone stencils and a wider central stencil
+    "2d_o1_c": HybridWENOParams(StencilFamilyParams([1], "c", [2.0]), [1.0]),
+    "2d_o2_b": HybridWENOParams(StencilFamilyParams([2], "b", [2.0]), [1.0]),
+    "2d_o3_c": HybridWENOParams(StencilFamilyParams([3], "c", [2.0]), [1.0]),
+    "2d_o4_c": HybridWENOParams(StencilFamilyParams([4], "c", [2.0]), [1.0]),
+    "2d_o3_wide": HybridWENOParams(StencilFamilyParams([3, 2, 2, 2], "cbbb", [3.0, 1.5, 1.5, 1.5]), [100.0, 1.0, 1.0, 1.0]),
+    "2d_o4_w10": HybridWENOParams(StencilFamilyParams([4, 2, 2, 2], "cbbb", [2.0, 1.5, 1.5, 1.5]), [10.0, 1.0, 1.0, 1.0]),
 }
 
 
