@@ -40,6 +40,10 @@ CASES = {
     "polytrope_nowb": lambda: cases.polytrope_2d(n=36, order=3, well_balanced=False),
     "atmosphere_wb": lambda: cases.stellar_atmosphere_3d(n=7, order=3, well_balanced=True),
     "atmosphere_nowb": lambda: cases.stellar_atmosphere_3d(n=7, order=2, well_balanced=False),
+    # BASELINE config 4 scheme: 3D order 4, well-balanced (cooperative kernel + equilibrium tables + source kernel)
+    "atmosphere_wb_o4": lambda: cases.stellar_atmosphere_3d(n=8, order=4, well_balanced=True),
+    "atmosphere_nowb_o4": lambda: cases.stellar_atmosphere_3d(n=8, order=4, well_balanced=False),
+    "polytrope_wb_o5": lambda: cases.polytrope_2d(n=30, order=5, well_balanced=True, amplitude=1e-3),
     # no ghost ring: the boundary is closed by FluxBC (boundary/flux_bc.hpp), stencils degrade towards the boundary
     "vortex_fluxbc": lambda: cases.isentropic_vortex(n=24, order=3, ghost_ring_cells=0, flux_bc="flux"),
     "blast_fluxbc": lambda: cases.blast_3d(n=6, order=3, kind="smooth", ghost_cubes=0, flux_bc="flux"),
@@ -221,12 +225,12 @@ def test_equilibrium_preservation():
     assert gpu_nowb.max() > 1e3 * gpu_wb.max()                 # the scheme without well-balancing does drift
 
 
-@pytest.mark.parametrize("maker", ["vortex_o3_hllc", "vortex_o4", "blast_o2", "blast_o3"])
+@pytest.mark.parametrize("maker", ["vortex_o3_hllc", "vortex_o4", "blast_o2", "blast_o3", "vortex_o3_weno_ao"])
 def test_reconstruction_kernels_agree(maker, monkeypatch):
-    """The persistent reconstruction kernel with 3 CTAs or 1 CTA (every warp walks many tiles: ring wrap-around,
-    header-buffer and table reuse) gives bit-identical tendencies to the default launch; the older streaming
-    kernel (ZFVM_RECON=stream) and the thread-per-cell kernel (ZFVM_RECON=v1), which read differently laid out
-    records chosen at context creation, agree with it to round-off."""
+    """The persistent tile kernel with 3 CTAs or 1 CTA (every warp walks many tiles: ring wrap-around, header-buffer
+    and table reuse), one warp per CTA, 16-bit list indices or a two-slot ring gives bit-identical tendencies to the
+    default launch; the cooperative kernel (ZFVM_RECON=coop: four warps per tile, the path of 3D order 4 / 2D order 5)
+    and the generic kernel (ZFVM_RECON=generic: plainer records, run-time family shape) agree with it to round-off."""
     case = CASES[maker]()
     st = case.ensure_stencils()
     n = case.grid.n_cells
@@ -235,7 +239,8 @@ def test_reconstruction_kernels_agree(maker, monkeypatch):
                      ("one_warp", {"ZFVM_TILE_WARPS": "1", "ZFVM_STREAM_MAX_CTAS": "2"}),
                      ("wide_index", {"ZFVM_TILE_MIN_CAP": "288"}),  # 16-bit list indices, larger table, fewer warps
                      ("two_slots", {"ZFVM_TILE_SLOTS": "2", "ZFVM_STREAM_MAX_CTAS": "5"}),
-                     ("stream", {"ZFVM_RECON": "stream"}), ("v1", {"ZFVM_RECON": "v1"})]:
+                     ("coop", {"ZFVM_RECON": "coop"}), ("coop_wide", {"ZFVM_RECON": "coop", "ZFVM_TILE_MIN_CAP": "288"}),
+                     ("generic", {"ZFVM_RECON": "generic"})]:
         for k in ("ZFVM_STREAM_MAX_CTAS", "ZFVM_RECON", "ZFVM_TILE_WARPS", "ZFVM_TILE_MIN_CAP", "ZFVM_TILE_SLOTS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -252,16 +257,18 @@ def test_reconstruction_kernels_agree(maker, monkeypatch):
     assert np.array_equal(out["default"], out["one_warp"])
     assert np.array_equal(out["default"], out["wide_index"])
     assert np.array_equal(out["default"], out["two_slots"])
+    assert np.array_equal(out["coop"], out["coop_wide"])
     scale = tendency_scales(case.u0, case.params.gamma, case.grid.array("inradii"))
-    assert (np.abs(out["default"] - out["v1"]).max(axis=0) / scale).max() < 1e-12
-    assert (np.abs(out["default"] - out["stream"]).max(axis=0) / scale).max() < 1e-12
+    assert (np.abs(out["default"] - out["coop"]).max(axis=0) / scale).max() < 1e-12
+    assert (np.abs(out["default"] - out["generic"]).max(axis=0) / scale).max() < 1e-12
 
 
 @pytest.mark.parametrize("maker", ["polytrope_wb_perturbed", "polytrope_nowb", "atmosphere_wb", "atmosphere_nowb"])
 def test_source_paths_agree(maker, monkeypatch):
-    """Gravity / well-balanced runs: tile kernel + equilibrium tables + source_kernel (default) against the older
-    records with the thread-per-cell kernel (ZFVM_SOURCE=v1: the path 3D order 4 and 2D order 5 still take), both
-    against the oracle: residual and three RK steps."""
+    """Gravity / well-balanced runs: tile kernel + equilibrium tables + source_kernel (default), the cooperative kernel
+    on the same tables (ZFVM_RECON=coop: the path 3D order 4 and 2D order 5 take) and the generic kernel, which evaluates
+    equilibrium subtraction, background and source terms itself (ZFVM_SOURCE=v1), all against the oracle: residual and
+    three RK steps."""
     case = CASES[maker]()
     st = case.ensure_stencils()
     n = case.grid.n_cells
@@ -275,8 +282,9 @@ def test_source_paths_agree(maker, monkeypatch):
     scale = tendency_scales(case.u0, case.params.gamma, case.grid.array("inradii"))
     sc = state_scales(case.u0, case.params.gamma)
     out = {}
-    for key, env in [("tile", {}), ("v1", {"ZFVM_SOURCE": "v1"})]:
+    for key, env in [("tile", {}), ("coop", {"ZFVM_RECON": "coop"}), ("v1", {"ZFVM_SOURCE": "v1"})]:
         monkeypatch.delenv("ZFVM_SOURCE", raising=False)
+        monkeypatch.delenv("ZFVM_RECON", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ctx = z.CudaContext(case.grid, st, case.params)
@@ -294,3 +302,4 @@ def test_source_paths_agree(maker, monkeypatch):
         out[key] = t.cvars.copy()
         ctx.close()
     assert (np.abs(out["tile"] - out["v1"]).max(axis=0) / scale).max() < 1e-12
+    assert (np.abs(out["tile"] - out["coop"]).max(axis=0) / scale).max() < 1e-12

@@ -417,7 +417,11 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
   for (int k = 1; k < ns; ++k) ctx->deg_lo = std::max(ctx->deg_lo, S.params.orders[(size_t)k] - 1);
   bool specialised = (ns == nd + 2) && S.params.orders[0] >= 2 && S.params.orders[0] - 1 == ctx->deg_hi;
   for (int k = 1; k < ns; ++k) specialised = specialised && S.params.orders[(size_t)k] == 2;
-  if (const char *e = std::getenv("ZFVM_RECON")) specialised = specialised && e[0] != 'g';  // tests: ZFVM_RECON=generic
+  // tests: ZFVM_RECON=generic (or v1, its older name) and, for runs with source terms, ZFVM_SOURCE=v1 put a family of the
+  // specialised shape on the generic kernel as a cross-check
+  if (const char *e = std::getenv("ZFVM_RECON")) specialised = specialised && e[0] != 'g' && e[0] != 'v';
+  if (const char *e = std::getenv("ZFVM_SOURCE"))
+    specialised = specialised && !(e[0] == 'v' && (params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0));
   ctx->generic = !specialised;
   if ((nd == 2 && ctx->deg_hi >= 5) || (nd == 3 && ctx->deg_hi >= 4))
     return fail("zfvm_create: LSQ matrices exist up to order 5 in 2D and 4 in 3D (lsq_solver.cpp:288,399)");
@@ -471,20 +475,9 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     }
     P.rec_bytes = off;  // every section is a multiple of 128 bytes
   }
-  // ---- tile kernel records (kernels/recon_tile.cuh): header | one-sided W | central W | geometry ----------
-  // Built instead of the records above whenever the tile kernel is compiled for the scheme (plain Euler,
-  // no gravity terms inside K1); ZFVM_RECON=v1|stream keeps the older kernels for comparisons.
-  bool use_tile = false;
-  {
-    const char *e_recon = std::getenv("ZFVM_RECON");
-    const bool other = e_recon && (e_recon[0] == 'v' || e_recon[0] == 's');
-    // (gravity / heating without well-balancing: the tile kernel stores the polynomial, source_kernel evaluates the
-    // cell-local source terms from it; ZFVM_SOURCE=v1 keeps those runs on the thread-per-cell kernel)
-    const char *e_src = std::getenv("ZFVM_SOURCE");
-    const bool source_v1 = e_src && e_src[0] == 'v';
-    use_tile = !ctx->generic && !other && !(sc.has_gravity && source_v1) && ns >= 2 &&
-               recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
-  }
+  // ---- tile records (kernels/recon_tile.cuh, recon_coop.cuh): header | one-sided W | central W | geometry ----------
+  // Built for every family of the specialised shape; the generic kernel reads the plainer records above.
+  bool use_tile = !ctx->generic && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
   if (use_tile) {
     // distinct cells read by a tile's stencils
     std::vector<std::int32_t> n_union((size_t)T, 0);
@@ -514,7 +507,10 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
     cap = (cap + 31) / 32 * 32;
     if (const char *e = std::getenv("ZFVM_TILE_MIN_CAP")) cap = std::max(cap, (std::atoi(e) + 31) / 32 * 32);  // tests: 16-bit indices
-    if (cap > 1024) use_tile = false;  // the shared-memory table would not fit; fall back to the older kernels
+    if (cap > 1024) {  // the shared-memory table would not fit: the generic kernel gathers through global indices
+      use_tile = false;
+      ctx->generic = true;
+    }
     P.rec2_cap = cap;
   }
   if (use_tile) {

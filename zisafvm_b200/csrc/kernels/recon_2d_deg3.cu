@@ -1,4 +1,4 @@
-// recon_kernel instantiations for n_dims = 2, high-order stencil degree 3 (order 4).
+// reconstruction kernel instantiations (tile + cooperative) for n_dims = 2, high-order stencil degree 3 (order 4).
 #include "recon_inst.cuh"
 namespace zfvm {
 ZFVM_DEFINE_RECON(2, 3, 18, 3)

@@ -28,11 +28,6 @@ void launch_eq_solve(const DevicePlan &plan, const SchemeConst &sc, const double
   eq_solve_kernel<POWN><<<grid, 256, 0, stream>>>(plan, sc, state, tile_list, n_tiles);
 }
 template <int POWN>
-void launch_eq_member(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
-                      unsigned grid, cudaStream_t stream) {
-  eq_member_kernel<POWN><<<grid, 256, 0, stream>>>(plan, sc, tile_list, n_tiles);
-}
-template <int POWN>
 void launch_eq_tile(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
                     cudaStream_t stream) {
   const unsigned g2 = (unsigned)((n_tiles * plan.eq_rows + 7) / 8);
@@ -51,8 +46,6 @@ void launch_eq_tile(const DevicePlan &plan, const SchemeConst &sc, const std::in
 #define ZFVM_EQ_INST(POWN)                                                                                          \
   template void launch_eq_solve<POWN>(const DevicePlan &, const SchemeConst &, const double *, const std::int32_t *,    \
                                       std::int64_t, unsigned, cudaStream_t);                                            \
-  template void launch_eq_member<POWN>(const DevicePlan &, const SchemeConst &, const std::int32_t *, std::int64_t,     \
-                                       unsigned, cudaStream_t);                                                         \
   template void launch_eq_tile<POWN>(const DevicePlan &, const SchemeConst &, const std::int32_t *, std::int64_t, cudaStream_t);
 ZFVM_EQ_INST(0)
 ZFVM_EQ_INST(2)
@@ -86,22 +79,9 @@ bool tile_prof_read(unsigned long long out[16]) {
 }
 
 bool recon_tile_compiled(const SchemeConst &sc, int deg_hi, int deg_lo) {
-  if (deg_lo != 1) return false;
-  if (sc.n_dims == 2) {
-    switch (deg_hi) {
-      case 1: return recon_tile_sizes_2d_deg1(sc);
-      case 2: return recon_tile_sizes_2d_deg2(sc);
-      case 3: return recon_tile_sizes_2d_deg3(sc);
-      case 4: return recon_tile_sizes_2d_deg4(sc);
-    }
-  } else if (sc.n_dims == 3) {
-    switch (deg_hi) {
-      case 1: return recon_tile_sizes_3d_deg1(sc);
-      case 2: return recon_tile_sizes_3d_deg2(sc);
-      case 3: return recon_tile_sizes_3d_deg3(sc);
-    }
-  }
-  return false;
+  // tile records serve the tile kernel and the cooperative kernel: every family of the specialised shape
+  if (deg_lo != 1 || deg_hi < 1) return false;
+  return (sc.n_dims == 2 && deg_hi <= 4) || (sc.n_dims == 3 && deg_hi <= 3);
 }
 
 }  // namespace zfvm

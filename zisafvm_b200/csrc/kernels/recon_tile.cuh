@@ -36,7 +36,8 @@
 #pragma once
 #include <type_traits>
 
-#include "recon_stream.cuh"
+#include "ptx.cuh"
+#include "recon.cuh"
 
 namespace zfvm {
 
@@ -146,11 +147,19 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
   const std::int64_t first = (std::int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const std::int64_t stride = (std::int64_t)gridDim.x * (blockDim.x >> 5);
   auto has_tile = [&](int m) { return first + (std::int64_t)m * stride < n_launch; };
-  auto tile_of = [&](int m) -> std::int64_t {
+  // Tile numbers come from a list in global memory when only some tiles are reconstructed (ghost tiles skipped,
+  // interior / exterior lists of a decomposed run).  Every use of a tile number sits in front of a copy that the
+  // warp is about to wait for, so the list entry of tile m + 2 is fetched at the start of tile m (t_nxt2) and has a
+  // whole tile's time to arrive: in the first version these loads were 12 % of all stall samples (long scoreboard).
+  auto load_tile_no = [&](int m) -> std::int32_t {
     const std::int64_t idx = first + (std::int64_t)m * stride;
-    return args.tile_list ? (std::int64_t)args.tile_list[idx] : idx;
+    if (idx >= n_launch) return 0;
+    return args.tile_list ? __ldg(args.tile_list + idx) : (std::int32_t)idx;
   };
   if (!has_tile(0)) return;
+  std::int32_t t_cur = load_tile_no(0), t_nxt = load_tile_no(1), t_nxt2 = load_tile_no(2);
+  int m_cur = 0;  // the tile the warp is working on: tile_of is only ever asked for m_cur and m_cur + 1
+  auto tile_of = [&](int m) -> std::int64_t { return (std::int64_t)(m == m_cur ? t_cur : t_nxt); };
   const bool prof = PROF && cfg.prof != nullptr && first == 0;  // PROF = false: the timers compile away
   long long t_mark = 0, t_segwait = 0;
   auto mark = [&](int phase) {
@@ -263,6 +272,12 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
 
 #pragma unroll 1
   for (int m = 0; has_tile(m); ++m) {
+    if (m > 0) {
+      t_cur = t_nxt;
+      t_nxt = t_nxt2;
+      t_nxt2 = load_tile_no(m + 2);
+      m_cur = m;
+    }
     mark(-1);
     // The list buffer holds tile m's part (its rows went into the table during tile m-1; only the meta words
     // are still needed): read them, then let tile m+1's part overwrite the buffer while tile m is applied.

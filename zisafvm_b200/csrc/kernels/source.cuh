@@ -29,13 +29,15 @@ __global__ void __launch_bounds__(128, 3) source_kernel(const __grid_constant__ 
   const bool active = cell < P.n_cells;
   const std::int64_t ci = active ? cell : P.n_cells - 1;
 
-  // hybridised polynomial, scale folded in: delta(x) = scale * p(x)
-  double coef[D][NVARS];
-  {
-    const double *pt = P.poly_tile + tile * ((D + 1) * NVARS * TILE) + lane;  // [tile][D + 1][5][32]
-    double scale[NVARS];
+  // hybridised polynomial, scale folded in: delta(x) = scale * p(x).  Up to 10 coefficients per variable they live in
+  // registers; above (3D order 4, 2D order 5) they are re-read per Gauss point (L1 hits: the block is 256-byte rows)
+  constexpr bool IN_REGS = D <= 10;
+  const double *pt = P.poly_tile + tile * ((D + 1) * NVARS * TILE) + lane;  // [tile][D + 1][5][32]
+  double scale[NVARS];
 #pragma unroll
-    for (int v = 0; v < NVARS; ++v) scale[v] = ld_stream(pt + (D * NVARS + v) * TILE);
+  for (int v = 0; v < NVARS; ++v) scale[v] = pt[(D * NVARS + v) * TILE];
+  double coef[IN_REGS ? D : 1][NVARS];
+  if constexpr (IN_REGS) {
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -123,10 +125,17 @@ __global__ void __launch_bounds__(128, 3) source_kernel(const __grid_constant__ 
                                     (ND == 3) ? (x[2] - xc[2]) * inv_len : 0.0, cmom, mono);
 #pragma unroll
     for (int v = 0; v < NVARS; ++v) {
-      double s = coef[0][v];
+      if constexpr (IN_REGS) {
+        double s = coef[0][v];
 #pragma unroll
-      for (int i = 1; i < D; ++i) s = fma(coef[i][v], mono[i], s);
-      du[v] = s;
+        for (int i = 1; i < D; ++i) s = fma(coef[i][v], mono[i], s);
+        du[v] = s;
+      } else {
+        double s = pt[v * TILE] * scale[v];
+#pragma unroll 5
+        for (int i = 1; i < D; ++i) s = fma(pt[(i * NVARS + v) * TILE] * scale[v], mono[i], s);
+        du[v] = s;
+      }
     }
     const double *gp = P.gradphi_cqp + (ci * sc.q_c + q) * 3;
     const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
