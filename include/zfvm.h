@@ -83,6 +83,18 @@ void zfvm_stencils_free(zfvm_stencils *st);
  * source grid (extraction of a partition's stencils, src/domain_decomposition.cpp /
  * src/zisa/grid/domain_decomposition.cpp:412-447).  Every used stencil member must be part of the sub-grid. */
 int zfvm_stencils_extract(const zfvm_stencils *src, int64_t n_local, const int32_t *local_to_src, zfvm_stencils **out);
+/* Import of stencil families the caller already holds -- the reference's array<StencilFamily, 1> as
+ * EulerGlobalReconstruction keeps it (include/zisa/reconstruction/global_reconstruction_decl.hpp:107-147) -- instead of
+ * re-running the selection: wherever the reference's choice is not deterministic (unordered ties of std::sort,
+ * std::random_device retries, src/zisa/reconstruction/stencil.cpp:240-250,332-334) this is how the drop-in works "on the
+ * same inputs".  orders / biases / overfit_factors: the StencilFamilyParams; n_family[i]: StencilFamily::size() (1 after
+ * truncate_to_first_order); order[i][k], size[i][k] ([n_cells][n_stencils]): Stencil::order() / size();
+ * global[global_offset[i * n_stencils + k] ..]: Stencil::global() (member 0 is cell i).  local2global() and
+ * Stencil::local() are rebuilt in the reference's order (assign_local_indices, stencil.cpp:82-104). */
+int zfvm_stencils_from_arrays(const zfvm_grid *grid, int n_stencils, const int *orders, const char *biases,
+                              const double *overfit_factors, const int32_t *n_family, const int32_t *order,
+                              const int32_t *size, const int64_t *global_offset, const int32_t *global,
+                              zfvm_stencils **out);
 /* Hilbert ordering of cell centres [n][3] (src/renumber_grid.cpp:60-126): perm[new] = old. */
 int zfvm_hilbert_permutation(int n_dims, int64_t n, const double *centers, int32_t *perm);
 /* LSQSolver::A of stencil k of cell i, row-major rows x cols (lsq_solver.cpp:40-47,168-403) */

@@ -243,6 +243,42 @@ def test_stencil_families(which, key, request):
     assert ((k_high >= 0) & (k_high < ns)).all()
 
 
+@pytest.mark.parametrize("which,key", [("square", "2d_o3"), ("cube", "3d_o3"), ("square", "2d_o1_c"), ("cube", "3d_o4_six_o3")])
+def test_stencil_import_round_trip(which, key, request):
+    """zfvm_stencils_from_arrays: families handed over as the reference holds them (Stencil::global(), order(), size()
+    per stencil; global_reconstruction_decl.hpp:107-147) give the same tables as the selection that produced them, and
+    the LSQ matrices built from them are bit-identical."""
+    g = request.getfixturevalue(which)
+    prm = z.WENO_PARAMS[key].stencil_family_params
+    st = z.compute_stencil_families(g, prm)
+    nf, order, size, go, gi = st.export_arrays()
+    imp = z.StencilFamilies.from_arrays(g, prm, nf, order, size, go, gi)
+    for name in ("l2g", "l2g_size", "local", "order", "size", "k_high", "n_family", "family_order", "max_size", "local_off"):
+        a, b = st.array(name), imp.array(name)
+        if name == "local":     # slots behind a stencil's size are never read; compare the used part
+            off = st.array("local_off")
+            for k in range(len(prm.orders)):
+                used = np.arange(off[k + 1] - off[k])[None, :] < np.where(np.arange(len(prm.orders))[None, :] < nf[:, None], size, 0)[:, k:k + 1]
+                assert (np.where(used, a[:, off[k]:off[k + 1]], 0) == np.where(used, b[:, off[k]:off[k + 1]], 0)).all(), name
+        else:
+            assert (a == b).all(), name
+    for i in (0, g.n_cells // 3, g.n_cells - 1):
+        for k in range(int(nf[i])):
+            if order[i, k] > 1:
+                assert (st.matrix(i, k) == imp.matrix(i, k)).all()
+    # what the import refuses: a stencil that does not start with its own cell, a size the order does not need
+    i_full = int(np.nonzero(nf == len(prm.orders))[0][0]) if (nf == len(prm.orders)).any() and len(prm.orders) > 1 else None
+    if i_full is not None:
+        bad = gi.copy()
+        bad[go[i_full * len(prm.orders)]] = (i_full + 1) % g.n_cells
+        with pytest.raises(_capi.ZfvmError, match="member 0"):
+            z.StencilFamilies.from_arrays(g, prm, nf, order, size, go, bad)
+        bad_size = size.copy()
+        bad_size[i_full, 0] -= 1
+        with pytest.raises(_capi.ZfvmError, match="required_stencil_size"):
+            z.StencilFamilies.from_arrays(g, prm, nf, order, bad_size, go, gi)
+
+
 def _monomial_exponents(nd, deg):
     """poly_index order (poly2d_impl.hpp:34-41): by total degree, then 2D (a, b) -> b ascending; 3D (a, b, c) ->
     idx2(b, c) ascending."""

@@ -303,6 +303,38 @@ int zfvm_stencils_extract(const zfvm_stencils *src, int64_t n_local, const int32
   }
 }
 
+int zfvm_stencils_from_arrays(const zfvm_grid *grid, int n_stencils, const int *orders, const char *biases,
+                              const double *overfit_factors, const int32_t *n_family, const int32_t *order,
+                              const int32_t *size, const int64_t *global_offset, const int32_t *global,
+                              zfvm_stencils **out) {
+  try {
+    if (n_stencils <= 0 || n_stencils > 6) return fail("zfvm_stencils_from_arrays: 1..6 stencils supported");
+    StencilFamilyParams p;
+    for (int k = 0; k < n_stencils; ++k) {
+      if (biases[k] != 'c' && biases[k] != 'b') return fail("zfvm_stencils_from_arrays: bias must be 'c' or 'b'");
+      if (orders[k] < 1) return fail("zfvm_stencils_from_arrays: a non-positive convergence order?");
+      if (!(overfit_factors[k] >= 1.0)) return fail("zfvm_stencils_from_arrays: overfit factors must be >= 1");
+      if (required_stencil_size(orders[k] - 1, overfit_factors[k], grid->g.n_dims) > 256)
+        return fail("zfvm_stencils_from_arrays: a stencil of more than 256 cells (order / overfit factor too large)");
+      if (poly_dof(orders[k] - 1, grid->g.n_dims) > grid->g.n_moments && orders[k] > 2)
+        return fail("zfvm_stencils_from_arrays: moments_deg of the grid is lower than the polynomial degree");
+      p.orders.push_back(orders[k]);
+      p.biases.push_back(biases[k] == 'b' ? 1 : 0);
+      p.overfit_factors.push_back(overfit_factors[k]);
+    }
+    auto *h = new zfvm_stencils();
+    std::string err;
+    if (!import_stencils(h->s, grid->g, p, n_family, order, size, global_offset, global, err)) {
+      delete h;
+      return fail("zfvm_stencils_from_arrays: " + err);
+    }
+    *out = h;
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_stencils_from_arrays: ") + e.what());
+  }
+}
+
 int zfvm_hilbert_permutation(int n_dims, int64_t n, const double *centers, int32_t *perm) {
   try {
     if (n_dims != 2 && n_dims != 3) return fail("zfvm_hilbert_permutation: n_dims must be 2 or 3");

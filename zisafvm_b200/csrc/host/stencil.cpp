@@ -521,4 +521,93 @@ bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, c
   return true;
 }
 
+bool import_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyParams &params, const i32 *n_family,
+                     const i32 *order, const i32 *size, const i64 *global_offset, const i32 *global, std::string &err) {
+  const i64 n = g.n_cells;
+  const int ns = params.n_stencils(), nd = g.n_dims;
+  S = HostStencils();
+  S.n_cells = n;
+  S.n_dims = nd;
+  S.n_stencils = ns;
+  S.params = params;
+  S.max_size.resize((size_t)ns);
+  S.local_off.assign((size_t)ns + 1, 0);
+  for (int k = 0; k < ns; ++k) {
+    S.max_size[(size_t)k] = required_stencil_size(params.orders[(size_t)k] - 1, params.overfit_factors[(size_t)k], nd);
+    S.local_off[(size_t)k + 1] = S.local_off[(size_t)k] + S.max_size[(size_t)k];
+  }
+  const int L = S.local_off[(size_t)ns];
+  S.l2g_stride = L;
+  S.l2g_size.assign((size_t)n, 1);
+  S.l2g.assign((size_t)(n * L), INVALID);
+  S.local.assign((size_t)(n * L), 0);
+  S.order.assign((size_t)(n * ns), 1);
+  S.size.assign((size_t)(n * ns), 0);
+  S.k_high.assign((size_t)n, 0);
+  S.family_order.assign((size_t)n, 1);
+  S.n_family.assign((size_t)n, 1);
+  i64 bad = -1;
+  int why = 0;
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n; ++i) {
+    i32 *l2g = &S.l2g[(size_t)(i * L)];
+    i32 *local = &S.local[(size_t)(i * L)];
+    const int nf = n_family[i];
+    int reason = 0;
+    if (nf != 1 && nf != ns) reason = 1;  // a family is the full parameter set or truncate_to_first_order
+    int n_l2g = 0;
+    for (int k = 0; k < nf && !reason; ++k) {
+      const int sz = size[i * ns + k], ord = order[i * ns + k];
+      const i32 *glob = global + global_offset[i * ns + k];
+      if (sz < 1 || sz > S.max_size[(size_t)k] || ord < 1 || ord > params.orders[(size_t)k]) reason = 2;
+      // Stencil::Stencil truncates to the size the achieved order needs (stencil.cpp:58-59,78-79)
+      else if (nf > 1 && sz != required_stencil_size(ord - 1, params.overfit_factors[(size_t)k], nd)) reason = 3;
+      else if (glob[0] != (i32)i) reason = 4;  // member 0 is the cell itself (stencil.cpp:200, LSQ rows start at 1)
+      if (reason) break;
+      i32 *loc = local + S.local_off[(size_t)k];
+      for (int j = 0; j < sz; ++j) {  // assign_local_indices, stencil.cpp:82-104
+        if (glob[j] < 0 || glob[j] >= n) {
+          reason = 5;
+          break;
+        }
+        i32 *it = std::find(l2g, l2g + n_l2g, glob[j]);
+        loc[j] = (i32)(it - l2g);
+        if (it == l2g + n_l2g) l2g[n_l2g++] = glob[j];
+      }
+      S.order[(size_t)(i * ns + k)] = ord;
+      S.size[(size_t)(i * ns + k)] = sz;
+    }
+    if (reason) {
+#pragma omp critical
+      {
+        bad = i;
+        why = reason;
+      }
+      continue;
+    }
+    S.l2g_size[(size_t)i] = n_l2g;
+    S.n_family[(size_t)i] = nf;
+    const i32 *ordi = &S.order[(size_t)(i * ns)];
+    int fo = 1, kh = 0;
+    for (int k = 0; k < nf; ++k) fo = std::max(fo, (int)ordi[k]);
+    for (int k = 1; k < nf; ++k) {  // highest_order_central_stencil, stencil_family.cpp:120-136
+      if (ordi[k] > ordi[kh])
+        kh = k;
+      else if (ordi[k] == ordi[kh] && params.biases[(size_t)k] == 0)
+        kh = k;
+    }
+    S.family_order[(size_t)i] = fo;
+    S.k_high[(size_t)i] = kh;
+  }
+  if (bad >= 0) {
+    static const char *const text[] = {"", "a family must hold one stencil or the full parameter set",
+                                       "stencil size or order outside the parameter set",
+                                       "stencil size does not match required_stencil_size(order - 1, overfit factor)",
+                                       "member 0 of a stencil must be the cell itself", "stencil member out of range"};
+    err = std::string("import_stencils: cell ") + std::to_string(bad) + ": " + text[why];
+    return false;
+  }
+  return true;
+}
+
 }  // namespace zfvm

@@ -199,4 +199,12 @@ void pseudo_inverse(const double *A, int rows, int cols, double *W);
 bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, const i32 *local_to_src,
                       std::string &err);
 
+/// Stencil families the caller already holds (the reference's array<StencilFamily, 1>,
+/// include/zisa/reconstruction/global_reconstruction_decl.hpp:107-147): stencil k of cell i has size[i][k] members whose
+/// global indices start at global[global_offset[i * n_stencils + k]] (Stencil::global(), member 0 = the cell), achieved
+/// order order[i][k]; n_family[i] is 1 for families truncated to first order.  l2g / local are rebuilt by
+/// assign_local_indices (stencil.cpp:82-104), k_high by stencil_family.cpp:120-136.
+bool import_stencils(HostStencils &out, const HostGrid &g, const StencilFamilyParams &params, const i32 *n_family,
+                     const i32 *order, const i32 *size, const i64 *global_offset, const i32 *global, std::string &err);
+
 }  // namespace zfvm

@@ -186,6 +186,49 @@ class StencilFamilies:
         self.n_stencils = src.n_stencils
         return self
 
+    @classmethod
+    def from_arrays(cls, grid: Grid, params: StencilFamilyParams, n_family, order, size, global_offset,
+                    global_indices) -> "StencilFamilies":
+        """Families the caller already holds (the reference's ``array<StencilFamily, 1>``,
+        global_reconstruction_decl.hpp:107-147) instead of a new selection: ``order[i][k]`` / ``size[i][k]`` are
+        ``Stencil::order()`` / ``size()``, ``global_indices[global_offset[i * ns + k]:][:size]`` is ``Stencil::global()``."""
+        ns = len(params.orders)
+        orders = (C.c_int * ns)(*[int(o) for o in params.orders])
+        biases = "".join(params.biases).encode()
+        factors = (C.c_double * ns)(*[float(f) for f in params.overfit_factors])
+        nf = np.ascontiguousarray(n_family, dtype=np.int32)
+        od = np.ascontiguousarray(order, dtype=np.int32).reshape(grid.n_cells, ns)
+        sz = np.ascontiguousarray(size, dtype=np.int32).reshape(grid.n_cells, ns)
+        go = np.ascontiguousarray(global_offset, dtype=np.int64).reshape(-1)
+        gi = np.ascontiguousarray(global_indices, dtype=np.int32).reshape(-1)
+        assert nf.shape == (grid.n_cells,) and go.size >= grid.n_cells * ns
+        h = C.c_void_p()
+        i32p, i64p = _capi.c_int32_p, _capi.c_int64_p
+        check(lib.zfvm_stencils_from_arrays(grid._h, ns, orders, biases, factors, nf.ctypes.data_as(i32p),
+                                            od.ctypes.data_as(i32p), sz.ctypes.data_as(i32p), go.ctypes.data_as(i64p),
+                                            gi.ctypes.data_as(i32p), C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        self.grid = grid
+        self.params = params
+        self.n_stencils = ns
+        return self
+
+    def export_arrays(self):
+        """(n_family, order, size, global_offset, global_indices): the inverse of :meth:`from_arrays`."""
+        ns, n = self.n_stencils, self.grid.n_cells
+        nf, order, size = self.array("n_family"), self.array("order"), self.array("size")
+        off, l2g, local = self.array("local_off"), self.array("l2g"), self.array("local")
+        used = np.where(np.arange(ns)[None, :] < nf[:, None], size, 0).astype(np.int64)
+        go = np.zeros(n * ns + 1, dtype=np.int64)
+        np.cumsum(used.reshape(-1), out=go[1:])
+        gi = np.zeros(int(go[-1]), dtype=np.int32)
+        for k in range(ns):
+            for j in range(int(used[:, k].max(initial=0))):
+                rows = np.nonzero(used[:, k] > j)[0]
+                gi[go[rows * ns + k] + j] = l2g[rows, local[rows, off[k] + j]]
+        return np.array(nf), np.array(order), np.array(size), go, gi
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
