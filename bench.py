@@ -60,6 +60,12 @@ def parse_args():
                          "ONE global n^3 mesh cut into N chunks of the Hilbert curve (the reference's SFC partition path)")
     ap.add_argument("--cpu-n", type=int, default=0, help="cubes (squares) per direction of the bounded CPU sample; 0 = "
                     "chosen from the requested steps so that the CPU run stays within about a minute")
+    ap.add_argument("--partition", default="sfc", choices=["sfc", "metis", "metis_stencils"],
+                    help="--scaling strong: contiguous chunks of the Hilbert curve (the reference's shipped path) or METIS "
+                         "k-way on the face-neighbour / stencil graph (domain_decomposition.cpp:27-113)")
+    ap.add_argument("--ghosts-interleaved", action="store_true",
+                    help="keep the first-order ghost cells of the FrozenBC shell interleaved along the Hilbert curve instead "
+                         "of numbering them behind the reconstructed cells (the default, like a partition's halo)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -143,7 +149,8 @@ def workload_name(args, method: str) -> str:
                 f"{args.order}, HLLC, {method}, FrozenBC for r > 0.5" + extra)
     per = "in total" if (args.scaling == "strong" and args.gpus > 1) else "per GPU"
     return (f"3D {args.kind} on [0,1]^3, {args.n}^3 cubes x 6 Kuhn tets {per}, CWENO-AO order {args.order} "
-            f"{{3,2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell" + extra)
+            f"{{{args.order},2,2,2,2}}, HLLC, {method}, FrozenBC ghost shell"
+            + ("" if (args.ghosts_interleaved or args.gpus > 1) else " numbered behind the reconstructed cells") + extra)
 
 
 def make_case(args, n: int):
@@ -156,7 +163,7 @@ def make_case(args, n: int):
     elif args.kind == "polytrope2d":
         case = cases.polytrope_2d(n=n, order=args.order, well_balanced=True)
     else:
-        case = cases.blast_3d(n=n, order=args.order, kind=args.kind)
+        case = cases.blast_3d(n=n, order=args.order, kind=args.kind, ghosts_last=not args.ghosts_interleaved)
     if args.avars > 0:
         cases.with_tracers(case, args.avars)
     return case
@@ -339,7 +346,8 @@ def run_b200(args):
         from zisafvm_b200 import distributed as zd
 
         maker = zd.make_strong_scaling_case if args.scaling == "strong" else zd.make_weak_scaling_case
-        sub = maker(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank, n_avars=args.avars)
+        extra = {"partition": args.partition} if args.scaling == "strong" else {}
+        sub = maker(rank, world, n=args.n, order=args.order, kind=args.kind, device=local_rank, n_avars=args.avars, **extra)
         case, ctx = sub.case, sub.ctx
         n_counted = sub.n_counted
     else:

@@ -95,6 +95,14 @@ int zfvm_stencils_from_arrays(const zfvm_grid *grid, int n_stencils, const int *
                               const double *overfit_factors, const int32_t *n_family, const int32_t *order,
                               const int32_t *size, const int64_t *global_offset, const int32_t *global,
                               zfvm_stencils **out);
+/* Owner part of every cell from METIS_PartGraphKway on the stencil graph (stencils != NULL: an edge between a cell and
+ * every member of its combined stencil) or on the face-neighbour graph (stencils == NULL), with the reference's options
+ * OBJTYPE_VOL, NCUTS 10, NITER 20, UFACTOR 100 (compute_partition_full_stencil / compute_partitioned_grid,
+ * src/zisa/parallelization/domain_decomposition.cpp:27-113,250-270).  The space-filling-curve partition
+ * (compute_partitioned_grid_by_sfc, :577-609) needs no entry point: contiguous chunks of the Hilbert order.
+ * zfvm_has_metis() == 0: built without the METIS archive, zfvm_partition_kway fails like ZISA_HAS_METIS == 0 does. */
+int zfvm_partition_kway(const zfvm_grid *grid, const zfvm_stencils *stencils, int n_parts, int32_t *partition);
+int zfvm_has_metis(void);
 /* Hilbert ordering of cell centres [n][3] (src/renumber_grid.cpp:60-126): perm[new] = old. */
 int zfvm_hilbert_permutation(int n_dims, int64_t n, const double *centers, int32_t *perm);
 /* LSQSolver::A of stencil k of cell i, row-major rows x cols (lsq_solver.cpp:40-47,168-403) */

@@ -7,7 +7,7 @@
 //   adapter_driver nodevice                   on a box without a GPU: the failure must arrive through LOG_ERR
 //
 // in.bin : i64 n_dims, n_vertices, n_cells, n_steps, order | f64 gamma, cfl | f64 vertices[nv][3] | i32 vertex_indices[nc][F]
-//          | u8 ghost[nc] | f64 u0[nc][5]
+//          | u8 cell_flags[nc] (bit0 interior, bit1 ghost_cell, bit2 ghost_cell_l1) | f64 u0[nc][5]
 // out.bin: f64 tendency[nc][5] | f64 tendency_imported_stencils[nc][5] | f64 u_final[nc][5] | f64 dt[n_steps]
 //          | f64 u_final_resident[nc][5]
 #include <cstdint>
@@ -96,11 +96,12 @@ int run(const char *in_path, const char *out_path) {
     std::vector<std::int32_t> vi(nc * F);
     read_into(in, vi.data(), vi.size());
     for (int_t a = 0; a < nc * F; ++a) grid.vertex_indices[a] = (int_t)vi[a];
-    std::vector<std::uint8_t> ghost(nc);
-    read_into(in, ghost.data(), nc);
-    for (int_t i = 0; i < nc; ++i) {  // mask_ghost_cells, src/zisa/grid/grid.cpp:1122-1136
-      grid.cell_flags[i].interior = !ghost[i];
-      grid.cell_flags[i].ghost_cell = ghost[i] != 0;
+    std::vector<std::uint8_t> flags(nc);
+    read_into(in, flags.data(), nc);
+    for (int_t i = 0; i < nc; ++i) {  // what mask_ghost_cells left behind, src/zisa/grid/grid.cpp:1122-1136
+      grid.cell_flags[i].interior = (flags[i] & 1) != 0;
+      grid.cell_flags[i].ghost_cell = (flags[i] & 2) != 0;
+      grid.cell_flags[i].ghost_cell_l1 = (flags[i] & 4) != 0;
     }
   }
   auto u0 = std::make_shared<AllVariables>(AllVariablesDimensions{nc, 5, 0});

@@ -68,7 +68,7 @@ def test_cpp_time_loop_matches_oracle(driver, tmp_path):
         f.write(struct.pack("<2d", case.params.gamma, case.cfl))
         f.write(np.ascontiguousarray(g.array("vertices"), dtype=np.float64).tobytes())
         f.write(np.ascontiguousarray(g.array("vertex_indices"), dtype=np.int32).tobytes())
-        f.write(np.ascontiguousarray(g.is_ghost, dtype=np.uint8).tobytes())
+        f.write(np.ascontiguousarray(g.array("cell_flags"), dtype=np.uint8).tobytes())
         f.write(np.ascontiguousarray(case.u0, dtype=np.float64).tobytes())
     r = subprocess.run([driver, "run", str(inp), str(outp)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)

@@ -38,6 +38,9 @@ def _worker(rank, world, port, out_dir, partition="lattice"):
     try:
         if partition == "sfc_wb":  # the same partition for a well-balanced run with gravity (equilibrium kernels per tile list)
             run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind="atmosphere", device=rank, n_avars=N_AVARS)
+        elif partition == "metis":  # METIS k-way on the stencil graph (domain_decomposition.cpp:27-113): ragged parts
+            run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS,
+                                              partition="metis_stencils")
         elif partition == "sfc":  # one global mesh, contiguous chunks of the Hilbert curve (the reference's shipped path)
             run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind=KIND, device=rank, n_avars=N_AVARS)
         else:
@@ -123,9 +126,11 @@ def test_two_gpu_run_matches_single_domain_oracle(tmp_path):
         assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)
 
 
-def test_two_gpu_sfc_partition_matches_single_domain_oracle(tmp_path):
-    """The same check for the reference's shipped partition: the Hilbert-ordered global mesh cut into two contiguous
-    chunks of the curve (ragged partition boundary, halo rows grouped per owner)."""
+@pytest.mark.parametrize("partition", ["sfc", "metis"])
+def test_two_gpu_sfc_partition_matches_single_domain_oracle(tmp_path, partition):
+    """The same check for the reference's partitions of one global mesh: "sfc" -- the Hilbert-ordered mesh cut into two
+    contiguous chunks of the curve, the shipped path -- and "metis" -- METIS k-way on the stencil graph
+    (domain_decomposition.cpp:27-113); ragged partition boundaries, halo rows grouped per owner."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -134,9 +139,12 @@ def test_two_gpu_sfc_partition_matches_single_domain_oracle(tmp_path):
 
     from oracle.binding import Oracle
     from zisafvm_b200 import cases
+    from zisafvm_b200 import distributed as zd
 
+    if partition == "metis" and not zd.has_metis():
+        pytest.skip("libzfvm_b200.so was built without METIS")
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "sfc"), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), partition), nprocs=world, join=True)
 
     case = cases.with_tracers(cases.blast_3d(n=N_SFC, order=ORDER, kind=KIND), N_AVARS)
     st = case.ensure_stencils()

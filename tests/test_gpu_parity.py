@@ -32,6 +32,8 @@ CASES = {
     "vortex_o5": lambda: cases.isentropic_vortex(n=30, order=5),
     "blast_o2": lambda: cases.blast_3d(n=7, order=2, kind="blast"),
     "blast_o3": lambda: cases.blast_3d(n=7, order=3, kind="blast"),
+    # numbering of a partition: reconstructed cells first, first-order ghost cells behind them (whole tiles are skipped)
+    "blast_o3_ghosts_last": lambda: cases.blast_3d(n=8, order=3, kind="blast", ghosts_last=True),
     "sod_o3": lambda: cases.blast_3d(n=6, order=3, kind="sod"),
     "smooth3d_o3": lambda: cases.blast_3d(n=7, order=3, kind="smooth"),
     "smooth3d_o4": lambda: cases.blast_3d(n=8, order=4, kind="smooth"),
@@ -190,6 +192,67 @@ def test_compute_step_host_matches_resident(setup):
     a = rk.download().cvars
     b = rk.compute_step(z.AllVariables(n, case.u0), 0.0, dt).cvars
     assert np.array_equal(a, b)
+
+
+PIPE_CASES = {
+    "blast_o3_ssp3": lambda: cases.blast_3d(n=8, order=3, kind="blast"),
+    "blast_o3_ghosts_last": lambda: cases.blast_3d(n=8, order=3, kind="blast", ghosts_last=True),
+    "smooth3d_forward_euler": lambda: cases.blast_3d(n=7, order=3, kind="smooth", method="forward_euler"),
+    "smooth3d_o2_ssp2": lambda: cases.blast_3d(n=8, order=2, kind="smooth"),
+    "vortex_rk4": lambda: cases.isentropic_vortex(n=40, order=3, method="rk4"),
+    "vortex_fluxbc": lambda: cases.isentropic_vortex(n=36, order=3, ghost_ring_cells=0, flux_bc="flux"),
+    "atmosphere_wb": lambda: cases.stellar_atmosphere_3d(n=8, order=3, well_balanced=True),
+    "smooth3d_o4": lambda: cases.blast_3d(n=8, order=4, kind="smooth"),
+}
+
+
+@pytest.mark.parametrize("maker", sorted(PIPE_CASES))
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_pipelined_host_step_matches_resident(maker, pinned, monkeypatch):
+    """zfvm_rk_step_host overlapped with its own copies (chunked upload gating the stage-0 reconstruction, last stage
+    finished and downloaded chunk by chunk; the bench's end-to-end path): bit-identical to uploading, stepping the
+    resident state and downloading, for one- to four-stage tableaux, skipped ghost tiles, FluxBC, well-balanced sources,
+    the cooperative kernel; two steps in a row (the three state buffers rotate), pageable and pinned host buffers."""
+    import torch
+
+    monkeypatch.setenv("ZFVM_HOST_PIPELINE_MIN_CELLS", "0")
+    monkeypatch.setenv("ZFVM_HOST_CHUNKS", "5")
+    case = PIPE_CASES[maker]()
+    st = case.ensure_stencils()
+    n = case.grid.n_cells
+    ctx = z.CudaContext(case.grid, st, case.params)
+    monkeypatch.setenv("ZFVM_HOST_PIPELINE_MIN_CELLS", str(1 << 40))
+    ref_ctx = z.CudaContext(case.grid, st, case.params)   # no pipeline plan: the plain sequence
+    try:
+        tables = cases.gravity_tables(case.grid, case.params.gravity) if case.params.gravity.kind != "none" else None
+        from oracle.binding import Oracle
+
+        dt = Oracle(case.grid, st, case.params, tables).cfl_dt(case.u0, case.cfl)
+        rk, rk_ref = z.CudaRungeKutta(ctx, case.method), z.CudaRungeKutta(ref_ctx, case.method)
+        for c in (ctx, ref_ctx):
+            z.FrozenBC(c, z.AllVariables(n, case.u0))
+
+        def host_array():
+            if pinned:
+                return torch.empty((n, 5), dtype=torch.float64, pin_memory=True).numpy()
+            return np.empty((n, 5))
+
+        u0, u1, u2 = host_array(), host_array(), host_array()
+        u0[:] = case.u0
+        u1[:] = np.nan
+        rk.compute_step(z.AllVariables(n, u0), 0.0, dt, out=z.AllVariables(n, u1))
+        rk.compute_step(z.AllVariables(n, u1), dt, dt, out=z.AllVariables(n, u2))
+        rk_ref.upload(z.AllVariables(n, case.u0))
+        rk_ref.step(0.0, dt)
+        a1 = rk_ref.download().cvars.copy()
+        rk_ref.step(dt, dt)
+        a2 = rk_ref.download().cvars
+        assert np.array_equal(u1, a1) and np.array_equal(u2, a2), (np.abs(u1 - a1).max(), np.abs(u2 - a2).max())
+        assert np.array_equal(rk.download().cvars, a2)   # the resident state is the step's result
+        assert ctx.counters()["launches"] > ref_ctx.counters()["launches"]   # the chunked path really ran
+    finally:
+        ctx.close()
+        ref_ctx.close()
 
 
 def test_equilibrium_preservation():

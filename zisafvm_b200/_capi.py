@@ -83,6 +83,8 @@ _SIGNATURES = {
     "zfvm_stencils_extract": (C.c_int, [_vp, C.c_int64, c_int32_p, C.POINTER(_vp)]),
     "zfvm_stencils_from_arrays": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.c_char_p, c_double_p, c_int32_p, c_int32_p, c_int32_p,
                                             c_int64_p, c_int32_p, C.POINTER(_vp)]),
+    "zfvm_partition_kway": (C.c_int, [_vp, _vp, C.c_int, c_int32_p]),
+    "zfvm_has_metis": (C.c_int, []),
     "zfvm_hilbert_permutation": (C.c_int, [C.c_int, C.c_int64, c_double_p, c_int32_p]),
     "zfvm_stencil_matrix": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, c_double_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "zfvm_stencil_matrices": (C.c_int, [_vp, _vp, c_double_p, C.c_int64, c_int64_p]),

@@ -86,6 +86,18 @@ def ghost_ring(grid: Grid, lo, hi, width):
     return mask
 
 
+def renumber_ghosts_last(grid: Grid, verts: np.ndarray, qr: QRDegrees) -> Grid:
+    """The same mesh with the ghost cells nobody reconstructs (ghost_cell without ghost_cell_l1: first-order families,
+    stencil_family.cpp:108-114) numbered behind all other cells; both groups keep their relative order."""
+    flags = np.array(grid.array("cell_flags"))
+    deep = ((flags & 2) != 0) & ((flags & 4) == 0)
+    perm = np.concatenate([np.nonzero(~deep)[0], np.nonzero(deep)[0]])
+    vi = np.array(grid.array("vertex_indices"))[perm]
+    out = Grid(grid.n_dims, verts, vi, qr)
+    out.set_flags(flags[perm])
+    return out
+
+
 # ---- C1: 2D isentropic vortex ------------------------------------------------------------------------
 def isentropic_vortex(n: int = 158, order: int = 3, flux: str = "hllc", seed: int = 0, jitter: float = 0.15,
                       ghost_ring_cells: int = 3, flux_bc: str = "none", reconstruction: str = "CWENO-AO",
@@ -187,8 +199,13 @@ def blast_3d_on_grid(grid: Grid, order: int = 3, kind: str = "blast", stencils=N
 def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, ghost_cubes: int = 2,
              hilbert: bool = True, offset=None, global_n: Optional[int] = None, shape=None, flux_bc: str = "none",
              reconstruction: str = "CWENO-AO", scaling: str = "euler", method: Optional[str] = None,
-             weno: Optional[HybridWENOParams] = None) -> Case:
-    """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}."""
+             weno: Optional[HybridWENOParams] = None, ghosts_last: bool = False) -> Case:
+    """[0,1]^3 (n^3 cubes x 6 Kuhn tetrahedra), gamma = 1.4; `kind` in {"blast", "sod", "smooth"}.
+
+    ``ghosts_last``: cells are numbered like the reference numbers a partition -- the cells whose reconstruction
+    somebody reads first (interior and ghost_cell_l1, in Hilbert order), the remaining ghost cells behind them
+    (domain_decomposition.cpp:300-326 puts the halo behind the owned cells) -- so that tiles of 32 consecutive cells are
+    either reconstructed or skipped as a whole."""
     gamma = 1.4
     gn = global_n or n
     h = 1.0 / gn
@@ -198,6 +215,8 @@ def blast_3d(n: int = 16, order: int = 3, kind: str = "blast", seed: int = 0, gh
     grid = Grid(3, verts, vi, blast_qr(order))
     if ghost_cubes > 0:
         grid.mask_ghost_cells(ghost_ring(grid, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), ghost_cubes * h))
+        if ghosts_last:
+            grid = renumber_ghosts_last(grid, verts, blast_qr(order))
 
     ic = blast_ic(kind, gamma)
 

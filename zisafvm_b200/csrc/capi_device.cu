@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -78,10 +79,11 @@ void parallel_copy(void *dst, const void *src, size_t bytes) {
 }
 
 // asynchronous with respect to the host only for pinned sources
-int copy_h2d(zfvm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+int copy_h2d(zfvm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream = nullptr) {
   if (bytes == 0) return 0;
+  if (!stream) stream = ctx->stream;
   if (is_pinned(src_host)) {
-    ZFVM_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZFVM_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
     return 0;
   }
   if (ensure_stage(ctx)) return 1;
@@ -90,18 +92,21 @@ int copy_h2d(zfvm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
     const size_t nb = std::min(STAGE_BYTES, bytes - off);
     ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));  // the previous transfer out of this chunk is done
     parallel_copy(ctx->stage[b], (const char *)src_host + off, nb);
-    ZFVM_CUDA(cudaMemcpyAsync((char *)dst_dev + off, ctx->stage[b], nb, cudaMemcpyHostToDevice, ctx->stream));
-    ZFVM_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    ZFVM_CUDA(cudaMemcpyAsync((char *)dst_dev + off, ctx->stage[b], nb, cudaMemcpyHostToDevice, stream));
+    ZFVM_CUDA(cudaEventRecord(ctx->stage_ev[b], stream));
   }
   return 0;
 }
 
-// returns after the data is in dst_host
-int copy_d2h(zfvm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+// pageable destinations: returns after the data is in dst_host; pinned ones: after the copy is queued when `wait` is
+// false (the caller synchronises the stream), after it has completed otherwise
+int copy_d2h(zfvm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream = nullptr,
+             bool wait = true) {
   if (bytes == 0) return 0;
+  if (!stream) stream = ctx->stream;
   if (is_pinned(dst_host)) {
-    ZFVM_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZFVM_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+    if (wait) ZFVM_CUDA(cudaStreamSynchronize(stream));
     return 0;
   }
   if (ensure_stage(ctx)) return 1;
@@ -110,8 +115,8 @@ int copy_d2h(zfvm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
   for (size_t off = 0; off < bytes; off += STAGE_BYTES, b ^= 1) {
     const size_t nb = std::min(STAGE_BYTES, bytes - off);
     ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));
-    ZFVM_CUDA(cudaMemcpyAsync(ctx->stage[b], (const char *)src_dev + off, nb, cudaMemcpyDeviceToHost, ctx->stream));
-    ZFVM_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    ZFVM_CUDA(cudaMemcpyAsync(ctx->stage[b], (const char *)src_dev + off, nb, cudaMemcpyDeviceToHost, stream));
+    ZFVM_CUDA(cudaEventRecord(ctx->stage_ev[b], stream));
     if (prev_nb) {  // drain the other chunk while this one is in flight
       ZFVM_CUDA(cudaEventSynchronize(ctx->stage_ev[b ^ 1]));
       parallel_copy((char *)dst_host + prev_off, ctx->stage[b ^ 1], prev_nb);
@@ -365,7 +370,95 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
 
 // The body of zfvm_create once the arguments are validated and the device is selected; any non-zero return is followed
 // by zfvm_destroy(ctx) in the caller (allocations are registered in ctx->allocations as they are made).
+// Plan of the chunked host step (zfvm_ctx::HostPipe).  Chunks are ranges of consecutive cells (multiples of 64: the
+// update kernel's block).  Interior faces are numbered in the order of their left (smaller) cell (host/grid.cpp), so
+// the faces whose left cell lies in a chunk are a range too, and every face of a cell has its other cell either in
+// the same or an earlier chunk (the cell is the right one: the face belongs to that chunk's range) or in a later one
+// (the cell is the left one: the right cell's tile is reconstructed early, with this chunk).
+static int build_host_pipe(zfvm_ctx *ctx, const HostGrid &g) {
+  zfvm_ctx::HostPipe &H = ctx->pipe;
+  const std::int64_t n = g.n_cells, T = ctx->n_tiles, EI = g.n_interior_edges;
+  int want = 12;
+  if (const char *e = std::getenv("ZFVM_HOST_CHUNKS")) want = std::atoi(e);
+  // small grids (the extra launches cost more than the copies take), advected scalars: the plain sequence
+  std::int64_t min_cells = 1 << 20;
+  if (const char *e = std::getenv("ZFVM_HOST_PIPELINE_MIN_CELLS")) min_cells = std::atoll(e);
+  if (want < 2 || n < min_cells || (n + 63) / 64 < 2 * want || ctx->n_avars > 0) return 0;
+  for (std::int64_t e = 1; e < EI; ++e)
+    if (g.left_right[(size_t)(2 * e)] < g.left_right[(size_t)(2 * e - 2)]) return 0;  // (not this library's numbering)
+  const std::int64_t blocks = (n + 63) / 64;
+  const int C = (int)std::min<std::int64_t>(want, blocks);
+  H.cell_begin.assign((size_t)C + 1, n);
+  for (int c = 0; c < C; ++c) H.cell_begin[(size_t)c] = std::min(n, (blocks * c / C) * 64);
+  auto chunk_of = [&](std::int64_t cell) {
+    return (int)(std::upper_bound(H.cell_begin.begin(), H.cell_begin.end(), cell) - H.cell_begin.begin()) - 1;
+  };
+  H.face_begin.assign((size_t)C + 1, EI);
+  {
+    std::int64_t e = 0;
+    for (int c = 0; c < C; ++c) {
+      while (e < EI && g.left_right[(size_t)(2 * e)] < H.cell_begin[(size_t)c]) ++e;
+      H.face_begin[(size_t)c] = e;
+    }
+  }
+  // stage 0: a tile is ready when the chunk holding the largest row index its stencils read has landed
+  std::vector<std::vector<std::int32_t>> up((size_t)C), dn((size_t)C);
+  for (std::int64_t t = 0; t < T; ++t)
+    if (ctx->tile_needed[(size_t)t]) up[(size_t)chunk_of(ctx->tile_max_ref[(size_t)t])].push_back((std::int32_t)t);
+  // last stage: chunk c needs its own tiles and the tiles of the right cells of its faces
+  std::vector<std::uint8_t> done((size_t)T, 0);
+  for (int c = 0; c < C; ++c) {
+    auto take = [&](std::int64_t t) {
+      if (ctx->tile_needed[(size_t)t] && !done[(size_t)t]) {
+        done[(size_t)t] = 1;
+        dn[(size_t)c].push_back((std::int32_t)t);
+      }
+    };
+    for (std::int64_t t = H.cell_begin[(size_t)c] / TILE; t * TILE < H.cell_begin[(size_t)c + 1]; ++t) take(t);
+    for (std::int64_t e = H.face_begin[(size_t)c]; e < H.face_begin[(size_t)c + 1]; ++e)
+      take(g.left_right[(size_t)(2 * e + 1)] / TILE);
+    std::sort(dn[(size_t)c].begin(), dn[(size_t)c].end());
+  }
+  std::vector<std::int32_t> up_all, dn_all;
+  H.up_off.assign((size_t)C + 1, 0);
+  H.dn_off.assign((size_t)C + 1, 0);
+  for (int c = 0; c < C; ++c) {
+    up_all.insert(up_all.end(), up[(size_t)c].begin(), up[(size_t)c].end());
+    dn_all.insert(dn_all.end(), dn[(size_t)c].begin(), dn[(size_t)c].end());
+    H.up_off[(size_t)c + 1] = (std::int64_t)up_all.size();
+    H.dn_off[(size_t)c + 1] = (std::int64_t)dn_all.size();
+  }
+  const std::int32_t *p = nullptr;
+  if (dev_upload(ctx, &p, up_all)) return 1;
+  H.up_tiles = const_cast<std::int32_t *>(p);
+  if (dev_upload(ctx, &p, dn_all)) return 1;
+  H.dn_tiles = const_cast<std::int32_t *>(p);
+  if (dev_alloc(ctx, &H.u_out, n * NVARS, true)) return 1;
+  ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  H.ev_up.resize((size_t)C);
+  H.ev_dn.resize((size_t)C);
+  for (int c = 0; c < C; ++c) {
+    ZFVM_CUDA(cudaEventCreateWithFlags(&H.ev_up[(size_t)c], cudaEventDisableTiming));
+    ZFVM_CUDA(cudaEventCreateWithFlags(&H.ev_dn[(size_t)c], cudaEventDisableTiming));
+  }
+  H.n_chunks = C;
+  return 0;
+}
+
+// ZFVM_VERBOSE=1: wall-clock seconds of the phases of zfvm_create on stderr
+struct CreateClock {
+  bool on = std::getenv("ZFVM_VERBOSE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[zfvm create] %-28s %7.2f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params) {
+  CreateClock clk;
   const HostGrid &g = grid->g;
   const HostStencils &S = stencils->s;
   const int nd = g.n_dims, F = g.max_neighbours, ns = S.n_stencils;
@@ -457,6 +550,7 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
   P.n_edges = E;
   P.n_interior_edges = EI;
 
+  clk.lap("scheme constants");
   // ---- tile records (meta | sidx_k | W_k), built and uploaded in chunks of tiles -------------------
   ctx->tile_max_ref.assign((size_t)T, 0);
   for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
@@ -512,6 +606,7 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
       ctx->generic = true;
     }
     P.rec2_cap = cap;
+    clk.lap("tile row-list sizes");
   }
   if (use_tile) {
     const int D2 = poly_dof(ctx->deg_hi, nd);
@@ -743,6 +838,7 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     }
   }
 
+  clk.lap("records (A, pinv, pack, H2D)");
   // ---- geometry -----------------------------------------------------------------------------
   const int D = poly_dof(ctx->deg_hi, nd);
   P.n_mom = std::max(D - 3, 0);
@@ -801,6 +897,7 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     }
     ctx->inradius = const_cast<double *>(inr);
   }
+  clk.lap("cell geometry");
   // ---- faces ----------------------------------------------------------------------------------
   {
     std::vector<std::int32_t> lr((size_t)(2 * E));
@@ -851,6 +948,7 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
       ZFVM_CUDA(cudaMemcpy(c, h_c.data(), h_c.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
   }
+  clk.lap("faces, gravity tables");
   // ---- work arrays ------------------------------------------------------------------------------
   // (+ dump blocks for the tile kernel's branch-free trace write-out)
   if (dev_alloc(ctx, &P.trace, (std::max<std::int64_t>(EI, 1) + TRACE_DUMP_BLOCKS / 2) * 2 * g.q_f * NVARS, true) ||
@@ -883,6 +981,7 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
       ctx->tiles_needed = const_cast<std::int32_t *>(p);
     }
   }
+  if (build_host_pipe(ctx, g)) return 1;
   ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));
   // ghost cells (FrozenBC::count_ghost_cells)
   {
@@ -927,6 +1026,10 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     }
   }
 
+  clk.lap("work arrays");
+  if (clk.on)
+    std::fprintf(stderr, "[zfvm create] %lld cells, %lld tiles, %lld reconstructed, row-list capacity %d, %lld B per tile record\n",
+                 (long long)n, (long long)T, (long long)ctx->n_tiles_needed, P.rec2_cap, (long long)P.rec2_bytes);
   // ---- algorithmic bytes per cell and stage -----------------------------------------
   {
     const double nc = (double)std::max<std::int64_t>(n_counted, 1);
@@ -963,6 +1066,9 @@ void zfvm_destroy(zfvm_ctx *ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  for (cudaEvent_t e : ctx->pipe.ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->pipe.ev_dn) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -1218,8 +1324,111 @@ int zfvm_rk_step(zfvm_ctx *ctx, double /*t*/, double dt, double cfl_number, doub
   return 0;
 }
 
+// Update arguments of stage s of a step (the Butcher row that follows the stage; runge_kutta.cpp:122-143)
+static UpdateArgs stage_update_args(zfvm_ctx *ctx, int s, double dt, bool reduce) {
+  const int S = ctx->n_stages;
+  const double *coefs = (s + 1 < S) ? ctx->tab_a[s + 1] : ctx->tab_b;
+  UpdateArgs A = base_update_args(ctx);
+  bool needed_later = false;  // k_s is needed again iff a later sum uses it
+  for (int r = s + 2; r <= S; ++r) {
+    const double *row = (r < S) ? ctx->tab_a[r] : ctx->tab_b;
+    if (row[s] != 0.0) needed_later = true;
+  }
+  A.tendency = needed_later ? ctx->k[s] : nullptr;
+  A.accumulate = 0;
+  A.u_next = ctx->u_tmp;
+  A.u_base = ctx->u_cur;
+  A.n_prev = s;
+  for (int j = 0; j < s; ++j) {
+    A.k_prev[j] = ctx->k[j];
+    A.coef_prev[j] = coefs[j];
+  }
+  A.coef_cur = coefs[s];
+  A.dt = dt;
+  A.frozen = ctx->frozen;
+  A.reduce_out = (reduce && s + 1 == S) ? ctx->reduce_dev : nullptr;
+  return A;
+}
+
+// K2 + K3 of a residual on a range of faces / cell blocks (the whole grid: face range [0, n_interior_edges), block 0)
+static void flux_and_update(zfvm_ctx *ctx, const double *state, UpdateArgs A, std::int64_t face_begin, std::int64_t face_end) {
+  launch_flux(ctx->plan, ctx->sc, nullptr, face_end - face_begin, ctx->stream, face_begin);
+  A.flux_bc_state = ctx->params.flux_bc ? state : nullptr;
+  A.flux_bc_kind = ctx->params.flux_bc;
+  launch_update(ctx->plan, ctx->sc, A, ctx->stream);
+  ctx->launches += 2;
+}
+
+// TimeIntegration::compute_step with host buffers, overlapped with its own copies (zfvm_ctx::HostPipe): u0 goes up in
+// chunks while stage 0 reconstructs the tiles whose rows have landed; the last stage finishes chunk after chunk and every
+// finished chunk goes down while the next one is computed.  Same kernels on the same data as the plain sequence: the
+// result is bit-identical (tests/test_gpu_parity.py::test_compute_step_host_matches_resident).
+static int rk_step_host_pipelined(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double dt) {
+  zfvm_ctx::HostPipe &H = ctx->pipe;
+  const int C = H.n_chunks, S = ctx->n_stages;
+  const std::int64_t EI = ctx->plan.n_interior_edges;
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));  // whatever still reads or writes the resident state is done
+  // ---- stage 0: upload chunk c, then the tiles chunk c completes ------------------------------------------------------
+  for (int c = 0; c < C; ++c) {
+    const std::int64_t r0 = H.cell_begin[(size_t)c] * NVARS, r1 = H.cell_begin[(size_t)c + 1] * NVARS;
+    if (copy_h2d(ctx, ctx->u_cur + r0, u0_host + r0, (size_t)(r1 - r0) * sizeof(double), ctx->copy_stream)) return 1;
+    ZFVM_CUDA(cudaEventRecord(H.ev_up[(size_t)c], ctx->copy_stream));
+    ZFVM_CUDA(cudaStreamWaitEvent(ctx->stream, H.ev_up[(size_t)c], 0));
+    const std::int64_t nt = H.up_off[(size_t)c + 1] - H.up_off[(size_t)c];
+    if (nt > 0) {
+      if (run_recon(ctx, ctx->u_cur, H.up_tiles + H.up_off[(size_t)c], nt))
+        return fail("no reconstruction kernel is compiled for this scheme");
+      ctx->launches += 1;
+    }
+  }
+  auto finish_in_chunks = [&](int s, const double *in, double *out) -> int {
+    // (K1 of the stage is done for s == 0 and S == 1; otherwise it runs chunk by chunk here)
+    UpdateArgs A = stage_update_args(ctx, s, dt, false);
+    A.u_next = out;
+    for (int c = 0; c < C; ++c) {
+      const std::int64_t nt = H.dn_off[(size_t)c + 1] - H.dn_off[(size_t)c];
+      if (s > 0 && nt > 0) {
+        if (run_recon(ctx, in, H.dn_tiles + H.dn_off[(size_t)c], nt)) return fail("no reconstruction kernel is compiled for this scheme");
+        ctx->launches += 1;
+      }
+      UpdateArgs Ac = A;
+      Ac.block_begin = H.cell_begin[(size_t)c] / 64;
+      Ac.n_cells_update = H.cell_begin[(size_t)c + 1];
+      flux_and_update(ctx, in, Ac, H.face_begin[(size_t)c], H.face_begin[(size_t)c + 1]);
+      ZFVM_CUDA(cudaEventRecord(H.ev_dn[(size_t)c], ctx->stream));
+    }
+    for (int c = 0; c < C; ++c) {  // (queued after all launches: a pageable destination blocks the host per chunk)
+      const std::int64_t r0 = H.cell_begin[(size_t)c] * NVARS, r1 = H.cell_begin[(size_t)c + 1] * NVARS;
+      ZFVM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, H.ev_dn[(size_t)c], 0));
+      if (copy_d2h(ctx, u1_host + r0, out + r0, (size_t)(r1 - r0) * sizeof(double), ctx->copy_stream, false)) return 1;
+    }
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return 0;
+  };
+  if (S == 1) {
+    if (finish_in_chunks(0, ctx->u_cur, ctx->u_tmp)) return 1;
+    std::swap(ctx->u_cur, ctx->u_tmp);
+  } else {
+    flux_and_update(ctx, ctx->u_cur, stage_update_args(ctx, 0, dt, false), 0, EI);
+    for (int s = 1; s + 1 < S; ++s)
+      if (residual(ctx, ctx->u_tmp, stage_update_args(ctx, s, dt, false))) return 1;
+    // the last stage reads u_tmp while its finished chunks are written: they go to the third buffer
+    if (finish_in_chunks(S - 1, ctx->u_tmp, H.u_out)) return 1;
+    std::swap(ctx->u_cur, H.u_out);
+  }
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ZFVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double /*t*/, double dt) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
+  static const bool pipeline_off = [] {
+    const char *e = std::getenv("ZFVM_HOST_PIPELINE");
+    return e != nullptr && e[0] == '0';
+  }();
+  if (ctx->pipe.n_chunks > 0 && ctx->n_ranks == 1 && !pipeline_off && ctx->n_stages >= 1)
+    return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
   if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes)) return 1;
   if (rk_step_impl(ctx, dt, false)) return 1;

@@ -335,6 +335,22 @@ int zfvm_stencils_from_arrays(const zfvm_grid *grid, int n_stencils, const int *
   }
 }
 
+int zfvm_partition_kway(const zfvm_grid *grid, const zfvm_stencils *stencils, int n_parts, int32_t *partition) {
+  try {
+    std::vector<i32> part;
+    std::string err;
+    if (stencils != nullptr && stencils->s.n_cells != grid->g.n_cells)
+      return fail("zfvm_partition_kway: stencils do not belong to this grid");
+    if (!partition_kway(part, grid->g, stencils ? &stencils->s : nullptr, n_parts, err)) return fail("zfvm_" + err);
+    std::memcpy(partition, part.data(), part.size() * sizeof(int32_t));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_partition_kway: ") + e.what());
+  }
+}
+
+int zfvm_has_metis(void) { return metis_available() ? 1 : 0; }
+
 int zfvm_hilbert_permutation(int n_dims, int64_t n, const double *centers, int32_t *perm) {
   try {
     if (n_dims != 2 && n_dims != 3) return fail("zfvm_hilbert_permutation: n_dims must be 2 or 3");

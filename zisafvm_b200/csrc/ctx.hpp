@@ -66,6 +66,21 @@ struct zfvm_ctx {
   void *stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 
+  // zfvm_rk_step_host overlapped with its own copies (single-rank contexts): the state travels in chunks of rows;
+  // stage 0 reconstructs a tile as soon as every row its stencils read has landed, the last stage finishes the cells
+  // chunk by chunk (reconstruction of the chunk's tiles and of its later face neighbours, the chunk's faces, its rows)
+  // and each finished chunk goes back while the next one is computed.
+  struct HostPipe {
+    int n_chunks = 0;
+    std::vector<std::int64_t> cell_begin, face_begin;   // [n_chunks + 1]: first cell / first interior face of a chunk
+    std::vector<std::int64_t> up_off, dn_off;           // [n_chunks + 1]: offsets into the two device tile lists
+    std::int32_t *up_tiles = nullptr;                   // stage 0: tiles that become ready with upload chunk c
+    std::int32_t *dn_tiles = nullptr;                   // last stage: tiles to reconstruct before chunk c can be finished
+    std::vector<cudaEvent_t> ev_up, ev_dn;
+    double *u_out = nullptr;                            // third state buffer: the chunked stage must not overwrite its input
+  } pipe;
+  cudaStream_t copy_stream = nullptr;
+
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, n_ranks = 1;

@@ -199,6 +199,11 @@ void pseudo_inverse(const double *A, int rows, int cols, double *W);
 bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, const i32 *local_to_src,
                       std::string &err);
 
+/// METIS k-way partition of the cells on the stencil graph (stencils != nullptr) or the face-neighbour graph, with the
+/// reference's options (compute_partition_full_stencil, src/zisa/parallelization/domain_decomposition.cpp:27-113).
+bool metis_available();
+bool partition_kway(std::vector<i32> &part, const HostGrid &g, const HostStencils *stencils, int n_parts, std::string &err);
+
 /// Stencil families the caller already holds (the reference's array<StencilFamily, 1>,
 /// include/zisa/reconstruction/global_reconstruction_decl.hpp:107-147): stencil k of cell i has size[i][k] members whose
 /// global indices start at global[global_offset[i * n_stencils + k]] (Stencil::global(), member 0 = the cell), achieved

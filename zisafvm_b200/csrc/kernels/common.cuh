@@ -82,6 +82,11 @@ ZFVM_DEVICE double fast_rsqrt(double x) {
   return y;
 }
 
+/// std::min / std::max as comparisons (the CPU path's zisa::min / zisa::max, flux/hllc.hpp:73-74): unlike fmin / fmax
+/// they do not drop a NaN operand, they return the first argument when the comparison is false.
+ZFVM_DEVICE double ref_min(double a, double b) { return (b < a) ? b : a; }
+ZFVM_DEVICE double ref_max(double a, double b) { return (a < b) ? b : a; }
+
 /// x^(1/(gamma-1)) for the density of an isentropic state.  For the adiabatic indices in practical use the exponent
 /// is a half-integer (gamma = 2, 5/3, 3/2, 7/5, 4/3 -> 1, 3/2, 2, 5/2, 3): square root and multiplications instead of
 /// pow(), which is what the well-balanced reconstruction spends its time in (one evaluation per stencil member and

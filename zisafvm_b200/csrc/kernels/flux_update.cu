@@ -19,20 +19,23 @@ namespace zfvm {
 
 namespace {
 
-// HLLCBatten::flux (flux/hllc.hpp:36-81,143-176).  1/rho and sqrt(rho_R/rho_L) come from rsqrt(rho_L), rsqrt(rho_R);
-// the sound speeds from rsqrt(gamma p); the remaining quotients from fast_rcp: 5 rsqrt + 4 rcp per Gauss point
-// instead of 21 divisions and 4 square roots.  Results differ from the operation-by-operation form by rounding only.
+// HLLCBatten::flux (flux/hllc.hpp:36-81,143-176).  Every quotient is a fast_rcp, every square root x * fast_rsqrt(x):
+// 4 rsqrt + 6 rcp per Gauss point instead of 21 divisions and 4 square roots; results differ from the
+// operation-by-operation form by rounding only.  The arguments of the roots are the reference's (rho_R / rho_L,
+// gamma p / rho, the Roe sound speed squared) and min / max are the comparisons std::min / std::max make, so that a
+// reconstruction that undershoots to a negative pressure or density at a Gauss point -- outside the scheme's domain, it
+// happens next to strong discontinuities -- takes the same path as in the CPU code: NaN sound speed, comparisons false.
 template <bool SPEEDS = false>
 ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], double gamma, double nf[NVARS],
                            double *speeds = nullptr) {
-  const double rL = fast_rsqrt(uL[0]), rR = fast_rsqrt(uR[0]);
-  const double iL = rL * rL, iR = rR * rR;
+  const double iL = fast_rcp(uL[0]), iR = fast_rcp(uR[0]);
   const double pL = (uL[4] - 0.5 * (uL[1] * uL[1] + uL[2] * uL[2] + uL[3] * uL[3]) * iL) * (gamma - 1.0);
   const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (gamma - 1.0);
-  const double gpL = gamma * pL, gpR = gamma * pR;
-  const double aL = gpL * fast_rsqrt(gpL) * rL, aR = gpR * fast_rsqrt(gpR) * rR;  // sqrt(gamma p / rho)
+  const double a2L = gamma * pL * iL, a2R = gamma * pR * iR;
+  const double aL = a2L * fast_rsqrt(a2L), aR = a2R * fast_rsqrt(a2R);  // sqrt(gamma p / rho)
 
-  const double roe_ratio = (uR[0] * rR) * rL;  // sqrt(rho_R / rho_L)
+  const double rho_ratio = uR[0] * iL;
+  const double roe_ratio = rho_ratio * fast_rsqrt(rho_ratio);  // sqrt(rho_R / rho_L)
   const double inv_den = fast_rcp(1.0 + roe_ratio);
   const double vL = uL[1] * iL, vR = uR[1] * iR;
   const double v_tilda = (vL + vR * roe_ratio) * inv_den;
@@ -44,8 +47,9 @@ ZFVM_DEVICE void hllc_flux(const double uL[NVARS], const double uR[NVARS], doubl
   const double a2 = (gamma - 1.0) * (H_tilda - 0.5 * vroe_square);
   const double a_tilda = a2 * fast_rsqrt(a2);
 
-  const double sL = fmin(vL - aL, v_tilda - a_tilda);
-  const double sR = fmax(vR + aR, v_tilda + a_tilda);
+  // (std::min / std::max written out, see ref_min: a reconstructed pressure below zero makes a sound speed NaN)
+  const double sL = ref_min(vL - aL, v_tilda - a_tilda);
+  const double sR = ref_max(vR + aR, v_tilda + a_tilda);
   const double s_star =
       (uR[1] * (sR - vR) - uL[1] * (sL - vL) + pL - pR) * fast_rcp(uR[0] * (sR - vR) - uL[0] * (sL - vL));
 
@@ -94,7 +98,7 @@ ZFVM_DEVICE void rusanov_flux(const double uL[NVARS], const double uR[NVARS], do
   fR[2] = vR * uR[2];
   fR[3] = vR * uR[3];
   fR[4] = vR * (uR[4] + pR);
-  const double lam = fmax(fabs(vL) + aL, fabs(vR) + aR);
+  const double lam = ref_max(fabs(vL) + aL, fabs(vR) + aR);
 #pragma unroll
   for (int v = 0; v < NVARS; ++v) nf[v] = 0.5 * (fL[v] + fR[v]) - 0.5 * lam * (uR[v] - uL[v]);
 }
@@ -113,7 +117,8 @@ ZFVM_DEVICE void cp_async16(void *dst_smem, const void *src) {
 // order (point 0 first, quadrature.hpp:43-48) and the fluxes go back through shared memory as contiguous rows.
 template <int FLUX, int QF>
 __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
-                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces) {
+                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces,
+                                                   std::int64_t face_begin) {
   constexpr int LPF = QF <= 1 ? 1 : (QF <= 2 ? 2 : (QF <= 4 ? 4 : 8));  // lanes per face
   constexpr int FPW = 32 / LPF;                                          // faces per warp
   constexpr int CHUNKS = QF * NVARS;                                     // 16-byte chunks of a trace block [2][QF][5]
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __g
   const int f = lane / LPF, q = lane - f * LPF;  // face within the warp, Gauss point
   const std::int64_t t = min(t0 + f, n_faces - 1);
   const bool in_range = t0 + f < n_faces;
-  const std::int64_t e = face_list ? (std::int64_t)face_list[t] : t;
+  const std::int64_t e = face_list ? (std::int64_t)face_list[t] : t + face_begin;
 
   // (uniform trip counts: every lane takes part in the shuffles)
 #pragma unroll
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(128) flux_kernel(const DevicePlan P, const __g
 template <int FLUX, bool TRACERS, bool WBBG>
 __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
                                                   const std::int32_t *__restrict__ face_list, std::int64_t n_faces,
-                                                  int pitch) {
+                                                  int pitch, std::int64_t face_begin) {
   extern __shared__ __align__(16) double flux_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   double *tr = flux_smem + (size_t)warp * (TILE * pitch + TILE * 10);
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
   if (t0 >= n_faces) return;
   const std::int64_t t = min(t0 + lane, n_faces - 1);
   const bool in_range = t0 + lane < n_faces;
-  const std::int64_t e = face_list ? (std::int64_t)face_list[t] : t;
+  const std::int64_t e = face_list ? (std::int64_t)face_list[t] : t + face_begin;
 
   const int chunks = sc.q_f * NVARS;  // 16-byte chunks of a face's trace block [2][q_f][5]
   for (int c = lane; c < TILE * chunks; c += TILE) {
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
           const double pR = (uR[4] - 0.5 * (uR[1] * uR[1] + uR[2] * uR[2] + uR[3] * uR[3]) * iR) * (sc.gamma - 1.0);
           const double aL = sqrt(sc.gamma * pL * iL), aR = sqrt(sc.gamma * pR * iR);
           const double vL = uL[1] * iL, vR = uR[1] * iR;
-          const double lam = fmax(fabs(vL) + aL, fabs(vR) + aR);
+          const double lam = ref_max(fabs(vL) + aL, fabs(vR) + aR);
 #pragma unroll
           for (int a = 0; a < MAX_AVARS; ++a) {
             if (a < NA) {
@@ -371,7 +376,8 @@ __global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const Devi
   constexpr int CELLS = 2 * TILE;
   __shared__ double s_un[CELLS * NVARS];
   const int cl = threadIdx.x / NVARS, v = threadIdx.x - cl * NVARS;  // cell within the block, variable
-  const std::int64_t i = (std::int64_t)blockIdx.x * CELLS + cl;
+  const std::int64_t blk = (std::int64_t)blockIdx.x + A.block_begin;  // (a range of cell blocks: chunked host steps)
+  const std::int64_t i = blk * CELLS + cl;
   const std::int64_t iv = i * NVARS + v;
   const bool active = i < A.n_cells_update;
   double un = 1.0, t = 0.0, ub = 0.0, kp[MAX_RK_STAGES - 1];
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const Devi
     s_un[threadIdx.x] = un;
     __syncthreads();
     if (threadIdx.x < CELLS) {
-      const std::int64_t ic = (std::int64_t)blockIdx.x * CELLS + threadIdx.x;
+      const std::int64_t ic = blk * CELLS + threadIdx.x;
       double dx_over_ev = 1e300;
       int bad = 0;
       if (ic < A.n_cells_update && A.u_next) {
@@ -648,7 +654,7 @@ void launch_pack_rows_n(double *out, const double *state, const std::int32_t *in
 
 template <int FLUX>
 static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
-                          cudaStream_t stream) {
+                          std::int64_t face_begin, cudaStream_t stream) {
   static const bool per_point = [] {
     const char *e = std::getenv("ZFVM_FLUX");
     return e != nullptr && e[0] == 'p';
@@ -663,21 +669,21 @@ static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std:
     const bool bg = P.eq_bg != nullptr;
     if (P.n_avars > 0) {
       if (bg)
-        flux_face_kernel<FLUX, true, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+        flux_face_kernel<FLUX, true, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch, face_begin);
       else
-        flux_face_kernel<FLUX, true, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+        flux_face_kernel<FLUX, true, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch, face_begin);
     } else {
       if (bg)
-        flux_face_kernel<FLUX, false, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+        flux_face_kernel<FLUX, false, true><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch, face_begin);
       else
-        flux_face_kernel<FLUX, false, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch);
+        flux_face_kernel<FLUX, false, false><<<grid, block, smem, stream>>>(P, sc, face_list, n_faces, pitch, face_begin);
     }
     return;
   }
   auto go = [&](auto kern, int lanes_per_face) {
     const int faces_per_block = 4 * (32 / lanes_per_face);
     const unsigned grid = (unsigned)((n_faces + faces_per_block - 1) / faces_per_block);
-    kern<<<grid, 128, 0, stream>>>(P, sc, face_list, n_faces);
+    kern<<<grid, 128, 0, stream>>>(P, sc, face_list, n_faces, face_begin);
   };
   switch (sc.q_f) {  // edge rules: 1-3 points, triangle rules: 1, 3, 4, 6, 7 points
     case 1: go(flux_kernel<FLUX, 1>, 1); break;
@@ -692,19 +698,21 @@ static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std:
 }
 
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, std::int64_t face_begin) {
   if (n_faces <= 0) return;
   if (sc.flux == FLUX_HLLC)
-    launch_flux_q<FLUX_HLLC>(P, sc, face_list, n_faces, stream);
+    launch_flux_q<FLUX_HLLC>(P, sc, face_list, n_faces, face_begin, stream);
   else
-    launch_flux_q<FLUX_RUSANOV>(P, sc, face_list, n_faces, stream);
+    launch_flux_q<FLUX_RUSANOV>(P, sc, face_list, n_faces, face_begin, stream);
 }
 
 void launch_update(const DevicePlan &P, const SchemeConst &sc, const UpdateArgs &A, cudaStream_t stream) {
   const int n_dims = sc.n_dims;
   if (A.n_cells_update <= 0) return;
   const int block = 2 * TILE * NVARS;
-  const unsigned grid = (unsigned)((A.n_cells_update + 2 * TILE - 1) / (2 * TILE));
+  const std::int64_t n_blocks = (A.n_cells_update + 2 * TILE - 1) / (2 * TILE) - A.block_begin;
+  if (n_blocks <= 0) return;
+  const unsigned grid = (unsigned)n_blocks;
   const bool bc = A.flux_bc_state != nullptr;
   if (n_dims == 2) {
     if (bc)

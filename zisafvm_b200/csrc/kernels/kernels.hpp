@@ -22,7 +22,8 @@ struct StagePtrs {
 };
 
 struct UpdateArgs {
-  std::int64_t n_cells_update;
+  std::int64_t n_cells_update;   // cells [64 * block_begin, n_cells_update) are updated
+  std::int64_t block_begin;      // first block of 64 cells of the launch (0: from the first cell)
   int has_source;
   // residual output (RateOfChange::compute): may be null when only the fused update is wanted
   double *tendency;
@@ -104,8 +105,9 @@ int launch_recon_generic(const DevicePlan &plan, const SchemeConst &sc, const do
 int launch_tracer_recon_generic(const DevicePlan &P, const SchemeConst &sc, const double *avars,
                                 const std::int32_t *tile_list, std::int64_t n_tiles, cudaStream_t stream);
 
+/// faces face_list[0 .. n_faces) or, without a list, faces [face_begin, face_begin + n_faces)
 void launch_flux(const DevicePlan &P, const SchemeConst &sc, const std::int32_t *face_list, std::int64_t n_faces,
-                 cudaStream_t stream);
+                 cudaStream_t stream, std::int64_t face_begin = 0);
 void launch_update(const DevicePlan &P, const SchemeConst &sc, const UpdateArgs &A, cudaStream_t stream);
 /// Advected scalars: T1 scalar reconstruction + traces, T3 gather / RK update; the tracer face flux
 /// is evaluated by launch_flux (K2) when the plan carries scalars (it needs the face's HLLC wave speeds).

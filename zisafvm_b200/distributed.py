@@ -4,6 +4,7 @@ Host-side mirror of the reference's distributed set-up:
 
 * ``partition_by_sfc``        <->  ``compute_partitioned_grid_by_sfc`` (contiguous balanced chunks of the
   Hilbert-ordered cells, src/zisa/parallelization/domain_decomposition.cpp:577-609);
+* ``partition_by_metis``      <->  ``compute_partitioned_grid`` (METIS k-way on the stencil graph, :27-113,250-270);
 * ``extract_subdomain``       <->  ``extract_subgrid`` / ``extract_stencils`` / ``StencilBasedIndicator``
   (:300-326, :412-447): owned cells first, then the halo -- every cell a stencil of an owned cell or of a
   face-neighbour of an owned cell reads -- grouped contiguously per owner;
@@ -38,6 +39,21 @@ def partition_by_sfc(n_cells: int, n_parts: int) -> np.ndarray:
         hi = (k + 1) * chunk + min(k + 1, n_large)
         part[lo:hi] = k
     return part
+
+
+def partition_by_metis(grid: Grid, stencils: Optional[StencilFamilies], n_parts: int) -> np.ndarray:
+    """Owner rank of every cell from ``METIS_PartGraphKway`` with the reference's options (OBJTYPE_VOL, NCUTS 10,
+    NITER 20, UFACTOR 100) on the stencil graph, or on the face-neighbour graph when ``stencils`` is None
+    (``compute_partition_full_stencil``, src/zisa/parallelization/domain_decomposition.cpp:27-113).  Cells of a part
+    keep their relative (Hilbert) order, like ``compute_cell_permutation`` (:160-176)."""
+    part = np.zeros(grid.n_cells, dtype=np.int32)
+    check(lib.zfvm_partition_kway(grid._h, stencils._h if stencils is not None else None, int(n_parts),
+                                  part.ctypes.data_as(_capi.c_int32_p)))
+    return part
+
+
+def has_metis() -> bool:
+    return bool(lib.zfvm_has_metis())
 
 
 @dataclass
@@ -328,11 +344,12 @@ def make_weak_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, kind
 
 
 def make_strong_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, kind: str = "blast", device: int = 0,
-                             group=None, n_avars: int = 0) -> RankRun:
+                             group=None, n_avars: int = 0, partition: str = "sfc") -> RankRun:
     """BASELINE config 5, strong scaling: ONE global ``n^3``-cube mesh (the single-GPU workload), Hilbert-ordered and cut
     into ``n_ranks`` contiguous chunks of the space-filling curve -- the reference's shipped partition path
     (``compute_partitioned_grid_by_sfc``, src/zisa/grid/domain_decomposition.cpp:577-609) -- each rank extracting its
-    sub-grid, halo and stencils from the global mesh (``extract_subgrid`` / ``extract_stencils``, :300-326,412-447)."""
+    sub-grid, halo and stencils from the global mesh (``extract_subgrid`` / ``extract_stencils``, :300-326,412-447).
+    ``partition = "metis" | "metis_stencils"``: the reference's other partitioner, METIS k-way (:27-113)."""
     from . import cases
     from .solver import CudaContext
 
@@ -344,7 +361,14 @@ def make_strong_scaling_case(rank: int, n_ranks: int, n: int, order: int = 3, ki
         cases.with_tracers(g_case, n_avars)
     g = g_case.grid
     n_cells = g.n_cells
-    part = partition_by_sfc(n_cells, n_ranks)
+    if partition == "sfc":
+        part = partition_by_sfc(n_cells, n_ranks)
+    elif partition == "metis":        # METIS k-way on the face-neighbour graph (compute_partitioned_grid(grid, n_parts), :266-270)
+        part = partition_by_metis(g, None, n_ranks)
+    elif partition == "metis_stencils":  # ... on the stencil graph (:250-264): needs the global stencils on every rank
+        part = partition_by_metis(g, g_case.ensure_stencils(), n_ranks)
+    else:
+        raise ValueError(f"unknown partition '{partition}'")
     sub = extract_subdomain(g.n_dims, g.array("vertices").copy(), g.array("vertex_indices").copy(), part, np.arange(n_cells),
                             rank, n_ranks, g.qr, g_case.params.weno.stencil_family_params, physical_ghost=g.is_ghost.copy())
     exchange_requests(sub, group)
