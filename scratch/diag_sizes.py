@@ -82,3 +82,9 @@ if which in ("all", "o2"):
 if which in ("all", "gl"):
     case = cases.blast_3d(n=48, order=3, kind="blast", ghosts_last=True)
     ora, st = residual_check(case, "o3_n48_ghosts_last")
+
+if which in ("o2s",):
+    for n in (24, 48):
+        case = cases.blast_3d(n=n, order=2, kind="smooth")
+        ora, st = residual_check(case, f"o2_n{n}_smooth")
+        steps_check(case, ora, st, 20, f"o2_n{n}_smooth")

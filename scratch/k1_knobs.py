@@ -48,14 +48,10 @@ def measure(label, env):
 CONFIGS = [
     ("default", {}),
     ("default again", {}),
-    ("phase timers", {"ZFVM_TILE_PROF": "1"}),
     ("l2_ahead 4608", {"ZFVM_TILE_L2_AHEAD": "4608"}),
     ("l2_ahead 9216", {"ZFVM_TILE_L2_AHEAD": "9216"}),
     ("l2_ahead 18432", {"ZFVM_TILE_L2_AHEAD": "18432"}),
-    ("warps 7", {"ZFVM_TILE_WARPS": "7"}),
-    ("warps 6", {"ZFVM_TILE_WARPS": "6"}),
-    ("slots 2", {"ZFVM_TILE_SLOTS": "2"}),
-    ("coop kernel", {"ZFVM_RECON": "coop"}),
+    ("l2_ahead 36864", {"ZFVM_TILE_L2_AHEAD": "36864"}),
     ("default end", {}),
 ]
 if os.environ.get("ZFVM_TILE_PROF"):

@@ -94,3 +94,26 @@ def test_all_variables_carries_avars():
     b = z.AllVariables(3, np.ones((3, 5)), np.arange(3.0))
     assert b.avars.shape == (3, 1) and b.avars.flags.c_contiguous
     assert z.AllVariables(3).avars.shape == (3, 0)
+
+
+def test_no_malformed_ldgsts_in_the_tile_kernels():
+    """ptxas 12.9 was seen to emit ``LDGSTS ... desc[UR1]`` (an odd uniform-register descriptor: 'illegal instruction'
+    at run time, only on the path that executes it) in the remainder of a partially unrolled cp.async loop of
+    recon_tile.cuh.  The loop is rolled now; this scans the built kernels so that the pattern cannot come back unseen."""
+    import glob
+    import re
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    objs = sorted(glob.glob(os.path.join(ROOT, "zisafvm_b200", "csrc", "build", "kernels", "recon_*d_deg*.o")))
+    if not objs:
+        pytest.skip("object files not present (library built elsewhere)")
+    bad = re.compile(r"LDGSTS.*desc\[UR\d*[13579]\]")
+    n_ldgsts = 0
+    for o in objs:
+        sass = subprocess.run(["cuobjdump", "-sass", o], capture_output=True, text=True).stdout
+        n_ldgsts += sass.count("LDGSTS")
+        assert not bad.search(sass), o
+    assert n_ldgsts > 0   # the tile kernels stream their records with cp.async

@@ -250,6 +250,15 @@ def test_pipelined_host_step_matches_resident(maker, pinned, monkeypatch):
         assert np.array_equal(u1, a1) and np.array_equal(u2, a2), (np.abs(u1 - a1).max(), np.abs(u2 - a2).max())
         assert np.array_equal(rk.download().cvars, a2)   # the resident state is the step's result
         assert ctx.counters()["launches"] > ref_ctx.counters()["launches"]   # the chunked path really ran
+        # RateOfChange::compute with host buffers takes the same chunked route: overwrite and accumulate contracts
+        base = np.random.default_rng(1).normal(size=(n, 5))
+        for accumulate in (False, True):
+            t_pipe, t_ref = host_array(), np.empty((n, 5))
+            t_pipe[:] = base
+            t_ref[:] = base
+            z.CudaEulerRateOfChange(ctx).compute(z.AllVariables(n, t_pipe), z.AllVariables(n, u1), accumulate=accumulate)
+            z.CudaEulerRateOfChange(ref_ctx).compute(z.AllVariables(n, t_ref), z.AllVariables(n, a1), accumulate=accumulate)
+            assert np.array_equal(t_pipe, t_ref), (accumulate, np.abs(t_pipe - t_ref).max())
     finally:
         ctx.close()
         ref_ctx.close()

@@ -1156,8 +1156,64 @@ int zfvm_rate_of_change_av(zfvm_ctx *ctx, double *tendency_host, double *tendenc
   return copy_d2h(ctx, tendency_host, ctx->tend_work, bytes);
 }
 
+static void flux_and_update(zfvm_ctx *ctx, const double *state, UpdateArgs A, std::int64_t face_begin, std::int64_t face_end);
+
+// RateOfChange::compute with host buffers overlapped with its own copies (zfvm_ctx::HostPipe, like the host time step):
+// the state goes up in chunks while the tiles whose rows have landed are reconstructed; then the faces and cells are
+// finished chunk by chunk and every finished chunk of the tendency goes down while the next one is computed.
+static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const double *state_host, int accumulate) {
+  zfvm_ctx::HostPipe &H = ctx->pipe;
+  const int C = H.n_chunks;
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < C; ++c) {
+    const std::int64_t r0 = H.cell_begin[(size_t)c] * NVARS, r1 = H.cell_begin[(size_t)c + 1] * NVARS;
+    if (copy_h2d(ctx, ctx->state_work + r0, state_host + r0, (size_t)(r1 - r0) * sizeof(double), ctx->copy_stream)) return 1;
+    ZFVM_CUDA(cudaEventRecord(H.ev_up[(size_t)c], ctx->copy_stream));
+    ZFVM_CUDA(cudaStreamWaitEvent(ctx->stream, H.ev_up[(size_t)c], 0));
+    const std::int64_t nt = H.up_off[(size_t)c + 1] - H.up_off[(size_t)c];
+    if (nt > 0) {
+      if (run_recon(ctx, ctx->state_work, H.up_tiles + H.up_off[(size_t)c], nt))
+        return fail("no reconstruction kernel is compiled for this scheme");
+      ctx->launches += 1;
+    }
+  }
+  if (accumulate) {  // the caller's tendency rows: behind the state on the copy stream, needed by the update kernel only
+    if (copy_h2d(ctx, ctx->tend_work, tendency_host, (size_t)(ctx->n_cells * NVARS) * sizeof(double), ctx->copy_stream)) return 1;
+    ZFVM_CUDA(cudaEventRecord(H.ev_up[0], ctx->copy_stream));
+    ZFVM_CUDA(cudaStreamWaitEvent(ctx->stream, H.ev_up[0], 0));
+  }
+  UpdateArgs A = base_update_args(ctx);
+  A.tendency = ctx->tend_work;
+  A.accumulate = accumulate;
+  for (int c = 0; c < C; ++c) {
+    UpdateArgs Ac = A;
+    Ac.block_begin = H.cell_begin[(size_t)c] / 64;
+    Ac.n_cells_update = H.cell_begin[(size_t)c + 1];
+    flux_and_update(ctx, ctx->state_work, Ac, H.face_begin[(size_t)c], H.face_begin[(size_t)c + 1]);
+    ZFVM_CUDA(cudaEventRecord(H.ev_dn[(size_t)c], ctx->stream));
+  }
+  for (int c = 0; c < C; ++c) {
+    const std::int64_t r0 = H.cell_begin[(size_t)c] * NVARS, r1 = H.cell_begin[(size_t)c + 1] * NVARS;
+    ZFVM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, H.ev_dn[(size_t)c], 0));
+    if (copy_d2h(ctx, tendency_host + r0, ctx->tend_work + r0, (size_t)(r1 - r0) * sizeof(double), ctx->copy_stream, false)) return 1;
+  }
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ZFVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool host_pipeline_enabled(const zfvm_ctx *ctx) {
+  static const bool off = [] {
+    const char *e = std::getenv("ZFVM_HOST_PIPELINE");
+    return e != nullptr && e[0] == '0';
+  }();
+  return ctx->pipe.n_chunks > 0 && ctx->n_ranks == 1 && !off;
+}
+
 int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
+  if (host_pipeline_enabled(ctx) && ctx->n_avars == 0) return rate_of_change_pipelined(ctx, tendency_host, state_host, accumulate);
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
   if (copy_h2d(ctx, ctx->state_work, state_host, bytes)) return 1;
   if (accumulate && copy_h2d(ctx, ctx->tend_work, tendency_host, bytes)) return 1;
@@ -1423,12 +1479,7 @@ static int rk_step_host_pipelined(zfvm_ctx *ctx, const double *u0_host, double *
 
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double /*t*/, double dt) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
-  static const bool pipeline_off = [] {
-    const char *e = std::getenv("ZFVM_HOST_PIPELINE");
-    return e != nullptr && e[0] == '0';
-  }();
-  if (ctx->pipe.n_chunks > 0 && ctx->n_ranks == 1 && !pipeline_off && ctx->n_stages >= 1)
-    return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
+  if (host_pipeline_enabled(ctx) && ctx->n_stages >= 1) return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
   if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes)) return 1;
   if (rk_step_impl(ctx, dt, false)) return 1;

@@ -35,6 +35,11 @@ ZFVM_DEVICE std::uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+ZFVM_DEVICE std::uint64_t policy_evict_normal() {
+  std::uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 /// TMA bulk copy global -> shared, completion counted in bytes on `bar`.
 ZFVM_DEVICE void bulk_g2s(void *dst, const void *src, std::uint32_t bytes, std::uint64_t *bar, std::uint64_t policy) {
   asm volatile(

@@ -29,18 +29,14 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  // one CTA per SM; as many warps (= tiles in flight) as fit with `slots` ring slots each, at most 8
-  int slots = 3;  // measured on B200: 8 warps x 3 slots beat 7 warps x 4 slots (and 8 x 2)
-  if (const char *e = std::getenv("ZFVM_TILE_SLOTS")) slots = std::max(2, std::min(13, std::atoi(e)));
+  // one CTA per SM; as many warps (= tiles in flight) as fit, at most 8
   TileCfg cfg;
-  if (!tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, 1 << 20, slots, cfg)) return 1;
+  if (!tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, optin, cfg)) return 1;
   int wpc = std::min(TILE_MAX_WARPS, optin / cfg.warp_bytes);
   if (const char *e = std::getenv("ZFVM_TILE_WARPS")) wpc = std::max(1, std::min(wpc, std::atoi(e)));
   if (wpc < 1) return 1;
-  // spend what is left on deeper rings
-  if (!std::getenv("ZFVM_TILE_SLOTS")) tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, (optin / wpc) / 128 * 128, 13, cfg);
   cfg.prof = tile_prof_buffer();
-  cfg.l2_ahead = 0;
+  if (const char *e = std::getenv("ZFVM_TILE_EVICT")) cfg.evict_normal = (e[0] == 'n') ? 1 : 0;
   if (const char *e = std::getenv("ZFVM_TILE_L2_AHEAD")) cfg.l2_ahead = std::max(0, std::atoi(e));
   const int smem_bytes = cfg.warp_bytes * wpc;
   const char *e_ctas = std::getenv("ZFVM_STREAM_MAX_CTAS");

@@ -4,12 +4,15 @@
 // HybridWENO::compute_polys_impl / eno_hybridize, CWENO_AO::reconstruct_impl, rc(i)(x) at the face Gauss
 // points; the reference lines are listed there).  What changes is how the bytes move:
 //
-//   * every table a tile needs is one contiguous *tile record* (layout below) that the warp streams itself
-//     with TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first) through a private ring of
-//     small shared-memory slots (one one-sided stencil or a few central-stencil rows each).  After the warp
-//     has consumed a slot, its lane 0 re-arms the barrier and issues the copy of the segment that is NSLOT
-//     positions ahead: no producer warp, no "empty" barriers, and the bytes in flight do not depend on
-//     registers.
+//   * every table a tile needs is one contiguous *tile record* (layout below) that the warp streams itself with
+//     16-byte cp.async copies (LDGSTS, L2 evict-first) through a private ring of N_SLOTS small shared-memory slots
+//     (one one-sided stencil or a few central-stencil rows each), one commit group per segment.  After the warp has
+//     consumed a slot it issues the copies of the segment that is N_SLOTS positions ahead: no producer warp, no
+//     barriers, and the bytes in flight do not depend on registers.  (The first versions moved the segments with TMA
+//     bulk copies and mbarriers.  Measured on B200, profiles/r02_tma_ubench.txt: a completed mbarrier.try_wait still
+//     costs ~125 cycles and arming + issuing one bulk copy ~275 cycles of the issuing warp, i.e. ~400 cycles for
+//     each of a tile's 17 copies -- a fifth of the tile's time at 4.6 KB per copy -- whereas the nine LDGSTS of a
+//     segment issue in ~70 cycles and cp.async.wait_group is a scoreboard wait.)
 //   * the neighbour states are not gathered through global indices.  The host lists the distinct cells a
 //     tile's stencils read (~125-250 of them for 32 Hilbert-consecutive cells, instead of 32 x 34 gathers) and
 //     stores 8/16-bit indices into that list; the warp copies those rows once into a shared-memory table
@@ -68,6 +71,7 @@ struct TileTraits {
   static constexpr int N_GEO = (GEO_SECTION + SLOT_BYTES - 1) / SLOT_BYTES;
   static constexpr int GEO_TAIL_BYTES = GEO_SECTION - (N_GEO - 1) * SLOT_BYTES;
   static constexpr int N_SEG = N_LO + N_HI + N_GEO;
+  static constexpr int N_SLOTS = 3;                         // ring slots per warp (8 warps x 3 slots measured best on B200)
   static constexpr int Q_STAGE = 1;                         // Gauss points staged per pass (shared memory is what limits the warps per SM)
   static constexpr int CHUNK = Q_STAGE * NVARS;             // doubles per (cell, face) block written per pass
   static constexpr int STAGE_PITCH = CHUNK | 1;
@@ -80,8 +84,10 @@ struct TileCfg {
   std::int64_t rec_bytes;
   const char *rec;
   // shared memory of one warp
-  int n_slots, s_list, s_lidx, s_table, s_ring, s_stage, warp_bytes;
-  int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off, -1 never used)
+  int s_list, s_lidx, s_table, s_ring, s_stage, warp_bytes;
+  int evict_normal;          // L2 policy of the record copies: 0 evict-first (default), 1 evict-normal
+  int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off)
+  int stream_bytes;          // bytes of a record's W | geometry stream (rec_bytes - off_wlo)
   int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
 };
@@ -92,18 +98,16 @@ namespace ptx {
 ZFVM_DEVICE void cp_async8(void *dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
-/// expect_tx + TMA bulk copy global -> shared, both predicated on `pred` inside one asm block (no divergent branch).
-ZFVM_DEVICE void bulk_g2s_if(bool pred, void *dst, const void *src, std::uint32_t bytes, std::uint64_t *bar,
-                             std::uint64_t policy) {
+/// 16-byte global -> shared copy past L1 with an L2 cache policy, predicated inside the asm block (no divergent branch)
+ZFVM_DEVICE void cp_async16_if(bool pred, void *dst_smem, const void *src, std::uint64_t policy) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %5, 0;\n\t"
-      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
-      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy), "r"((std::uint32_t)pred)
+      "setp.ne.u32 p, %3, 0;\n\t"
+      "@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n\t}" ::"r"(smem_u32(dst_smem)),
+      "l"(src), "l"(policy), "r"((std::uint32_t)pred)
       : "memory");
 }
-/// L2 prefetch of a global range (no shared-memory destination, no completion tracking), predicated like bulk_g2s_if.
+/// L2 prefetch of a global range (no shared-memory destination, no completion tracking), predicated inside the asm block
 ZFVM_DEVICE void bulk_prefetch_l2_if(bool pred, const void *src, std::uint32_t bytes) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -112,8 +116,18 @@ ZFVM_DEVICE void bulk_prefetch_l2_if(bool pred, const void *src, std::uint32_t b
       "r"(bytes), "r"((std::uint32_t)pred)
       : "memory");
 }
+ZFVM_DEVICE void cp_async16(void *dst_smem, const void *src, std::uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "l"(policy)
+               : "memory");
+}
+ZFVM_DEVICE void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 ZFVM_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 ZFVM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+/// waits until at most N of this thread's most recent commit groups are still pending
+template <int N>
+ZFVM_DEVICE void cp_async_wait_pending() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 }  // namespace ptx
 
 // WB (well-balanced runs): the equilibrium kernels (equilibrium.cuh: E1, E2, E3) have written, per tile, the cell
@@ -133,15 +147,12 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
   extern __shared__ __align__(128) unsigned char smem_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *smem = smem_all + (size_t)warp * cfg.warp_bytes;
-  std::uint64_t *list_full = reinterpret_cast<std::uint64_t *>(smem);  // [1] (+1 unused)
-  std::uint64_t *lidx_full = list_full + 2;                            // [1]
-  std::uint64_t *seg_full = list_full + 3;                             // [n_slots]
   unsigned char *list_base = smem + cfg.s_list;
   const LIDX *lidx = reinterpret_cast<const LIDX *>(smem + cfg.s_lidx) + lane;
   double *table = reinterpret_cast<double *>(smem + cfg.s_table);
   unsigned char *ring = smem + cfg.s_ring;
   double *stage = reinterpret_cast<double *>(smem + cfg.s_stage);
-  const int NSLOT = cfg.n_slots;
+  constexpr int NSLOT = T::N_SLOTS;
 
   const std::int64_t n_launch = args.n_tiles_launch;
   const std::int64_t first = (std::int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -170,80 +181,96 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     }
   };
 
-  if (lane == 0) {
-    ptx::mbar_init(&list_full[0], 1);
-    ptx::mbar_init(&lidx_full[0], 1);
-    for (int s = 0; s < NSLOT; ++s) ptx::mbar_init(&seg_full[s], 1);
-    ptx::fence_barrier_init();
-  }
-  __syncwarp();
+  // (records are read once per stage: evict-first keeps them from flushing the state rows and traces out of L2;
+  // cfg.evict_normal is an experiment switch, ZFVM_TILE_EVICT=normal)
+  const std::uint64_t pol = cfg.evict_normal ? ptx::policy_evict_normal() : ptx::policy_evict_first();
 
-  const std::uint64_t pol = ptx::policy_evict_first();
-
-  // ---- issue side (lane 0 only) ---------------------------------------------------------------------
+  // ---- issue side: every lane copies 16 bytes of each 512-byte row of a range ---------------------------
+  // Commit-group bookkeeping (cp.async.wait_group counts a thread's most recent groups, so the order of the commits is
+  // part of the algorithm): every issue_seg commits one group -- also when it has nothing to copy -- and so does every
+  // load_table; the list part and the index rows of the next tile ride in the group of whatever is committed next.
+  auto copy_range = [&](unsigned char *dst, const char *src, int bytes, auto max_bytes_tag) {
+    constexpr int MAXB = decltype(max_bytes_tag)::value;
+#pragma unroll
+    for (int j = 0; j < (MAXB + 511) / 512; ++j)
+      ptx::cp_async16_if(j * 512 + lane * 16 < bytes, dst + j * 512 + lane * 16, src + j * 512 + lane * 16, pol);
+  };
+  auto copy_range_rt = [&](unsigned char *dst, const char *src, int bytes) {  // run-time length (list part, index rows)
+    // (rolled on purpose: ptxas 12.9 emits LDGSTS with an odd descriptor register -- an illegal instruction at run
+    // time -- in the remainder of the partially unrolled form of this loop)
+#pragma unroll 1
+    for (int off = lane * 16; off < bytes; off += 512) ptx::cp_async16(dst + off, src + off, pol);
+  };
   auto issue_list = [&](int m) {  // n_list | meta | list of tile m (one buffer: see the tile loop for its life time)
-    if (lane == 0 && has_tile(m)) {
-      ptx::mbar_expect_tx(&list_full[0], (std::uint32_t)cfg.list_bytes);
-      ptx::bulk_g2s(list_base, cfg.rec + tile_of(m) * cfg.rec_bytes, (std::uint32_t)cfg.list_bytes, &list_full[0], pol);
-    }
+    if (has_tile(m)) copy_range_rt(list_base, cfg.rec + tile_of(m) * cfg.rec_bytes, cfg.list_bytes);
   };
   auto issue_lidx = [&](int m) {
-    if (lane == 0 && has_tile(m)) {
-      ptx::mbar_expect_tx(&lidx_full[0], (std::uint32_t)cfg.lidx_bytes);
-      ptx::bulk_g2s(smem + cfg.s_lidx, cfg.rec + tile_of(m) * cfg.rec_bytes + cfg.off_lidx, (std::uint32_t)cfg.lidx_bytes,
-                    &lidx_full[0], pol);
-    }
+    if (has_tile(m)) copy_range_rt(smem + cfg.s_lidx, cfg.rec + tile_of(m) * cfg.rec_bytes + cfg.off_lidx, cfg.lidx_bytes);
   };
-  // The W and geometry sections of a record are contiguous: the issue pointer walks through them.  All lanes
-  // keep the (warp-uniform) bookkeeping; only the two asynchronous-copy instructions are predicated on lane 0.
-  // The ring is shorter than a record's segment list, so while tile m is consumed the issue side moves from
-  // tile m's record to tile m+1's exactly once: `nxt_ptr` is set at the start of tile m.
-  int iss_s = 0;
+  // The W and geometry sections of a record are contiguous: the issue pointer walks through them.  The ring is
+  // shorter than a record's segment list, so while tile m is consumed the issue side moves from tile m's record to
+  // tile m+1's exactly once: `nxt_ptr` is set at the start of tile m.
+  int iss_s = 0, iss_left = cfg.stream_bytes;  // segment index; bytes of the record's W | geometry stream not yet issued
   const char *iss_ptr = cfg.rec + tile_of(0) * cfg.rec_bytes + cfg.off_wlo;
   const char *nxt_ptr = nullptr;
   auto issue_seg = [&](int slot) {
-    // branch-free: when the tile list is exhausted iss_ptr is null and nothing is issued
+    // branch-free: when the tile list is exhausted iss_ptr is null and nothing is copied (the group is still committed)
     const bool live = iss_ptr != nullptr;
     const int bytes = live ? cfg.seg_bytes[iss_s] : 0;
-    ptx::bulk_g2s_if(live && lane == 0, ring + (size_t)slot * T::SLOT_BYTES, iss_ptr, (std::uint32_t)bytes, &seg_full[slot],
-                     pol);
-    // the ring is short (shared memory): pull the bytes behind it towards L2 so that the next copies are L2 hits
+    copy_range(ring + (size_t)slot * T::SLOT_BYTES, iss_ptr, bytes, std::integral_constant<int, T::SLOT_BYTES>{});
+    ptx::cp_async_commit();
+    // the ring is short (shared memory): pull the lines `l2_ahead` bytes behind it towards L2 (one line per lane, the
+    // range is about the segment that will be issued l2_ahead / SLOT_BYTES positions later, within this record)
     if (cfg.l2_ahead > 0) {
-      const bool in_rec = iss_s + 1 < N_SEG;  // stay inside this record's W | geometry stream
-      ptx::bulk_prefetch_l2_if(live && in_rec && lane == 0, iss_ptr + bytes + cfg.l2_ahead, (std::uint32_t)T::SLOT_BYTES);
+      iss_left -= bytes;
+#pragma unroll
+      for (int j = 0; j < (T::SLOT_BYTES + 4095) / 4096; ++j) {
+        const int off = cfg.l2_ahead + (j * 32 + lane) * 128;
+        if (live && (j * 32 + lane) * 128 < bytes && off < iss_left) ptx::prefetch_l2(iss_ptr + bytes + off);
+      }
     }
     const bool last = (iss_s == N_SEG - 1);
+    if (last) iss_left = cfg.stream_bytes;
     iss_ptr = last ? nxt_ptr : (live ? iss_ptr + bytes : nullptr);
     nxt_ptr = last ? nullptr : nxt_ptr;
     iss_s = last ? 0 : iss_s + 1;
   };
   // ---- consume side ---------------------------------------------------------------------------------
-  int cslot = 0, cphase = 0;
-  auto wait_seg = [&]() -> const unsigned char * {
+  // `PENDING` = commit groups that may still be in flight behind the awaited segment: the NSLOT - 1 segments issued
+  // after it, plus the table group when that was committed in between (the geometry segments, see the tile loop)
+  int cslot = 0;
+  auto wait_seg = [&](auto pending_tag) -> const unsigned char * {
+    constexpr int PENDING = decltype(pending_tag)::value;
     if (prof) {
       const long long a = clock64();
-      ptx::mbar_wait(&seg_full[cslot], cphase);
+      ptx::cp_async_wait_pending<PENDING>();
       t_segwait += clock64() - a;
     } else {
-      ptx::mbar_wait(&seg_full[cslot], cphase);
+      ptx::cp_async_wait_pending<PENDING>();
     }
+    __syncwarp();  // every lane's copies of the segment are complete: the slot is visible to the whole warp
     return ring + (size_t)cslot * T::SLOT_BYTES;
   };
+  using PendW = std::integral_constant<int, NSLOT - 1>;
+  using PendGeo = std::integral_constant<int, NSLOT>;
   auto release_seg = [&]() {
     __syncwarp();  // every lane has read what it needs from the slot
     issue_seg(cslot);
-    if (++cslot == NSLOT) {
-      cslot = 0;
-      cphase ^= 1;
-    }
+    if (++cslot == NSLOT) cslot = 0;
   };
   // copy the rows of tile m's list into the table (asynchronously)
+  // (tile m's list part was copied at least a whole W phase ago and a wait_seg + __syncwarp has covered its group)
   auto load_table = [&](int m) {
-    if (!has_tile(m)) return;
+    if (!has_tile(m)) {
+      ptx::cp_async_commit();
+      return;
+    }
     const unsigned char *lb = list_base;
-    ptx::mbar_wait(&list_full[0], m & 1);
     const int n_list = *reinterpret_cast<const int *>(lb);
     const std::int32_t *list = reinterpret_cast<const std::int32_t *>(lb + cfg.off_list);
+    // (measured alternatives, same time or worse at the bench size: consecutive lanes copying consecutive doubles of a
+    // row; the copies issued in four portions spread over the first trace evaluations -- the ~4 k cycles per tile this
+    // loop takes are the load-store unit working through ~200 scattered rows, wherever they are issued)
 #pragma unroll 2
     for (int row = lane; row < n_list; row += 32) {  // a lane copies whole 40-byte rows
       const double *src = args.state + (std::int64_t)list[row] * NVARS;
@@ -257,6 +284,8 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
   issue_list(0);
   issue_lidx(0);
   for (int s = 0; s < NSLOT; ++s) issue_seg(s);
+  ptx::cp_async_wait_pending<NSLOT - 1>();  // the first group carries tile 0's list part
+  __syncwarp();
   load_table(0);
 
   const bool cweno = sc.recon_mode == RECON_CWENO_AO;
@@ -285,9 +314,8 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     __syncwarp();
     issue_list(m + 1);
     nxt_ptr = has_tile(m + 1) ? cfg.rec + tile_of(m + 1) * cfg.rec_bytes + cfg.off_wlo : nullptr;
-    ptx::cp_async_wait_all();
-    ptx::mbar_wait(&lidx_full[0], m & 1);
-    __syncwarp();  // the table of tile m is complete and visible to the whole warp
+    ptx::cp_async_wait_all();  // (the segments in flight were issued before the previous tile's trace phase)
+    __syncwarp();  // the table and the index rows of tile m are complete and visible to the whole warp
     mark(TP_TABLE_WAIT);
     const std::int64_t tile = tile_of(m);
     if constexpr (WB) {
@@ -391,7 +419,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
       double al_sum = 0.0;  // sum of the non-linear weights folded so far
 #pragma unroll 1
       for (int k = 1; k < NS; ++k) {  // rolled: instruction-cache footprint
-        const double *wseg = reinterpret_cast<const double *>(wait_seg()) + lane;
+        const double *wseg = reinterpret_cast<const double *>(wait_seg(PendW{})) + lane;
         double acc[CLO][NVARS];
 #pragma unroll
         for (int c = 0; c < CLO; ++c)
@@ -482,7 +510,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
       };
 #pragma unroll 2
       for (int hs = 0; hs < N_HI - 1; ++hs) {
-        const double *wseg = reinterpret_cast<const double *>(wait_seg()) + lane;
+        const double *wseg = reinterpret_cast<const double *>(wait_seg(PendW{})) + lane;
         double w_first = wseg[0];  // start the weight loads before the next segment's table reads are queued
         double rhs_next[R_HI][NVARS];
 #pragma unroll
@@ -500,7 +528,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
           for (int v = 0; v < NVARS; ++v) rhs_hi[r][v] = rhs_next[r][v];
       }
       {
-        const double *wseg = reinterpret_cast<const double *>(wait_seg()) + lane;
+        const double *wseg = reinterpret_cast<const double *>(wait_seg(PendW{})) + lane;
         central_rows(wseg, rhs_hi, std::integral_constant<int, R_TAIL>{});
         release_seg();
       }
@@ -629,7 +657,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     for (int i = 0; i < D; ++i) cmom[i] = 0.0;
 #pragma unroll
     for (int gs = 0; gs < N_GEO; ++gs) {
-      const unsigned char *gseg = wait_seg();
+      const unsigned char *gseg = wait_seg(PendGeo{});
       // row j of the geometry section lives in segment j / GEO_ROWS_PER_SEG
       const double *geo = reinterpret_cast<const double *>(gseg) + lane - gs * T::GEO_ROWS_PER_SEG * TILE;
 #pragma unroll
@@ -733,7 +761,7 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
 
 /// Shared-memory plan; returns false if the tile kernel does not apply.
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
-bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, int want_slots, TileCfg &c) {
+bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, TileCfg &c) {
   using T = TileTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>;
   if (P.rec2 == nullptr) return false;
   if (NS < 2 || T::CLO < 1 || sc.n_stencils != NS || sc.q_f != QF) return false;
@@ -751,18 +779,15 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   c.off_wlo = L.off_wlo;
   c.rec_bytes = L.rec_bytes;
   c.rec = P.rec2;
-  c.s_list = 128;
+  c.s_list = 0;
   c.s_lidx = c.s_list + c.list_bytes;
   c.s_table = c.s_lidx + c.lidx_bytes;
   c.s_stage = c.s_table + (L.cap * NVARS * 8 + 127) / 128 * 128;
   c.s_ring = c.s_stage + T::STAGE_BYTES;
-  int ns = (smem_per_warp - c.s_ring) / T::SLOT_BYTES;
-  if (ns > 13) ns = 13;
-  if (ns > T::N_SEG - 1) ns = T::N_SEG - 1;  // the issue side changes records at most once per consumed tile
-  if (want_slots > 0 && ns > want_slots) ns = want_slots;
-  if (ns < 2) return false;
-  c.n_slots = ns;
-  c.warp_bytes = c.s_ring + ns * T::SLOT_BYTES;
+  // (the issue side changes records at most once per consumed tile: the ring must be shorter than a record's segments)
+  if (T::N_SLOTS > T::N_SEG - 1) return false;
+  c.warp_bytes = c.s_ring + T::N_SLOTS * T::SLOT_BYTES;
+  if (c.warp_bytes > smem_per_warp) return false;
   if (T::N_SEG > 64) return false;
   for (int i = 0; i < T::N_SEG; ++i) {
     int bytes = T::LO_ST_BYTES;
@@ -772,8 +797,10 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
     if (i == T::N_SEG - 1) bytes = T::GEO_TAIL_BYTES;
     c.seg_bytes[i] = bytes;
   }
-  c.l2_ahead = 0;
   c.prof = nullptr;
+  c.evict_normal = 0;
+  c.l2_ahead = 0;
+  c.stream_bytes = (int)(L.rec_bytes - L.off_wlo);
   return true;
 }
 
