@@ -5,6 +5,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["ZFVM_GRAPH"] = "0"  # the knobs are read at launch: no replayed graphs here
 import numpy as np
 
 import zisafvm_b200 as z
@@ -47,12 +48,12 @@ def measure(label, env):
 
 CONFIGS = [
     ("default", {}),
-    ("default again", {}),
     ("l2_ahead 4608", {"ZFVM_TILE_L2_AHEAD": "4608"}),
-    ("l2_ahead 9216", {"ZFVM_TILE_L2_AHEAD": "9216"}),
-    ("l2_ahead 18432", {"ZFVM_TILE_L2_AHEAD": "18432"}),
-    ("l2_ahead 36864", {"ZFVM_TILE_L2_AHEAD": "36864"}),
-    ("default end", {}),
+    ("l2_ahead 4608 sector", {"ZFVM_TILE_L2_AHEAD": "4608", "ZFVM_TILE_L2_GRAN": "32"}),
+    ("l2_ahead 9216 sector", {"ZFVM_TILE_L2_AHEAD": "9216", "ZFVM_TILE_L2_GRAN": "32"}),
+    ("l2_ahead 18432 sector", {"ZFVM_TILE_L2_AHEAD": "18432", "ZFVM_TILE_L2_GRAN": "32"}),
+    ("default again", {}),
+    ("l2_ahead 4608 again", {"ZFVM_TILE_L2_AHEAD": "4608"}),
 ]
 if os.environ.get("ZFVM_TILE_PROF"):
     CONFIGS = [("phase timers", {"ZFVM_TILE_PROF": "1"})] * 2

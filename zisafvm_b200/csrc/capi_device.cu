@@ -304,6 +304,7 @@ UpdateArgs base_update_args(zfvm_ctx *ctx) {
   A.has_source = ctx->sc.has_gravity;
   A.gamma = ctx->sc.gamma;
   A.inradius = ctx->inradius;
+  A.dt_dev = ctx->capturing_dt;  // (non-null only while a step is being captured into a graph)
   return A;
 }
 
@@ -1066,6 +1067,10 @@ void zfvm_destroy(zfvm_ctx *ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  for (auto &row : ctx->step_graph)
+    for (auto &g : row)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (ctx->dt_host) cudaFreeHost(ctx->dt_host);
   for (cudaEvent_t e : ctx->pipe.ev_up) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->pipe.ev_dn) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1229,6 +1234,7 @@ int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *stat
 }
 
 int zfvm_set_time_integration(zfvm_ctx *ctx, const char *method) {
+  ++ctx->graph_epoch;  // captured steps are stale
   Tableau t;
   if (!make_tableau(method, t)) return fail(std::string("Unknown Butcher Tableau. [") + method + "]");
   ZFVM_CUDA(cudaSetDevice(ctx->device));
@@ -1279,6 +1285,7 @@ int zfvm_download_avars(zfvm_ctx *ctx, double *avars_host) {
 double *zfvm_avars_device(zfvm_ctx *ctx) { return ctx->a_cur; }
 
 int zfvm_set_frozen_bc_av(zfvm_ctx *ctx, const double *steady_state_host, const double *steady_avars_host) {
+  ++ctx->graph_epoch;  // captured steps are stale
   if (zfvm_set_frozen_bc(ctx, steady_state_host)) return 1;
   if (!steady_state_host || !steady_avars_host || ctx->n_avars <= 0) {
     ctx->frozen_a = nullptr;
@@ -1292,6 +1299,7 @@ int zfvm_set_frozen_bc_av(zfvm_ctx *ctx, const double *steady_state_host, const 
 }
 
 int zfvm_set_frozen_bc(zfvm_ctx *ctx, const double *steady_state_host) {
+  ++ctx->graph_epoch;  // captured steps are stale
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   if (!steady_state_host) {
     ctx->frozen = nullptr;
@@ -1364,9 +1372,92 @@ static int rk_step_impl(zfvm_ctx *ctx, double dt, bool reduce) {
 }
 
 
+// One step replayed from a captured graph.  Returns 0 when the step has been queued, 1 on an error, -1 when graphs do
+// not apply (the caller then launches the kernels one by one).
+static int rk_step_graph(zfvm_ctx *ctx, double dt, bool reduce) {
+  static const bool off = [] {
+    const char *e = std::getenv("ZFVM_GRAPH");
+    return (e != nullptr && e[0] == '0') || std::getenv("ZFVM_TILE_PROF") != nullptr;
+  }();
+  if (off || ctx->n_ranks > 1 || ctx->nccl_comm || ctx->prof_enabled || ctx->n_stages < 1) return -1;
+  if (ctx->warm_epoch != ctx->graph_epoch) {  // the first step after a change runs plainly: every kernel it needs is
+    ctx->warm_epoch = ctx->graph_epoch;       // loaded and configured before anything is captured
+    return -1;
+  }
+  if (!ctx->dt_dev) {
+    if (dev_alloc(ctx, &ctx->dt_dev, 1, true)) return 1;
+    ZFVM_CUDA(cudaMallocHost((void **)&ctx->dt_host, sizeof(double)));
+  }
+  // the two state buffers alternate: one graph per buffer the step starts from
+  zfvm_ctx::StepGraph *g = nullptr;
+  for (int k = 0; k < 2; ++k) {
+    zfvm_ctx::StepGraph &c = ctx->step_graph[reduce ? 1 : 0][k];
+    if (c.exec && c.epoch == ctx->graph_epoch && c.u_cur == ctx->u_cur && c.u_tmp == ctx->u_tmp) g = &c;
+  }
+  if (!g) {
+    zfvm_ctx::StepGraph *row = ctx->step_graph[reduce ? 1 : 0];
+    zfvm_ctx::StepGraph *slot = (!row[0].exec || row[0].epoch != ctx->graph_epoch)   ? &row[0]
+                                : (!row[1].exec || row[1].epoch != ctx->graph_epoch) ? &row[1]
+                                                                                     : &row[ctx->graph_victim++ & 1];
+    if (slot->exec) {
+      cudaGraphExecDestroy(slot->exec);
+      slot->exec = nullptr;
+    }
+    const std::int64_t launches_before = ctx->launches;
+    double *u_cur = ctx->u_cur, *u_tmp = ctx->u_tmp, *a_cur = ctx->a_cur, *a_tmp = ctx->a_tmp;
+    cudaGraph_t graph = nullptr;
+    ZFVM_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    cudaMemcpyAsync(ctx->dt_dev, ctx->dt_host, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    ctx->capturing_dt = ctx->dt_dev;
+    const int rc = rk_step_impl(ctx, dt, reduce);
+    ctx->capturing_dt = nullptr;
+    if (reduce) cudaMemcpyAsync(ctx->reduce_host, ctx->reduce_dev, sizeof(ReduceOut), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t end = cudaStreamEndCapture(ctx->stream, &graph);
+    // the capture recorded the step, it did not run it: undo the bookkeeping of rk_step_impl
+    ctx->u_cur = u_cur;
+    ctx->u_tmp = u_tmp;
+    ctx->a_cur = a_cur;
+    ctx->a_tmp = a_tmp;
+    slot->launches = ctx->launches - launches_before;
+    ctx->launches = launches_before;
+    if (rc != 0 || end != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != 0 ? 1 : -1;
+    }
+    const cudaError_t inst = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) {
+      slot->exec = nullptr;
+      cudaGetLastError();
+      return -1;
+    }
+    slot->u_cur = ctx->u_cur;
+    slot->u_tmp = ctx->u_tmp;
+    slot->epoch = ctx->graph_epoch;
+    g = slot;
+  }
+  *ctx->dt_host = dt;
+  ZFVM_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
+  std::swap(ctx->u_cur, ctx->u_tmp);
+  std::swap(ctx->a_cur, ctx->a_tmp);
+  return 0;
+}
+
 int zfvm_rk_step(zfvm_ctx *ctx, double /*t*/, double dt, double cfl_number, double *dt_next, int *not_plausible) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
   const bool reduce = (dt_next != nullptr) || (not_plausible != nullptr);
+  const int graphed = rk_step_graph(ctx, dt, reduce);
+  if (graphed > 0) return 1;
+  if (graphed == 0) {
+    if (reduce) {  // (the 16-byte copy of the reduction is part of the graph)
+      ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (dt_next) *dt_next = cfl_number * ctx->reduce_host->min_dx_over_ev;
+      if (not_plausible) *not_plausible = ctx->reduce_host->not_plausible;
+    }
+    return 0;
+  }
   if (rk_step_impl(ctx, dt, reduce)) return 1;
   if (reduce) {
     // every rank gets the same verdict: min of the CFL quotient, max of the plausibility flag (the reference aborts the

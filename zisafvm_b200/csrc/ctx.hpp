@@ -81,6 +81,22 @@ struct zfvm_ctx {
   } pipe;
   cudaStream_t copy_stream = nullptr;
 
+  // zfvm_rk_step replayed as a CUDA graph (single-rank contexts, no profiling): one captured step per (which buffer holds
+  // the state, with / without the CFL reduction); the time step travels through a device scalar.  Small grids are bound
+  // by launch latency otherwise (49 928 triangles: ~35 us of launches per 10 us of kernels per stage).
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    const double *u_cur = nullptr, *u_tmp = nullptr;  // the state buffers of the captured step
+    int epoch = -1;
+    std::int64_t launches = 0;      // kernels in the graph (zfvm_counters)
+  } step_graph[2][2];
+  unsigned graph_victim = 0;
+  int warm_epoch = -1;              // epoch in which a step has already run without a graph
+  int graph_epoch = 0;              // bumped by whatever changes the captured launches (tableau, boundary condition)
+  double *dt_dev = nullptr;         // device scalar
+  double *dt_host = nullptr;        // pinned
+  const double *capturing_dt = nullptr;  // set while rk_step_impl is being captured
+
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, n_ranks = 1;

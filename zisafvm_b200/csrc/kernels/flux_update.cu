@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const Devi
     for (int s = 0; s < MAX_RK_STAGES - 1; ++s)
       if (s < A.n_prev && A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * kp[s];
     if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
-    un = ub + A.dt * dudt;
+    un = ub + (A.dt_dev ? *A.dt_dev : A.dt) * dudt;
     if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[iv];
     A.u_next[iv] = un;
   }
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(256) tracer_update_kernel(const DevicePlan P, 
     for (int s = 0; s < A.n_prev; ++s)
       if (A.coef_prev[s] != 0.0) dudt += A.coef_prev[s] * A.k_prev[s][idx];
     if (A.coef_cur != 0.0) dudt += A.coef_cur * t;
-    double un = A.u_base[idx] + A.dt * dudt;
+    double un = A.u_base[idx] + (A.dt_dev ? *A.dt_dev : A.dt) * dudt;
     if (A.frozen && (P.cell_flags[i] & 2)) un = A.frozen[idx];
     A.u_next[idx] = un;
   }

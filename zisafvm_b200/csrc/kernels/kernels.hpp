@@ -36,6 +36,7 @@ struct UpdateArgs {
   int n_prev;
   double coef_cur;
   double dt;
+  const double *dt_dev;    // non-null: the time step is read from device memory (steps replayed as CUDA graphs)
   const double *frozen;    // FrozenBC steady state (null: no boundary condition)
   // FluxBC (boundary/flux_bc.hpp:24-42): exterior faces of the cell, evaluated on `state`; null = NoFluxBC
   const double *flux_bc_state;

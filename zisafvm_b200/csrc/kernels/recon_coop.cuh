@@ -127,24 +127,24 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 3)
     const double *w0 = reinterpret_cast<const double *>(rec + cfg.off_whi) + lane + warp * TILE;
     const int row_c0 = cfg.rows_total - cfg.rows0;  // first lidx row of the central stencil
     int r = 0;
-    for (; r + 2 <= cfg.rows0; r += 2) {  // two rows at a time: 2 * CPW independent weight loads in flight
-      double wa[CPW], wb[CPW], ra[NVARS], rb[NVARS];
+    // RB rows at a time: RB * CPW independent weight loads in flight per thread (the kernel has no staging ring; what
+    // hides the latency of the weight stream is occupancy times loads in flight)
+    constexpr int RB = 4;
+    for (; r + RB <= cfg.rows0; r += RB) {
+      double wv[RB][CPW], rv[RB][NVARS];
 #pragma unroll
-      for (int j = 0; j < CPW; ++j) {
-        const bool ok = warp + COOP_WARPS * j < CHI;
-        wa[j] = ok ? ld_stream(w0 + ((std::int64_t)r * CHI + COOP_WARPS * j) * TILE) : 0.0;
-        wb[j] = ok ? ld_stream(w0 + ((std::int64_t)(r + 1) * CHI + COOP_WARPS * j) * TILE) : 0.0;
-      }
-      load_rhs(row_c0 + r, ra);
-      load_rhs(row_c0 + r + 1, rb);
+      for (int b = 0; b < RB; ++b)
 #pragma unroll
-      for (int j = 0; j < CPW; ++j)
+        for (int j = 0; j < CPW; ++j)
+          wv[b][j] = (warp + COOP_WARPS * j < CHI) ? ld_stream(w0 + ((std::int64_t)(r + b) * CHI + COOP_WARPS * j) * TILE) : 0.0;
 #pragma unroll
-        for (int v = 0; v < NVARS; ++v) acc[j][v] = fma(wa[j], ra[v], acc[j][v]);
+      for (int b = 0; b < RB; ++b) load_rhs(row_c0 + r + b, rv[b]);
 #pragma unroll
-      for (int j = 0; j < CPW; ++j)
+      for (int b = 0; b < RB; ++b)
 #pragma unroll
-        for (int v = 0; v < NVARS; ++v) acc[j][v] = fma(wb[j], rb[v], acc[j][v]);
+        for (int j = 0; j < CPW; ++j)
+#pragma unroll
+          for (int v = 0; v < NVARS; ++v) acc[j][v] = fma(wv[b][j], rv[b][v], acc[j][v]);
     }
     for (; r < cfg.rows0; ++r) {
       double wa[CPW], ra[NVARS];

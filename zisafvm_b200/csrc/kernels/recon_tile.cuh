@@ -87,6 +87,7 @@ struct TileCfg {
   int s_list, s_lidx, s_table, s_ring, s_stage, warp_bytes;
   int evict_normal;          // L2 policy of the record copies: 0 evict-first (default), 1 evict-normal
   int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off)
+  int l2_gran;               // bytes covered by one lane's prefetch (experiment: 128 = line, 32 = sector)
   int stream_bytes;          // bytes of a record's W | geometry stream (rec_bytes - off_wlo)
   int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
@@ -223,10 +224,11 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
     // range is about the segment that will be issued l2_ahead / SLOT_BYTES positions later, within this record)
     if (cfg.l2_ahead > 0) {
       iss_left -= bytes;
-#pragma unroll
-      for (int j = 0; j < (T::SLOT_BYTES + 4095) / 4096; ++j) {
-        const int off = cfg.l2_ahead + (j * 32 + lane) * 128;
-        if (live && (j * 32 + lane) * 128 < bytes && off < iss_left) ptx::prefetch_l2(iss_ptr + bytes + off);
+      const int gran = cfg.l2_gran;  // bytes one prefetch instruction of one lane is assumed to cover (128 or 32)
+#pragma unroll 1
+      for (int j = 0; j * 32 * gran < bytes; ++j) {
+        const int rel = (j * 32 + lane) * gran;
+        if (live && rel < bytes && cfg.l2_ahead + rel < iss_left) ptx::prefetch_l2(iss_ptr + bytes + cfg.l2_ahead + rel);
       }
     }
     const bool last = (iss_s == N_SEG - 1);
@@ -799,7 +801,8 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   }
   c.prof = nullptr;
   c.evict_normal = 0;
-  c.l2_ahead = 0;
+  c.l2_ahead = T::SLOT_BYTES;  // measured at the bench size: K1 -1 .. -4 %; 2, 4, 8 slots ahead: none or worse
+  c.l2_gran = 128;
   c.stream_bytes = (int)(L.rec_bytes - L.off_wlo);
   return true;
 }
