@@ -343,6 +343,7 @@ def run_b200(args):
     parity_check = multi_gpu_parity_check(args, rank, world, local_rank) if distributed else None
 
     t_setup = time.perf_counter()
+    setup_parts = None
     if distributed:
         from zisafvm_b200 import distributed as zd
 
@@ -353,8 +354,13 @@ def run_b200(args):
         n_counted = sub.n_counted
     else:
         case = make_case(args, args.n)
+        t_case = time.perf_counter()
         st = case.ensure_stencils()
+        t_st = time.perf_counter()
         ctx = z.CudaContext(case.grid, st, case.params, device=local_rank)
+        t_ctx = time.perf_counter()
+        setup_parts = {"mesh_geometry_initial_data": round(t_case - t_setup, 1), "stencil_search_host": round(t_st - t_case, 1),
+                       "records_weights_on_device_upload": round(t_ctx - t_st, 1)}
         n_counted = int((~case.grid.is_ghost).sum())
     n = case.grid.n_cells
     rk = z.CudaRungeKutta(ctx, case.method)
@@ -505,7 +511,7 @@ def run_b200(args):
                     f"; ONE global mesh of {args.n}^3 cubes cut into {world} chunks of the Hilbert curve (SFC partition)"
                     if distributed and args.scaling == "strong" else ""),
                 "cells_per_gpu": int(n), "counted_cells": int(total_counted), "stages_per_step": stages,
-                "device_bytes": int(dev_bytes), "setup_seconds": round(setup_s, 1),
+                "device_bytes": int(dev_bytes), "setup_seconds": round(setup_s, 1), "setup_parts": setup_parts,
                 "l2_flush": "inputs larger than L2 (weights + state >> 126 MB per stage)",
                 "parallelism": f"domain decomposition x{world}" if distributed else "single GPU",
             },

@@ -407,3 +407,34 @@ def test_source_paths_agree(maker, monkeypatch):
         ctx.close()
     assert (np.abs(out["tile"] - out["v1"]).max(axis=0) / scale).max() < 1e-12
     assert (np.abs(out["tile"] - out["coop"]).max(axis=0) / scale).max() < 1e-12
+
+
+@pytest.mark.parametrize("maker,env", [
+    ("vortex_o2", {}), ("vortex_o3_hllc", {}), ("vortex_o4", {}), ("vortex_o5", {}), ("blast_o2", {}), ("blast_o3", {}),
+    ("smooth3d_o4", {}), ("vortex_fluxbc", {}), ("blast_fluxbc", {}),            # ragged stencils next to open boundaries
+    ("blast_o3", {"ZFVM_TILE_MIN_CAP": "288"}),                                  # 16-bit row-list indices
+    ("blast_o3", {"ZFVM_RECON": "generic"}), ("smooth3d_six_stencils", {}),      # plainer records, any family
+    ("vortex_o3_wide_central", {}), ("vortex_lone_o2_biased", {}),
+])
+def test_device_built_weights_are_bit_identical_to_the_host_path(maker, env, monkeypatch):
+    """the stencil weights W_k = pinv(A_k) are built on the device (kernels/precompute.cu) from the same
+    source as the host builder (host/lsq_shared.hpp, no fused multiply-adds on either side).  The whole record array --
+    headers, index rows, weights, geometry -- of a context created with ZFVM_PRECOMPUTE=host must equal the default
+    one byte for byte."""
+    case = CASES[maker]()
+    st = case.ensure_stencils()
+    for k in ("ZFVM_RECON", "ZFVM_TILE_MIN_CAP", "ZFVM_PRECOMPUTE"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ctx = z.CudaContext(case.grid, st, case.params)
+    dev = ctx.records().copy()
+    ctx.close()
+    monkeypatch.setenv("ZFVM_PRECOMPUTE", "host")
+    ctx = z.CudaContext(case.grid, st, case.params)
+    host = ctx.records().copy()
+    ctx.close()
+    assert dev.size == host.size and dev.size > 0
+    words = host.view(np.float64)
+    assert np.count_nonzero(words) > 0.05 * words.size  # the records really carry weights
+    assert np.array_equal(dev, host)

@@ -446,6 +446,88 @@ static int build_host_pipe(zfvm_ctx *ctx, const HostGrid &g) {
   return 0;
 }
 
+// Record pieces the host builds (header, geometry -- and the weights when ZFVM_PRECOMPUTE=host) travel through two
+// pinned staging slots as strided copies into the record array; the device builds the weights meanwhile.
+struct RecordStager {
+  static constexpr int MAX_PIECES = 3;
+  int n_pieces = 0;
+  std::int64_t off[MAX_PIECES] = {0, 0, 0}, bytes[MAX_PIECES] = {0, 0, 0};
+  std::int64_t chunk = 0, rec_bytes = 0;
+  char *dev = nullptr;
+  char *host[2][MAX_PIECES] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+
+  void add_piece(std::int64_t offset, std::int64_t n_bytes) {
+    if (n_bytes <= 0) return;
+    off[n_pieces] = offset;
+    bytes[n_pieces] = n_bytes;
+    ++n_pieces;
+  }
+  cudaError_t init(char *dev_records, std::int64_t record_bytes, std::int64_t tiles_per_chunk, cudaStream_t st) {
+    dev = dev_records;
+    rec_bytes = record_bytes;
+    chunk = tiles_per_chunk;
+    stream = st;
+    for (int s = 0; s < 2; ++s) {
+      cudaError_t e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+      for (int p = 0; p < n_pieces; ++p) {
+        e = cudaHostAlloc((void **)&host[s][p], (size_t)(chunk * bytes[p]), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+      }
+    }
+    return cudaSuccess;
+  }
+  /// Waits until slot s may be overwritten and clears it.
+  cudaError_t begin(int s) {
+    cudaError_t e = cudaEventSynchronize(done[s]);
+    if (e != cudaSuccess) return e;
+#pragma omp parallel for schedule(static)
+    for (std::int64_t t = 0; t < chunk; ++t)
+      for (int p = 0; p < n_pieces; ++p) std::memset(host[s][p] + t * bytes[p], 0, (size_t)bytes[p]);
+    return cudaSuccess;
+  }
+  char *piece(int s, int p, std::int64_t tile_in_chunk) const { return host[s][p] + tile_in_chunk * bytes[p]; }
+  cudaError_t upload(int s, std::int64_t t0, std::int64_t n_tiles) {
+    for (int p = 0; p < n_pieces; ++p) {
+      cudaError_t e = cudaMemcpy2DAsync(dev + t0 * rec_bytes + off[p], (size_t)rec_bytes, host[s][p], (size_t)bytes[p],
+                                        (size_t)bytes[p], (size_t)n_tiles, cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaEventRecord(done[s], stream);
+  }
+  ~RecordStager() {
+    for (int s = 0; s < 2; ++s) {
+      if (done[s]) cudaEventDestroy(done[s]);
+      for (int p = 0; p < MAX_PIECES; ++p)
+        if (host[s][p]) cudaFreeHost(host[s][p]);
+    }
+  }
+};
+
+// The device builds the stencil weights (kernels/precompute.cu) unless ZFVM_PRECOMPUTE=host asks for the host path,
+// which is kept as the bit-for-bit cross-check.
+static bool weights_on_device() {
+  const char *e = std::getenv("ZFVM_PRECOMPUTE");
+  return !(e && e[0] == 'h');
+}
+
+struct TempDeviceBuffers {
+  std::vector<void *> ptrs;
+  cudaError_t upload(const double **out, const double *host, size_t count, cudaStream_t st) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(double));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    *out = (const double *)p;
+    return cudaMemcpyAsync(p, host, count * sizeof(double), cudaMemcpyHostToDevice, st);
+  }
+  ~TempDeviceBuffers() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+};
+
 // ZFVM_VERBOSE=1: wall-clock seconds of the phases of zfvm_create on stderr
 struct CreateClock {
   bool on = std::getenv("ZFVM_VERBOSE") != nullptr;
@@ -609,6 +691,35 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     P.rec2_cap = cap;
     clk.lap("tile row-list sizes");
   }
+  // ---- weights on the device: the members' centres / lengths / moments, the (order -> rows) table of every stencil -------
+  const bool dev_w = weights_on_device();
+  TempDeviceBuffers temp;
+  LsqWeightArgs lsq{};
+  struct ScratchGuard {
+    double *p = nullptr;
+    ~ScratchGuard() {
+      if (p) cudaFree(p);
+    }
+  } lsq_scratch_guard;
+  double *&lsq_scratch = lsq_scratch_guard.p;
+  std::int64_t lsq_scratch_bytes = 0;
+  int n_sms = 148;
+  ZFVM_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  if (dev_w) {
+    lsq.n_dims = nd;
+    lsq.n_stencils = ns;
+    lsq.n_moments = g.n_moments;
+    for (int k = 0; k < ns; ++k) {
+      lsq.ncoef[k] = sc.ncoef[k];
+      lsq.max_order[k] = S.params.orders[(size_t)k];
+      if (lsq.max_order[k] > 7) return fail("zfvm_create: stencil order above 7");
+      for (int o = 2; o <= lsq.max_order[k]; ++o)
+        lsq.rows_of_order[k][o] = required_stencil_size(o - 1, S.params.overfit_factors[(size_t)k], nd) - 1;
+    }
+    ZFVM_CUDA(temp.upload(&lsq.centers, g.cell_centers.data(), g.cell_centers.size(), ctx->stream));
+    ZFVM_CUDA(temp.upload(&lsq.length, g.characteristic_length.data(), g.characteristic_length.size(), ctx->stream));
+    ZFVM_CUDA(temp.upload(&lsq.moments, g.moments.data(), g.moments.size(), ctx->stream));
+  }
   if (use_tile) {
     const int D2 = poly_dof(ctx->deg_hi, nd);
     const TileRecLayout L = tile_rec_layout(sc, nd, D2, P.rec2_cap);
@@ -646,10 +757,21 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     }
     const int n_mom2 = std::max(D2 - 3, 0);
     const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / L.rec_bytes));
-    std::vector<char> h_rec((size_t)(chunk * L.rec_bytes));
-    for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
+    RecordStager stage;
+    stage.add_piece(0, L.off_wlo);                       // n_list, meta, row list, local index rows
+    stage.add_piece(L.off_geo, L.rec_bytes - L.off_geo);  // geometry
+    if (!dev_w) stage.add_piece(L.off_wlo, L.off_geo - L.off_wlo);
+    ZFVM_CUDA(stage.init(d_rec, L.rec_bytes, chunk, ctx->stream));
+    ZFVM_CUDA(cudaMemsetAsync(d_rec, 0, (size_t)(T * L.rec_bytes + 65536), ctx->stream));
+    if (dev_w) {
+      lsq.rec = d_rec;
+      lsq.rec_bytes = L.rec_bytes;
+      lsq.view = ctx->tracer_view;
+    }
+    int slot = 0;
+    for (std::int64_t t0 = 0; t0 < T; t0 += chunk, slot ^= 1) {
       const std::int64_t t1 = std::min(T, t0 + chunk);
-      std::memset(h_rec.data(), 0, h_rec.size());
+      ZFVM_CUDA(stage.begin(slot));
 #pragma omp parallel
       {
         std::vector<double> A, W;
@@ -657,7 +779,9 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
         std::vector<std::int32_t> refs;
 #pragma omp for schedule(dynamic, 8)
         for (std::int64_t t = t0; t < t1; ++t) {
-          char *rec = h_rec.data() + (size_t)((t - t0) * L.rec_bytes);
+          char *rec = stage.piece(slot, 0, t - t0);
+          char *rec_geo = stage.piece(slot, 1, t - t0);
+          char *rec_w = dev_w ? nullptr : stage.piece(slot, 2, t - t0) - L.off_wlo;  // addressed with record offsets
           std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec + TILE_OFF_META);
           std::int32_t *list = reinterpret_cast<std::int32_t *>(rec + L.off_list);
           unsigned char *lidx = reinterpret_cast<unsigned char *>(rec + L.off_lidx);
@@ -700,8 +824,8 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
             return (int)it->second;
           };
           // pass 2: per cell meta, local indices, weights, geometry
-          double *geo = reinterpret_cast<double *>(rec + L.off_geo);
-          std::uint32_t *gref = reinterpret_cast<std::uint32_t *>(rec + L.off_geo + (size_t)L.geo_doubles * TILE * 8);
+          double *geo = reinterpret_cast<double *>(rec_geo);
+          std::uint32_t *gref = reinterpret_cast<std::uint32_t *>(rec_geo + (size_t)L.geo_doubles * TILE * 8);
           for (int lane = 0; lane < TILE; ++lane) {
             const std::int64_t i = t * TILE + lane;
             std::uint64_t m = 0;
@@ -712,15 +836,17 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
               if (i >= n || k >= S.n_family[(size_t)i]) continue;
               const int order = S.order[(size_t)(i * ns + k)];
               if (order <= 1) continue;
-              int rows, cols;
-              stencil_matrix(A, rows, cols, g, S, i, k);
+              int rows = S.size[(size_t)(i * ns + k)] - 1, cols = poly_dof(order - 1, nd) - 1;
               if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
-              W.resize((size_t)(rows * cols));
-              pseudo_inverse(A.data(), rows, cols, W.data());
               for (int j = 0; j < rows; ++j) put_lidx(row0 + j, lane, local_of(S.global(i, k, j + 1)));
-              double *w = reinterpret_cast<double *>(rec + (k == 0 ? L.off_whi : L.off_wlo + lo_w0[(size_t)k])) + lane;
-              for (int j = 0; j < rows; ++j)
-                for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+              if (!dev_w) {
+                stencil_matrix(A, rows, cols, g, S, i, k);
+                W.resize((size_t)(rows * cols));
+                pseudo_inverse(A.data(), rows, cols, W.data());
+                double *w = reinterpret_cast<double *>(rec_w + (k == 0 ? L.off_whi : L.off_wlo + lo_w0[(size_t)k])) + lane;
+                for (int j = 0; j < rows; ++j)
+                  for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+              }
               m |= ((std::uint64_t)rows) << (8 * k);
             }
             if (i < n) {
@@ -760,8 +886,15 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
           ctx->tile_max_ref[(size_t)t] = tile_mx;
         }
       }
-      ZFVM_CUDA(cudaMemcpy(d_rec + t0 * L.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * L.rec_bytes), cudaMemcpyHostToDevice));
+      ZFVM_CUDA(stage.upload(slot, t0, t1 - t0));
+      if (dev_w) {
+        lsq.tile_begin = t0;
+        lsq.tile_end = t1;
+        if (launch_lsq_weights(lsq, n_sms, &lsq_scratch, &lsq_scratch_bytes, ctx->stream))
+          return fail("zfvm_create: the stencil-weight kernel could not be launched");
+      }
     }
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
   } else {
     char *d_rec = nullptr;
     if (dev_alloc(ctx, &d_rec, T * P.rec_bytes)) {
@@ -778,16 +911,27 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
       }
     }
     const std::int64_t chunk = std::max<std::int64_t>(1, std::min<std::int64_t>(4096, (256ll << 20) / P.rec_bytes));
-    std::vector<char> h_rec((size_t)(chunk * P.rec_bytes));
-    for (std::int64_t t0 = 0; t0 < T; t0 += chunk) {
+    RecordStager stage;
+    stage.add_piece(0, P.hdr_bytes);  // meta, global index rows
+    if (!dev_w) stage.add_piece(P.hdr_bytes, P.rec_bytes - P.hdr_bytes);
+    ZFVM_CUDA(stage.init(d_rec, P.rec_bytes, chunk, ctx->stream));
+    ZFVM_CUDA(cudaMemsetAsync(d_rec, 0, (size_t)(T * P.rec_bytes), ctx->stream));
+    if (dev_w) {
+      lsq.rec = d_rec;
+      lsq.rec_bytes = P.rec_bytes;
+      lsq.view = ctx->tracer_view;
+    }
+    int slot = 0;
+    for (std::int64_t t0 = 0; t0 < T; t0 += chunk, slot ^= 1) {
       const std::int64_t t1 = std::min(T, t0 + chunk);
-      std::memset(h_rec.data(), 0, h_rec.size());
+      ZFVM_CUDA(stage.begin(slot));
 #pragma omp parallel
       {
         std::vector<double> A, W;
 #pragma omp for schedule(dynamic, 8)
         for (std::int64_t t = t0; t < t1; ++t) {
-          char *rec = h_rec.data() + (size_t)((t - t0) * P.rec_bytes);
+          char *rec = stage.piece(slot, 0, t - t0);
+          char *rec_w = dev_w ? nullptr : stage.piece(slot, 1, t - t0) - P.hdr_bytes;  // addressed with record offsets
           std::uint64_t *meta = reinterpret_cast<std::uint64_t *>(rec);
           std::int32_t tile_mx = ctx->tile_max_ref[(size_t)t];
           for (int lane = 0; lane < TILE; ++lane) {
@@ -801,18 +945,20 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
               if (i >= n || k >= S.n_family[(size_t)i]) continue;
               const int order = S.order[(size_t)(i * ns + k)];
               if (order <= 1) continue;
-              int rows, cols;
-              stencil_matrix(A, rows, cols, g, S, i, k);
+              int rows = S.size[(size_t)(i * ns + k)] - 1, cols = poly_dof(order - 1, nd) - 1;
               if (cols > NC || rows > RM) continue;  // cannot happen: orders only degrade
-              W.resize((size_t)(rows * cols));
-              pseudo_inverse(A.data(), rows, cols, W.data());
               for (int j = 0; j < rows; ++j) {
                 si[(size_t)j * TILE] = S.global(i, k, j + 1);
                 tile_mx = std::max(tile_mx, si[(size_t)j * TILE]);
               }
-              double *w = reinterpret_cast<double *>(rec + P.off_W[k]) + lane;
-              for (int j = 0; j < rows; ++j)
-                for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+              if (!dev_w) {
+                stencil_matrix(A, rows, cols, g, S, i, k);
+                W.resize((size_t)(rows * cols));
+                pseudo_inverse(A.data(), rows, cols, W.data());
+                double *w = reinterpret_cast<double *>(rec_w + P.off_W[k]) + lane;
+                for (int j = 0; j < rows; ++j)
+                  for (int c = 0; c < cols; ++c) w[(size_t)(j * NC + c) * TILE] = W[(size_t)(c * rows + j)];
+              }
               m |= ((std::uint64_t)rows) << (8 * k);
             }
             if (i < n) {
@@ -824,8 +970,19 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
           ctx->tile_max_ref[(size_t)t] = tile_mx;
         }
       }
-      ZFVM_CUDA(cudaMemcpy(d_rec + t0 * P.rec_bytes, h_rec.data(), (size_t)((t1 - t0) * P.rec_bytes), cudaMemcpyHostToDevice));
+      ZFVM_CUDA(stage.upload(slot, t0, t1 - t0));
+      if (dev_w) {
+        lsq.tile_begin = t0;
+        lsq.tile_end = t1;
+        if (launch_lsq_weights(lsq, n_sms, &lsq_scratch, &lsq_scratch_bytes, ctx->stream))
+          return fail("zfvm_create: the stencil-weight kernel could not be launched");
+      }
     }
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (lsq_scratch) {
+    cudaFree(lsq_scratch);
+    lsq_scratch = nullptr;
   }
   for (std::int64_t i = 0; i < n; ++i) {
     if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
@@ -1697,6 +1854,9 @@ int zfvm_download_work(zfvm_ctx *ctx, const char *name, double *host, int64_t ma
   } else if (s == "source") {
     src = ctx->plan.source;
     count = ctx->n_cells * NVARS;
+  } else if (s == "records") {  // the tile records as raw 8-byte words (tests: device-built weights vs host-built ones)
+    src = reinterpret_cast<const double *>(ctx->plan.rec2 ? ctx->plan.rec2 : ctx->plan.rec);
+    count = ctx->n_tiles * (ctx->plan.rec2 ? ctx->plan.rec2_bytes : ctx->plan.rec_bytes) / 8;
   } else {
     return fail("zfvm_download_work: unknown array");
   }

@@ -6,6 +6,9 @@
 #include <stdexcept>
 #if defined(_OPENMP)
 #include <omp.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <parallel/algorithm>
 #endif
 
@@ -192,8 +195,19 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
   g.vertex_indices = std::move(vertex_indices);
   const i64 n = g.n_cells;
 
+  // ZFVM_VERBOSE=1: wall-clock seconds of the phases on stderr
+  const bool verbose = std::getenv("ZFVM_VERBOSE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!verbose) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[zfvm grid]   %-28s %7.2f s\n", what, std::chrono::duration<double>(t1 - t_last).count());
+    t_last = t1;
+  };
   enforce_standard_vertex_order(n_dims, g.vertices, g.vertex_indices);
+  lap("vertex order");
   compute_neighbours(n_dims, g.vertex_indices, g.neighbours);
+  lap("neighbours");
 
   // edge numbering: interior edges first, in (cell, local face) order of the smaller cell;
   // then boundary edges in (cell, local face) order.  grid.cpp:385-413
@@ -234,6 +248,7 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
       }
   }
 
+  lap("edge numbering");
   // per-cell geometry and quadrature
   g.cell_rule = (n_dims == 2) ? make_triangular_rule(deg.volume_deg) : make_tetrahedral_rule(deg.volume_deg);
   g.face_rule = (n_dims == 2) ? make_edge_rule(deg.face_deg) : make_triangular_rule(deg.face_deg);
@@ -301,6 +316,7 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
     }
   }
 
+  lap("cells, quadrature, moments");
   // faces: geometry defined by the left cell's local face (grid.cpp:583-649, face_factory.cpp)
   const i64 E = g.n_edges;
   g.face_qp.resize((size_t)(E * g.q_f * 3));
@@ -368,6 +384,7 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
       }
     }
   }
+  lap("faces");
 }
 
 void mask_ghost_cells(HostGrid &g, const std::uint8_t *mask) {

@@ -10,6 +10,7 @@
 #include <random>
 #include <stdexcept>
 
+#include "lsq_shared.hpp"
 #include "vec3.hpp"
 #include "zfvm_host.hpp"
 
@@ -185,80 +186,11 @@ void assemble_weno_ao_matrix(std::vector<double> &A, int &n_rows, int &n_cols, c
   const Vec3 x0 = g.center(i0);
   const double l0 = g.characteristic_length[i0];
   const double *C0 = &g.moments[(size_t)i0 * g.n_moments];
-  auto idx = [nd](int a, int b) { return nd == 2 ? poly_index2(a, b) : poly_index3(a, b, 0); };
-
   for (int ii = 0; ii < n_rows; ++ii) {
     const i32 j = stencil[ii + 1];
-    double *row = &A[(size_t)ii * n_cols];
     const Vec3 d = (g.center(j) - x0) / l0;
-    const double x_10 = d.x, x_01 = d.y;
-    const double lj = g.characteristic_length[j] / l0;
-    const double *Cj = &g.moments[(size_t)j * g.n_moments];
-
-    row[idx(1, 0) - 1] = x_10;
-    row[idx(0, 1) - 1] = x_01;
-    if (order >= 3) {
-      const int i_20 = idx(2, 0), i_11 = idx(1, 1), i_02 = idx(0, 2);
-      const double x_20 = x_10 * x_10, x_11 = x_10 * x_01, x_02 = x_01 * x_01;
-      const double lj_2 = lj * lj;
-      row[i_20 - 1] = x_20 - C0[i_20] + lj_2 * Cj[i_20];
-      row[i_11 - 1] = x_11 - C0[i_11] + lj_2 * Cj[i_11];
-      row[i_02 - 1] = x_02 - C0[i_02] + lj_2 * Cj[i_02];
-      if (order >= 4) {
-        const int i_30 = idx(3, 0), i_21 = idx(2, 1), i_12 = idx(1, 2), i_03 = idx(0, 3);
-        const double x_30 = x_20 * x_10, x_21 = x_20 * x_01, x_12 = x_11 * x_01, x_03 = x_02 * x_01;
-        const double lj_3 = lj_2 * lj;
-        row[i_30 - 1] = x_30 - C0[i_30] + 3.0 * x_10 * lj_2 * Cj[i_20] + lj_3 * Cj[i_30];
-        row[i_21 - 1] = x_21 - C0[i_21] + x_01 * lj_2 * Cj[i_20] + 2.0 * x_10 * lj_2 * Cj[i_11] + lj_3 * Cj[i_21];
-        row[i_12 - 1] = x_12 - C0[i_12] + x_10 * lj_2 * Cj[i_02] + 2.0 * x_01 * lj_2 * Cj[i_11] + lj_3 * Cj[i_12];
-        row[i_03 - 1] = x_03 - C0[i_03] + 3.0 * x_01 * lj_2 * Cj[i_02] + lj_3 * Cj[i_03];
-        if (order >= 5) {
-          const int i_40 = idx(4, 0), i_31 = idx(3, 1), i_22 = idx(2, 2), i_13 = idx(1, 3), i_04 = idx(0, 4);
-          const double x_40 = x_30 * x_10, x_31 = x_30 * x_01, x_22 = x_21 * x_01, x_13 = x_12 * x_01,
-                       x_04 = x_03 * x_01;
-          const double lj_4 = lj_3 * lj;
-          row[i_40 - 1] = x_40 - C0[i_40] + 6.0 * x_20 * lj_2 * Cj[i_20] + 4.0 * x_10 * lj_3 * Cj[i_30] +
-                          lj_4 * Cj[i_40];
-          row[i_31 - 1] = x_31 - C0[i_31] + 3 * x_11 * lj_2 * Cj[i_20] + 3.0 * x_20 * lj_2 * Cj[i_11] +
-                          x_01 * lj_3 * Cj[i_30] + 3.0 * x_10 * lj_3 * Cj[i_21] + lj_4 * Cj[i_31];
-          row[i_22 - 1] = x_22 - C0[i_22] + x_02 * lj_2 * Cj[i_20] + x_20 * lj_2 * Cj[i_02] +
-                          4 * x_11 * lj_2 * Cj[i_11] + 2.0 * x_01 * lj_3 * Cj[i_21] +
-                          2 * x_10 * lj_3 * Cj[i_12] + lj_4 * Cj[i_22];
-          row[i_13 - 1] = x_13 - C0[i_13] + 3 * x_11 * lj_2 * Cj[i_02] + 3.0 * x_02 * lj_2 * Cj[i_11] +
-                          x_10 * lj_3 * Cj[i_03] + 3.0 * x_01 * lj_3 * Cj[i_12] + lj_4 * Cj[i_13];
-          row[i_04 - 1] = x_04 - C0[i_04] + 6.0 * x_02 * lj_2 * Cj[i_02] + 4.0 * x_01 * lj_3 * Cj[i_03] +
-                          lj_4 * Cj[i_04];
-        }
-      }
-    }
-    if (nd == 3) {
-      const double x = d.x, y = d.y, z = d.z;
-      row[poly_index3(0, 0, 1) - 1] = z;
-      if (order >= 3) {
-        const int i_002 = poly_index3(0, 0, 2), i_101 = poly_index3(1, 0, 1), i_011 = poly_index3(0, 1, 1);
-        const double lj_2 = lj * lj;
-        row[i_002 - 1] = z * z - C0[i_002] + lj_2 * Cj[i_002];
-        row[i_101 - 1] = x * z - C0[i_101] + lj_2 * Cj[i_101];
-        row[i_011 - 1] = y * z - C0[i_011] + lj_2 * Cj[i_011];
-        if (order >= 4) {
-          const int i_003 = poly_index3(0, 0, 3), i_102 = poly_index3(1, 0, 2), i_012 = poly_index3(0, 1, 2),
-                    i_201 = poly_index3(2, 0, 1), i_111 = poly_index3(1, 1, 1), i_021 = poly_index3(0, 2, 1),
-                    i_200 = poly_index3(2, 0, 0), i_020 = poly_index3(0, 2, 0), i_110 = poly_index3(1, 1, 0);
-          const double lj_3 = lj * lj * lj;
-          row[i_003 - 1] = z * z * z - C0[i_003] + 3.0 * z * lj_2 * Cj[i_002] + lj_3 * Cj[i_003];
-          row[i_102 - 1] = x * z * z - C0[i_102] + x * lj_2 * Cj[i_002] + 2.0 * z * lj_2 * Cj[i_101] +
-                           lj_3 * Cj[i_102];
-          row[i_012 - 1] = y * z * z - C0[i_012] + y * lj_2 * Cj[i_002] + 2.0 * z * lj_2 * Cj[i_011] +
-                           lj_3 * Cj[i_012];
-          row[i_201 - 1] = x * x * z - C0[i_201] + z * lj_2 * Cj[i_200] + 2.0 * x * lj_2 * Cj[i_101] +
-                           lj_3 * Cj[i_201];
-          row[i_021 - 1] = y * y * z - C0[i_021] + z * lj_2 * Cj[i_020] + 2.0 * y * lj_2 * Cj[i_011] +
-                           lj_3 * Cj[i_021];
-          row[i_111 - 1] = x * y * z - C0[i_111] + z * lj_2 * Cj[i_110] + y * lj_2 * Cj[i_101] +
-                           x * lj_2 * Cj[i_011] + lj_3 * Cj[i_111];
-        }
-      }
-    }
+    lsq::lsq_row(&A[(size_t)ii * n_cols], nd, order, d.x, d.y, d.z, g.characteristic_length[j] / l0, C0,
+                 &g.moments[(size_t)j * g.n_moments]);
   }
 }
 
@@ -305,47 +237,13 @@ int matrix_rank(const double *A, int rows, int cols) {
   return rank;
 }
 
-// W = R^{-1} Q^T by Householder QR in extended precision (rows >= cols, full column rank).
+// W = R^{-1} Q^T by Householder QR (lsq_shared.hpp: the same code builds the weights on the device).
 void pseudo_inverse(const double *A, int rows, int cols, double *W) {
-  using real = long double;
-  std::vector<real> R((size_t)rows * cols), Qt((size_t)rows * rows, 0.0L);
-  for (size_t a = 0; a < R.size(); ++a) R[a] = A[a];
-  for (int r = 0; r < rows; ++r) Qt[(size_t)r * rows + r] = 1.0L;
-  std::vector<real> v((size_t)rows);
-  for (int k = 0; k < cols; ++k) {
-    real nrm = 0.0L;
-    for (int r = k; r < rows; ++r) nrm += R[(size_t)r * cols + k] * R[(size_t)r * cols + k];
-    nrm = std::sqrt(nrm);
-    if (nrm == 0.0L) continue;
-    real alpha = (R[(size_t)k * cols + k] > 0 ? -nrm : nrm);
-    real vn = 0.0L;
-    for (int r = k; r < rows; ++r) {
-      v[(size_t)r] = R[(size_t)r * cols + k] - (r == k ? alpha : 0.0L);
-      vn += v[(size_t)r] * v[(size_t)r];
-    }
-    if (vn == 0.0L) continue;
-    for (int c = k; c < cols; ++c) {
-      real s = 0.0L;
-      for (int r = k; r < rows; ++r) s += v[(size_t)r] * R[(size_t)r * cols + c];
-      s = 2.0L * s / vn;
-      for (int r = k; r < rows; ++r) R[(size_t)r * cols + c] -= s * v[(size_t)r];
-    }
-    for (int c = 0; c < rows; ++c) {
-      real s = 0.0L;
-      for (int r = k; r < rows; ++r) s += v[(size_t)r] * Qt[(size_t)r * rows + c];
-      s = 2.0L * s / vn;
-      for (int r = k; r < rows; ++r) Qt[(size_t)r * rows + c] -= s * v[(size_t)r];
-    }
-  }
-  // back substitution: W[:, c] = R^{-1} Qt[0:cols, c]
-  for (int c = 0; c < rows; ++c) {
-    for (int i = cols - 1; i >= 0; --i) {
-      real s = Qt[(size_t)i * rows + c];
-      for (int j = i + 1; j < cols; ++j) s -= R[(size_t)i * cols + j] * v[(size_t)j];
-      v[(size_t)i] = s / R[(size_t)i * cols + i];
-    }
-    for (int i = 0; i < cols; ++i) W[(size_t)i * rows + c] = (double)v[(size_t)i];
-  }
+  std::vector<double> work((size_t)rows * cols + 2 * (size_t)cols + (size_t)rows);
+  double *R = work.data(), *vk = R + (size_t)rows * cols, *vn = vk + cols, *y = vn + cols;
+  for (size_t a = 0; a < (size_t)rows * cols; ++a) R[a] = A[a];
+  lsq::pinv_householder(lsq::Strided{R, 1}, lsq::Strided{vk, 1}, lsq::Strided{vn, 1}, lsq::Strided{y, 1}, rows, cols,
+                        [&](int i, int c, double v) { W[(size_t)i * rows + c] = v; });
 }
 
 // ---- families --------------------------------------------------------------------------------------

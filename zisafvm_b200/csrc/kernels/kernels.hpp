@@ -87,6 +87,27 @@ struct TracerRecView {
   int off_w[MAX_STENCILS];     // W_k f64[rows_max_k][ncoef_k][32]
 };
 
+/// P1 `lsq_weights_kernel` (precompute.cu): W_k = pinv(A_k) of the cells of tiles [tile_begin, tile_end), written into the
+/// records whose headers (meta, member indices) are already on the device.
+struct LsqWeightArgs {
+  char *rec;                 // records of either kind
+  std::int64_t rec_bytes;
+  TracerRecView view;        // where the members and the weights of stencil k are
+  int n_dims, n_stencils, n_moments;
+  int ncoef[MAX_STENCILS];             // column count W_k is padded to in the record
+  int max_order[MAX_STENCILS];         // the family's order of stencil k
+  int rows_of_order[MAX_STENCILS][8];  // rows (members - 1) of stencil k when it achieves order o (stencil.cpp:168-175)
+  const double *centers;     // [n_cells][3]   cell barycentres
+  const double *length;      // [n_cells]      characteristic lengths
+  const double *moments;     // [n_cells][n_moments] normalised moments (grid.cpp:1049-1098)
+  double *scratch;           // set by the launcher
+  std::int64_t tile_begin, tile_end;
+};
+/// 0 on success, 1 when no kernel covers the family (more than 34 columns), 2 on a CUDA error.  `*scratch` is a
+/// device buffer the launcher grows on demand for stencils too large for shared memory; the caller frees it.
+int launch_lsq_weights(const LsqWeightArgs &args, int n_sms, double **scratch, std::int64_t *scratch_bytes,
+                       cudaStream_t stream);
+
 /// Phase timers of the tile kernel (ZFVM_TILE_PROF=1): device buffer of 16 counters, or null when profiling is off.
 unsigned long long *tile_prof_buffer();
 /// Copies the counters to the host and clears them; returns false when profiling is off.

@@ -181,6 +181,14 @@ class CudaContext:
         return out
 
 
+    def records(self) -> np.ndarray:
+        """The tile records (headers, stencil weights, geometry) as raw bytes -- for tests of the record builders."""
+        dev_bytes, _ = self.memory_info()
+        out = np.zeros(dev_bytes // 8 + 1)
+        check(lib.zfvm_download_work(self._h, b"records", _capi.ptr_f64(out), out.size))
+        return out.view(np.uint8)
+
+
 class CudaEulerRateOfChange:
     """Drop-in for the reference's ``Sum[FluxLoop, GravitySourceLoop]`` rate of change."""
 
