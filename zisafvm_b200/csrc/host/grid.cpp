@@ -2,13 +2,13 @@
 // src/zisa/grid/grid.cpp (see zfvm_host.hpp for the line map).
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #if defined(_OPENMP)
 #include <omp.h>
-#include <chrono>
-#include <cstdio>
-#include <cstdlib>
 #include <parallel/algorithm>
 #endif
 

@@ -21,6 +21,20 @@ namespace {
 struct Region {
   int kind = 0;  // 0 full sphere, 2 triangular cone, 3 tetrahedral cone
   Vec3 A, dB, dC, dD;
+  Vec3 nrm[3];   // inward normals of the cone's faces (the membership tests below are n . (x - A) >= 0 written out)
+  int n_planes = 0;
+  void set_planes() {
+    if (kind == 2) {
+      nrm[0] = Vec3{-dB.y, dB.x, 0.0};
+      nrm[1] = Vec3{dC.y, -dC.x, 0.0};
+      n_planes = 2;
+    } else if (kind == 3) {
+      nrm[0] = cross(dB, dC);
+      nrm[1] = cross(dC, dD);
+      nrm[2] = cross(dD, dB);
+      n_planes = 3;
+    }
+  }
   bool is_inside(Vec3 x) const {
     if (kind == 0) return true;
     Vec3 dx = x - A;
@@ -44,6 +58,47 @@ struct Selector {
     const int F = g.max_neighbours;
     Vec3 v[4];
     for (int k = 0; k < F; ++k) v[k] = g.vertex(cand, k);
+    // The cone's faces are planes through its apex, n_p . (x - A) >= 0, and a query point is a convex combination of the
+    // cell's vertices (positive barycentric coordinates): its plane values are the same combination of the vertices'
+    // values.  Deciding the points from those 3 x F numbers is exact whenever a value clears zero by a margin nine orders
+    // of magnitude above the round-off of either evaluation; otherwise the cell takes the reference's point-by-point
+    // test below.  (Most tested cells touch the cone's boundary: this is where the stencil search spends its time.)
+    double h[3][4], mag[3][4];
+    const int np = region.n_planes;
+    for (int p = 0; p < np; ++p) {
+      bool all_behind = true;
+      for (int k = 0; k < F; ++k) {
+        const Vec3 dx = v[k] - region.A;
+        const double tx = region.nrm[p].x * dx.x, ty = region.nrm[p].y * dx.y, tz = region.nrm[p].z * dx.z;
+        h[p][k] = tx + ty + tz;
+        mag[p][k] = std::fabs(tx) + std::fabs(ty) + std::fabs(tz);
+        all_behind = all_behind && h[p][k] < -1e-7 * mag[p][k];
+      }
+      if (all_behind) return false;  // the whole cell lies behind one face
+    }
+    bool ambiguous = false;
+    for (int q = 0; q < query_rule.n_points && !ambiguous; ++q) {
+      const double *lam = &query_rule.bary[(size_t)q * F];
+      bool inside = true;
+      for (int p = 0; p < np; ++p) {
+        double val = 0.0, m = 0.0;
+        for (int k = 0; k < F; ++k) {
+          val += lam[k] * h[p][k];
+          m += lam[k] * mag[p][k];
+        }
+        if (val < -1e-7 * m) {
+          inside = false;
+          break;
+        }
+        if (!(val > 1e-7 * m)) {
+          ambiguous = true;
+          break;
+        }
+      }
+      if (ambiguous) break;
+      if (inside) return true;
+    }
+    if (!ambiguous) return false;
     for (int q = 0; q < query_rule.n_points; ++q) {
       const double *lam = &query_rule.bary[(size_t)q * F];
       Vec3 x = v[0] * lam[0] + v[1] * lam[1] + v[2] * lam[2];
@@ -100,8 +155,30 @@ struct Selector {
       std::sort(cands.begin(), cands.end(), closer);
     } else {
       for (size_t a = 0; a < m; ++a) keyed[a] = Keyed{norm(g.center(cands[a]) - xc), cands[a]};
-      std::sort(keyed, keyed + m, [](const Keyed &a, const Keyed &b) { return a.d < b.d; });
-      for (size_t a = 0; a < m; ++a) cands[a] = keyed[a].c;
+      auto less = [](const Keyed &a, const Keyed &b) { return a.d < b.d; };
+      const size_t np = (size_t)n_points;
+      bool done = false;
+      if (m > 2 * np) {
+        // Only the n_points closest cells are kept.  When their distances are pairwise distinct and smaller than all the
+        // others, every sort yields the same first n_points entries: select them, sort them, check; ties fall back to
+        // the full std::sort on the untouched array, whose permutation is the reference's.
+        Keyed part[512];
+        std::copy(keyed, keyed + m, part);
+        std::nth_element(part, part + np, part + m, less);
+        std::sort(part, part + np, less);
+        double rest_min = part[np].d;
+        for (size_t a = np + 1; a < m; ++a) rest_min = std::min(rest_min, part[a].d);
+        bool distinct = part[np - 1].d < rest_min;
+        for (size_t a = 1; a < np && distinct; ++a) distinct = part[a - 1].d < part[a].d;
+        if (distinct) {
+          for (size_t a = 0; a < np; ++a) cands[a] = part[a].c;
+          done = true;
+        }
+      }
+      if (!done) {
+        std::sort(keyed, keyed + m, less);
+        for (size_t a = 0; a < m; ++a) cands[a] = keyed[a].c;
+      }
     }
     if ((int)cands.size() > n_points) cands.resize((size_t)n_points);
   }
@@ -117,6 +194,7 @@ struct Selector {
       r.kind = 3;
       r.dD = g.vertex(i, relative_vertex_index(g.n_dims, k, 2)) - apex;
     }
+    r.set_planes();
     return r;
   }
 
