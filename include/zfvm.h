@@ -66,6 +66,16 @@ int zfvm_mesh_square(int nx, int ny, double x0, double x1, double y0, double y1,
 int zfvm_mesh_cube(int nx, int ny, int nz, double h, double x0, double y0, double z0, double jitter,
                    uint64_t seed, int hilbert, const int offset[3], const int global[3], int64_t *n_vertices,
                    double **vertices, int64_t *n_cells, int32_t **vertex_indices);
+/* The reference's grid file *.msh.h5 (load_grid_gmsh_h5, src/zisa/grid/grid.cpp:889-901: datasets n_dims, vertex_indices,
+ * vertices; written by src/renumber_grid.cpp:129-132).  A dependency-free subset of the HDF5 file format
+ * (csrc/host/msh_h5.cpp: superblock 0-3, symbol-table or compact-link root group, contiguous / compact datasets of
+ * little-endian integers and IEEE floats); anything else is rejected with the reason in zfvm_last_error.  The writer
+ * emits what libhdf5 1.8 / h5py write by default, with the reference's 64-bit unsigned indices.  Outputs are
+ * malloc'ed; free with zfvm_free.  The result goes to zfvm_grid_from_mesh like a generated mesh. */
+int zfvm_mesh_read_msh_h5(const char *path, int *n_dims, int64_t *n_vertices, double **vertices, int64_t *n_cells,
+                          int32_t **vertex_indices);
+int zfvm_mesh_write_msh_h5(const char *path, int n_dims, int64_t n_vertices, const double *vertices, int64_t n_cells,
+                           const int32_t *vertex_indices);
 void zfvm_free(void *p);
 
 /* ---- host precompute: stencils -------------------------------------------------------------------

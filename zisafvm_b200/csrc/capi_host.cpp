@@ -168,6 +168,33 @@ int zfvm_mesh_cube(int nx, int ny, int nz, double h, double x0, double y0, doubl
   }
 }
 
+int zfvm_mesh_read_msh_h5(const char *path, int *n_dims, int64_t *n_vertices, double **vertices, int64_t *n_cells,
+                          int32_t **vertex_indices) {
+  try {
+    RawMesh m;
+    read_msh_h5(path, m);
+    *n_dims = m.n_dims;
+    return export_mesh(m, 0, n_vertices, vertices, n_cells, vertex_indices);
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_mesh_read_msh_h5: ") + e.what());
+  }
+}
+
+int zfvm_mesh_write_msh_h5(const char *path, int n_dims, int64_t n_vertices, const double *vertices, int64_t n_cells,
+                           const int32_t *vertex_indices) {
+  try {
+    if (n_dims != 2 && n_dims != 3) return fail("zfvm_mesh_write_msh_h5: n_dims must be 2 or 3");
+    RawMesh m;
+    m.n_dims = n_dims;
+    m.vertices.assign(vertices, vertices + 3 * n_vertices);
+    m.vertex_indices.assign(vertex_indices, vertex_indices + (n_dims + 1) * n_cells);
+    write_msh_h5(path, m);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_mesh_write_msh_h5: ") + e.what());
+  }
+}
+
 void zfvm_free(void *p) { std::free(p); }
 
 int zfvm_stencils_compute(const zfvm_grid *grid, int n_stencils, const int *orders, const char *biases,

@@ -137,6 +137,10 @@ RawMesh make_cube_mesh(int nx, int ny, int nz, double h, double x0, double y0, d
                        std::uint64_t seed, int ox = 0, int oy = 0, int oz = 0, int gx = -1, int gy = -1,
                        int gz = -1);
 void renumber_mesh_cells(RawMesh &m, const std::vector<i32> &perm);
+/// The reference's grid file `*.msh.h5` (load_grid_gmsh_h5, grid.cpp:889-901): datasets n_dims, vertex_indices, vertices.
+/// Dependency-free subset of the HDF5 file format (msh_h5.cpp); both throw std::runtime_error with the reason.
+void read_msh_h5(const std::string &path, RawMesh &mesh);
+void write_msh_h5(const std::string &path, const RawMesh &mesh);
 
 // ---- stencils -------------------------------------------------------------------------------
 struct StencilFamilyParams {

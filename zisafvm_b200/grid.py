@@ -109,6 +109,25 @@ def cube_mesh(nx: int, ny: int, nz: int, h: float, origin=(0.0, 0.0, 0.0), jitte
     return _take_mesh(nv, verts, nc, vi, 3)
 
 
+def read_msh_h5(path: str):
+    """``zisa::load_grid_gmsh_h5`` (src/zisa/grid/grid.cpp:889-901): (n_dims, vertices [nv][3], vertex_indices [nc][n_dims+1])
+    of a ``*.msh.h5`` grid file, read by the library's own HDF5-subset reader; feed them to ``Grid``."""
+    nd, nv, nc = C.c_int(), C.c_int64(), C.c_int64()
+    verts, vi = _capi.c_double_p(), _capi.c_int32_p()
+    check(lib.zfvm_mesh_read_msh_h5(str(path).encode(), C.byref(nd), C.byref(nv), C.byref(verts), C.byref(nc), C.byref(vi)))
+    v, c = _take_mesh(nv, verts, nc, vi, nd.value)
+    return nd.value, v, c
+
+
+def write_msh_h5(path: str, n_dims: int, vertices: np.ndarray, vertex_indices: np.ndarray) -> None:
+    """Writes a mesh the way src/renumber_grid.cpp:129-132 does (datasets n_dims, vertex_indices, vertices), so that the
+    reference can load the synthetic grids of this package."""
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    c = np.ascontiguousarray(vertex_indices, dtype=np.int32)
+    check(lib.zfvm_mesh_write_msh_h5(str(path).encode(), int(n_dims), v.shape[0], _capi.ptr_f64(v), c.shape[0],
+                                     c.ctypes.data_as(_capi.c_int32_p)))
+
+
 @dataclass
 class StencilFamilyParams:
     """``zisa::StencilFamilyParams{orders, biases, overfit_factors}``."""
