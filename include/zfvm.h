@@ -149,8 +149,12 @@ typedef struct zfvm_params {
   int gravity_kind, gravity_alignment;
   double gravity_p[4];
   double gravity_axis[3];
-  /* LocalRCParams{steps_per_recompute, recompute_threshold}: only steps_per_recompute == 1 is
-   * supported (the equilibrium is refreshed every stage, local_reconstruction.hpp:87-100) */
+  /* LocalRCParams{steps_per_recompute, recompute_threshold} (local_reconstruction.hpp:22-25, 87-100; JSON keys
+   * "reconstruction.steps_per_recompute" / ".recompute_threshold", euler_experiment_impl.hpp:83-90): a cell's local
+   * equilibrium, its averages over the stencil, its values at the cell's Gauss points and the characteristic scale are
+   * refreshed every steps_per_recompute-th evaluation of the rate of change, or earlier when (rho, E_int) has moved
+   * away from the cached equilibrium average by recompute_threshold in units of the cached scale (the threshold is the
+   * last member of this struct).  1 = every evaluation.  Other values need a family of the experiments' shape. */
   int steps_per_recompute;
   int keep_polynomials;      /* diagnostics: store every cell's WENO polynomial */
   /* "flux-bc" (numerical_experiment.cpp:238-256 adds it to the FVM rate of change): 0 NoFluxBC, 1 FluxBC
@@ -165,6 +169,7 @@ typedef struct zfvm_params {
   /* Heating (include/zisa/model/heating.hpp:18-80): dE/dt += average(rho * heating_rate * [r0 <= |x| <= r1]);
    * heating_rate == 0: no heating term */
   double heating_rate, heating_r0, heating_r1;
+  double recompute_threshold; /* LocalRCParams::recompute_threshold, see steps_per_recompute */
 } zfvm_params;
 
 void zfvm_params_default(zfvm_params *p);

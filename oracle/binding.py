@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         _lib.oracle_local_equilibrium.restype = C.c_int
         _lib.oracle_set_tracers.argtypes = [C.c_void_p, C.c_int]
         _lib.oracle_set_heating.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        _lib.oracle_set_local_rc_params.argtypes = [C.c_void_p, C.c_int, C.c_double]
         _lib.oracle_set_flux_bc.argtypes = [C.c_void_p, C.c_int]
         _lib.oracle_set_frozen_bc_av.argtypes = [C.c_void_p, dp, dp]
         _lib.oracle_rate_of_change_av.argtypes = [C.c_void_p, dp, dp, dp, dp]
@@ -157,6 +158,9 @@ class Oracle:
         self._h = L.oracle_create(C.byref(g), C.byref(s), C.byref(p))
         self.n_avars = int(getattr(params, "n_avars", 0))
         L.oracle_set_tracers(self._h, self.n_avars)
+        spr = int(getattr(params, "steps_per_recompute", 1))
+        if spr != 1:
+            L.oracle_set_local_rc_params(self._h, spr, float(getattr(params, "recompute_threshold", 0.0)))
         heating = getattr(params, "heating", None)
         if heating is not None:
             L.oracle_set_heating(self._h, float(heating[0]), float(heating[1]), float(heating[2]))

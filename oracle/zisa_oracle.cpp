@@ -13,7 +13,6 @@
 //
 // Deliberate deviations (all documented in DESIGN.md):
 //   * face-flux scatter order is fixed (the reference uses OpenMP atomics, order nondeterministic);
-//   * steps_per_recompute == 1 only.
 //
 // Reference map (all under /root/reference):
 //   PolyND, smoothness_indicator            include/zisa/math/poly2d_impl.hpp:34-41,272-337
@@ -306,6 +305,9 @@ struct Params {
   int flux_bc = 0;  // 0 NoFluxBC, 1 FluxBC (boundary/flux_bc.hpp:13-52), 2 EquilibriumFluxBC (equilibrium_flux_bc.hpp:18-75)
   int n_avars = 0;  // advected scalars, AllVariables::avars (all_variables.hpp:31-35)
   double heating_rate = 0.0, heating_r0 = 0.0, heating_r1 = 0.0;  // make_heating_source, heating.hpp:54-80
+  // LocalRCParams (local_reconstruction.hpp:22-25; read from JSON at euler_experiment_impl.hpp:83-90)
+  int steps_per_recompute = 1;
+  double recompute_threshold = 0.0;
 };
 
 struct Grid {
@@ -512,6 +514,8 @@ struct Oracle {
   std::vector<PointValues> pv_cell;   // [n_cells][q_c]
   std::vector<PointValues> pv_face;   // [n_cells][F][q_f]
   std::vector<Poly<1>> scalar_polys;   // [n_cells][n_avars]  (LocalReconstruction::scalar_polys)
+  std::vector<i32> steps_since;        // [n_cells]  LocalReconstruction::steps_since_recompute
+  std::vector<double> rhoEbar_cache;   // [n_cells][l2g_stride][2]  LocalReconstruction::rhoEbar_cache
   std::vector<double> frozen, frozen_av;
   std::vector<i32> ghost_index;
   bool has_frozen = false;
@@ -539,6 +543,8 @@ struct Oracle {
     eq.resize((size_t)n);
     pv_cell.assign((size_t)(n * g.q_c), PointValues());
     pv_face.assign((size_t)(n * g.F * g.q_f), PointValues());
+    steps_since.assign((size_t)n, 0);
+    rhoEbar_cache.assign((size_t)(n * st.l2g_stride * 2), 0.0);
     for (i64 i = 0; i < n; ++i)
       if (g.cell_flags[i] & 2) ghost_index.push_back((i32)i);
   }
@@ -620,51 +626,66 @@ struct Oracle {
     for (int il = 0; il < m; ++il)  // set_qbar_local, global_reconstruction_impl.hpp:166-174
       for (int v = 0; v < NV; ++v) wk.qbar[(size_t)il * NV + v] = state[(size_t)l2g[il] * NV + v];
 
-    // compute_equilibrium (steps_per_recompute == 1 -> every call)
+    // recompute_equilibrium, local_reconstruction.hpp:87-100: every steps_per_recompute-th call, or when the cell has
+    // drifted from the cached equilibrium average by recompute_threshold (in units of the cached scale)
     const double *u0 = &wk.qbar[0];
     const double rho_self = u0[0], E_self = eos.internal_energy(u0);
     double *sc = &scale[(size_t)i * NV];
-    if (prm.scaling == 1) {  // EulerScaling, characteristic_scale.hpp:24-33
-      const double p = eos.pressure_rhoE(E_self);
-      const double cs = eos.sound_speed_rhoP(rho_self, p);
-      sc[0] = rho_self;
-      sc[1] = sc[2] = sc[3] = cs;
-      sc[4] = E_self;
-    } else {
-      for (int v = 0; v < NV; ++v) sc[v] = 1.0;
+    double *cache = &rhoEbar_cache[(size_t)(i * st.l2g_stride) * 2];
+    bool recompute = (steps_since[(size_t)i] % prm.steps_per_recompute) == 0;
+    if (!recompute) {
+      const double d0 = (rho_self - cache[0]) / sc[0], d1 = (E_self - cache[1]) / sc[4];
+      recompute = std::sqrt(d0 * d0 + d1 * d1) >= prm.recompute_threshold;
     }
     LocalEquilibrium &le = eq[(size_t)i];
-    if (prm.well_balanced) {
-      le.solve(eos, g, i, rho_self, E_self);
-      if (!le.found) {
+    if (recompute) {  // compute_equilibrium, local_reconstruction.hpp:69-85
+      if (prm.scaling == 1) {  // EulerScaling, characteristic_scale.hpp:24-33
+        const double p = eos.pressure_rhoE(E_self);
+        const double cs = eos.sound_speed_rhoP(rho_self, p);
+        sc[0] = rho_self;
+        sc[1] = sc[2] = sc[3] = cs;
+        sc[4] = E_self;
+      } else {
+        for (int v = 0; v < NV; ++v) sc[v] = 1.0;
+      }
+      if (prm.well_balanced) {
+        le.solve(eos, g, i, rho_self, E_self);
+        if (!le.found) {
 #pragma omp atomic
-        eq_failures += 1;
-      }
-      // point_values_cache.update: extrapolate_full at own cell + face points
-      for (int q = 0; q < g.q_c; ++q) {
-        PointValues &pv = pv_cell[(size_t)(i * g.q_c + q)];
-        le.extrapolate(eos, g.phi_cqp[(size_t)(i * g.q_c + q)], pv.rho, pv.E);
-        pv.p = le.found ? eos.pressure_rhoE(pv.E) : 0.0;
-        pv.a = le.found ? eos.sound_speed_rhoP(pv.rho, pv.p) : 0.0;
-      }
-      for (int k = 0; k < g.F; ++k) {
-        const i64 e = g.edge_indices[i * g.F + k];
-        for (int q = 0; q < g.q_f; ++q) {
-          PointValues &pv = pv_face[(size_t)((i * g.F + k) * g.q_f + q)];
-          le.extrapolate(eos, g.phi_fqp[(size_t)(e * g.q_f + q)], pv.rho, pv.E);
+          eq_failures += 1;
+        }
+        // point_values_cache.update: extrapolate_full at own cell + face points
+        for (int q = 0; q < g.q_c; ++q) {
+          PointValues &pv = pv_cell[(size_t)(i * g.q_c + q)];
+          le.extrapolate(eos, g.phi_cqp[(size_t)(i * g.q_c + q)], pv.rho, pv.E);
           pv.p = le.found ? eos.pressure_rhoE(pv.E) : 0.0;
           pv.a = le.found ? eos.sound_speed_rhoP(pv.rho, pv.p) : 0.0;
         }
+        for (int k = 0; k < g.F; ++k) {
+          const i64 e = g.edge_indices[i * g.F + k];
+          for (int q = 0; q < g.q_f; ++q) {
+            PointValues &pv = pv_face[(size_t)((i * g.F + k) * g.q_f + q)];
+            le.extrapolate(eos, g.phi_fqp[(size_t)(e * g.q_f + q)], pv.rho, pv.E);
+            pv.p = le.found ? eos.pressure_rhoE(pv.E) : 0.0;
+            pv.a = le.found ? eos.sound_speed_rhoP(pv.rho, pv.p) : 0.0;
+          }
+        }
       }
+      for (int il = 0; il < m; ++il) {
+        double rho_eq_bar = 0.0, E_eq_bar = 0.0;
+        if (prm.well_balanced) le.extrapolate_cell(eos, g, l2g[il], rho_eq_bar, E_eq_bar);
+        cache[2 * il] = rho_eq_bar;
+        cache[2 * il + 1] = E_eq_bar;
+      }
+      steps_since[(size_t)i] = 0;
     }
     for (int il = 0; il < m; ++il) {
-      double rho_eq_bar = 0.0, E_eq_bar = 0.0;
-      if (prm.well_balanced) le.extrapolate_cell(eos, g, l2g[il], rho_eq_bar, E_eq_bar);
       double *u = &wk.qbar[(size_t)il * NV];
-      u[0] -= rho_eq_bar;
-      u[4] -= E_eq_bar;
+      u[0] -= cache[2 * il];
+      u[4] -= cache[2 * il + 1];
       for (int v = 0; v < NV; ++v) u[v] = u[v] / sc[v];
     }
+    steps_since[(size_t)i] += 1;
 
     // compute_polys_impl, hybrid_weno.cpp:72-92
     wk.polys.resize((size_t)n_st);
@@ -1284,6 +1305,13 @@ void oracle_set_heating(void *h, double rate, double r0, double r1) {
   o->prm.heating_r1 = r1;
 }
 void oracle_set_flux_bc(void *h, int kind) { ((Oracle *)h)->prm.flux_bc = kind; }
+/* LocalRCParams{steps_per_recompute, recompute_threshold}; resets the per-cell counters */
+void oracle_set_local_rc_params(void *h, int steps_per_recompute, double recompute_threshold) {
+  Oracle *o = (Oracle *)h;
+  o->prm.steps_per_recompute = steps_per_recompute < 1 ? 1 : steps_per_recompute;
+  o->prm.recompute_threshold = recompute_threshold;
+  std::fill(o->steps_since.begin(), o->steps_since.end(), 0);
+}
 void oracle_set_frozen_bc_av(void *h, const double *steady, const double *steady_av) {
   Oracle *o = (Oracle *)h;
   oracle_set_frozen_bc(h, steady);

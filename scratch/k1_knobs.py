@@ -55,6 +55,8 @@ CONFIGS = [
     ("default again", {}),
     ("l2_ahead 4608 again", {"ZFVM_TILE_L2_AHEAD": "4608"}),
 ]
+if os.environ.get("ZFVM_KNOB_DEFAULT_ONLY"):
+    CONFIGS = [(os.environ["ZFVM_KNOB_DEFAULT_ONLY"], {})] * 2
 if os.environ.get("ZFVM_TILE_PROF"):
     CONFIGS = [("phase timers", {"ZFVM_TILE_PROF": "1"})] * 2
 if os.environ.get("ZFVM_KNOB_GHOSTS_LAST"):

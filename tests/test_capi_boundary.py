@@ -40,8 +40,9 @@ def test_params_struct_layout_matches_header():
     assert p.keep_polynomials == 0 and p.flux == 0 and p.scaling == 1
     # the fields behind flux_bc (appended later): defaults are "off"
     assert p.flux_bc == 0 and p.n_avars == 0 and p.heating_rate == 0.0 and p.heating_r0 == 0.0 and p.heating_r1 == 0.0
-    p.n_avars, p.heating_r1 = 3, 0.75  # and they are the last fields: sizeof agrees with the header's layout
-    assert C.sizeof(_capi.ZfvmParams) == _capi.ZfvmParams.heating_r1.offset + 8
+    assert p.recompute_threshold == 0.0
+    p.n_avars, p.recompute_threshold = 3, 0.75  # and it is the last field: sizeof agrees with the header's layout
+    assert C.sizeof(_capi.ZfvmParams) == _capi.ZfvmParams.recompute_threshold.offset + 8
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -86,6 +87,9 @@ def test_scheme_parameters_reach_the_c_struct():
     assert (p.heating_rate, p.heating_r0, p.heating_r1) == (0.3, 0.4, 0.8)
     q = z.EulerParams(weno=WENO_PARAMS["2d_o3"]).to_c()
     assert q.flux_bc == 0 and q.n_avars == 0 and q.heating_rate == 0.0
+    assert q.steps_per_recompute == 1 and q.recompute_threshold == 0.0
+    r = z.EulerParams(weno=WENO_PARAMS["2d_o3"], steps_per_recompute=4, recompute_threshold=1e-3).to_c()
+    assert r.steps_per_recompute == 4 and r.recompute_threshold == 1e-3
 
 
 def test_all_variables_carries_avars():

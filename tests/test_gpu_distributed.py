@@ -64,8 +64,9 @@ def _worker(rank, world, port, out_dir, partition="lattice"):
         u = out.cvars
         np.save(os.path.join(out_dir, f"a_{rank}.npy"), out.avars[: sub.n_owned])
         cnt = ctx.counters()
-        # a METIS part of this small mesh is ragged enough for every tile to read a halo row: no interior tile there
-        assert cnt["tiles_exterior"] > 0 and (cnt["tiles_interior"] > 0 or partition == "metis"), cnt
+        # (a METIS part of this small mesh may consist of ghost cells only, or be so ragged that every tile reads a halo
+        # row: the overlap split is only asserted for the contiguous partitions)
+        assert partition == "metis" or (cnt["tiles_exterior"] > 0 and cnt["tiles_interior"] > 0), cnt
         np.save(os.path.join(out_dir, f"u_{rank}.npy"), u[: sub.n_owned])
         np.save(os.path.join(out_dir, f"gid_{rank}.npy"), sub.global_index[: sub.n_owned])
         np.save(os.path.join(out_dir, f"dt_{rank}.npy"), np.array(dts))

@@ -232,3 +232,65 @@ def test_equilibrium_flux_bc_needs_gravity():
     case.params.flux_bc = "equilibrium"
     with pytest.raises(z.ZfvmError, match="EquilibriumFluxBC needs a gravity model"):
         z.CudaContext(case.grid, case.ensure_stencils(), case.params)
+
+
+# ---- LocalRCParams: history-dependent refresh of the local equilibrium (local_reconstruction.hpp:87-100) ----------------
+RC_CASES = {
+    "polytrope_wb": lambda: cases.polytrope_2d(n=30, order=3, well_balanced=True, amplitude=1e-3),
+    "atmosphere_wb": lambda: cases.stellar_atmosphere_3d(n=6, order=3, well_balanced=True),
+    "atmosphere_wb_o4": lambda: cases.stellar_atmosphere_3d(n=7, order=4, well_balanced=True),   # cooperative kernel
+    "polytrope_nowb": lambda: cases.polytrope_2d(n=30, order=3, well_balanced=False),            # only the scale is cached
+    "vortex": lambda: cases.isentropic_vortex(n=30, order=3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RC_CASES))
+@pytest.mark.parametrize("spr,threshold", [(3, 1e300), (4, 2e-4), (2, 0.0)])
+def test_steps_per_recompute(name, spr, threshold):
+    """`steps_per_recompute` / `recompute_threshold` (JSON "reconstruction", euler_experiment_impl.hpp:83-90): the cell's
+    equilibrium, its stencil averages, its point values and the characteristic scale are kept between evaluations of the
+    rate of change.  Four SSP3 steps (twelve evaluations) against the oracle, which restates recompute_equilibrium:
+    refresh every third evaluation only; every fourth or when a cell has drifted by 2e-4 scaled units (some do, most do
+    not); threshold 0 = refresh always, which must reproduce the steps_per_recompute = 1 run bit for bit."""
+    case = RC_CASES[name]()
+    case.params.steps_per_recompute, case.params.recompute_threshold = spr, threshold
+    st = case.ensure_stencils()
+    n = case.grid.n_cells
+    ctx = z.CudaContext(case.grid, st, case.params)
+    ora = _oracle(case, st)
+    rk = z.CudaRungeKutta(ctx, case.method)
+    z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+    ora.set_frozen_bc(case.u0)
+    rk.upload(z.AllVariables(n, case.u0))
+    u_ref = case.u0.copy()
+    dt = 0.8 * ora.cfl_dt(u_ref, case.cfl)
+    for _ in range(4):
+        _, bad = rk.step(0.0, dt)
+        assert not bad
+        u_ref = ora.rk_step(case.method, u_ref, dt)
+    u = rk.download().cvars
+    assert ctx.counters()["eq_failures"] == ora.eq_failures()
+    ctx.close()
+    sc = state_scales(case.u0, case.params.gamma)
+    assert (np.abs(u - u_ref).max(axis=0) / sc).max() < 1e-11, (name, np.abs(u - u_ref).max(axis=0) / sc)
+    if threshold == 0.0:
+        case.params.steps_per_recompute, case.params.recompute_threshold = 1, 0.0
+        ctx = z.CudaContext(case.grid, st, case.params)
+        rk = z.CudaRungeKutta(ctx, case.method)
+        z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+        rk.upload(z.AllVariables(n, case.u0))
+        for _ in range(4):
+            rk.step(0.0, dt)
+        assert np.array_equal(rk.download().cvars, u)
+        ctx.close()
+    elif name.endswith("_wb") or name.endswith("_o4"):
+        # the cached equilibrium is history: the run differs from the refresh-always run (else the test tests nothing)
+        case.params.steps_per_recompute, case.params.recompute_threshold = 1, 0.0
+        ctx = z.CudaContext(case.grid, st, case.params)
+        rk = z.CudaRungeKutta(ctx, case.method)
+        z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+        rk.upload(z.AllVariables(n, case.u0))
+        for _ in range(4):
+            rk.step(0.0, dt)
+        assert not np.array_equal(rk.download().cvars, u)
+        ctx.close()

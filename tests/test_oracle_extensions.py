@@ -148,3 +148,30 @@ def test_equilibrium_flux_bc_closes_a_hydrostatic_domain():
     assert np.abs(closed[:, 1:3]).max() <= 1e-11 * scale                 # closed: round-off
     assert np.array_equal(closed[~boundary], open_res[~boundary])
     assert a.min() > 0
+
+
+def test_steps_per_recompute_in_the_oracle():
+    """recompute_equilibrium (local_reconstruction.hpp:87-100): threshold 0 refreshes at every evaluation and reproduces
+    steps_per_recompute = 1 bit for bit; an unreachable threshold keeps the cached equilibrium between refreshes, which
+    changes a perturbed run but leaves an unperturbed hydrostatic state in equilibrium to round-off."""
+    from oracle.binding import Oracle
+
+    def run(case, spr, thr, steps=3):
+        case.params.steps_per_recompute, case.params.recompute_threshold = spr, thr
+        ora = Oracle(case.grid, case.ensure_stencils(), case.params, cases.gravity_tables(case.grid, case.params.gravity))
+        ora.set_frozen_bc(case.u0)
+        u = case.u0.copy()
+        dt = 0.8 * ora.cfl_dt(u, case.cfl)
+        for _ in range(steps):
+            u = ora.rk_step(case.method, u, dt)
+        return u
+
+    pert = cases.polytrope_2d(n=16, order=3, well_balanced=True, amplitude=1e-3)
+    base = run(pert, 1, 0.0)
+    assert np.array_equal(run(pert, 5, 0.0), base)
+    cached = run(pert, 3, 1e300)
+    assert not np.array_equal(cached, base)
+    assert np.abs(cached - base).max() < 1e-5          # second order in the perturbation over a few steps
+    rest = cases.polytrope_2d(n=16, order=3, well_balanced=True, amplitude=0.0)
+    u = run(rest, 3, 1e300)
+    assert np.abs(u - rest.u0).max() < 1e-12

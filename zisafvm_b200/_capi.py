@@ -43,6 +43,7 @@ class ZfvmParams(C.Structure):
         ("heating_rate", C.c_double),
         ("heating_r0", C.c_double),
         ("heating_r1", C.c_double),
+        ("recompute_threshold", C.c_double),
     ]
 
 
@@ -51,6 +52,8 @@ class ZfvmError(RuntimeError):
 
 
 def _load() -> C.CDLL:
+    global LIB_PATH
+    LIB_PATH = os.environ.get("ZFVM_LIB_PATH", LIB_PATH)  # kernel experiments: a variant build of the same library
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

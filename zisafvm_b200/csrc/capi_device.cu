@@ -326,6 +326,7 @@ void zfvm_params_default(zfvm_params *p) {
   p->gas_constant = 1.0;
   p->gravity_kind = GRAVITY_NONE;
   p->steps_per_recompute = 1;
+  p->recompute_threshold = 0.0;
   p->flux_bc = 0;
 }
 
@@ -339,8 +340,7 @@ int zfvm_create(const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm
     const HostStencils &S = stencils->s;
     const int ns = S.n_stencils;
     if (S.n_cells != g.n_cells) return fail("zfvm_create: stencils do not belong to this grid");
-    if (params->steps_per_recompute != 1)
-      return fail("zfvm_create: only steps_per_recompute == 1 is supported (local_reconstruction.hpp:87-100)");
+    if (params->steps_per_recompute < 1) return fail("zfvm_create: steps_per_recompute must be >= 1");
     if (params->well_balanced && params->gravity_kind == GRAVITY_NONE)
       return fail("zfvm_create: isentropic well-balancing needs a gravity model");
     if (g.q_f > MAX_QF || g.q_c > MAX_QC) return fail("zfvm_create: quadrature rule too large");
@@ -575,6 +575,8 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     const double twice = 2.0 * sc.eos_pow_e, r = std::rint(twice);
     sc.eos_pow_n = (std::fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) ? (int)r : 0;
   }
+  sc.steps_per_recompute = params->steps_per_recompute;
+  sc.recompute_threshold = params->recompute_threshold;
   sc.heating_rate = params->heating_rate;
   sc.heating_r0 = params->heating_r0;
   sc.heating_r1 = params->heating_r1;
@@ -1169,6 +1171,16 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     P.eq_rows = P.rec2 ? r + 1 : r;  // tile records: rows in lidx order plus one row for the cell itself
     if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)P.eq_rows * 2 * TILE, true) ||
         (P.rec2 && dev_alloc(ctx, &P.eq_bg, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * 2, true))) {
+      return 1;
+    }
+  }
+  // steps_per_recompute != 1: the per-cell history of LocalReconstruction (local_reconstruction.hpp:87-100).  The cached
+  // equilibrium, its averages / point values and the scale live in the arrays the equilibrium kernels write anyway.
+  if (params->steps_per_recompute != 1) {
+    if (!P.rec2)
+      return fail("zfvm_create: steps_per_recompute != 1 needs a stencil family of the experiments' shape (tile records)");
+    if (dev_alloc(ctx, &P.eq_steps, n, true) || dev_alloc(ctx, &P.scale_state, n * 2, true) ||
+        dev_alloc(ctx, &P.eq_flag, n, true)) {
       return 1;
     }
   }

@@ -62,6 +62,10 @@ struct SchemeConst {
   // multiplication forms), else 0 -> pow(x, eos_pow_e)
   int eos_pow_n;
   double eos_pow_e;
+  // LocalRCParams (local_reconstruction.hpp:22-25): the equilibrium, its averages and the characteristic scale of a cell
+  // are refreshed every steps_per_recompute-th evaluation or when the cell has drifted by recompute_threshold
+  int steps_per_recompute;
+  double recompute_threshold;
 };
 
 /// Raw device pointers of one context. Sizes in comments use n = n_cells, T = n_tiles, E = n_edges.
@@ -121,6 +125,11 @@ struct DevicePlan {
   int eq_rows;                              // sum_k rows_max_k (+ 1 with tile records: the last row is the cell itself)
   int eq_row0[MAX_STENCILS];                // older records: first row of stencil k (tile records: lidx row order)
   double *eq_bg;                            // tile records: [E_int][2][q_f][2] equilibrium (rho, E) at the face Gauss points
+  // steps_per_recompute != 1 (null otherwise): LocalReconstruction::steps_since_recompute, the (rho, E_int) the cached
+  // scale was formed from, and this evaluation's verdict of recompute_equilibrium (local_reconstruction.hpp:87-100)
+  std::int32_t *eq_steps;                   // [n]
+  double *scale_state;                      // [n][2]
+  std::uint8_t *eq_flag;                    // [n] 1: the cell's equilibrium data are recomputed in this evaluation
   int rec2_off_list, rec2_off_lidx, rec2_lidx_elem;  // where a tile record keeps its row list and local indices
   // advected scalars (tracers.cu): traces and face fluxes of the n_avars scalars; null when n_avars == 0
   int n_avars;

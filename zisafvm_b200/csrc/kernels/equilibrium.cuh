@@ -196,6 +196,47 @@ ZFVM_DEVICE LocalEq solve_local_equilibrium(double rho_bar, double E_bar, const 
 }
 
 
+/// E0 (steps_per_recompute != 1 only).  One thread per cell: recompute_equilibrium's verdict
+/// (local_reconstruction.hpp:87-100) -- every steps_per_recompute-th evaluation, or when (rho, E_int) has moved away from
+/// the cached equilibrium average by recompute_threshold in units of the cached scale -- and the bookkeeping of
+/// compute_equilibrium / compute (:69-85, :102-120): the scale's (rho, E_int), steps_since_recompute.
+template <int UNUSED = 0>  // (a template only so that the header can be included by several translation units)
+__global__ void __launch_bounds__(256) eq_decide_kernel(const DevicePlan P, const __grid_constant__ SchemeConst sc,
+                                                        const double *__restrict__ state,
+                                                        const std::int32_t *__restrict__ tile_list, std::int64_t n_tiles) {
+  const std::int64_t t = (std::int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles * TILE) return;
+  const std::int64_t tw = t / TILE;
+  const int lane = (int)(t - tw * TILE);
+  const std::int64_t tile = tile_list ? (std::int64_t)tile_list[tw] : tw;
+  const std::int64_t i = tile * TILE + lane;
+  if (i >= P.n_cells) return;
+  const double *u = state + i * NVARS;
+  const double rho = u[0];
+  const double eint = u[4] - 0.5 * (u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) / rho;
+  int steps = P.eq_steps[i];
+  bool recompute = (steps % sc.steps_per_recompute) == 0;
+  if (!recompute) {
+    double rho_c = 0.0, E_c = 0.0;  // rhoEbar_cache(0): the cell's own equilibrium average (NoEquilibrium: zero)
+    if (sc.well_balanced) {
+      const double *e0 = P.eq_avg + ((tile * P.eq_rows + (P.eq_rows - 1)) * 2) * TILE + lane;
+      rho_c = e0[0];
+      E_c = e0[TILE];
+    }
+    const double s0 = sc.scaling == SCALING_EULER ? P.scale_state[2 * i] : 1.0;
+    const double s4 = sc.scaling == SCALING_EULER ? P.scale_state[2 * i + 1] : 1.0;
+    const double d0 = (rho - rho_c) / s0, d1 = (eint - E_c) / s4;
+    recompute = sqrt(d0 * d0 + d1 * d1) >= sc.recompute_threshold;
+  }
+  if (recompute) {
+    P.scale_state[2 * i] = rho;
+    P.scale_state[2 * i + 1] = eint;
+    steps = 0;
+  }
+  P.eq_flag[i] = recompute ? 1 : 0;
+  P.eq_steps[i] = steps + 1;
+}
+
 /// E1.  One thread per cell: the local equilibrium of the cell's average state (LocalEquilibrium::solve,
 /// local_equilibrium_impl.hpp:34-94) -> eq_par[cell] = (h_ref, K, phi_ref, found).  Kept out of the reconstruction
 /// kernel: the Newton iteration needs few registers and no stencil data, so it runs at full occupancy here.
@@ -208,6 +249,7 @@ __global__ void __launch_bounds__(256) eq_solve_kernel(const DevicePlan P, const
   const std::int64_t tw = t / TILE;
   const std::int64_t i = (tile_list ? (std::int64_t)tile_list[tw] : tw) * TILE + (t - tw * TILE);
   if (i >= P.n_cells) return;
+  if (P.eq_flag != nullptr && !P.eq_flag[i]) return;  // cached equilibrium kept (recompute_equilibrium)
   const double *u = state + i * NVARS;
   const double rho = u[0];
   const double eint = u[4] - 0.5 * (u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) / rho;
@@ -280,6 +322,7 @@ __global__ void __launch_bounds__(256) eq_member_tile_kernel(const DevicePlan P,
                                            : (int)reinterpret_cast<const std::uint16_t *>(lrow)[lane];
     g = reinterpret_cast<const std::int32_t *>(rec + P.rec2_off_list)[li];
   }
+  if (P.eq_flag != nullptr && !P.eq_flag[ci]) return;  // cached averages kept
   const double *par = P.eq_par + ci * 4;
   LocalEq eq{par[0], par[1], par[2], par[3] != 0.0};
   eq.prepare(sc.gamma);
@@ -304,6 +347,11 @@ __global__ void __launch_bounds__(256) eq_member_tile_smem_kernel(const DevicePl
   const int n_list = *reinterpret_cast<const int *>(rec);
   const std::int32_t *list = reinterpret_cast<const std::int32_t *>(rec + P.rec2_off_list);
   const int q_c = sc.q_c;
+  if (P.eq_flag != nullptr) {  // nothing to do when every cell of the tile keeps its cached averages
+    const std::int64_t c = tile * TILE + (threadIdx.x & 31);
+    const int mine = (threadIdx.x < TILE && c < P.n_cells) ? (int)P.eq_flag[c] : 0;
+    if (!__syncthreads_or(mine)) return;
+  }
   for (int idx = threadIdx.x; idx < n_list * q_c; idx += blockDim.x) {
     const int row = idx / q_c;
     eq_phi_s[idx] = P.phi_cqp[(std::int64_t)list[row] * q_c + (idx - row * q_c)];
@@ -319,6 +367,7 @@ __global__ void __launch_bounds__(256) eq_member_tile_smem_kernel(const DevicePl
       li = (P.rec2_lidx_elem == 1) ? (int)reinterpret_cast<const std::uint8_t *>(lrow)[lane]
                                    : (int)reinterpret_cast<const std::uint16_t *>(lrow)[lane];
     }
+    if (P.eq_flag != nullptr && !P.eq_flag[ci]) continue;  // cached averages kept
     const double *par = P.eq_par + ci * 4;
     LocalEq eq{par[0], par[1], par[2], par[3] != 0.0};
     eq.prepare(sc.gamma);
@@ -347,6 +396,7 @@ __global__ void __launch_bounds__(256) eq_face_kernel(const DevicePlan P, const 
   const std::int64_t ci = cell < P.n_cells ? cell : P.n_cells - 1;
   const std::uint32_t fref = cell < P.n_cells ? P.face_ref[(tile * F + k) * TILE + lane] : 0u;
   if (!(fref & FREF_TRACE)) return;
+  if (P.eq_flag != nullptr && !P.eq_flag[ci]) return;  // cached point values kept (FewPointsCache not updated)
   const std::int64_t e = fref & FREF_EDGE_MASK;
   const int side = (fref & FREF_SIDE) ? 1 : 0;
   const double *par = P.eq_par + ci * 4;

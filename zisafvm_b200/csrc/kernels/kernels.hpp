@@ -49,7 +49,7 @@ struct UpdateArgs {
 };
 
 constexpr int TILE_OFF_META = 16;
-constexpr int TRACE_DUMP_BLOCKS = 2048;  // per-warp dump blocks behind the trace array (tile kernel write-out)
+constexpr int TRACE_DUMP_BLOCKS = 4096;  // per-warp dump blocks behind the trace array (tile kernel write-out)
 
 /// Generic description of the tile record for a scheme (used by the host when it builds the records).
 struct TileRecLayout {

@@ -78,11 +78,16 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 3)
 #pragma unroll
     for (int v = 0; v < NVARS; ++v) u0[v] = table[lane * NVARS + v];
     const double ekin0 = 0.5 * (u0[1] * u0[1] + u0[2] * u0[2] + u0[3] * u0[3]) / u0[0];
-    const double eint0 = u0[4] - ekin0;
+    double rho_s = u0[0], eint0 = u0[4] - ekin0;
+    if (P.scale_state != nullptr) {  // steps_per_recompute != 1: the scale of the last compute_equilibrium
+      const double *ss = P.scale_state + 2 * (active ? cell : P.n_cells - 1);
+      rho_s = ss[0];
+      eint0 = ss[1];
+    }
     if (sc.scaling == SCALING_EULER) {
       const double p = eint0 * (sc.gamma - 1.0);
-      const double cs = sqrt(sc.gamma * p / u0[0]);
-      scale[0] = u0[0];
+      const double cs = sqrt(sc.gamma * p / rho_s);
+      scale[0] = rho_s;
       scale[1] = scale[2] = scale[3] = cs;
       scale[4] = eint0;
     } else {

@@ -22,6 +22,11 @@ int launch_recon(const DevicePlan &plan, const SchemeConst &sc, int deg_hi, int 
   return 1;
 }
 
+void launch_eq_decide(const DevicePlan &plan, const SchemeConst &sc, const double *state, const std::int32_t *tile_list,
+                      std::int64_t n_tiles, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((n_tiles * TILE + 255) / 256);
+  eq_decide_kernel<0><<<grid, 256, 0, stream>>>(plan, sc, state, tile_list, n_tiles);
+}
 template <int POWN>
 void launch_eq_solve(const DevicePlan &plan, const SchemeConst &sc, const double *state, const std::int32_t *tile_list,
                      std::int64_t n_tiles, unsigned grid, cudaStream_t stream) {

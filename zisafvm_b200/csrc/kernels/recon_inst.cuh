@@ -32,7 +32,7 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
   // one CTA per SM; as many warps (= tiles in flight) as fit, at most 8
   TileCfg cfg;
   if (!tile_config<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>(args.plan, sc, optin, cfg)) return 1;
-  int wpc = std::min(TILE_MAX_WARPS, optin / cfg.warp_bytes);
+  int wpc = std::min(tile_max_warps(ND, DEG_HI), optin / cfg.warp_bytes);
   if (const char *e = std::getenv("ZFVM_TILE_WARPS")) wpc = std::max(1, std::min(wpc, std::atoi(e)));
   if (wpc < 1) return 1;
   cfg.prof = tile_prof_buffer();
@@ -74,6 +74,10 @@ template <int POWN>
 void launch_eq_solve(const DevicePlan &plan, const SchemeConst &sc, const double *state, const std::int32_t *tile_list,
                      std::int64_t n_tiles, unsigned grid, cudaStream_t stream);
 
+/// E0: recompute_equilibrium's verdict per cell (steps_per_recompute != 1 only; plan.eq_flag is null otherwise).
+void launch_eq_decide(const DevicePlan &plan, const SchemeConst &sc, const double *state, const std::int32_t *tile_list,
+                      std::int64_t n_tiles, cudaStream_t stream);
+
 /// E2 + E3 for tile records (members through the tile's row list; equilibrium at the face Gauss points).
 template <int POWN>
 void launch_eq_tile(const DevicePlan &plan, const SchemeConst &sc, const std::int32_t *tile_list, std::int64_t n_tiles,
@@ -90,6 +94,7 @@ int launch_recon_variants(const DevicePlan &plan, const SchemeConst &sc, const d
   if (n_tiles <= 0) return 0;
   if (plan.rec2 == nullptr) return 1;
   const bool wb = sc.well_balanced != 0;
+  if (plan.eq_flag != nullptr) launch_eq_decide(plan, sc, state, tile_list, n_tiles, stream);
   if (wb) {  // E1 equilibrium solve, E2 its averages over the stencil members, E3 its values at the face points
     const unsigned g1 = (unsigned)((n_tiles * TILE + 255) / 256);
     switch (sc.eos_pow_n) {

@@ -45,7 +45,17 @@
 namespace zfvm {
 
 constexpr int TILE_MAX_WARPS = 8;       // warps per CTA the kernel is compiled for (register budget 65536 / (32 * TILE_MAX_WARPS))
-constexpr int TILE_SLOT_TARGET = 4608;  // bytes of a ring slot aimed at (two central rows of the 3D order-3 scheme)
+/// Sixteen warps per SM (128 registers) for the schemes with few accumulators (2D orders 2-3, 3D order 2) were measured
+/// and lost: 0.7-1.7 KB of spills per thread, K1 +25 % (2D order 3) to +120 % (3D order 2) -- profiles/README.md, round 2.
+__host__ __device__ constexpr int tile_max_warps(int /*nd*/, int /*deg_hi*/) { return TILE_MAX_WARPS; }
+// Ring geometry; the -D overrides exist for the measurements in scratch/build_variants.sh.
+#ifndef ZFVM_SLOT_TARGET
+#define ZFVM_SLOT_TARGET 4608
+#endif
+#ifndef ZFVM_NSLOTS
+#define ZFVM_NSLOTS 3
+#endif
+constexpr int TILE_SLOT_TARGET = ZFVM_SLOT_TARGET;  // bytes of a ring slot aimed at (two central rows of the 3D order-3 scheme)
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
 struct TileTraits {
@@ -71,7 +81,7 @@ struct TileTraits {
   static constexpr int N_GEO = (GEO_SECTION + SLOT_BYTES - 1) / SLOT_BYTES;
   static constexpr int GEO_TAIL_BYTES = GEO_SECTION - (N_GEO - 1) * SLOT_BYTES;
   static constexpr int N_SEG = N_LO + N_HI + N_GEO;
-  static constexpr int N_SLOTS = 3;                         // ring slots per warp (8 warps x 3 slots measured best on B200)
+  static constexpr int N_SLOTS = ZFVM_NSLOTS;               // ring slots per warp (8 warps x 3 slots measured best on B200)
   static constexpr int Q_STAGE = 1;                         // Gauss points staged per pass (shared memory is what limits the warps per SM)
   static constexpr int CHUNK = Q_STAGE * NVARS;             // doubles per (cell, face) block written per pass
   static constexpr int STAGE_PITCH = CHUNK | 1;
@@ -137,7 +147,7 @@ ZFVM_DEVICE void cp_async_wait_pending() {
 // the perturbation; the equilibrium background at the face Gauss points (local_reconstruction.hpp:149-163) is added by
 // the face-flux kernel from E3's table (eq_bg).
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF, typename LIDX, bool PROF, bool WB = false>
-__global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
+__global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
     recon_tile_kernel(const __grid_constant__ ReconArgs args, const __grid_constant__ SchemeConst sc,
                       const __grid_constant__ TileCfg cfg) {
   using T = TileTraits<ND, DEG_HI, DEG_LO, NS, RM0, RLO, QF>;
@@ -341,11 +351,16 @@ __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 1)
 #pragma unroll
       for (int v = 0; v < NVARS; ++v) u0[v] = table[lane * NVARS + v];
       const double ekin0 = 0.5 * (u0[1] * u0[1] + u0[2] * u0[2] + u0[3] * u0[3]) / u0[0];
-      const double eint0 = u0[4] - ekin0;
+      double rho_s = u0[0], eint0 = u0[4] - ekin0;
+      if (P.scale_state != nullptr) {  // steps_per_recompute != 1: the scale of the last compute_equilibrium
+        const double *ss = P.scale_state + 2 * (active ? cell : P.n_cells - 1);
+        rho_s = ss[0];
+        eint0 = ss[1];
+      }
       if (sc.scaling == SCALING_EULER) {
         const double p = eint0 * (sc.gamma - 1.0);
-        const double cs = sqrt(sc.gamma * p / u0[0]);
-        scale[0] = u0[0];
+        const double cs = sqrt(sc.gamma * p / rho_s);
+        scale[0] = rho_s;
         scale[1] = scale[2] = scale[3] = cs;
         scale[4] = eint0;
       } else {

@@ -54,6 +54,9 @@ class EulerParams:
     flux_bc: str = "none"  # "flux-bc": none | flux (FluxBC, boundary/flux_bc.hpp) | equilibrium (EquilibriumFluxBC)
     n_avars: int = 0  # advected scalars, AllVariables::avars (all_variables.hpp:31-35)
     heating: Optional[tuple] = None  # (rate, lower_boundary, upper_boundary) of "heating" (model/heating.hpp:54-80)
+    # LocalRCParams, "reconstruction.steps_per_recompute" / ".recompute_threshold" (euler_experiment_impl.hpp:83-90)
+    steps_per_recompute: int = 1
+    recompute_threshold: float = 0.0
 
     def to_c(self) -> ZfvmParams:
         p = ZfvmParams()
@@ -76,7 +79,8 @@ class EulerParams:
             p.gravity_p[k] = float(v)
         for k, v in enumerate(self.gravity.axis):
             p.gravity_axis[k] = float(v)
-        p.steps_per_recompute = 1
+        p.steps_per_recompute = int(self.steps_per_recompute)
+        p.recompute_threshold = float(self.recompute_threshold)
         p.keep_polynomials = int(self.keep_polynomials)
         p.flux_bc = {"none": 0, "flux": 1, "equilibrium": 2}[self.flux_bc]
         p.n_avars = int(self.n_avars)
