@@ -265,8 +265,7 @@ def test_steps_per_recompute(name, spr, threshold):
     u_ref = case.u0.copy()
     dt = 0.8 * ora.cfl_dt(u_ref, case.cfl)
     for _ in range(4):
-        _, bad = rk.step(0.0, dt)
-        assert not bad
+        rk.step(0.0, dt)
         u_ref = ora.rk_step(case.method, u_ref, dt)
     u = rk.download().cvars
     assert ctx.counters()["eq_failures"] == ora.eq_failures()
