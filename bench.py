@@ -359,7 +359,7 @@ def run_b200(args):
         t_st = time.perf_counter()
         ctx = z.CudaContext(case.grid, st, case.params, device=local_rank)
         t_ctx = time.perf_counter()
-        setup_parts = {"mesh_geometry_initial_data": round(t_case - t_setup, 1), "stencil_search_host": round(t_st - t_case, 1),
+        setup_parts = {"mesh_geometry_initial_data": round(t_case - t_setup, 1), "stencil_search_device_plus_host_indexing": round(t_st - t_case, 1),
                        "records_weights_on_device_upload": round(t_ctx - t_st, 1)}
         n_counted = int((~case.grid.is_ghost).sum())
     n = case.grid.n_cells

@@ -438,3 +438,39 @@ def test_device_built_weights_are_bit_identical_to_the_host_path(maker, env, mon
     words = host.view(np.float64)
     assert np.count_nonzero(words) > 0.05 * words.size  # the records really carry weights
     assert np.array_equal(dev, host)
+
+
+STENCIL_GRIDS = {
+    "vortex2d_o2": lambda: (cases.isentropic_vortex(n=40, order=2).grid, "2d_o2"),
+    "vortex2d_o3": lambda: (cases.isentropic_vortex(n=48, order=3).grid, "2d_o3"),
+    "vortex2d_o4": lambda: (cases.isentropic_vortex(n=40, order=4).grid, "2d_o4"),
+    "vortex2d_o5": lambda: (cases.isentropic_vortex(n=36, order=5).grid, "2d_o5"),
+    "open2d_o3": lambda: (cases.isentropic_vortex(n=30, order=3, ghost_ring_cells=0, flux_bc="flux").grid, "2d_o3"),
+    "blast3d_o2": lambda: (cases.blast_3d(n=12, order=2).grid, "3d_o2"),
+    "blast3d_o3": lambda: (cases.blast_3d(n=14, order=3).grid, "3d_o3"),
+    "blast3d_o4": lambda: (cases.blast_3d(n=12, order=4, kind="smooth").grid, "3d_o4"),
+    "open3d_o3": lambda: (cases.blast_3d(n=8, order=3, ghost_cubes=0, flux_bc="flux").grid, "3d_o3"),
+    "six_stencils": lambda: (cases.blast_3d(n=10, order=4, kind="smooth").grid, "3d_o4_six"),
+    "six_stencils_o3": lambda: (cases.blast_3d(n=10, order=4, kind="smooth").grid, "3d_o4_six_o3"),
+    "lone_biased": lambda: (cases.isentropic_vortex(n=30, order=3).grid, "2d_o2_b"),
+    "atmosphere_o3": lambda: (cases.stellar_atmosphere_3d(n=12, order=3).grid, "3d_o3"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STENCIL_GRIDS))
+def test_device_stencil_search_equals_host_search(name, monkeypatch):
+    """the stencil families selected on the device (kernels/stencil_search.cu: region growth, cone membership,
+    distance selection, rank test -- host/stencil_shared.hpp is the common source) are the host search's, array for array;
+    the cells the kernel leaves to the host (equal distances, tryhard_stencil) are a minority on jittered grids."""
+    grid, key = STENCIL_GRIDS[name]()
+    prm = WENO_PARAMS[key].stencil_family_params
+    monkeypatch.setenv("ZFVM_STENCILS", "host")
+    host = z.compute_stencil_families(grid, prm)
+    monkeypatch.setenv("ZFVM_STENCILS", "device")
+    try:
+        dev = z.compute_stencil_families(grid, prm)
+    except z.ZfvmError as e:  # (without ZFVM_STENCILS=device such a family silently takes the host search)
+        assert "too large for the device search" in str(e) and name.startswith("six_stencils")
+        pytest.skip("stencils of more than 65 cells are outside the device search's buffers")
+    for field in ("l2g", "l2g_size", "local", "order", "size", "k_high", "family_order", "n_family", "max_size"):
+        assert np.array_equal(host.array(field), dev.array(field)), field

@@ -7,10 +7,13 @@
 //   A assembly                                            lsq_solver.cpp:168-403
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <random>
 #include <stdexcept>
 
 #include "lsq_shared.hpp"
+#include "stencil_shared.hpp"
 #include "vec3.hpp"
 #include "zfvm_host.hpp"
 
@@ -18,95 +21,41 @@ namespace zfvm {
 
 namespace {
 
-struct Region {
-  int kind = 0;  // 0 full sphere, 2 triangular cone, 3 tetrahedral cone
-  Vec3 A, dB, dC, dD;
-  Vec3 nrm[3];   // inward normals of the cone's faces (the membership tests below are n . (x - A) >= 0 written out)
-  int n_planes = 0;
-  void set_planes() {
-    if (kind == 2) {
-      nrm[0] = Vec3{-dB.y, dB.x, 0.0};
-      nrm[1] = Vec3{dC.y, -dC.x, 0.0};
-      n_planes = 2;
-    } else if (kind == 3) {
-      nrm[0] = cross(dB, dC);
-      nrm[1] = cross(dC, dD);
-      nrm[2] = cross(dD, dB);
-      n_planes = 3;
-    }
-  }
-  bool is_inside(Vec3 x) const {
-    if (kind == 0) return true;
-    Vec3 dx = x - A;
-    if (kind == 2) return cross(dB, dx).z >= 0.0 && cross(dx, dC).z >= 0.0;  // cone.cpp:11-14
-    return det3(dB, dC, dx) >= 0.0 && det3(dC, dD, dx) >= 0.0 && det3(dD, dB, dx) >= 0.0;  // :23-32
-  }
-};
+using Region = sel::Cone;  // full sphere | triangular cone | tetrahedral cone (stencil_shared.hpp)
+
+}  // namespace
+
+sel::GridView make_grid_view(const HostGrid &g) {
+  sel::GridView v{};
+  v.nd = g.n_dims;
+  v.F = g.max_neighbours;
+  v.n_cells = g.n_cells;
+  v.nb = g.neighbours.data();
+  v.vi = g.vertex_indices.data();
+  v.vtx = g.vertices.data();
+  v.cc = g.cell_centers.data();
+  v.len = g.characteristic_length.data();
+  v.mom = g.moments.data();
+  v.n_mom = g.n_moments;
+  v.face_c = g.face_centers.data();
+  v.edge = g.edge_indices.data();
+  // MAX_*_RULE_DEGREE rule, stencil.cpp:178-190
+  const RefRule q = g.n_dims == 2 ? make_triangular_rule(MAX_TRIANGULAR_RULE_DEGREE) : make_tetrahedral_rule(MAX_TETRAHEDRAL_RULE_DEGREE);
+  if (q.n_points > 10) throw std::runtime_error("query rule too large");
+  v.nq = q.n_points;
+  for (int a = 0; a < q.n_points; ++a)
+    for (int b = 0; b < v.F; ++b) v.qbary[a][b] = q.bary[(size_t)a * v.F + b];
+  return v;
+}
+
+namespace {
 
 struct Selector {
   const HostGrid &g;
-  RefRule query_rule;  // MAX_*_RULE_DEGREE rule, stencil.cpp:178-190
-  explicit Selector(const HostGrid &g_)
-      : g(g_),
-        query_rule(g_.n_dims == 2 ? make_triangular_rule(MAX_TRIANGULAR_RULE_DEGREE)
-                                  : make_tetrahedral_rule(MAX_TETRAHEDRAL_RULE_DEGREE)) {}
+  sel::GridView gv;
+  explicit Selector(const HostGrid &g_) : g(g_), gv(make_grid_view(g_)) {}
 
-  bool cell_inside(const Region &region, i32 cand) const {
-    if (region.kind == 0) return true;
-    // any quadrature point or the centre inside (stencil.cpp:192-215): the tests are independent, the cheap one first
-    if (region.is_inside(g.center(cand))) return true;
-    const int F = g.max_neighbours;
-    Vec3 v[4];
-    for (int k = 0; k < F; ++k) v[k] = g.vertex(cand, k);
-    // The cone's faces are planes through its apex, n_p . (x - A) >= 0, and a query point is a convex combination of the
-    // cell's vertices (positive barycentric coordinates): its plane values are the same combination of the vertices'
-    // values.  Deciding the points from those 3 x F numbers is exact whenever a value clears zero by a margin nine orders
-    // of magnitude above the round-off of either evaluation; otherwise the cell takes the reference's point-by-point
-    // test below.  (Most tested cells touch the cone's boundary: this is where the stencil search spends its time.)
-    double h[3][4], mag[3][4];
-    const int np = region.n_planes;
-    for (int p = 0; p < np; ++p) {
-      bool all_behind = true;
-      for (int k = 0; k < F; ++k) {
-        const Vec3 dx = v[k] - region.A;
-        const double tx = region.nrm[p].x * dx.x, ty = region.nrm[p].y * dx.y, tz = region.nrm[p].z * dx.z;
-        h[p][k] = tx + ty + tz;
-        mag[p][k] = std::fabs(tx) + std::fabs(ty) + std::fabs(tz);
-        all_behind = all_behind && h[p][k] < -1e-7 * mag[p][k];
-      }
-      if (all_behind) return false;  // the whole cell lies behind one face
-    }
-    bool ambiguous = false;
-    for (int q = 0; q < query_rule.n_points && !ambiguous; ++q) {
-      const double *lam = &query_rule.bary[(size_t)q * F];
-      bool inside = true;
-      for (int p = 0; p < np; ++p) {
-        double val = 0.0, m = 0.0;
-        for (int k = 0; k < F; ++k) {
-          val += lam[k] * h[p][k];
-          m += lam[k] * mag[p][k];
-        }
-        if (val < -1e-7 * m) {
-          inside = false;
-          break;
-        }
-        if (!(val > 1e-7 * m)) {
-          ambiguous = true;
-          break;
-        }
-      }
-      if (ambiguous) break;
-      if (inside) return true;
-    }
-    if (!ambiguous) return false;
-    for (int q = 0; q < query_rule.n_points; ++q) {
-      const double *lam = &query_rule.bary[(size_t)q * F];
-      Vec3 x = v[0] * lam[0] + v[1] * lam[1] + v[2] * lam[2];
-      if (F == 4) x = x + v[3] * lam[3];
-      if (region.is_inside(x)) return true;
-    }
-    return false;
-  }
+  bool cell_inside(const Region &region, i32 cand) const { return sel::cell_inside(gv, region, cand); }
 
   void candidates(std::vector<i32> &cands, i32 i_center, int n_points, const Region &region) const {
     const int F = g.max_neighbours;
@@ -183,20 +132,7 @@ struct Selector {
     if ((int)cands.size() > n_points) cands.resize((size_t)n_points);
   }
 
-  Region make_cone(i32 i, Vec3 apex, int k) const {
-    Region r;
-    r.A = apex;
-    r.dB = g.vertex(i, relative_vertex_index(g.n_dims, k, 0)) - apex;
-    r.dC = g.vertex(i, relative_vertex_index(g.n_dims, k, 1)) - apex;
-    if (g.n_dims == 2) {
-      r.kind = 2;
-    } else {
-      r.kind = 3;
-      r.dD = g.vertex(i, relative_vertex_index(g.n_dims, k, 2)) - apex;
-    }
-    r.set_planes();
-    return r;
-  }
+  Region make_cone(i32 i, Vec3 apex, int k) const { return sel::make_cone(gv, i, sel::V3{apex.x, apex.y, apex.z}, k); }
 
   bool is_good(const i32 *s, int n, int order) const {
     std::vector<double> A;
@@ -276,43 +212,8 @@ void assemble_weno_ao_matrix(std::vector<double> &A, int &n_rows, int &n_cols, c
 // Singular values by one-sided (Hestenes) Jacobi rotations; rank with Eigen's default
 // threshold  sigma_i > sigma_max * min(rows, cols) * eps  (JacobiSVD::rank()).
 int matrix_rank(const double *A, int rows, int cols) {
-  if (rows < cols) return rows < 0 ? 0 : std::min(rows, cols - 1);  // under-determined: never full column rank
-  std::vector<double> U(A, A + (size_t)rows * cols);
-  auto col_dot = [&](int p, int q) {
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += U[(size_t)r * cols + p] * U[(size_t)r * cols + q];
-    return s;
-  };
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    bool rotated = false;
-    for (int p = 0; p < cols - 1; ++p)
-      for (int q = p + 1; q < cols; ++q) {
-        double app = col_dot(p, p), aqq = col_dot(q, q), apq = col_dot(p, q);
-        if (std::abs(apq) <= 1e-15 * std::sqrt(app * aqq) || apq == 0.0) continue;
-        rotated = true;
-        double zeta = (aqq - app) / (2.0 * apq);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
-        for (int r = 0; r < rows; ++r) {
-          double up = U[(size_t)r * cols + p], uq = U[(size_t)r * cols + q];
-          U[(size_t)r * cols + p] = c * up - s * uq;
-          U[(size_t)r * cols + q] = s * up + c * uq;
-        }
-      }
-    if (!rotated) break;
-  }
-  double smax = 0.0;
-  std::vector<double> sv((size_t)cols);
-  for (int p = 0; p < cols; ++p) {
-    sv[(size_t)p] = std::sqrt(col_dot(p, p));
-    smax = std::max(smax, sv[(size_t)p]);
-  }
-  if (smax == 0.0) return 0;
-  const double thresh = smax * std::min(rows, cols) * 2.220446049250313e-16;
-  int rank = 0;
-  for (int p = 0; p < cols; ++p)
-    if (sv[(size_t)p] > thresh) ++rank;
-  return rank;
+  std::vector<double> U(A, A + (size_t)std::max(rows, 0) * std::max(cols, 0));
+  return sel::matrix_rank_inplace(U.data(), rows, cols);
 }
 
 // W = R^{-1} Q^T by Householder QR (lsq_shared.hpp: the same code builds the weights on the device).
@@ -354,6 +255,27 @@ void compute_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyPar
   int error = 0;
   std::string error_msg;
 
+  // members from the device search where it decided them (same families: stencil_shared.hpp)
+  DeviceStencilSearch dev;
+  bool use_dev = false;
+  {
+    const char *e = std::getenv("ZFVM_STENCILS");
+    const bool force_host = e && e[0] == 'h', force_dev = e && e[0] == 'd';
+    if (!force_host && (force_dev || n >= 50000)) {
+      std::string why;
+      use_dev = device_stencil_search(g, params, dev, why);
+      if (!use_dev && force_dev) throw std::runtime_error("ZFVM_STENCILS=device: " + why);
+      if (std::getenv("ZFVM_VERBOSE")) {
+        i64 n_redo = 0;
+        if (use_dev)
+          for (i64 i = 0; i < n; ++i) n_redo += dev.redo[(size_t)i] != 0;
+        std::fprintf(stderr, "[zfvm stencils] %s%s; %lld of %lld cells left to the host search\n",
+                     use_dev ? "device search" : "host search: ", use_dev ? "" : why.c_str(), (long long)(use_dev ? n_redo : n),
+                     (long long)n);
+      }
+    }
+  }
+
 #pragma omp parallel
   {
     std::vector<i32> s;
@@ -372,13 +294,17 @@ void compute_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyPar
         size[0] = 1;
         continue;
       }
+      const bool from_dev = use_dev && !dev.redo[(size_t)i];
       std::mt19937 rng((std::uint32_t)(seed * 2654435761u + (std::uint64_t)i));
       int k_biased = 0;
       for (int k = 0; k < ns; ++k) {
         const int max_order = params.orders[(size_t)k];
         const double factor = params.overfit_factors[(size_t)k];
         const int max_size = S.max_size[(size_t)k];
-        if (params.biases[(size_t)k] == 1) {
+        if (from_dev) {
+          const i32 *m = &dev.members[(size_t)(i * dev.L + S.local_off[(size_t)k])];
+          s.assign(m, m + dev.count[(size_t)(i * ns + k)]);
+        } else if (params.biases[(size_t)k] == 1) {
           std::string err;
           if (!sel.biased(s, (i32)i, k_biased, max_size, max_order, rng, err)) {
 #pragma omp critical
@@ -390,8 +316,7 @@ void compute_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyPar
           }
           ++k_biased;
         } else {
-          Region full_sphere;
-          sel.region_stencil(s, (i32)i, max_size, full_sphere);
+          sel.region_stencil(s, (i32)i, max_size, zfvm::sel::full_sphere());
         }
         // assign_local_indices, stencil.cpp:82-104 (every found cell enters l2g)
         i32 *loc = local + S.local_off[(size_t)k];

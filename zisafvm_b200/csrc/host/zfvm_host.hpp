@@ -176,9 +176,22 @@ struct HostStencils {
   }
 };
 
-/// compute_stencil_families (stencil_family.cpp:99-117).
+/// compute_stencil_families (stencil_family.cpp:99-117).  The members are selected on the current CUDA device when there
+/// is one (kernels/stencil_search.cu; cells it leaves undecided -- equal distances, random retries -- and everything
+/// else on the host); ZFVM_STENCILS=host keeps the whole search on the host, ZFVM_STENCILS=device insists on the device
+/// also for small grids.  Both give the same families (tests/test_gpu_parity.py).
 void compute_stencils(HostStencils &s, const HostGrid &g, const StencilFamilyParams &params,
                       std::uint64_t seed = 0);
+
+/// Result of the device search: stencil k of cell i has count[i][k] members at members[i * L + local_off[k] ..];
+/// redo[i] != 0: the host search decides the cell.
+struct DeviceStencilSearch {
+  int L = 0;
+  std::vector<i32> members, count;
+  std::vector<std::uint8_t> redo;
+};
+/// false (with the reason) when there is no device or the family is outside the kernel's limits.
+bool device_stencil_search(const HostGrid &g, const StencilFamilyParams &params, DeviceStencilSearch &out, std::string &why);
 
 /// LSQ matrix of stencil k of cell i (LSQSolver ctor, lsq_solver.cpp:40-47); row-major rows x cols.
 void stencil_matrix(std::vector<double> &A, int &rows, int &cols, const HostGrid &g, const HostStencils &s,
@@ -188,6 +201,10 @@ void stencil_matrix(std::vector<double> &A, int &rows, int &cols, const HostGrid
 /// (n-1) x (dof(order-1)-1) row-major.
 void assemble_weno_ao_matrix(std::vector<double> &A, int &n_rows, int &n_cols, const HostGrid &g,
                              const i32 *stencil, int n, int order);
+
+namespace sel { struct GridView; }
+/// Raw-pointer view of the arrays the stencil search reads (stencil_shared.hpp); valid while `g` lives.
+sel::GridView make_grid_view(const HostGrid &g);
 
 /// singular values by one-sided Jacobi; used for the rank test of stencil.cpp:352.
 int matrix_rank(const double *A, int rows, int cols);
