@@ -10,4 +10,4 @@ nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler
 objs=$(ls build/kernels/*.o build/*.o build/host/*.o | grep -v "kernels/$unit.o")
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -Xcompiler -fopenmp -o ../../scratch/variants/libzfvm_$name.so $objs ../../scratch/variants/${unit}_$name.o \
   /usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a -lcudart -lgomp -ldl
-grep -A1 "recon_tile_kernelILi3ELi2ELi1ELi5ELi18ELi4ELi4EhLb0ELb0" ../../scratch/variants/${unit}_$name.ptxas.log | grep -E "registers|spill" | head -3
+grep -E "spill|registers" ../../scratch/variants/${unit}_$name.ptxas.log | sort | uniq -c | sort -rn | head -4

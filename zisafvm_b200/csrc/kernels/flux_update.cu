@@ -15,6 +15,16 @@
 #include "equilibrium.cuh"
 #include "kernels.hpp"
 
+// measured at 9.86 M tets (scratch/build_variants.sh, profiles/README.md round 2): the face frames read straight into
+// registers instead of staged through shared memory: K2 1.886 -> 1.733 ms (22 instead of 17 warps per SM);
+// update_kernel with 5 blocks per SM: no change, with 4: 0.60 -> 0.77 ms
+#ifndef ZFVM_K2_FRAMES_DIRECT
+#define ZFVM_K2_FRAMES_DIRECT 1
+#endif
+#ifndef ZFVM_K3_MIN_BLOCKS
+#define ZFVM_K3_MIN_BLOCKS 6
+#endif
+
 namespace zfvm {
 
 namespace {
@@ -232,8 +242,12 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
                                                   int pitch, std::int64_t face_begin) {
   extern __shared__ __align__(16) double flux_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+#if ZFVM_K2_FRAMES_DIRECT
+  double *tr = flux_smem + (size_t)warp * (TILE * pitch);
+#else
   double *tr = flux_smem + (size_t)warp * (TILE * pitch + TILE * 10);
   double *frs = tr + TILE * pitch;
+#endif
   const std::int64_t t0 = ((std::int64_t)blockIdx.x * wpc + warp) * TILE;
   if (t0 >= n_faces) return;
   const std::int64_t t = min(t0 + lane, n_faces - 1);
@@ -246,6 +260,18 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
     const std::int64_t ef = __shfl_sync(0xffffffffu, e, f);
     cp_async16(tr + f * pitch + part * 2, P.trace + ef * (2 * chunks) + part * 2);
   }
+#if ZFVM_K2_FRAMES_DIRECT
+  // the face frame (n, t1, t2, area: 80 bytes) straight into registers while the traces are in flight: 2.5 KB less shared
+  // memory per warp, 22 instead of 17 warps per SM
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const double2 *frg = reinterpret_cast<const double2 *>(P.face_frame + e * 10);
+  const double2 g0 = __ldg(frg), g1 = __ldg(frg + 1), g2 = __ldg(frg + 2), g3 = __ldg(frg + 3), g4 = __ldg(frg + 4);
+  const bool skip = !in_range || P.left_right[2 * e] < 0;
+  const double n[3] = {g0.x, g0.y, g1.x}, t1[3] = {g1.y, g2.x, g2.y}, t2[3] = {g3.x, g3.y, g4.x};
+  const double area = g4.y;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+#else
   for (int c = lane; c < TILE * 5; c += TILE) {
     const int f = c / 5, part = c - f * 5;
     const std::int64_t ef = __shfl_sync(0xffffffffu, e, f);
@@ -265,6 +291,7 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
     t2[d] = fr[6 + d];
   }
   const double area = fr[9];
+#endif
   double nf[NVARS] = {0.0, 0.0, 0.0, 0.0, 0.0};
   const double *trL = tr + lane * pitch;
   const double *trR = trL + sc.q_f * NVARS;
@@ -371,7 +398,7 @@ __global__ void __launch_bounds__(64) flux_face_kernel(const DevicePlan P, const
 // [n][5] arrays (state, tendencies, fluxes) is then contiguous across the warp, and a face's flux row is read by
 // five adjacent lanes.  The face fluxes are gathered in the fixed order of the cell's face list (no atomics).
 template <int F, bool FLUX_BC>
-__global__ void __launch_bounds__(320, FLUX_BC ? 3 : 6) update_kernel(const DevicePlan P, const UpdateArgs A,
+__global__ void __launch_bounds__(320, FLUX_BC ? 3 : ZFVM_K3_MIN_BLOCKS) update_kernel(const DevicePlan P, const UpdateArgs A,
                                                                       const __grid_constant__ SchemeConst sc) {
   constexpr int CELLS = 2 * TILE;
   __shared__ double s_un[CELLS * NVARS];
@@ -664,7 +691,11 @@ static void launch_flux_q(const DevicePlan &P, const SchemeConst &sc, const std:
     // doubles per staged face row: even (16-byte cp.async) with an odd number of 16-byte units, so that the 64-bit
     // reads of 32 consecutive rows spread over all banks (q_f = 3 would otherwise give a pitch of 32 doubles)
     const int pitch = 2 * ((sc.q_f * NVARS + 1) | 1);
+#if ZFVM_K2_FRAMES_DIRECT
+    const size_t smem = (size_t)wpc * (TILE * pitch) * sizeof(double);
+#else
     const size_t smem = (size_t)wpc * (TILE * pitch + TILE * 10) * sizeof(double);
+#endif
     const unsigned grid = (unsigned)((n_faces + block - 1) / block);
     const bool bg = P.eq_bg != nullptr;
     if (P.n_avars > 0) {
