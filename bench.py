@@ -413,6 +413,24 @@ def run_b200(args):
     value = total_counted * stages * args.steps / (ms_total * 1e-3)
     state_ok = not rk.step(0.0, dt, case.cfl)[1]
 
+    # The metric is per RK stage with a fixed dt.  A driver also asks for the next time step once per step (LocalCFL +
+    # SanityCheck fused into the last stage's K3, with N > 1 an ncclAllReduce(min) and a 16-byte read-back: the one
+    # latency-bound collective of the design): the same steps again with it, reported next to `value`.
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(args.steps):
+        rk.step(0.0, dt, case.cfl)
+    c1.record(stream)
+    barrier()
+    ms_cfl = c0.elapsed_time(c1)
+    if distributed:
+        tmax = torch.tensor([ms_cfl], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_cfl = float(tmax.item())
+    with_cfl = {"value": total_counted * stages * args.steps / (ms_cfl * 1e-3), "ms_per_step": ms_cfl / args.steps,
+                "what": "the same steps with dt_next = LocalCFL (+ ncclAllReduce(min) with N > 1) read back every step"}
+
     # ---- per-kernel timing for the roofline (separate pass; event pairs around every launch) ----------------
     ctx.profile(True)
     prof_steps = max(2, min(args.steps, 5))
@@ -520,10 +538,11 @@ def run_b200(args):
                     if distributed and args.scaling == "strong" else ""),
                 "cells_per_gpu": int(n), "counted_cells": int(total_counted), "stages_per_step": stages,
                 "device_bytes": int(dev_bytes), "setup_seconds": round(setup_s, 1), "setup_parts": setup_parts,
+                "time_step": "fixed dt inside the timed region; with the per-step CFL reduction: see with_cfl",
                 "l2_flush": "inputs larger than L2 (weights + state >> 126 MB per stage)",
                 "parallelism": f"domain decomposition x{world}" if distributed else "single GPU",
             },
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "with_cfl": with_cfl, "gpu_launches": int(launches),
             "clocks": clocks, "state_plausible": bool(state_ok),
         }
         if parity_check is not None:
