@@ -540,162 +540,23 @@ struct CreateClock {
   }
 };
 
-static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params) {
+// zfvm_create in phases; the members are what more than one phase needs.
+struct ContextBuilder {
+  zfvm_ctx *ctx;
+  const zfvm_params *params;
+  const HostGrid &g;
+  const HostStencils &S;
+  const int nd, F, ns;
+  const std::int64_t n, T, E, EI;
+  SchemeConst &sc;
+  DevicePlan &P;
   CreateClock clk;
-  const HostGrid &g = grid->g;
-  const HostStencils &S = stencils->s;
-  const int nd = g.n_dims, F = g.max_neighbours, ns = S.n_stencils;
-  ctx->params = *params;
-  ctx->n_dims = nd;
-  ctx->n_cells = g.n_cells;
-  ctx->n_owned = g.n_cells;
-  const std::int64_t n = g.n_cells, T = (n + TILE - 1) / TILE, E = g.n_edges, EI = g.n_interior_edges;
-  ctx->n_tiles = T;
-  ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
-  ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
-  ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
-
-  // ---- scheme constants ------------------------------------------------------------------
-  SchemeConst &sc = ctx->sc;
-  std::memset(&sc, 0, sizeof(sc));
-  sc.n_dims = nd;
-  sc.n_stencils = ns;
-  sc.q_f = g.q_f;
-  sc.q_c = g.q_c;
-  sc.recon_mode = params->recon_mode;
-  sc.scaling = params->scaling;
-  sc.flux = params->flux;
-  sc.well_balanced = params->well_balanced;
-  // the cell-local source pass (GravitySourceLoop and / or Heating) runs when either term is present; without a
-  // gravity model its potential tables stay zero
-  sc.has_gravity = params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0;
-  {
-    sc.eos_pow_e = 1.0 / (params->gamma - 1.0);
-    const double twice = 2.0 * sc.eos_pow_e, r = std::rint(twice);
-    sc.eos_pow_n = (std::fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) ? (int)r : 0;
-  }
-  sc.steps_per_recompute = params->steps_per_recompute;
-  sc.recompute_threshold = params->recompute_threshold;
-  sc.heating_rate = params->heating_rate;
-  sc.heating_r0 = params->heating_r0;
-  sc.heating_r1 = params->heating_r1;
-  ctx->n_avars = params->n_avars;
-  sc.epsilon = params->epsilon;
-  sc.exponent = params->exponent;
-  sc.gamma = params->gamma;
-  // Families the specialised kernels (tile / thread-per-cell with compile-time degrees) are built for: the shape of
-  // every parameter set the reference's experiments use -- one leading stencil of the highest order followed by
-  // n_dims + 1 stencils of order 2.  Anything else the reference's JSON can describe (first-order families, several
-  // central stencils, one-sided stencils of order 3, a lone stencil; test/.../weno_ao.cpp:47-55, cweno_ao.cpp:144-160)
-  // runs the generic kernel (kernels/recon_generic.cu), where every stencil keeps its own coefficient count.
-  ctx->deg_hi = 0;
-  for (int k = 0; k < ns; ++k) ctx->deg_hi = std::max(ctx->deg_hi, S.params.orders[(size_t)k] - 1);
-  ctx->deg_lo = 0;
-  for (int k = 1; k < ns; ++k) ctx->deg_lo = std::max(ctx->deg_lo, S.params.orders[(size_t)k] - 1);
-  bool specialised = (ns == nd + 2) && S.params.orders[0] >= 2 && S.params.orders[0] - 1 == ctx->deg_hi;
-  for (int k = 1; k < ns; ++k) specialised = specialised && S.params.orders[(size_t)k] == 2;
-  // tests: ZFVM_RECON=generic (or v1, its older name) and, for runs with source terms, ZFVM_SOURCE=v1 put a family of the
-  // specialised shape on the generic kernel as a cross-check
-  if (const char *e = std::getenv("ZFVM_RECON")) specialised = specialised && e[0] != 'g' && e[0] != 'v';
-  if (const char *e = std::getenv("ZFVM_SOURCE"))
-    specialised = specialised && !(e[0] == 'v' && (params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0));
-  ctx->generic = !specialised;
-  if ((nd == 2 && ctx->deg_hi >= 5) || (nd == 3 && ctx->deg_hi >= 4))
-    return fail("zfvm_create: LSQ matrices exist up to order 5 in 2D and 4 in 3D (lsq_solver.cpp:288,399)");
-  if (g.n_moments < poly_dof(ctx->deg_hi, nd))
-    return fail("zfvm_create: grid moments_deg is lower than the polynomial degree");
-  double wsum = 0.0;
-  for (int k = 0; k < ns; ++k) wsum += params->linear_weights[k];
-  for (int k = 0; k < ns; ++k) {
-    sc.lin_w[k] = params->linear_weights[k] / wsum;  // hybrid_weno.cpp:26-31
-    sc.rows_max[k] = S.max_size[(size_t)k] - 1;
-    if (sc.rows_max[k] > 255)
-      return fail("zfvm_create: a stencil may have at most 256 cells (8-bit row counts in the tile meta word)");
-    sc.ncoef[k] = ctx->generic ? poly_dof(S.params.orders[(size_t)k] - 1, nd) - 1
-                               : poly_dof(k == 0 ? ctx->deg_hi : ctx->deg_lo, nd) - 1;
-  }
-  // probe the dispatch now: a family no kernel is compiled for must fail here, not in the first residual evaluation
-  // (in a multi-rank run that would be after the NCCL group has been posted)
-  if (ctx->generic && !recon_generic_supported(sc, poly_dof(ctx->deg_hi, nd)))
-    return fail("zfvm_create: no reconstruction kernel for this stencil family (at most 6 stencils, order <= 5 in 2D / 4 in 3D)");
-  for (int q = 0; q < g.q_f; ++q) {
-    sc.face_w[q] = g.face_rule.weights[(size_t)q];
-    for (int b = 0; b < g.face_rule.n_bary; ++b) sc.face_bary[q][b] = g.face_rule.bary[(size_t)(q * g.face_rule.n_bary + b)];
-  }
-  for (int q = 0; q < g.q_c; ++q) {
-    sc.cell_w[q] = g.cell_rule.weights[(size_t)q];
-    for (int b = 0; b < g.cell_rule.n_bary; ++b) sc.cell_bary[q][b] = g.cell_rule.bary[(size_t)(q * g.cell_rule.n_bary + b)];
-  }
-
-  DevicePlan &P = ctx->plan;
-  std::memset(&P, 0, sizeof(P));
-  P.n_cells = n;
-  P.n_tiles = T;
-  P.n_edges = E;
-  P.n_interior_edges = EI;
-
-  clk.lap("scheme constants");
-  // ---- tile records (meta | sidx_k | W_k), built and uploaded in chunks of tiles -------------------
-  ctx->tile_max_ref.assign((size_t)T, 0);
-  for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
-  double bytes_W = 0.0, bytes_idx = 0.0, bytes_m = 0.0;
+  double bytes_W = 0.0, bytes_idx = 0.0, bytes_m = 0.0;  // of the counted (non-ghost) cells: SURVEY 8d
   std::int64_t n_counted = 0;
-  {
-    int off = TILE * (int)sizeof(std::uint64_t);
-    for (int k = 0; k < ns; ++k) {
-      P.off_sidx[k] = off;
-      off += sc.rows_max[k] * TILE * (int)sizeof(std::int32_t);
-    }
-    P.hdr_bytes = off;
-    for (int k = 0; k < ns; ++k) {
-      P.off_W[k] = off;
-      off += sc.rows_max[k] * sc.ncoef[k] * TILE * (int)sizeof(double);
-    }
-    P.rec_bytes = off;  // every section is a multiple of 128 bytes
-  }
-  // ---- tile records (kernels/recon_tile.cuh, recon_coop.cuh): header | one-sided W | central W | geometry ----------
-  // Built for every family of the specialised shape; the generic kernel reads the plainer records above.
-  bool use_tile = !ctx->generic && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
-  if (use_tile) {
-    // distinct cells read by a tile's stencils
-    std::vector<std::int32_t> n_union((size_t)T, 0);
-#pragma omp parallel
-    {
-      std::vector<std::int32_t> seen;
-#pragma omp for schedule(dynamic, 64)
-      for (std::int64_t t = 0; t < T; ++t) {
-        seen.clear();
-        for (int lane = 0; lane < TILE; ++lane) {
-          const std::int64_t i = t * TILE + lane;
-          seen.push_back((std::int32_t)std::min(i, n - 1));
-          if (i >= n) continue;
-          for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
-            if (S.order[(size_t)(i * ns + k)] <= 1) continue;
-            const int size = S.size[(size_t)(i * ns + k)];
-            for (int j = 1; j < size; ++j) seen.push_back(S.global(i, k, j));
-          }
-        }
-        std::sort(seen.begin(), seen.end());
-        // the own cells occupy 32 list entries even when the last tile repeats the last cell
-        const std::int64_t n_own_distinct = std::min<std::int64_t>(TILE, n - t * TILE);
-        n_union[(size_t)t] = (std::int32_t)((std::unique(seen.begin(), seen.end()) - seen.begin()) + (TILE - n_own_distinct));
-      }
-    }
-    int cap = TILE;
-    for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
-    cap = (cap + 31) / 32 * 32;
-    if (const char *e = std::getenv("ZFVM_TILE_MIN_CAP")) cap = std::max(cap, (std::atoi(e) + 31) / 32 * 32);  // tests: 16-bit indices
-    if (cap > 1024) {  // the shared-memory table would not fit: the generic kernel gathers through global indices
-      use_tile = false;
-      ctx->generic = true;
-    }
-    P.rec2_cap = cap;
-    clk.lap("tile row-list sizes");
-  }
-  // ---- weights on the device: the members' centres / lengths / moments, the (order -> rows) table of every stencil -------
-  const bool dev_w = weights_on_device();
-  TempDeviceBuffers temp;
+  bool use_tile = false;   // tile records (recon_tile.cuh / recon_coop.cuh) or the generic kernel's plainer records
+  bool dev_w = true;       // stencil weights built on the device (precompute.cu)
+  int D = 0;               // coefficients of the highest-order polynomial
+  TempDeviceBuffers temp;  // inputs of the weight kernel, freed when the builder goes
   LsqWeightArgs lsq{};
   struct ScratchGuard {
     double *p = nullptr;
@@ -706,23 +567,207 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
   double *&lsq_scratch = lsq_scratch_guard.p;
   std::int64_t lsq_scratch_bytes = 0;
   int n_sms = 148;
-  ZFVM_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-  if (dev_w) {
-    lsq.n_dims = nd;
-    lsq.n_stencils = ns;
-    lsq.n_moments = g.n_moments;
-    for (int k = 0; k < ns; ++k) {
-      lsq.ncoef[k] = sc.ncoef[k];
-      lsq.max_order[k] = S.params.orders[(size_t)k];
-      if (lsq.max_order[k] > 7) return fail("zfvm_create: stencil order above 7");
-      for (int o = 2; o <= lsq.max_order[k]; ++o)
-        lsq.rows_of_order[k][o] = required_stencil_size(o - 1, S.params.overfit_factors[(size_t)k], nd) - 1;
+
+  ContextBuilder(zfvm_ctx *c, const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *prm)
+      : ctx(c), params(prm), g(grid->g), S(stencils->s), nd(grid->g.n_dims), F(grid->g.max_neighbours),
+        ns(stencils->s.n_stencils), n(grid->g.n_cells), T((grid->g.n_cells + TILE - 1) / TILE), E(grid->g.n_edges),
+        EI(grid->g.n_interior_edges), sc(c->sc), P(c->plan) {}
+
+  int run() {
+    if (int rc = streams_and_scheme_constants()) return rc;
+    if (int rc = record_layouts()) return rc;
+    if (int rc = weight_kernel_inputs()) return rc;
+    if (int rc = use_tile ? tile_records() : generic_records()) return rc;
+    if (lsq_scratch) {
+      cudaFree(lsq_scratch);
+      lsq_scratch = nullptr;
     }
-    ZFVM_CUDA(temp.upload(&lsq.centers, g.cell_centers.data(), g.cell_centers.size(), ctx->stream));
-    ZFVM_CUDA(temp.upload(&lsq.length, g.characteristic_length.data(), g.characteristic_length.size(), ctx->stream));
-    ZFVM_CUDA(temp.upload(&lsq.moments, g.moments.data(), g.moments.size(), ctx->stream));
+    count_algorithmic_bytes();
+    clk.lap("records (A, pinv, pack, H2D)");
+    if (int rc = cell_geometry()) return rc;
+    if (int rc = faces_and_gravity()) return rc;
+    if (int rc = work_arrays()) return rc;
+    return finish();
   }
-  if (use_tile) {
+
+  /// streams, SchemeConst (quadrature tables, linear weights, kernel family), empty DevicePlan
+  int streams_and_scheme_constants() {
+    ctx->params = *params;
+    ctx->n_dims = nd;
+    ctx->n_cells = g.n_cells;
+    ctx->n_owned = g.n_cells;
+    ctx->n_tiles = T;
+    ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ZFVM_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    ZFVM_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+
+    // ---- scheme constants ------------------------------------------------------------------
+    std::memset(&sc, 0, sizeof(sc));
+    sc.n_dims = nd;
+    sc.n_stencils = ns;
+    sc.q_f = g.q_f;
+    sc.q_c = g.q_c;
+    sc.recon_mode = params->recon_mode;
+    sc.scaling = params->scaling;
+    sc.flux = params->flux;
+    sc.well_balanced = params->well_balanced;
+    // the cell-local source pass (GravitySourceLoop and / or Heating) runs when either term is present; without a
+    // gravity model its potential tables stay zero
+    sc.has_gravity = params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0;
+    {
+      sc.eos_pow_e = 1.0 / (params->gamma - 1.0);
+      const double twice = 2.0 * sc.eos_pow_e, r = std::rint(twice);
+      sc.eos_pow_n = (std::fabs(twice - r) <= 1e-12 * twice && r >= 2.0 && r <= 8.0) ? (int)r : 0;
+    }
+    sc.steps_per_recompute = params->steps_per_recompute;
+    sc.recompute_threshold = params->recompute_threshold;
+    sc.heating_rate = params->heating_rate;
+    sc.heating_r0 = params->heating_r0;
+    sc.heating_r1 = params->heating_r1;
+    ctx->n_avars = params->n_avars;
+    sc.epsilon = params->epsilon;
+    sc.exponent = params->exponent;
+    sc.gamma = params->gamma;
+    // Families the specialised kernels (tile / thread-per-cell with compile-time degrees) are built for: the shape of
+    // every parameter set the reference's experiments use -- one leading stencil of the highest order followed by
+    // n_dims + 1 stencils of order 2.  Anything else the reference's JSON can describe (first-order families, several
+    // central stencils, one-sided stencils of order 3, a lone stencil; test/.../weno_ao.cpp:47-55, cweno_ao.cpp:144-160)
+    // runs the generic kernel (kernels/recon_generic.cu), where every stencil keeps its own coefficient count.
+    ctx->deg_hi = 0;
+    for (int k = 0; k < ns; ++k) ctx->deg_hi = std::max(ctx->deg_hi, S.params.orders[(size_t)k] - 1);
+    ctx->deg_lo = 0;
+    for (int k = 1; k < ns; ++k) ctx->deg_lo = std::max(ctx->deg_lo, S.params.orders[(size_t)k] - 1);
+    bool specialised = (ns == nd + 2) && S.params.orders[0] >= 2 && S.params.orders[0] - 1 == ctx->deg_hi;
+    for (int k = 1; k < ns; ++k) specialised = specialised && S.params.orders[(size_t)k] == 2;
+    // tests: ZFVM_RECON=generic (or v1, its older name) and, for runs with source terms, ZFVM_SOURCE=v1 put a family of the
+    // specialised shape on the generic kernel as a cross-check
+    if (const char *e = std::getenv("ZFVM_RECON")) specialised = specialised && e[0] != 'g' && e[0] != 'v';
+    if (const char *e = std::getenv("ZFVM_SOURCE"))
+      specialised = specialised && !(e[0] == 'v' && (params->gravity_kind != GRAVITY_NONE || params->heating_rate != 0.0));
+    ctx->generic = !specialised;
+    if ((nd == 2 && ctx->deg_hi >= 5) || (nd == 3 && ctx->deg_hi >= 4))
+      return fail("zfvm_create: LSQ matrices exist up to order 5 in 2D and 4 in 3D (lsq_solver.cpp:288,399)");
+    if (g.n_moments < poly_dof(ctx->deg_hi, nd))
+      return fail("zfvm_create: grid moments_deg is lower than the polynomial degree");
+    double wsum = 0.0;
+    for (int k = 0; k < ns; ++k) wsum += params->linear_weights[k];
+    for (int k = 0; k < ns; ++k) {
+      sc.lin_w[k] = params->linear_weights[k] / wsum;  // hybrid_weno.cpp:26-31
+      sc.rows_max[k] = S.max_size[(size_t)k] - 1;
+      if (sc.rows_max[k] > 255)
+        return fail("zfvm_create: a stencil may have at most 256 cells (8-bit row counts in the tile meta word)");
+      sc.ncoef[k] = ctx->generic ? poly_dof(S.params.orders[(size_t)k] - 1, nd) - 1
+                                 : poly_dof(k == 0 ? ctx->deg_hi : ctx->deg_lo, nd) - 1;
+    }
+    // probe the dispatch now: a family no kernel is compiled for must fail here, not in the first residual evaluation
+    // (in a multi-rank run that would be after the NCCL group has been posted)
+    if (ctx->generic && !recon_generic_supported(sc, poly_dof(ctx->deg_hi, nd)))
+      return fail("zfvm_create: no reconstruction kernel for this stencil family (at most 6 stencils, order <= 5 in 2D / 4 in 3D)");
+    for (int q = 0; q < g.q_f; ++q) {
+      sc.face_w[q] = g.face_rule.weights[(size_t)q];
+      for (int b = 0; b < g.face_rule.n_bary; ++b) sc.face_bary[q][b] = g.face_rule.bary[(size_t)(q * g.face_rule.n_bary + b)];
+    }
+    for (int q = 0; q < g.q_c; ++q) {
+      sc.cell_w[q] = g.cell_rule.weights[(size_t)q];
+      for (int b = 0; b < g.cell_rule.n_bary; ++b) sc.cell_bary[q][b] = g.cell_rule.bary[(size_t)(q * g.cell_rule.n_bary + b)];
+    }
+
+    std::memset(&P, 0, sizeof(P));
+    P.n_cells = n;
+    P.n_tiles = T;
+    P.n_edges = E;
+    P.n_interior_edges = EI;
+
+    clk.lap("scheme constants");
+    return 0;
+  }
+
+  /// byte layout of either record kind; row-list capacity of the tile records
+  int record_layouts() {
+    // ---- tile records (meta | sidx_k | W_k), built and uploaded in chunks of tiles -------------------
+    ctx->tile_max_ref.assign((size_t)T, 0);
+    for (std::int64_t t = 0; t < T; ++t) ctx->tile_max_ref[(size_t)t] = (std::int32_t)(std::min(n, (t + 1) * TILE) - 1);
+    {
+      int off = TILE * (int)sizeof(std::uint64_t);
+      for (int k = 0; k < ns; ++k) {
+        P.off_sidx[k] = off;
+        off += sc.rows_max[k] * TILE * (int)sizeof(std::int32_t);
+      }
+      P.hdr_bytes = off;
+      for (int k = 0; k < ns; ++k) {
+        P.off_W[k] = off;
+        off += sc.rows_max[k] * sc.ncoef[k] * TILE * (int)sizeof(double);
+      }
+      P.rec_bytes = off;  // every section is a multiple of 128 bytes
+    }
+    // ---- tile records (kernels/recon_tile.cuh, recon_coop.cuh): header | one-sided W | central W | geometry ----------
+    // Built for every family of the specialised shape; the generic kernel reads the plainer records above.
+    use_tile = !ctx->generic && ns >= 2 && recon_tile_compiled(sc, ctx->deg_hi, ctx->deg_lo);
+    if (use_tile) {
+      // distinct cells read by a tile's stencils
+      std::vector<std::int32_t> n_union((size_t)T, 0);
+  #pragma omp parallel
+      {
+        std::vector<std::int32_t> seen;
+  #pragma omp for schedule(dynamic, 64)
+        for (std::int64_t t = 0; t < T; ++t) {
+          seen.clear();
+          for (int lane = 0; lane < TILE; ++lane) {
+            const std::int64_t i = t * TILE + lane;
+            seen.push_back((std::int32_t)std::min(i, n - 1));
+            if (i >= n) continue;
+            for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+              if (S.order[(size_t)(i * ns + k)] <= 1) continue;
+              const int size = S.size[(size_t)(i * ns + k)];
+              for (int j = 1; j < size; ++j) seen.push_back(S.global(i, k, j));
+            }
+          }
+          std::sort(seen.begin(), seen.end());
+          // the own cells occupy 32 list entries even when the last tile repeats the last cell
+          const std::int64_t n_own_distinct = std::min<std::int64_t>(TILE, n - t * TILE);
+          n_union[(size_t)t] = (std::int32_t)((std::unique(seen.begin(), seen.end()) - seen.begin()) + (TILE - n_own_distinct));
+        }
+      }
+      int cap = TILE;
+      for (std::int64_t t = 0; t < T; ++t) cap = std::max(cap, (int)n_union[(size_t)t]);
+      cap = (cap + 31) / 32 * 32;
+      if (const char *e = std::getenv("ZFVM_TILE_MIN_CAP")) cap = std::max(cap, (std::atoi(e) + 31) / 32 * 32);  // tests: 16-bit indices
+      if (cap > 1024) {  // the shared-memory table would not fit: the generic kernel gathers through global indices
+        use_tile = false;
+        ctx->generic = true;
+      }
+      P.rec2_cap = cap;
+      clk.lap("tile row-list sizes");
+    }
+    return 0;
+  }
+
+  /// what lsq_weights_kernel reads: centres, lengths, moments, the (order -> rows) table of every stencil
+  int weight_kernel_inputs() {
+    // ---- weights on the device: the members' centres / lengths / moments, the (order -> rows) table of every stencil -------
+    dev_w = weights_on_device();
+    ZFVM_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (dev_w) {
+      lsq.n_dims = nd;
+      lsq.n_stencils = ns;
+      lsq.n_moments = g.n_moments;
+      for (int k = 0; k < ns; ++k) {
+        lsq.ncoef[k] = sc.ncoef[k];
+        lsq.max_order[k] = S.params.orders[(size_t)k];
+        if (lsq.max_order[k] > 7) return fail("zfvm_create: stencil order above 7");
+        for (int o = 2; o <= lsq.max_order[k]; ++o)
+          lsq.rows_of_order[k][o] = required_stencil_size(o - 1, S.params.overfit_factors[(size_t)k], nd) - 1;
+      }
+      ZFVM_CUDA(temp.upload(&lsq.centers, g.cell_centers.data(), g.cell_centers.size(), ctx->stream));
+      ZFVM_CUDA(temp.upload(&lsq.length, g.characteristic_length.data(), g.characteristic_length.size(), ctx->stream));
+      ZFVM_CUDA(temp.upload(&lsq.moments, g.moments.data(), g.moments.size(), ctx->stream));
+    }
+    return 0;
+  }
+
+  /// tile records: header | one-sided W | central W | geometry (recon_tile.cuh, recon_coop.cuh)
+  int tile_records() {
     const int D2 = poly_dof(ctx->deg_hi, nd);
     const TileRecLayout L = tile_rec_layout(sc, nd, D2, P.rec2_cap);
     P.rec2_bytes = L.rec_bytes;
@@ -774,12 +819,12 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     for (std::int64_t t0 = 0; t0 < T; t0 += chunk, slot ^= 1) {
       const std::int64_t t1 = std::min(T, t0 + chunk);
       ZFVM_CUDA(stage.begin(slot));
-#pragma omp parallel
+  #pragma omp parallel
       {
         std::vector<double> A, W;
         std::vector<std::pair<std::int32_t, std::int32_t>> map;  // (global, local), sorted by global
         std::vector<std::int32_t> refs;
-#pragma omp for schedule(dynamic, 8)
+  #pragma omp for schedule(dynamic, 8)
         for (std::int64_t t = t0; t < t1; ++t) {
           char *rec = stage.piece(slot, 0, t - t0);
           char *rec_geo = stage.piece(slot, 1, t - t0);
@@ -897,7 +942,11 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
       }
     }
     ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
-  } else {
+    return 0;
+  }
+
+  /// records of the generic kernel: meta | global index rows | W_k
+  int generic_records() {
     char *d_rec = nullptr;
     if (dev_alloc(ctx, &d_rec, T * P.rec_bytes)) {
       return 1;
@@ -927,10 +976,10 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
     for (std::int64_t t0 = 0; t0 < T; t0 += chunk, slot ^= 1) {
       const std::int64_t t1 = std::min(T, t0 + chunk);
       ZFVM_CUDA(stage.begin(slot));
-#pragma omp parallel
+  #pragma omp parallel
       {
         std::vector<double> A, W;
-#pragma omp for schedule(dynamic, 8)
+  #pragma omp for schedule(dynamic, 8)
         for (std::int64_t t = t0; t < t1; ++t) {
           char *rec = stage.piece(slot, 0, t - t0);
           char *rec_w = dev_w ? nullptr : stage.piece(slot, 1, t - t0) - P.hdr_bytes;  // addressed with record offsets
@@ -981,240 +1030,262 @@ static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils
       }
     }
     ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  if (lsq_scratch) {
-    cudaFree(lsq_scratch);
-    lsq_scratch = nullptr;
-  }
-  for (std::int64_t i = 0; i < n; ++i) {
-    if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
-      ++n_counted;
-      bytes_m += S.l2g_size[(size_t)i];
-      for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
-        const int order = S.order[(size_t)(i * ns + k)], size = S.size[(size_t)(i * ns + k)];
-        if (order > 1) bytes_W += 8.0 * (size - 1) * (poly_dof(order - 1, nd) - 1);
-        bytes_idx += 4.0 * (size - 1);
-      }
-    }
+    return 0;
   }
 
-  clk.lap("records (A, pinv, pack, H2D)");
-  // ---- geometry -----------------------------------------------------------------------------
-  const int D = poly_dof(ctx->deg_hi, nd);
-  P.n_mom = std::max(D - 3, 0);
-  {
-    std::vector<double> vtx((size_t)(T * F * 3 * TILE), 0.0), center((size_t)(T * 3 * TILE), 0.0),
-        inv_len((size_t)(T * TILE), 1.0), volume((size_t)(T * TILE), 1.0),
-        mom((size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
-    std::vector<std::uint32_t> fref((size_t)(T * F * TILE), 0u);
-    std::vector<std::uint8_t> fslots((size_t)(T * F * TILE), 0);
-#pragma omp parallel for schedule(static)
+  void count_algorithmic_bytes() {
     for (std::int64_t i = 0; i < n; ++i) {
-      const std::int64_t t = i / TILE;
-      const int lane = (int)(i % TILE);
-      for (int k = 0; k < F; ++k) {
-        const Vec3 v = g.vertex(i, k);
-        for (int d = 0; d < 3; ++d) vtx[(size_t)(((t * F + k) * 3 + d) * TILE + lane)] = v[d];
-        const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
-        const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
-        std::uint32_t r = (std::uint32_t)e & FREF_EDGE_MASK;
-        if (iL != (std::int32_t)i) r |= FREF_SIDE;
-        if (iR != INVALID) {
-          r |= FREF_INTERIOR;
-          const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
-          if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
+      if (!(g.cell_flags[(size_t)i] & FLAG_GHOST)) {
+        ++n_counted;
+        bytes_m += S.l2g_size[(size_t)i];
+        for (int k = 0; k < S.n_family[(size_t)i]; ++k) {
+          const int order = S.order[(size_t)(i * ns + k)], size = S.size[(size_t)(i * ns + k)];
+          if (order > 1) bytes_W += 8.0 * (size - 1) * (poly_dof(order - 1, nd) - 1);
+          bytes_idx += 4.0 * (size - 1);
         }
-        fref[(size_t)((t * F + k) * TILE + lane)] = r;
-        fslots[(size_t)((t * F + k) * TILE + lane)] = g.face_vertex_slots[(size_t)(i * F + k)];
-      }
-      for (int d = 0; d < 3; ++d) center[(size_t)((t * 3 + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * i + d)];
-      inv_len[(size_t)i] = 1.0 / g.characteristic_length[(size_t)i];
-      volume[(size_t)i] = g.volumes[(size_t)i];
-      for (int m = 0; m < P.n_mom; ++m)
-        mom[(size_t)((t * P.n_mom + m) * TILE + lane)] = g.moments[(size_t)(i * g.n_moments + 3 + m)];
-    }
-    // tiles none of whose cells contributes a trace to the flux loop (ghost cells deeper than the l1 layer)
-    // are not reconstructed at all -- unless the caller wants every cell's polynomial back
-    ctx->tile_needed.assign((size_t)T, 1);
-    if (!params->keep_polynomials && !sc.has_gravity) {  // (the source loop visits every cell)
-      for (std::int64_t t = 0; t < T; ++t) {
-        bool any = false;
-        for (std::int64_t a = t * F * TILE; a < (t + 1) * F * TILE && !any; ++a) any = (fref[(size_t)a] & FREF_TRACE) != 0;
-        ctx->tile_needed[(size_t)t] = any ? 1 : 0;
       }
     }
-    if (E > (std::int64_t)FREF_EDGE_MASK) {
-      return fail("zfvm_create: too many faces for the packed face reference");
-    }
-    if (dev_upload(ctx, &P.vtx, vtx) || dev_upload(ctx, &P.center, center) || dev_upload(ctx, &P.inv_len, inv_len) ||
-        dev_upload(ctx, &P.volume, volume) || dev_upload(ctx, &P.moments, mom) || dev_upload(ctx, &P.face_ref, fref) ||
-        dev_upload(ctx, &P.face_slots, fslots) || dev_upload(ctx, &P.cell_flags, g.cell_flags)) {
-      return 1;
-    }
-    const double *inr = nullptr;
-    if (dev_upload(ctx, &inr, g.inradii)) {
-      return 1;
-    }
-    ctx->inradius = const_cast<double *>(inr);
   }
-  clk.lap("cell geometry");
-  // ---- faces ----------------------------------------------------------------------------------
-  {
-    std::vector<std::int32_t> lr((size_t)(2 * E));
-    std::vector<double> frame((size_t)(10 * E));
-#pragma omp parallel for schedule(static)
-    for (std::int64_t e = 0; e < E; ++e) {
-      std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
-      bool skip = (iR == INVALID);
-      if (!skip) skip = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
-      lr[(size_t)(2 * e)] = skip ? -1 : iL;
-      lr[(size_t)(2 * e + 1)] = iR;
-      for (int d = 0; d < 3; ++d) {
-        frame[(size_t)(10 * e + d)] = g.face_normal[(size_t)(3 * e + d)];
-        frame[(size_t)(10 * e + 3 + d)] = g.face_t1[(size_t)(3 * e + d)];
-        frame[(size_t)(10 * e + 6 + d)] = g.face_t2[(size_t)(3 * e + d)];
+
+  /// tile-interleaved cell geometry for K3 and the generic kernel, face references, tiles that need no reconstruction
+  int cell_geometry() {
+    // ---- geometry -----------------------------------------------------------------------------
+    D = poly_dof(ctx->deg_hi, nd);
+    P.n_mom = std::max(D - 3, 0);
+    {
+      std::vector<double> vtx((size_t)(T * F * 3 * TILE), 0.0), center((size_t)(T * 3 * TILE), 0.0),
+          inv_len((size_t)(T * TILE), 1.0), volume((size_t)(T * TILE), 1.0),
+          mom((size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
+      std::vector<std::uint32_t> fref((size_t)(T * F * TILE), 0u);
+      std::vector<std::uint8_t> fslots((size_t)(T * F * TILE), 0);
+  #pragma omp parallel for schedule(static)
+      for (std::int64_t i = 0; i < n; ++i) {
+        const std::int64_t t = i / TILE;
+        const int lane = (int)(i % TILE);
+        for (int k = 0; k < F; ++k) {
+          const Vec3 v = g.vertex(i, k);
+          for (int d = 0; d < 3; ++d) vtx[(size_t)(((t * F + k) * 3 + d) * TILE + lane)] = v[d];
+          const std::int64_t e = g.edge_indices[(size_t)(i * F + k)];
+          const std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+          std::uint32_t r = (std::uint32_t)e & FREF_EDGE_MASK;
+          if (iL != (std::int32_t)i) r |= FREF_SIDE;
+          if (iR != INVALID) {
+            r |= FREF_INTERIOR;
+            const bool both_ghost = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+            if (!both_ghost) r |= FREF_TRACE;  // flux_loop.hpp:82-87
+          }
+          fref[(size_t)((t * F + k) * TILE + lane)] = r;
+          fslots[(size_t)((t * F + k) * TILE + lane)] = g.face_vertex_slots[(size_t)(i * F + k)];
+        }
+        for (int d = 0; d < 3; ++d) center[(size_t)((t * 3 + d) * TILE + lane)] = g.cell_centers[(size_t)(3 * i + d)];
+        inv_len[(size_t)i] = 1.0 / g.characteristic_length[(size_t)i];
+        volume[(size_t)i] = g.volumes[(size_t)i];
+        for (int m = 0; m < P.n_mom; ++m)
+          mom[(size_t)((t * P.n_mom + m) * TILE + lane)] = g.moments[(size_t)(i * g.n_moments + 3 + m)];
       }
-      frame[(size_t)(10 * e + 9)] = g.face_area[(size_t)e];
-    }
-    if (dev_upload(ctx, &P.left_right, lr) || dev_upload(ctx, &P.face_frame, frame)) {
-      return 1;
-    }
-  }
-  // ---- gravity ----------------------------------------------------------------------------------
-  if (sc.has_gravity) {
-    double *a = nullptr, *b = nullptr, *c = nullptr;
-    if (dev_alloc(ctx, &a, n * g.q_c, true) || dev_alloc(ctx, &b, n * g.q_c * 3, true) ||
-        dev_alloc(ctx, &c, E * g.q_f, true)) {
-      return 1;
-    }
-    P.phi_cqp = a;
-    P.gradphi_cqp = b;
-    P.phi_fqp = c;
-    if (params->gravity_kind >= GRAVITY_CONSTANT && params->gravity_kind <= GRAVITY_POLYTROPE) {
-      GravityModel gm;
-      gm.kind = params->gravity_kind;
-      gm.alignment = params->gravity_alignment;
-      for (int q = 0; q < 4; ++q) gm.p[q] = params->gravity_p[q];
-      if (gm.kind == GRAVITY_POINT_MASS && params->gravity_p[2] != 0.0) {
-        // PointMassGravity(G, M, X): GM = G * M
-        gm.p[0] = params->gravity_p[0] * params->gravity_p[1];
-        gm.p[1] = params->gravity_p[2];
+      // tiles none of whose cells contributes a trace to the flux loop (ghost cells deeper than the l1 layer)
+      // are not reconstructed at all -- unless the caller wants every cell's polynomial back
+      ctx->tile_needed.assign((size_t)T, 1);
+      if (!params->keep_polynomials && !sc.has_gravity) {  // (the source loop visits every cell)
+        for (std::int64_t t = 0; t < T; ++t) {
+          bool any = false;
+          for (std::int64_t a = t * F * TILE; a < (t + 1) * F * TILE && !any; ++a) any = (fref[(size_t)a] & FREF_TRACE) != 0;
+          ctx->tile_needed[(size_t)t] = any ? 1 : 0;
+        }
       }
-      for (int d = 0; d < 3; ++d) gm.axis[d] = params->gravity_axis[d];
-      std::vector<double> h_a, h_b, h_c;
-      tabulate_gravity(gm, g, h_a, h_b, h_c);
-      ZFVM_CUDA(cudaMemcpy(a, h_a.data(), h_a.size() * sizeof(double), cudaMemcpyHostToDevice));
-      ZFVM_CUDA(cudaMemcpy(b, h_b.data(), h_b.size() * sizeof(double), cudaMemcpyHostToDevice));
-      ZFVM_CUDA(cudaMemcpy(c, h_c.data(), h_c.size() * sizeof(double), cudaMemcpyHostToDevice));
-    }
-  }
-  clk.lap("faces, gravity tables");
-  // ---- work arrays ------------------------------------------------------------------------------
-  // (+ dump blocks for the tile kernel's branch-free trace write-out)
-  if (dev_alloc(ctx, &P.trace, (std::max<std::int64_t>(EI, 1) + TRACE_DUMP_BLOCKS / 2) * 2 * g.q_f * NVARS, true) ||
-      dev_alloc(ctx, &P.flux, std::max<std::int64_t>(EI, 1) * NVARS, true) || dev_alloc(ctx, &P.source, n * NVARS, true) ||
-      dev_alloc(ctx, &ctx->eq_fail_dev, 1, true) || dev_alloc(ctx, &ctx->reduce_dev, 1, true)) {
-    return 1;
-    }
-  P.eq_fail = ctx->eq_fail_dev;
-  P.n_poly_coef = D;
-  if (P.rec2 != nullptr && sc.has_gravity) {  // the tile kernel hands the polynomial to source_kernel
-    if (dev_alloc(ctx, &P.poly_tile, T * (std::int64_t)(D + 1) * NVARS * TILE, true)) {
-      return 1;
-    }
-  }
-  if (params->keep_polynomials) {
-    if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
-      return 1;
-    }
-  }
-  {
-    std::vector<std::int32_t> tl;
-    for (std::int64_t t = 0; t < T; ++t)
-      if (ctx->tile_needed[(size_t)t]) tl.push_back((std::int32_t)t);
-    ctx->n_tiles_needed = (std::int64_t)tl.size();
-    if (ctx->n_tiles_needed < T) {
-      const std::int32_t *p = nullptr;
-      if (dev_upload(ctx, &p, tl)) {
+      if (E > (std::int64_t)FREF_EDGE_MASK) {
+        return fail("zfvm_create: too many faces for the packed face reference");
+      }
+      if (dev_upload(ctx, &P.vtx, vtx) || dev_upload(ctx, &P.center, center) || dev_upload(ctx, &P.inv_len, inv_len) ||
+          dev_upload(ctx, &P.volume, volume) || dev_upload(ctx, &P.moments, mom) || dev_upload(ctx, &P.face_ref, fref) ||
+          dev_upload(ctx, &P.face_slots, fslots) || dev_upload(ctx, &P.cell_flags, g.cell_flags)) {
         return 1;
+      }
+      const double *inr = nullptr;
+      if (dev_upload(ctx, &inr, g.inradii)) {
+        return 1;
+      }
+      ctx->inradius = const_cast<double *>(inr);
     }
-      ctx->tiles_needed = const_cast<std::int32_t *>(p);
-    }
-  }
-  if (build_host_pipe(ctx, g)) return 1;
-  ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));
-  // ghost cells (FrozenBC::count_ghost_cells)
-  {
-    std::vector<std::int32_t> gi;
-    for (std::int64_t i = 0; i < n; ++i)
-      if (g.cell_flags[(size_t)i] & FLAG_GHOST) gi.push_back((std::int32_t)i);
-    ctx->n_ghost = (std::int64_t)gi.size();
-    const std::int32_t *p = nullptr;
-    if (dev_upload(ctx, &p, gi)) {
-      return 1;
-    }
-    ctx->ghost_index = const_cast<std::int32_t *>(p);
-  }
-  // resident state / RK buffers
-  if (dev_alloc(ctx, &ctx->u_cur, n * NVARS, true) || dev_alloc(ctx, &ctx->u_tmp, n * NVARS, true) ||
-      dev_alloc(ctx, &ctx->tend_work, n * NVARS, true) || dev_alloc(ctx, &ctx->state_work, n * NVARS, true)) {
-    return 1;
-    }
-
-  // well-balanced runs: equilibrium parameters per cell and equilibrium averages per (cell, stencil row)
-  if (sc.well_balanced) {
-    int r = 0;
-    for (int k = 0; k < ns; ++k) {
-      P.eq_row0[k] = r;
-      r += sc.rows_max[k];
-    }
-    P.eq_rows = P.rec2 ? r + 1 : r;  // tile records: rows in lidx order plus one row for the cell itself
-    if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)P.eq_rows * 2 * TILE, true) ||
-        (P.rec2 && dev_alloc(ctx, &P.eq_bg, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * 2, true))) {
-      return 1;
-    }
-  }
-  // steps_per_recompute != 1: the per-cell history of LocalReconstruction (local_reconstruction.hpp:87-100).  The cached
-  // equilibrium, its averages / point values and the scale live in the arrays the equilibrium kernels write anyway.
-  if (params->steps_per_recompute != 1) {
-    if (!P.rec2)
-      return fail("zfvm_create: steps_per_recompute != 1 needs a stencil family of the experiments' shape (tile records)");
-    if (dev_alloc(ctx, &P.eq_steps, n, true) || dev_alloc(ctx, &P.scale_state, n * 2, true) ||
-        dev_alloc(ctx, &P.eq_flag, n, true)) {
-      return 1;
-    }
-  }
-  // advected scalars: traces, face fluxes, resident rows and host-entry work rows
-  P.n_avars = ctx->n_avars;
-  if (ctx->n_avars > 0) {
-    const std::int64_t na = ctx->n_avars;
-    if (dev_alloc(ctx, &P.qtrace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * na, true) ||
-        dev_alloc(ctx, &P.qflux, std::max<std::int64_t>(EI, 1) * na, true) || dev_alloc(ctx, &ctx->a_cur, n * na, true) ||
-        dev_alloc(ctx, &ctx->a_tmp, n * na, true) || dev_alloc(ctx, &ctx->tend_work_a, n * na, true) ||
-        dev_alloc(ctx, &ctx->state_work_a, n * na, true)) {
-      return 1;
-    }
+    clk.lap("cell geometry");
+    return 0;
   }
 
-  clk.lap("work arrays");
-  if (clk.on)
-    std::fprintf(stderr, "[zfvm create] %lld cells, %lld tiles, %lld reconstructed, row-list capacity %d, %lld B per tile record\n",
-                 (long long)n, (long long)T, (long long)ctx->n_tiles_needed, P.rec2_cap, (long long)P.rec2_bytes);
-  // ---- algorithmic bytes per cell and stage -----------------------------------------
-  {
-    const double nc = (double)std::max<std::int64_t>(n_counted, 1);
-    const double B_W = bytes_W / nc, B_idx = bytes_idx / nc + 4.0 * bytes_m / nc, m = bytes_m / nc;
-    const double B_state = 80.0, B_poly = 2.0 * 40.0 * D;
-    const double B_cell = 8.0 * (3 + 1 + 1 + D + 5) + (sc.has_gravity ? 8.0 * 4 * g.q_c : 0.0);
-    const double B_face = (F / 2.0) * (8.0 * (9 + 4 * g.q_f) + 8.0);
-    const double B_wb = sc.well_balanced ? 8.0 * (2 * m + 4.0 * (g.q_c + F * g.q_f)) : 0.0;
-    ctx->algorithmic_bytes = B_W + B_idx + B_state + B_poly + B_cell + B_face + B_wb;  // + B_rk added per tableau
-  }
-  if (zfvm_set_time_integration(ctx, "ssp3")) {
-    return 1;
+  /// face frames, left / right cells, gravity tables at all Gauss points
+  int faces_and_gravity() {
+    // ---- faces ----------------------------------------------------------------------------------
+    {
+      std::vector<std::int32_t> lr((size_t)(2 * E));
+      std::vector<double> frame((size_t)(10 * E));
+  #pragma omp parallel for schedule(static)
+      for (std::int64_t e = 0; e < E; ++e) {
+        std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];
+        bool skip = (iR == INVALID);
+        if (!skip) skip = (g.cell_flags[(size_t)iL] & FLAG_GHOST) && (g.cell_flags[(size_t)iR] & FLAG_GHOST);
+        lr[(size_t)(2 * e)] = skip ? -1 : iL;
+        lr[(size_t)(2 * e + 1)] = iR;
+        for (int d = 0; d < 3; ++d) {
+          frame[(size_t)(10 * e + d)] = g.face_normal[(size_t)(3 * e + d)];
+          frame[(size_t)(10 * e + 3 + d)] = g.face_t1[(size_t)(3 * e + d)];
+          frame[(size_t)(10 * e + 6 + d)] = g.face_t2[(size_t)(3 * e + d)];
+        }
+        frame[(size_t)(10 * e + 9)] = g.face_area[(size_t)e];
+      }
+      if (dev_upload(ctx, &P.left_right, lr) || dev_upload(ctx, &P.face_frame, frame)) {
+        return 1;
+      }
     }
-  ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+    // ---- gravity ----------------------------------------------------------------------------------
+    if (sc.has_gravity) {
+      double *a = nullptr, *b = nullptr, *c = nullptr;
+      if (dev_alloc(ctx, &a, n * g.q_c, true) || dev_alloc(ctx, &b, n * g.q_c * 3, true) ||
+          dev_alloc(ctx, &c, E * g.q_f, true)) {
+        return 1;
+      }
+      P.phi_cqp = a;
+      P.gradphi_cqp = b;
+      P.phi_fqp = c;
+      if (params->gravity_kind >= GRAVITY_CONSTANT && params->gravity_kind <= GRAVITY_POLYTROPE) {
+        GravityModel gm;
+        gm.kind = params->gravity_kind;
+        gm.alignment = params->gravity_alignment;
+        for (int q = 0; q < 4; ++q) gm.p[q] = params->gravity_p[q];
+        if (gm.kind == GRAVITY_POINT_MASS && params->gravity_p[2] != 0.0) {
+          // PointMassGravity(G, M, X): GM = G * M
+          gm.p[0] = params->gravity_p[0] * params->gravity_p[1];
+          gm.p[1] = params->gravity_p[2];
+        }
+        for (int d = 0; d < 3; ++d) gm.axis[d] = params->gravity_axis[d];
+        std::vector<double> h_a, h_b, h_c;
+        tabulate_gravity(gm, g, h_a, h_b, h_c);
+        ZFVM_CUDA(cudaMemcpy(a, h_a.data(), h_a.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ZFVM_CUDA(cudaMemcpy(b, h_b.data(), h_b.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ZFVM_CUDA(cudaMemcpy(c, h_c.data(), h_c.size() * sizeof(double), cudaMemcpyHostToDevice));
+      }
+    }
+    clk.lap("faces, gravity tables");
+    return 0;
+  }
+
+  /// traces, fluxes, sources, equilibrium tables, resident state, scalars
+  int work_arrays() {
+    // ---- work arrays ------------------------------------------------------------------------------
+    // (+ dump blocks for the tile kernel's branch-free trace write-out)
+    if (dev_alloc(ctx, &P.trace, (std::max<std::int64_t>(EI, 1) + TRACE_DUMP_BLOCKS / 2) * 2 * g.q_f * NVARS, true) ||
+        dev_alloc(ctx, &P.flux, std::max<std::int64_t>(EI, 1) * NVARS, true) || dev_alloc(ctx, &P.source, n * NVARS, true) ||
+        dev_alloc(ctx, &ctx->eq_fail_dev, 1, true) || dev_alloc(ctx, &ctx->reduce_dev, 1, true)) {
+      return 1;
+      }
+    P.eq_fail = ctx->eq_fail_dev;
+    P.n_poly_coef = D;
+    if (P.rec2 != nullptr && sc.has_gravity) {  // the tile kernel hands the polynomial to source_kernel
+      if (dev_alloc(ctx, &P.poly_tile, T * (std::int64_t)(D + 1) * NVARS * TILE, true)) {
+        return 1;
+      }
+    }
+    if (params->keep_polynomials) {
+      if (dev_alloc(ctx, &P.poly, n * D * NVARS, true) || dev_alloc(ctx, &P.poly_scale, n * NVARS, true)) {
+        return 1;
+      }
+    }
+    {
+      std::vector<std::int32_t> tl;
+      for (std::int64_t t = 0; t < T; ++t)
+        if (ctx->tile_needed[(size_t)t]) tl.push_back((std::int32_t)t);
+      ctx->n_tiles_needed = (std::int64_t)tl.size();
+      if (ctx->n_tiles_needed < T) {
+        const std::int32_t *p = nullptr;
+        if (dev_upload(ctx, &p, tl)) {
+          return 1;
+      }
+        ctx->tiles_needed = const_cast<std::int32_t *>(p);
+      }
+    }
+    if (build_host_pipe(ctx, g)) return 1;
+    ZFVM_CUDA(cudaMallocHost((void **)&ctx->reduce_host, sizeof(ReduceOut)));
+    // ghost cells (FrozenBC::count_ghost_cells)
+    {
+      std::vector<std::int32_t> gi;
+      for (std::int64_t i = 0; i < n; ++i)
+        if (g.cell_flags[(size_t)i] & FLAG_GHOST) gi.push_back((std::int32_t)i);
+      ctx->n_ghost = (std::int64_t)gi.size();
+      const std::int32_t *p = nullptr;
+      if (dev_upload(ctx, &p, gi)) {
+        return 1;
+      }
+      ctx->ghost_index = const_cast<std::int32_t *>(p);
+    }
+    // resident state / RK buffers
+    if (dev_alloc(ctx, &ctx->u_cur, n * NVARS, true) || dev_alloc(ctx, &ctx->u_tmp, n * NVARS, true) ||
+        dev_alloc(ctx, &ctx->tend_work, n * NVARS, true) || dev_alloc(ctx, &ctx->state_work, n * NVARS, true)) {
+      return 1;
+      }
+
+    // well-balanced runs: equilibrium parameters per cell and equilibrium averages per (cell, stencil row)
+    if (sc.well_balanced) {
+      int r = 0;
+      for (int k = 0; k < ns; ++k) {
+        P.eq_row0[k] = r;
+        r += sc.rows_max[k];
+      }
+      P.eq_rows = P.rec2 ? r + 1 : r;  // tile records: rows in lidx order plus one row for the cell itself
+      if (dev_alloc(ctx, &P.eq_par, n * 4, true) || dev_alloc(ctx, &P.eq_avg, T * (std::int64_t)P.eq_rows * 2 * TILE, true) ||
+          (P.rec2 && dev_alloc(ctx, &P.eq_bg, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * 2, true))) {
+        return 1;
+      }
+    }
+    // steps_per_recompute != 1: the per-cell history of LocalReconstruction (local_reconstruction.hpp:87-100).  The cached
+    // equilibrium, its averages / point values and the scale live in the arrays the equilibrium kernels write anyway.
+    if (params->steps_per_recompute != 1) {
+      if (!P.rec2)
+        return fail("zfvm_create: steps_per_recompute != 1 needs a stencil family of the experiments' shape (tile records)");
+      if (dev_alloc(ctx, &P.eq_steps, n, true) || dev_alloc(ctx, &P.scale_state, n * 2, true) ||
+          dev_alloc(ctx, &P.eq_flag, n, true)) {
+        return 1;
+      }
+    }
+    // advected scalars: traces, face fluxes, resident rows and host-entry work rows
+    P.n_avars = ctx->n_avars;
+    if (ctx->n_avars > 0) {
+      const std::int64_t na = ctx->n_avars;
+      if (dev_alloc(ctx, &P.qtrace, std::max<std::int64_t>(EI, 1) * 2 * g.q_f * na, true) ||
+          dev_alloc(ctx, &P.qflux, std::max<std::int64_t>(EI, 1) * na, true) || dev_alloc(ctx, &ctx->a_cur, n * na, true) ||
+          dev_alloc(ctx, &ctx->a_tmp, n * na, true) || dev_alloc(ctx, &ctx->tend_work_a, n * na, true) ||
+          dev_alloc(ctx, &ctx->state_work_a, n * na, true)) {
+        return 1;
+      }
+    }
+
+    clk.lap("work arrays");
+    if (clk.on)
+      std::fprintf(stderr, "[zfvm create] %lld cells, %lld tiles, %lld reconstructed, row-list capacity %d, %lld B per tile record\n",
+                   (long long)n, (long long)T, (long long)ctx->n_tiles_needed, P.rec2_cap, (long long)P.rec2_bytes);
+    return 0;
+  }
+
+  /// algorithmic bytes per cell and stage, default tableau
+  int finish() {
+    // ---- algorithmic bytes per cell and stage -----------------------------------------
+    {
+      const double nc = (double)std::max<std::int64_t>(n_counted, 1);
+      const double B_W = bytes_W / nc, B_idx = bytes_idx / nc + 4.0 * bytes_m / nc, m = bytes_m / nc;
+      const double B_state = 80.0, B_poly = 2.0 * 40.0 * D;
+      const double B_cell = 8.0 * (3 + 1 + 1 + D + 5) + (sc.has_gravity ? 8.0 * 4 * g.q_c : 0.0);
+      const double B_face = (F / 2.0) * (8.0 * (9 + 4 * g.q_f) + 8.0);
+      const double B_wb = sc.well_balanced ? 8.0 * (2 * m + 4.0 * (g.q_c + F * g.q_f)) : 0.0;
+      ctx->algorithmic_bytes = B_W + B_idx + B_state + B_poly + B_cell + B_face + B_wb;  // + B_rk added per tableau
+    }
+    if (zfvm_set_time_integration(ctx, "ssp3")) {
+      return 1;
+      }
+    ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+};
+
+static int create_impl(zfvm_ctx *ctx, const zfvm_grid *grid, const zfvm_stencils *stencils, const zfvm_params *params) {
+  ContextBuilder b(ctx, grid, stencils, params);
+  return b.run();
 }
 
 void zfvm_destroy(zfvm_ctx *ctx) {
