@@ -249,6 +249,7 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
     const int k1_launches = (ctx->n_ranks > 1 && ctx->nccl_comm) ? 2 : 1;
     if (ctx->sc.well_balanced) ctx->launches += k1_launches * (ctx->plan.rec2 ? 4 : 2);  // E1, E2 (+ E3, S1 with tile records)
     else if (ctx->sc.has_gravity && ctx->plan.rec2) ctx->launches += k1_launches;        // S1
+    if (ctx->plan.eq_flag != nullptr) ctx->launches += k1_launches;                      // E0
   }
   prof_mark(ctx, 0);
   if (ctx->n_avars > 0) {
