@@ -55,6 +55,9 @@ __host__ __device__ constexpr int tile_max_warps(int /*nd*/, int /*deg_hi*/) { r
 #ifndef ZFVM_NSLOTS
 #define ZFVM_NSLOTS 3
 #endif
+#ifndef ZFVM_Q_STAGE
+#define ZFVM_Q_STAGE 1
+#endif
 constexpr int TILE_SLOT_TARGET = ZFVM_SLOT_TARGET;  // bytes of a ring slot aimed at (two central rows of the 3D order-3 scheme)
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
@@ -82,7 +85,7 @@ struct TileTraits {
   static constexpr int GEO_TAIL_BYTES = GEO_SECTION - (N_GEO - 1) * SLOT_BYTES;
   static constexpr int N_SEG = N_LO + N_HI + N_GEO;
   static constexpr int N_SLOTS = ZFVM_NSLOTS;               // ring slots per warp (8 warps x 3 slots measured best on B200)
-  static constexpr int Q_STAGE = 1;                         // Gauss points staged per pass (shared memory is what limits the warps per SM)
+  static constexpr int Q_STAGE = (QF % ZFVM_Q_STAGE == 0) ? ZFVM_Q_STAGE : 1;                         // Gauss points staged per pass (shared memory is what limits the warps per SM)
   static constexpr int CHUNK = Q_STAGE * NVARS;             // doubles per (cell, face) block written per pass
   static constexpr int STAGE_PITCH = CHUNK | 1;
   static constexpr int STAGE_BYTES = (TILE * STAGE_PITCH * 8 + 127) / 128 * 128;
