@@ -55,6 +55,10 @@ CONFIGS = [
     ("default again", {}),
     ("l2_ahead 4608 again", {"ZFVM_TILE_L2_AHEAD": "4608"}),
 ]
+if os.environ.get("ZFVM_KNOB_L2_WHOLE"):
+    CONFIGS = [("default", {}), ("whole record prefetch", {"ZFVM_TILE_L2_WHOLE": "1"}),
+               ("whole record prefetch, no per-segment prefetch", {"ZFVM_TILE_L2_WHOLE": "1", "ZFVM_TILE_L2_AHEAD": "0"}),
+               ("default again", {}), ("whole again", {"ZFVM_TILE_L2_WHOLE": "1", "ZFVM_TILE_L2_AHEAD": "0"})]
 if os.environ.get("ZFVM_KNOB_DEFAULT_ONLY"):
     CONFIGS = [(os.environ["ZFVM_KNOB_DEFAULT_ONLY"], {})] * 2
 if os.environ.get("ZFVM_TILE_PROF"):

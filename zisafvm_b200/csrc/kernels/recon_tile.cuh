@@ -101,6 +101,7 @@ struct TileCfg {
   int evict_normal;          // L2 policy of the record copies: 0 evict-first (default), 1 evict-normal
   int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off)
   int l2_gran;               // bytes covered by one lane's prefetch (experiment: 128 = line, 32 = sector)
+  int l2_whole;              // experiment: one bulk L2 prefetch of the whole next record at the start of a tile
   int stream_bytes;          // bytes of a record's W | geometry stream (rec_bytes - off_wlo)
   int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
     __syncwarp();
     issue_list(m + 1);
     nxt_ptr = has_tile(m + 1) ? cfg.rec + tile_of(m + 1) * cfg.rec_bytes + cfg.off_wlo : nullptr;
+    if (cfg.l2_whole) ptx::bulk_prefetch_l2_if(nxt_ptr != nullptr && lane == 0, nxt_ptr, (std::uint32_t)cfg.stream_bytes);
     ptx::cp_async_wait_all();  // (the segments in flight were issued before the previous tile's trace phase)
     __syncwarp();  // the table and the index rows of tile m are complete and visible to the whole warp
     mark(TP_TABLE_WAIT);
@@ -821,6 +823,7 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   c.evict_normal = 0;
   c.l2_ahead = T::SLOT_BYTES;  // measured at the bench size: K1 -1 .. -4 %; 2, 4, 8 slots ahead: none or worse
   c.l2_gran = 128;
+  c.l2_whole = 0;
   c.stream_bytes = (int)(L.rec_bytes - L.off_wlo);
   return true;
 }
