@@ -227,7 +227,11 @@ int zfvm_set_frozen_bc_av(zfvm_ctx *ctx, const double *steady_state_host, const 
  * cfl_number * min inradius/(|v|+a) (LocalCFL, model/local_cfl_condition_impl.hpp:25-40) and the
  * SanityCheckFor<Euler> flag of the new state come back with it (one 16-byte D2H copy). */
 int zfvm_rk_step(zfvm_ctx *ctx, double t, double dt, double cfl_number, double *dt_next, int *not_plausible);
-/* Same with host buffers: u0_host -> u1_host (one H2D + one D2H copy of the state). */
+/* Same with host buffers: u0_host -> u1_host (one H2D + one D2H copy of the state).  Grids of a million cells and more
+ * take a chunked route -- the rows go up in chunks that gate the stage-0 reconstruction of the tiles they complete, the
+ * last stage is finished and sent back chunk by chunk -- with bit-identical results; in a multi-rank context the route
+ * posts the same halo exchanges (one per stage) as the plain sequence, after the last upload of stage 0 and ahead of the
+ * last stage's chunks, so ranks may mix the two routes. */
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double t, double dt);
 int zfvm_rk_step_host_av(zfvm_ctx *ctx, const double *u0_host, const double *a0_host, double *u1_host, double *a1_host,
                          double t, double dt);

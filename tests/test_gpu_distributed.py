@@ -209,3 +209,68 @@ def test_two_gpu_well_balanced_matches_single_domain_oracle(tmp_path):
         assert (np.abs(u - u_ref[gid]).max(axis=0) / scale).max() < 1e-11, r
         assert (np.abs(a - a_ref[gid]).max(axis=0) / np.abs(a_ref).max(axis=0)).max() < 1e-11, r
         assert np.allclose(np.load(tmp_path / f"dt_{r}.npy"), dts, rtol=1e-11, atol=0)
+
+
+def _worker_host_step(rank, world, port, partition):
+    """compute_step with host buffers in a decomposed run: the chunked route (uploads gating the interior tiles, the halo
+    exchange posted once every row is up, last stage finished and downloaded chunk by chunk) against the resident step."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      ZFVM_HOST_PIPELINE_MIN_CELLS="0", ZFVM_HOST_CHUNKS="5")
+    import torch
+    import torch.distributed as dist
+
+    import zisafvm_b200 as z
+    from zisafvm_b200 import distributed as zd
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        if partition == "sfc_wb":
+            run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind="atmosphere", device=rank)
+        elif partition == "sfc":
+            run = zd.make_strong_scaling_case(rank, world, n=N_SFC, order=ORDER, kind=KIND, device=rank)
+        else:
+            run = zd.make_weak_scaling_case(rank, world, n=N_PER_RANK, order=ORDER, kind=KIND, device=rank)
+        sub, case, ctx = run.sub, run.case, run.ctx
+        n, no = sub.n_local, sub.n_owned
+        z.FrozenBC(ctx, z.AllVariables(n, case.u0))
+        u0 = case.u0.copy()
+        u0[no:] = 1e300  # halo rows must come from the exchange, not from the upload
+        for method in (case.method, "forward_euler", "rk4"):
+            rk = z.CudaRungeKutta(ctx, method)
+            rk.upload(z.AllVariables(n, u0))
+            dt, bad = z.LocalCFL(ctx, CFL)()
+            l0 = ctx.counters()["launches"]
+            rk.step(0.0, dt)
+            rk.step(dt, dt)
+            l1 = ctx.counters()["launches"]
+            a2 = rk.download().cvars.copy()
+            h0 = torch.from_numpy(u0.copy()).pin_memory().numpy()
+            h1 = torch.full((n, 5), float("nan"), dtype=torch.float64).pin_memory().numpy()
+            h2 = np.full((n, 5), np.nan)   # pageable destination
+            rk.compute_step(z.AllVariables(n, h0), 0.0, dt, out=z.AllVariables(n, h1))
+            rk.compute_step(z.AllVariables(n, h1), dt, dt, out=z.AllVariables(n, h2))
+            l2 = ctx.counters()["launches"]
+            assert np.array_equal(h2[:no], a2[:no]), (method, np.abs(h2[:no] - a2[:no]).max())
+            assert np.isfinite(h2).all() and np.abs(h2).max() < 1e200, method   # halo rows of the result: exchanged values
+            assert np.array_equal(rk.download().cvars[:no], a2[:no]), method     # the resident state is the step's result
+            assert l2 - l1 > l1 - l0, (method, l0, l1, l2)                       # the chunked route really ran
+        ctx.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("partition", ["lattice", "sfc", "sfc_wb"])
+def test_two_gpu_host_step_matches_resident_step(partition):
+    """zfvm_rk_step_host of a multi-rank context takes the chunked, copy-overlapped route too: bit-identical owned rows to
+    upload + zfvm_rk_step + download for three-, one- and four-stage tableaux (lattice boxes, ragged SFC chunks, the
+    well-balanced kernels per tile list), the same number of NCCL groups per step on every rank."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker_host_step, args=(2, _free_port(), partition), nprocs=2, join=True)

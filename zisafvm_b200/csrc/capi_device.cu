@@ -218,6 +218,15 @@ int run_recon(zfvm_ctx *ctx, const double *state, const std::int32_t *tiles, std
   return launch_recon(ctx->plan, ctx->sc, ctx->deg_hi, ctx->deg_lo, state, tiles, n_tiles, ctx->stream);
 }
 
+// kernels behind one run_recon call: K1 itself plus the equilibrium / source kernels that follow the same tile list
+int recon_group_launches(const zfvm_ctx *ctx) {
+  int n = 1;
+  if (ctx->sc.well_balanced) n += ctx->plan.rec2 ? 4 : 2;          // E1, E2 (+ E3, S1 with tile records)
+  else if (ctx->sc.has_gravity && ctx->plan.rec2) n += 1;          // S1
+  if (ctx->plan.eq_flag != nullptr) n += 1;                        // E0
+  return n;
+}
+
 void prof_mark(zfvm_ctx *ctx, int which) {
   if (!ctx->prof_enabled) return;
   if (ctx->prof_events[which].size() >= 2 * 16384) return;  // bounded: profiling left on keeps the first 16 k residuals
@@ -239,17 +248,11 @@ int residual(zfvm_ctx *ctx, const double *state, const UpdateArgs &upd, const do
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
     rc = run_recon(ctx, state, ctx->tiles_exterior, ctx->n_tiles_exterior);
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
-    ctx->launches += 2;
+    ctx->launches += 2 * recon_group_launches(ctx);
   } else {
     rc = run_recon(ctx, state, ctx->tiles_needed, ctx->n_tiles_needed);
     if (rc) return fail("no reconstruction kernel is compiled for this scheme");
-    ctx->launches += 1;
-  }
-  {
-    const int k1_launches = (ctx->n_ranks > 1 && ctx->nccl_comm) ? 2 : 1;
-    if (ctx->sc.well_balanced) ctx->launches += k1_launches * (ctx->plan.rec2 ? 4 : 2);  // E1, E2 (+ E3, S1 with tile records)
-    else if (ctx->sc.has_gravity && ctx->plan.rec2) ctx->launches += k1_launches;        // S1
-    if (ctx->plan.eq_flag != nullptr) ctx->launches += k1_launches;                      // E0
+    ctx->launches += recon_group_launches(ctx);
   }
   prof_mark(ctx, 0);
   if (ctx->n_avars > 0) {
@@ -1420,7 +1423,7 @@ static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const 
     if (nt > 0) {
       if (run_recon(ctx, ctx->state_work, H.up_tiles + H.up_off[(size_t)c], nt))
         return fail("no reconstruction kernel is compiled for this scheme");
-      ctx->launches += 1;
+      ctx->launches += recon_group_launches(ctx);
     }
   }
   if (accumulate) {  // the caller's tendency rows: behind the state on the copy stream, needed by the update kernel only
@@ -1449,12 +1452,13 @@ static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const 
   return 0;
 }
 
-static bool host_pipeline_enabled(const zfvm_ctx *ctx) {
+static bool host_pipeline_enabled(const zfvm_ctx *ctx, bool allow_multi_rank = false) {
   static const bool off = [] {
     const char *e = std::getenv("ZFVM_HOST_PIPELINE");
     return e != nullptr && e[0] == '0';
   }();
-  return ctx->pipe.n_chunks > 0 && ctx->n_ranks == 1 && !off;
+  // (multi-rank contexts: the chunked time step posts its own halo exchanges; the chunked RateOfChange::compute does not)
+  return ctx->pipe.n_chunks > 0 && (ctx->n_ranks == 1 || allow_multi_rank) && !off;
 }
 
 int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate) {
@@ -1751,10 +1755,27 @@ static void flux_and_update(zfvm_ctx *ctx, const double *state, UpdateArgs A, st
 // chunks while stage 0 reconstructs the tiles whose rows have landed; the last stage finishes chunk after chunk and every
 // finished chunk goes down while the next one is computed.  Same kernels on the same data as the plain sequence: the
 // result is bit-identical (tests/test_gpu_parity.py::test_compute_step_host_matches_resident).
+//
+// Multi-rank contexts (local numbering: owned rows first, then the halo rows): a tile whose stencils read a halo row
+// becomes ready with a chunk that holds halo rows (tile_max_ref >= n_owned), so the chunks in front of the first such
+// chunk `c_halo` gate interior tiles only.  Stage 0 reconstructs those while the rest goes up, then posts the halo
+// exchange (HaloExchange::operator(), the same NCCL group as in residual()) and reconstructs what is left in one launch;
+// the last stage exchanges first and then finishes the chunks that hold owned rows.  Every rank posts exactly one
+// exchange per stage, as in the plain sequence, whether or not it takes this route.
 static int rk_step_host_pipelined(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double dt) {
   zfvm_ctx::HostPipe &H = ctx->pipe;
   const int C = H.n_chunks, S = ctx->n_stages;
   const std::int64_t EI = ctx->plan.n_interior_edges;
+  const bool multi = ctx->n_ranks > 1 && ctx->nccl_comm != nullptr;
+  const std::int64_t n_upd = (ctx->n_ranks > 1) ? ctx->n_owned : ctx->n_cells;  // rows the update kernel writes (base_update_args)
+  int c_halo = C;  // first chunk that holds a halo row
+  if (multi)
+    for (int c = C - 1; c >= 0; --c)
+      if (H.cell_begin[(size_t)c + 1] > ctx->n_owned) c_halo = c;
+  auto exchange = [&](const double *state) -> int {
+    if (zfvm_halo_post_internal(ctx, const_cast<double *>(state), nullptr)) return 1;
+    return zfvm_halo_wait_internal(ctx);
+  };
   ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));  // whatever still reads or writes the resident state is done
   // ---- stage 0: upload chunk c, then the tiles chunk c completes ------------------------------------------------------
   for (int c = 0; c < C; ++c) {
@@ -1763,25 +1784,46 @@ static int rk_step_host_pipelined(zfvm_ctx *ctx, const double *u0_host, double *
     ZFVM_CUDA(cudaEventRecord(H.ev_up[(size_t)c], ctx->copy_stream));
     ZFVM_CUDA(cudaStreamWaitEvent(ctx->stream, H.ev_up[(size_t)c], 0));
     const std::int64_t nt = H.up_off[(size_t)c + 1] - H.up_off[(size_t)c];
-    if (nt > 0) {
+    if (nt > 0 && c < c_halo) {
       if (run_recon(ctx, ctx->u_cur, H.up_tiles + H.up_off[(size_t)c], nt))
         return fail("no reconstruction kernel is compiled for this scheme");
-      ctx->launches += 1;
+      ctx->launches += recon_group_launches(ctx);
+    }
+  }
+  if (multi) {  // every row is up: exchange, then the tiles that waited for a chunk with halo rows
+    if (exchange(ctx->u_cur)) return 1;
+    const std::int64_t nt = H.up_off[(size_t)C] - H.up_off[(size_t)c_halo];
+    if (nt > 0) {
+      if (run_recon(ctx, ctx->u_cur, H.up_tiles + H.up_off[(size_t)c_halo], nt))
+        return fail("no reconstruction kernel is compiled for this scheme");
+      ctx->launches += recon_group_launches(ctx);
     }
   }
   auto finish_in_chunks = [&](int s, const double *in, double *out) -> int {
     // (K1 of the stage is done for s == 0 and S == 1; otherwise it runs chunk by chunk here)
     UpdateArgs A = stage_update_args(ctx, s, dt, false);
     A.u_next = out;
+    if (multi) {
+      if (s > 0 && exchange(in)) return 1;
+      // the update kernel writes owned rows only: the halo rows of the result buffer are those of the stage's input,
+      // as in the plain sequence (where the result is written into the buffer the exchange has just filled)
+      const std::int64_t h0 = ctx->n_owned * NVARS, h1 = ctx->n_cells * NVARS;
+      if (h1 > h0)
+        ZFVM_CUDA(cudaMemcpyAsync(out + h0, in + h0, (size_t)(h1 - h0) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     for (int c = 0; c < C; ++c) {
+      if (H.cell_begin[(size_t)c] >= n_upd) {  // a chunk of halo rows: nothing to compute, it only travels
+        ZFVM_CUDA(cudaEventRecord(H.ev_dn[(size_t)c], ctx->stream));
+        continue;
+      }
       const std::int64_t nt = H.dn_off[(size_t)c + 1] - H.dn_off[(size_t)c];
       if (s > 0 && nt > 0) {
         if (run_recon(ctx, in, H.dn_tiles + H.dn_off[(size_t)c], nt)) return fail("no reconstruction kernel is compiled for this scheme");
-        ctx->launches += 1;
+        ctx->launches += recon_group_launches(ctx);
       }
       UpdateArgs Ac = A;
       Ac.block_begin = H.cell_begin[(size_t)c] / 64;
-      Ac.n_cells_update = H.cell_begin[(size_t)c + 1];
+      Ac.n_cells_update = std::min(H.cell_begin[(size_t)c + 1], n_upd);
       flux_and_update(ctx, in, Ac, H.face_begin[(size_t)c], H.face_begin[(size_t)c + 1]);
       ZFVM_CUDA(cudaEventRecord(H.ev_dn[(size_t)c], ctx->stream));
     }
@@ -1811,7 +1853,7 @@ static int rk_step_host_pipelined(zfvm_ctx *ctx, const double *u0_host, double *
 
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double /*t*/, double dt) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
-  if (host_pipeline_enabled(ctx) && ctx->n_stages >= 1) return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
+  if (host_pipeline_enabled(ctx, true) && ctx->n_stages >= 1) return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
   if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes)) return 1;
   if (rk_step_impl(ctx, dt, false)) return 1;

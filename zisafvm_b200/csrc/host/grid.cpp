@@ -256,6 +256,7 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
   g.q_c = g.cell_rule.n_points;
   g.q_f = g.face_rule.n_points;
   g.n_moments = poly_dof(deg.moments_deg, n_dims);
+  if (deg.moments_deg > 8 || mom_rule.n_points > 16) throw std::runtime_error("moment rule beyond the compiled bounds (degree 8, 16 points)");
 
   g.volumes.resize((size_t)n);
   g.inradii.resize((size_t)n);
@@ -288,11 +289,17 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
     double mp[3 * 16], mw[16];
     denormalize(mom_rule, v, cg.volume, mp, mw);
     Vec3 mc = rule_barycenter(mom_rule.n_points, mp, mw, cg.volume);
+    // powers of the centred coordinates, formed once per point (the same std::pow calls cell.cpp:17-27 makes for every
+    // monomial: 3 (deg + 1) of them per point instead of 3 per point and monomial)
+    constexpr int MAX_MOM_DEG = 8;
+    double pw[16][3][MAX_MOM_DEG + 1];
+    for (int q = 0; q < mom_rule.n_points; ++q) {
+      const double xyz[3] = {mp[3 * q] - mc.x, mp[3 * q + 1] - mc.y, mp[3 * q + 2] - mc.z};
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e <= deg.moments_deg; ++e) pw[q][d][e] = std::pow(xyz[d], (double)e);
+    }
     auto avg_moment = [&](int a, int b, int c2) {
-      auto f = [&](int q) {
-        double x = mp[3 * q] - mc.x, y = mp[3 * q + 1] - mc.y, z = mp[3 * q + 2] - mc.z;
-        return std::pow(x, (double)a) * std::pow(y, (double)b) * std::pow(z, (double)c2);
-      };
+      auto f = [&](int q) { return pw[q][0][a] * pw[q][1][b] * pw[q][2][c2]; };
       double ret = mw[0] * f(0);
       for (int q = 1; q < mom_rule.n_points; ++q) ret = ret + mw[q] * f(q);
       ret = 1.0 * ret;
