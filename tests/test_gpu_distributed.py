@@ -256,6 +256,28 @@ def _worker_host_step(rank, world, port, partition):
             assert np.isfinite(h2).all() and np.abs(h2).max() < 1e200, method   # halo rows of the result: exchanged values
             assert np.array_equal(rk.download().cvars[:no], a2[:no]), method     # the resident state is the step's result
             assert l2 - l1 > l1 - l0, (method, l0, l1, l2)                       # the chunked route really ran
+        # RateOfChange::compute with host buffers takes the same chunked route: against the residual on device buffers
+        # (overwrite and accumulate contracts; the halo rows of the caller's state come back filled, flux_loop.hpp:100)
+        roc = z.CudaEulerRateOfChange(ctx)
+        base = np.random.default_rng(1).normal(size=(n, 5))
+        dev = torch.device("cuda", rank)
+        for accumulate in (False, True):
+            s_dev = torch.from_numpy(u0).to(dev)
+            t_dev = torch.from_numpy(base).to(dev)
+            torch.cuda.synchronize()
+            roc.compute_device(t_dev.data_ptr(), s_dev.data_ptr(), 0.0, accumulate=accumulate)
+            ctx.synchronize()
+            t_ref, s_ref = t_dev.cpu().numpy(), s_dev.cpu().numpy()
+            for pinned in (True, False):
+                s_host = torch.from_numpy(u0.copy()).pin_memory().numpy() if pinned else u0.copy()
+                t_host = torch.from_numpy(base.copy()).pin_memory().numpy() if pinned else base.copy()
+                l3 = ctx.counters()["launches"]
+                roc.compute(z.AllVariables(n, t_host), z.AllVariables(n, s_host), 0.0, accumulate=accumulate)
+                l4 = ctx.counters()["launches"]
+                assert np.array_equal(t_host[:no], t_ref[:no]), (accumulate, pinned, np.abs(t_host[:no] - t_ref[:no]).max())
+                assert np.array_equal(s_host, s_ref), (accumulate, pinned)   # owned rows untouched, halo rows exchanged
+                assert np.abs(s_host).max() < 1e200
+                assert l4 > l3
         ctx.close()
         dist.barrier()
     finally:
@@ -264,9 +286,10 @@ def _worker_host_step(rank, world, port, partition):
 
 @pytest.mark.parametrize("partition", ["lattice", "sfc", "sfc_wb"])
 def test_two_gpu_host_step_matches_resident_step(partition):
-    """zfvm_rk_step_host of a multi-rank context takes the chunked, copy-overlapped route too: bit-identical owned rows to
-    upload + zfvm_rk_step + download for three-, one- and four-stage tableaux (lattice boxes, ragged SFC chunks, the
-    well-balanced kernels per tile list), the same number of NCCL groups per step on every rank."""
+    """zfvm_rk_step_host and zfvm_rate_of_change of a multi-rank context take the chunked, copy-overlapped route too:
+    bit-identical owned rows to upload + zfvm_rk_step + download for three-, one- and four-stage tableaux (lattice boxes,
+    ragged SFC chunks, the well-balanced kernels per tile list) and to the residual on device buffers, the same number
+    of NCCL groups per call on every rank."""
     import torch
 
     if torch.cuda.device_count() < 2:

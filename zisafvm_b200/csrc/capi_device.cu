@@ -1413,6 +1413,14 @@ static void flux_and_update(zfvm_ctx *ctx, const double *state, UpdateArgs A, st
 static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const double *state_host, int accumulate) {
   zfvm_ctx::HostPipe &H = ctx->pipe;
   const int C = H.n_chunks;
+  // multi-rank contexts: as in rk_step_host_pipelined -- the chunks in front of the first one with halo rows gate interior
+  // tiles only, the exchange is posted once every row is up, chunks of halo rows are not computed
+  const bool multi = ctx->n_ranks > 1 && ctx->nccl_comm != nullptr;
+  const std::int64_t n_upd = (ctx->n_ranks > 1) ? ctx->n_owned : ctx->n_cells;
+  int c_halo = C;
+  if (multi)
+    for (int c = C - 1; c >= 0; --c)
+      if (H.cell_begin[(size_t)c + 1] > ctx->n_owned) c_halo = c;
   ZFVM_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int c = 0; c < C; ++c) {
     const std::int64_t r0 = H.cell_begin[(size_t)c] * NVARS, r1 = H.cell_begin[(size_t)c + 1] * NVARS;
@@ -1420,10 +1428,27 @@ static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const 
     ZFVM_CUDA(cudaEventRecord(H.ev_up[(size_t)c], ctx->copy_stream));
     ZFVM_CUDA(cudaStreamWaitEvent(ctx->stream, H.ev_up[(size_t)c], 0));
     const std::int64_t nt = H.up_off[(size_t)c + 1] - H.up_off[(size_t)c];
-    if (nt > 0) {
+    if (nt > 0 && c < c_halo) {
       if (run_recon(ctx, ctx->state_work, H.up_tiles + H.up_off[(size_t)c], nt))
         return fail("no reconstruction kernel is compiled for this scheme");
       ctx->launches += recon_group_launches(ctx);
+    }
+  }
+  if (multi) {
+    if (zfvm_halo_post_internal(ctx, ctx->state_work, nullptr) || zfvm_halo_wait_internal(ctx)) return 1;
+    const std::int64_t nt = H.up_off[(size_t)C] - H.up_off[(size_t)c_halo];
+    if (nt > 0) {
+      if (run_recon(ctx, ctx->state_work, H.up_tiles + H.up_off[(size_t)c_halo], nt))
+        return fail("no reconstruction kernel is compiled for this scheme");
+      ctx->launches += recon_group_launches(ctx);
+    }
+    // FluxLoop fills the halo rows of the caller's state (flux_loop.hpp:100, const_cast): they go back behind the exchange
+    ZFVM_CUDA(cudaEventRecord(H.ev_up[0], ctx->stream));
+    ZFVM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, H.ev_up[0], 0));
+    for (auto &p : ctx->peers) {
+      const size_t off = (size_t)(p.recv_begin * NVARS), cnt = (size_t)((p.recv_end - p.recv_begin) * NVARS);
+      if (copy_d2h(ctx, const_cast<double *>(state_host) + off, ctx->state_work + off, cnt * sizeof(double), ctx->copy_stream, false))
+        return 1;
     }
   }
   if (accumulate) {  // the caller's tendency rows: behind the state on the copy stream, needed by the update kernel only
@@ -1435,10 +1460,12 @@ static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const 
   A.tendency = ctx->tend_work;
   A.accumulate = accumulate;
   for (int c = 0; c < C; ++c) {
-    UpdateArgs Ac = A;
-    Ac.block_begin = H.cell_begin[(size_t)c] / 64;
-    Ac.n_cells_update = H.cell_begin[(size_t)c + 1];
-    flux_and_update(ctx, ctx->state_work, Ac, H.face_begin[(size_t)c], H.face_begin[(size_t)c + 1]);
+    if (H.cell_begin[(size_t)c] < n_upd) {  // (a chunk of halo rows only travels)
+      UpdateArgs Ac = A;
+      Ac.block_begin = H.cell_begin[(size_t)c] / 64;
+      Ac.n_cells_update = std::min(H.cell_begin[(size_t)c + 1], n_upd);
+      flux_and_update(ctx, ctx->state_work, Ac, H.face_begin[(size_t)c], H.face_begin[(size_t)c + 1]);
+    }
     ZFVM_CUDA(cudaEventRecord(H.ev_dn[(size_t)c], ctx->stream));
   }
   for (int c = 0; c < C; ++c) {
@@ -1452,13 +1479,13 @@ static int rate_of_change_pipelined(zfvm_ctx *ctx, double *tendency_host, const 
   return 0;
 }
 
-static bool host_pipeline_enabled(const zfvm_ctx *ctx, bool allow_multi_rank = false) {
+static bool host_pipeline_enabled(const zfvm_ctx *ctx) {
   static const bool off = [] {
     const char *e = std::getenv("ZFVM_HOST_PIPELINE");
     return e != nullptr && e[0] == '0';
   }();
-  // (multi-rank contexts: the chunked time step posts its own halo exchanges; the chunked RateOfChange::compute does not)
-  return ctx->pipe.n_chunks > 0 && (ctx->n_ranks == 1 || allow_multi_rank) && !off;
+  // (multi-rank contexts: the chunked routes post the same halo exchanges as the plain sequences)
+  return ctx->pipe.n_chunks > 0 && !off;
 }
 
 int zfvm_rate_of_change(zfvm_ctx *ctx, double *tendency_host, const double *state_host, double t, int accumulate) {
@@ -1853,7 +1880,7 @@ static int rk_step_host_pipelined(zfvm_ctx *ctx, const double *u0_host, double *
 
 int zfvm_rk_step_host(zfvm_ctx *ctx, const double *u0_host, double *u1_host, double /*t*/, double dt) {
   ZFVM_CUDA(cudaSetDevice(ctx->device));
-  if (host_pipeline_enabled(ctx, true) && ctx->n_stages >= 1) return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
+  if (host_pipeline_enabled(ctx) && ctx->n_stages >= 1) return rk_step_host_pipelined(ctx, u0_host, u1_host, dt);
   const size_t bytes = (size_t)(ctx->n_cells * NVARS) * sizeof(double);
   if (copy_h2d(ctx, ctx->u_cur, u0_host, bytes)) return 1;
   if (rk_step_impl(ctx, dt, false)) return 1;
