@@ -102,6 +102,7 @@ struct TileCfg {
   int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off)
   int l2_gran;               // bytes covered by one lane's prefetch (experiment: 128 = line, 32 = sector)
   int l2_whole;              // experiment: one bulk L2 prefetch of the whole next record at the start of a tile
+  int l2_bulk;               // experiment: the per-segment prefetch as one bulk instruction of lane 0
   int stream_bytes;          // bytes of a record's W | geometry stream (rec_bytes - off_wlo)
   int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
@@ -238,11 +239,17 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
     // range is about the segment that will be issued l2_ahead / SLOT_BYTES positions later, within this record)
     if (cfg.l2_ahead > 0) {
       iss_left -= bytes;
-      const int gran = cfg.l2_gran;  // bytes one prefetch instruction of one lane is assumed to cover (128 or 32)
+      if (cfg.l2_bulk) {  // experiment (ZFVM_TILE_L2_BULK=1): one bulk prefetch by lane 0 instead of a line per lane
+        const int room = iss_left - cfg.l2_ahead;
+        const int nb = room < bytes ? room : bytes;
+        ptx::bulk_prefetch_l2_if(live && lane == 0 && nb > 0, iss_ptr + bytes + cfg.l2_ahead, (std::uint32_t)(nb > 0 ? nb : 16));
+      } else {
+        const int gran = cfg.l2_gran;  // bytes one prefetch instruction of one lane is assumed to cover (128 or 32)
 #pragma unroll 1
-      for (int j = 0; j * 32 * gran < bytes; ++j) {
-        const int rel = (j * 32 + lane) * gran;
-        if (live && rel < bytes && cfg.l2_ahead + rel < iss_left) ptx::prefetch_l2(iss_ptr + bytes + cfg.l2_ahead + rel);
+        for (int j = 0; j * 32 * gran < bytes; ++j) {
+          const int rel = (j * 32 + lane) * gran;
+          if (live && rel < bytes && cfg.l2_ahead + rel < iss_left) ptx::prefetch_l2(iss_ptr + bytes + cfg.l2_ahead + rel);
+        }
       }
     }
     const bool last = (iss_s == N_SEG - 1);
@@ -824,6 +831,7 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   c.l2_ahead = T::SLOT_BYTES;  // measured at the bench size: K1 -1 .. -4 %; 2, 4, 8 slots ahead: none or worse
   c.l2_gran = 128;
   c.l2_whole = 0;
+  c.l2_bulk = 0;
   c.stream_bytes = (int)(L.rec_bytes - L.off_wlo);
   return true;
 }
