@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 3)
       double beta = 0.0;
 #pragma unroll
       for (int c = 0; c < CLO; ++c) beta += a[c][v] * a[c][v];
-      is_max = (v == 0) ? beta : fmax(is_max, beta);
+      is_max = (v == 0) ? beta : ref_max(is_max, beta);
     }
     const double g_k = sc.lin_w[k];
     const double a_k = nonlinear_weight(is_max, single ? 1.0 : g_k);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 3)
     }
   double is_max0 = is0[0];
 #pragma unroll
-  for (int v = 1; v < NVARS; ++v) is_max0 = fmax(is_max0, is0[v]);
+  for (int v = 1; v < NVARS; ++v) is_max0 = ref_max(is_max0, is0[v]);
   const double alpha0 = nonlinear_weight(is_max0, single ? 1.0 : sc.lin_w[0]);
   al_sum += alpha0;
   double alpha_h = alpha0;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 3)
         keep[c][v] = inv_gh * (raw - fma(sc.lin_w[0], lo0[c][v], corr[c][v]));
         beta += keep[c][v] * keep[c][v];
       }
-      is_max = (v == 0) ? beta : fmax(is_max, beta);
+      is_max = (v == 0) ? beta : ref_max(is_max, beta);
     }
     alpha_h = nonlinear_weight(is_max, gh);
     al_sum += alpha_h;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) recon_generic_kernel(const __grid_constan
     for (int v = 0; v < NVARS; ++v) {
       double beta = 0.0;
       for (int c = 0; c < nck; ++c) beta += pk[k][c][v] * pk[k][c][v];
-      is_max = (v == 0) ? beta : fmax(is_max, beta);
+      is_max = (v == 0) ? beta : ref_max(is_max, beta);
     }
     double is_pow;
     if (sc.exponent == 4.0) {

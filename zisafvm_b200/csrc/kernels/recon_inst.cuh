@@ -38,9 +38,7 @@ int launch_tile(const ReconArgs &args, const SchemeConst &sc, std::int64_t n_til
   cfg.prof = tile_prof_buffer();
   if (const char *e = std::getenv("ZFVM_TILE_EVICT")) cfg.evict_normal = (e[0] == 'n') ? 1 : 0;
   if (const char *e = std::getenv("ZFVM_TILE_L2_AHEAD")) cfg.l2_ahead = std::max(0, std::atoi(e));
-  if (const char *e = std::getenv("ZFVM_TILE_L2_GRAN")) cfg.l2_gran = (std::atoi(e) == 32) ? 32 : 128;
   if (const char *e = std::getenv("ZFVM_TILE_L2_WHOLE")) cfg.l2_whole = (e[0] == '1') ? 1 : 0;
-  if (const char *e = std::getenv("ZFVM_TILE_L2_BULK")) cfg.l2_bulk = (e[0] == '1') ? 1 : 0;
   const int smem_bytes = cfg.warp_bytes * wpc;
   const char *e_ctas = std::getenv("ZFVM_STREAM_MAX_CTAS");
   const int max_ctas = e_ctas ? std::max(1, std::atoi(e_ctas)) : (1 << 30);

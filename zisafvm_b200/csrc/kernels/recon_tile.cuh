@@ -58,6 +58,15 @@ __host__ __device__ constexpr int tile_max_warps(int /*nd*/, int /*deg_hi*/) { r
 #ifndef ZFVM_Q_STAGE
 #define ZFVM_Q_STAGE 1
 #endif
+// Per-segment bookkeeping (profiles/README.md, round 2, "per-segment bookkeeping of K1"): measured at 9.86 M tets, K1 ms
+// on one box -- prefetch as a rolled loop of one line per lane 5.48, one bulk prefetch by lane 0 5.20 (adopted); on a
+// second box bulk 5.30, bulk + unpredicated copies of full slots 5.32 (more spills), a line per lane unrolled 5.28.
+#ifndef ZFVM_COPY_FAST
+#define ZFVM_COPY_FAST 0   // 1: full ring slots (all but a record's last segment) are copied without per-piece predicates
+#endif
+#ifndef ZFVM_L2_MODE
+#define ZFVM_L2_MODE 1     // prefetch behind the ring: 1 = one cp.async.bulk.prefetch.L2 by lane 0, 2 = a line per lane, unrolled
+#endif
 constexpr int TILE_SLOT_TARGET = ZFVM_SLOT_TARGET;  // bytes of a ring slot aimed at (two central rows of the 3D order-3 scheme)
 
 template <int ND, int DEG_HI, int DEG_LO, int NS, int RM0, int RLO, int QF>
@@ -100,9 +109,7 @@ struct TileCfg {
   int s_list, s_lidx, s_table, s_ring, s_stage, warp_bytes;
   int evict_normal;          // L2 policy of the record copies: 0 evict-first (default), 1 evict-normal
   int l2_ahead;              // L2 prefetch distance behind the ring in bytes (0: off)
-  int l2_gran;               // bytes covered by one lane's prefetch (experiment: 128 = line, 32 = sector)
   int l2_whole;              // experiment: one bulk L2 prefetch of the whole next record at the start of a tile
-  int l2_bulk;               // experiment: the per-segment prefetch as one bulk instruction of lane 0
   int stream_bytes;          // bytes of a record's W | geometry stream (rec_bytes - off_wlo)
   int seg_bytes[64];         // bytes of segment s of a record's W | geometry stream
   unsigned long long *prof;  // optional phase timers of warp 0 (clock cycles): see TilePhase; null = off
@@ -207,6 +214,13 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
   // load_table; the list part and the index rows of the next tile ride in the group of whatever is committed next.
   auto copy_range = [&](unsigned char *dst, const char *src, int bytes, auto max_bytes_tag) {
     constexpr int MAXB = decltype(max_bytes_tag)::value;
+#if ZFVM_COPY_FAST
+    if (bytes == MAXB && MAXB % 512 == 0) {  // warp-uniform: a full slot (every segment but a record's last one)
+#pragma unroll
+      for (int j = 0; j < MAXB / 512; ++j) ptx::cp_async16(dst + j * 512 + lane * 16, src + j * 512 + lane * 16, pol);
+      return;
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < (MAXB + 511) / 512; ++j)
       ptx::cp_async16_if(j * 512 + lane * 16 < bytes, dst + j * 512 + lane * 16, src + j * 512 + lane * 16, pol);
@@ -239,18 +253,17 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
     // range is about the segment that will be issued l2_ahead / SLOT_BYTES positions later, within this record)
     if (cfg.l2_ahead > 0) {
       iss_left -= bytes;
-      if (cfg.l2_bulk) {  // experiment (ZFVM_TILE_L2_BULK=1): one bulk prefetch by lane 0 instead of a line per lane
-        const int room = iss_left - cfg.l2_ahead;
-        const int nb = room < bytes ? room : bytes;
-        ptx::bulk_prefetch_l2_if(live && lane == 0 && nb > 0, iss_ptr + bytes + cfg.l2_ahead, (std::uint32_t)(nb > 0 ? nb : 16));
-      } else {
-        const int gran = cfg.l2_gran;  // bytes one prefetch instruction of one lane is assumed to cover (128 or 32)
-#pragma unroll 1
-        for (int j = 0; j * 32 * gran < bytes; ++j) {
-          const int rel = (j * 32 + lane) * gran;
-          if (live && rel < bytes && cfg.l2_ahead + rel < iss_left) ptx::prefetch_l2(iss_ptr + bytes + cfg.l2_ahead + rel);
-        }
+      const int room = iss_left - cfg.l2_ahead;       // what is left of this record's stream behind the prefetch distance
+      const int nb = room < bytes ? room : bytes;     // (<= 0: nothing; the next record is reached by the ring itself)
+#if ZFVM_L2_MODE == 1
+      ptx::bulk_prefetch_l2_if(live && lane == 0 && nb > 0, iss_ptr + bytes + cfg.l2_ahead, (std::uint32_t)(nb > 0 ? nb : 16));
+#else
+#pragma unroll
+      for (int j = 0; j < (T::SLOT_BYTES + 4095) / 4096; ++j) {  // a 128-byte line per lane
+        const int rel = (j * 32 + lane) * 128;
+        if (live && rel < nb) ptx::prefetch_l2(iss_ptr + bytes + cfg.l2_ahead + rel);
       }
+#endif
     }
     const bool last = (iss_s == N_SEG - 1);
     if (last) iss_left = cfg.stream_bytes;
@@ -473,7 +486,7 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
           double beta = 0.0;
 #pragma unroll
           for (int c = 0; c < CLO; ++c) beta += acc[c][v] * acc[c][v];
-          is_max = (v == 0) ? beta : fmax(is_max, beta);
+          is_max = (v == 0) ? beta : ref_max(is_max, beta);
         }
         const double g_k = sc.lin_w[k];
         const double a_k = nonlinear_weight(is_max, single ? 1.0 : g_k);
@@ -595,7 +608,7 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
           for (int c = 0; c < CLO; ++c) beta += lo0[c][v] * lo0[c][v];
 #pragma unroll
           for (int c = 0; c < NHI; ++c) beta += hi[c][v] * hi[c][v];
-          is_max = (v == 0) ? beta : fmax(is_max, beta);
+          is_max = (v == 0) ? beta : ref_max(is_max, beta);
         }
         alpha0 = nonlinear_weight(is_max, single ? 1.0 : sc.lin_w[0]);
       }
@@ -616,7 +629,7 @@ __global__ void __launch_bounds__(tile_max_warps(ND, DEG_HI) * 32, 1)
               keep[c][v] = inv_gh * (keep[c][v] - fma(sc.lin_w[0], lo0[c][v], corr[c][v]));
               beta += keep[c][v] * keep[c][v];
             }
-            is_max = (v == 0) ? beta : fmax(is_max, beta);
+            is_max = (v == 0) ? beta : ref_max(is_max, beta);
           }
           alpha_h = nonlinear_weight(is_max, gh);
           al_sum += alpha_h;
@@ -829,9 +842,7 @@ bool tile_config(const DevicePlan &P, const SchemeConst &sc, int smem_per_warp, 
   c.prof = nullptr;
   c.evict_normal = 0;
   c.l2_ahead = T::SLOT_BYTES;  // measured at the bench size: K1 -1 .. -4 %; 2, 4, 8 slots ahead: none or worse
-  c.l2_gran = 128;
   c.l2_whole = 0;
-  c.l2_bulk = 0;
   c.stream_bytes = (int)(L.rec_bytes - L.off_wlo);
   return true;
 }
