@@ -244,8 +244,8 @@ void compute_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyPar
   const int L = S.local_off[(size_t)ns];
   S.l2g_stride = L;
   S.l2g_size.assign((size_t)n, 1);
-  S.l2g.assign((size_t)(n * L), INVALID);
-  S.local.assign((size_t)(n * L), 0);
+  parallel_assign(S.l2g, (size_t)(n * L), INVALID);
+  parallel_assign(S.local, (size_t)(n * L), 0);
   S.order.assign((size_t)(n * ns), 1);
   S.size.assign((size_t)(n * ns), 0);
   S.k_high.assign((size_t)n, 0);
@@ -368,8 +368,8 @@ bool extract_stencils(HostStencils &out, const HostStencils &src, i64 n_local, c
   out.local_off = src.local_off;
   out.l2g_stride = L;
   out.l2g_size.assign((size_t)n_local, 1);
-  out.l2g.assign((size_t)(n_local * L), INVALID);
-  out.local.assign((size_t)(n_local * L), 0);
+  parallel_assign(out.l2g, (size_t)(n_local * L), INVALID);
+  parallel_assign(out.local, (size_t)(n_local * L), 0);
   out.order.assign((size_t)(n_local * ns), 1);
   out.size.assign((size_t)(n_local * ns), 0);
   out.k_high.assign((size_t)n_local, 0);
@@ -440,8 +440,8 @@ bool import_stencils(HostStencils &S, const HostGrid &g, const StencilFamilyPara
   const int L = S.local_off[(size_t)ns];
   S.l2g_stride = L;
   S.l2g_size.assign((size_t)n, 1);
-  S.l2g.assign((size_t)(n * L), INVALID);
-  S.local.assign((size_t)(n * L), 0);
+  parallel_assign(S.l2g, (size_t)(n * L), INVALID);
+  parallel_assign(S.local, (size_t)(n * L), 0);
   S.order.assign((size_t)(n * ns), 1);
   S.size.assign((size_t)(n * ns), 0);
   S.k_high.assign((size_t)n, 0);

@@ -13,7 +13,10 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace zfvm {
@@ -152,6 +155,33 @@ struct StencilFamilyParams {
 
 /// All stencil families of a grid, fixed-stride storage. Mirrors StencilFamily / Stencil
 /// (stencil_family.cpp:15-45, stencil.cpp:42-104).
+/// std::vector whose resize() leaves trivially constructible elements uninitialised, and a fill that touches the pages from
+/// all threads: the [n_cells][l2g_stride] index tables are 1.6 GB each at 10 M tetrahedra, and value-initialising them
+/// from one thread was a quarter of the stencil bookkeeping time.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = NoInitAlloc<U>;
+  };
+  template <class U>
+  void construct(U *p) {
+    ::new ((void *)p) U;
+  }
+  template <class U, class... A>
+  void construct(U *p, A &&...a) {
+    ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+using BigVecI32 = std::vector<i32, NoInitAlloc<i32>>;
+inline void parallel_assign(BigVecI32 &v, size_t n, i32 value) {
+  v.clear();
+  v.resize(n);
+  i32 *p = v.data();
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) p[i] = value;
+}
+
 struct HostStencils {
   i64 n_cells = 0;
   int n_dims = 0;
@@ -161,10 +191,10 @@ struct HostStencils {
   std::vector<int> local_off;    // [n_stencils+1] prefix sums of max_size
   int l2g_stride = 0;            // = local_off[n_stencils]
   std::vector<i32> l2g_size;     // [n_cells]
-  std::vector<i32> l2g;          // [n_cells][l2g_stride]; l2g[i][0] == i
+  BigVecI32 l2g;                 // [n_cells][l2g_stride]; l2g[i][0] == i
   std::vector<i32> order;        // [n_cells][n_stencils] achieved order (1 for unused slots)
   std::vector<i32> size;         // [n_cells][n_stencils] cells actually used (0 for unused slots)
-  std::vector<i32> local;        // [n_cells][l2g_stride]; stencil k at local_off[k], `size` entries
+  BigVecI32 local;               // [n_cells][l2g_stride]; stencil k at local_off[k], `size` entries
   std::vector<i32> k_high;       // [n_cells]
   std::vector<i32> family_order; // [n_cells]
   std::vector<i32> n_family;     // [n_cells] number of stencils in the family (1 for o1 cells)
