@@ -37,8 +37,8 @@ void dev_release(zfvm_ctx *ctx, T *&ptr, std::int64_t count) {
   ptr = nullptr;
 }
 
-template <class T>
-int dev_upload(zfvm_ctx *ctx, const T **ptr, const std::vector<T> &host) {
+template <class T, class A>
+int dev_upload(zfvm_ctx *ctx, const T **ptr, const std::vector<T, A> &host) {
   T *p = nullptr;
   if (dev_alloc(ctx, &p, (std::int64_t)host.size())) return 1;
   if (!host.empty()) ZFVM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -1057,11 +1057,17 @@ struct ContextBuilder {
     D = poly_dof(ctx->deg_hi, nd);
     P.n_mom = std::max(D - 3, 0);
     {
-      std::vector<double> vtx((size_t)(T * F * 3 * TILE), 0.0), center((size_t)(T * 3 * TILE), 0.0),
-          inv_len((size_t)(T * TILE), 1.0), volume((size_t)(T * TILE), 1.0),
-          mom((size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
-      std::vector<std::uint32_t> fref((size_t)(T * F * TILE), 0u);
-      std::vector<std::uint8_t> fslots((size_t)(T * F * TILE), 0);
+      // (filled from all threads: 2 GB of tables at 10 M tetrahedra; the padding lanes of the last tile keep the defaults)
+      BigVec<double> vtx, center, inv_len, volume, mom;
+      BigVec<std::uint32_t> fref;
+      BigVec<std::uint8_t> fslots;
+      parallel_assign(vtx, (size_t)(T * F * 3 * TILE), 0.0);
+      parallel_assign(center, (size_t)(T * 3 * TILE), 0.0);
+      parallel_assign(inv_len, (size_t)(T * TILE), 1.0);
+      parallel_assign(volume, (size_t)(T * TILE), 1.0);
+      parallel_assign(mom, (size_t)(T * std::max(P.n_mom, 1) * TILE), 0.0);
+      parallel_assign(fref, (size_t)(T * F * TILE), (std::uint32_t)0);
+      parallel_assign(fslots, (size_t)(T * F * TILE), (std::uint8_t)0);
   #pragma omp parallel for schedule(static)
       for (std::int64_t i = 0; i < n; ++i) {
         const std::int64_t t = i / TILE;
@@ -1119,8 +1125,10 @@ struct ContextBuilder {
   int faces_and_gravity() {
     // ---- faces ----------------------------------------------------------------------------------
     {
-      std::vector<std::int32_t> lr((size_t)(2 * E));
-      std::vector<double> frame((size_t)(10 * E));
+      BigVec<std::int32_t> lr;  // (every element is written by the loop below: no value-initialisation pass)
+      BigVec<double> frame;
+      lr.resize((size_t)(2 * E));
+      frame.resize((size_t)(10 * E));
   #pragma omp parallel for schedule(static)
       for (std::int64_t e = 0; e < E; ++e) {
         std::int32_t iL = g.left_right[(size_t)(2 * e)], iR = g.left_right[(size_t)(2 * e + 1)];

@@ -265,7 +265,7 @@ void build_grid(HostGrid &g, int n_dims, std::vector<double> vertices, std::vect
   g.cell_centers.resize((size_t)(3 * n));
   g.cell_qp.resize((size_t)(n * g.q_c * 3));
   g.cell_qw.resize((size_t)(n * g.q_c));
-  g.moments.assign((size_t)(n * g.n_moments), 0.0);
+  parallel_assign(g.moments, (size_t)(n * g.n_moments), 0.0);
   g.cell_flags.assign((size_t)n, FLAG_INTERIOR);  // CellFlags() default: interior (cell_flags.hpp)
 
 #pragma omp parallel for schedule(static)

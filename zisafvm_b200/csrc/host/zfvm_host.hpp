@@ -66,6 +66,36 @@ struct QRDegrees {
 };
 
 /// Flattened grid. Mirrors zisa::Grid (grid_decl.hpp:34-107) as plain arrays.
+/// std::vector whose resize() leaves trivially constructible elements uninitialised, and a fill that touches the pages from
+/// all threads: the per-cell / per-face tables are 0.1-1.6 GB each at 10 M tetrahedra (every element is written by the
+/// parallel loop that follows the resize), and value-initialising them from one thread does not scale with the cores.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = NoInitAlloc<U>;
+  };
+  template <class U>
+  void construct(U *p) {
+    ::new ((void *)p) U;
+  }
+  template <class U, class... A>
+  void construct(U *p, A &&...a) {
+    ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T>
+using BigVec = std::vector<T, NoInitAlloc<T>>;
+using BigVecI32 = BigVec<i32>;
+template <class T>
+inline void parallel_assign(BigVec<T> &v, size_t n, T value) {
+  v.clear();
+  v.resize(n);
+  T *p = v.data();
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) p[i] = value;
+}
+
 struct HostGrid {
   int n_dims = 0;
   int max_neighbours = 0;  // faces (= vertices) per cell: 3 or 4
@@ -78,24 +108,24 @@ struct HostGrid {
   std::vector<i32> edge_indices;      // [n_cells][F]
   std::vector<i32> left_right;        // [n_edges][2], right = INVALID on the boundary
 
-  std::vector<double> volumes, inradii, circum_radii, characteristic_length;  // [n_cells]
-  std::vector<double> cell_centers;   // [n_cells][3] quadrature barycentre (cell.cpp:9-11)
+  BigVec<double> volumes, inradii, circum_radii, characteristic_length;  // [n_cells]
+  BigVec<double> cell_centers;   // [n_cells][3] quadrature barycentre (cell.cpp:9-11)
 
   RefRule cell_rule, face_rule;
   int q_c = 0, q_f = 0;
-  std::vector<double> cell_qp;        // [n_cells][q_c][3]
-  std::vector<double> cell_qw;        // [n_cells][q_c]     (physical weights)
-  std::vector<double> face_qp;        // [n_edges][q_f][3]
-  std::vector<double> face_qw;        // [n_edges][q_f]
-  std::vector<double> face_area;      // [n_edges]
-  std::vector<double> face_normal, face_t1, face_t2;  // [n_edges][3]
-  std::vector<double> face_centers;   // [n_edges][3]
+  BigVec<double> cell_qp;        // [n_cells][q_c][3]
+  BigVec<double> cell_qw;        // [n_cells][q_c]     (physical weights)
+  BigVec<double> face_qp;        // [n_edges][q_f][3]
+  BigVec<double> face_qw;        // [n_edges][q_f]
+  BigVec<double> face_area;      // [n_edges]
+  BigVec<double> face_normal, face_t1, face_t2;  // [n_edges][3]
+  BigVec<double> face_centers;   // [n_edges][3]
   /// For cell i, local face k: positions (within cell i's vertex list) of the face's
   /// vertices *in the order used by the left cell* (2 bits each, v0 | v1<<2 | v2<<4).
   std::vector<std::uint8_t> face_vertex_slots;  // [n_cells][F]
 
   int n_moments = 0;                  // poly_dof(moments_deg)
-  std::vector<double> moments;        // [n_cells][n_moments]
+  BigVec<double> moments;        // [n_cells][n_moments]
 
   std::vector<std::uint8_t> cell_flags;  // [n_cells]
 
@@ -155,33 +185,6 @@ struct StencilFamilyParams {
 
 /// All stencil families of a grid, fixed-stride storage. Mirrors StencilFamily / Stencil
 /// (stencil_family.cpp:15-45, stencil.cpp:42-104).
-/// std::vector whose resize() leaves trivially constructible elements uninitialised, and a fill that touches the pages from
-/// all threads: the [n_cells][l2g_stride] index tables are 1.6 GB each at 10 M tetrahedra, and value-initialising them
-/// from one thread was a quarter of the stencil bookkeeping time.
-template <class T>
-struct NoInitAlloc : std::allocator<T> {
-  template <class U>
-  struct rebind {
-    using other = NoInitAlloc<U>;
-  };
-  template <class U>
-  void construct(U *p) {
-    ::new ((void *)p) U;
-  }
-  template <class U, class... A>
-  void construct(U *p, A &&...a) {
-    ::new ((void *)p) U(std::forward<A>(a)...);
-  }
-};
-using BigVecI32 = std::vector<i32, NoInitAlloc<i32>>;
-inline void parallel_assign(BigVecI32 &v, size_t n, i32 value) {
-  v.clear();
-  v.resize(n);
-  i32 *p = v.data();
-#pragma omp parallel for schedule(static)
-  for (long long i = 0; i < (long long)n; ++i) p[i] = value;
-}
-
 struct HostStencils {
   i64 n_cells = 0;
   int n_dims = 0;
@@ -217,7 +220,8 @@ void compute_stencils(HostStencils &s, const HostGrid &g, const StencilFamilyPar
 /// redo[i] != 0: the host search decides the cell.
 struct DeviceStencilSearch {
   int L = 0;
-  std::vector<i32> members, count;
+  BigVecI32 members;             // [n_cells][L] (1.6 GB at 10 M tetrahedra: pages touched from all threads)
+  std::vector<i32> count;
   std::vector<std::uint8_t> redo;
 };
 /// false (with the reason) when there is no device or the family is outside the kernel's limits.

@@ -266,7 +266,7 @@ bool device_stencil_search(const HostGrid &g, const StencilFamilyParams &params,
     return false;
   lap("search kernel");
   out.L = p.L;
-  out.members.resize((size_t)(n * p.L));
+  parallel_assign(out.members, (size_t)(n * p.L), (i32)INVALID);
   out.count.resize((size_t)(n * ns));
   out.redo.resize((size_t)n);
   if (!check(cudaMemcpy(out.members.data(), members.p, out.members.size() * sizeof(int), cudaMemcpyDeviceToHost), "members") ||
