@@ -452,13 +452,16 @@ def run_b200(args):
     wb = case.params.well_balancing == "isentropic"
     k1_name = (recon_name if case.params.gravity.kind == "none" and case.params.heating is None
                else ("equilibrium kernels E1-E3 + " if wb else "") + recon_name + " + source_kernel")
+    traffic = measured_traffic(args, int(n), world)
     roofline = {
         # well-balanced runs: the equilibrium kernels (Newton solve per cell, rows x q_c equilibrium evaluations per cell)
         # are FP64-pipe bound (committed ncu captures: E1 73 %, E2 62.5 % pipe utilisation), so the HBM fraction below is
         # reported for comparison, not as the bound of the stage
         "bound": "fp64" if wb else "hbm", "kernel": k1_name + " (K1: stencil-weight apply + CWENO-AO + traces)",
         "achieved": ach_k1, "peak": peak, "unit": "GB/s", "frac": ach_k1 / peak,
-        "traffic": measured_traffic(args, int(n), world),
+        # DRAM bytes of one K1 launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), a number like `achieved`'s
+        # numerator; where it comes from: traffic_detail
+        "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_unit": "bytes per K1 launch", "traffic_detail": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_cell": {"K1": b_k1, "K2": b_k2, "K3": b_k3, "stage": alg_bytes},
         "kernel_ms": {"K1_recon": kms[0] / max(kcnt[0], 1), "K2_flux": kms[1] / max(kcnt[1], 1),
                       "K3_update": kms[2] / max(kcnt[2], 1),
