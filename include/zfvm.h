@@ -76,6 +76,15 @@ int zfvm_mesh_read_msh_h5(const char *path, int *n_dims, int64_t *n_vertices, do
                           int32_t **vertex_indices);
 int zfvm_mesh_write_msh_h5(const char *path, int n_dims, int64_t n_vertices, const double *vertices, int64_t n_cells,
                            const int32_t *vertex_indices);
+/* Sub-grid files subgrid-%04d.msh.h5 of the reference's partition tool (src/domain_decomposition.cpp:70-88: the datasets of
+ * a grid file plus `partition` and `global_cell_indices`, one int_t per local cell; read back by load_distributed_grid,
+ * src/zisa/parallelization/distributed_grid.cpp:10-17): a rank's cells in the reference's local numbering -- owned cells
+ * first, then the halo grouped per owner (make_halo, src/zisa/mpi/parallelization/mpi_halo_exchange.cpp:203-238) -- with
+ * the owner rank and the global index of every cell.  zfvm_set_halo takes exactly the ranges make_halo derives from them. */
+int zfvm_mesh_read_subgrid_h5(const char *path, int *n_dims, int64_t *n_vertices, double **vertices, int64_t *n_cells,
+                              int32_t **vertex_indices, int64_t **partition, int64_t **global_cell_indices);
+int zfvm_mesh_write_subgrid_h5(const char *path, int n_dims, int64_t n_vertices, const double *vertices, int64_t n_cells,
+                               const int32_t *vertex_indices, const int64_t *partition, const int64_t *global_cell_indices);
 void zfvm_free(void *p);
 
 /* ---- host precompute: stencils -------------------------------------------------------------------

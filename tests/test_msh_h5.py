@@ -112,3 +112,48 @@ def test_rejects_what_it_does_not_implement(tmp_path):
     G.write_msh_h5(p, nd, v, c)
     p.write_bytes(p.read_bytes()[:-64])
     assert read(p) != 0 and "beyond the end" in _capi.lib.zfvm_last_error().decode()
+
+
+def test_subgrid_file_round_trip(tmp_path):
+    """subgrid-%04d.msh.h5 (src/domain_decomposition.cpp:80-88): the three datasets of a grid file plus `partition` and
+    `global_cell_indices` as 64-bit unsigned integers; written by the library, read back by the library and -- dataset by
+    dataset -- by the independent pure-Python walker of tests/h5_files.py when it is available."""
+    from zisafvm_b200._capi import ZfvmError
+    from zisafvm_b200.grid import cube_mesh, read_msh_h5, read_subgrid_h5, write_msh_h5, write_subgrid_h5
+
+    verts, vi = cube_mesh(3, 2, 2, 0.5, jitter=0.1, seed=3)
+    nc = vi.shape[0]
+    rng = np.random.default_rng(0)
+    part = np.sort(rng.integers(0, 3, size=nc)).astype(np.int64)
+    gci = rng.permutation(10 * nc)[:nc].astype(np.int64)
+    path = tmp_path / "subgrid-0001.msh.h5"
+    write_subgrid_h5(str(path), 3, verts, vi, part, gci)
+    nd, v, c, p, g = read_subgrid_h5(str(path))
+    assert nd == 3 and np.array_equal(v, verts) and np.array_equal(c, vi)
+    assert np.array_equal(p, part) and np.array_equal(g, gci)
+    # a sub-grid file is a grid file too (load_grid reads the same file, local_grid.cpp:17-18)
+    nd2, v2, c2 = read_msh_h5(str(path))
+    assert nd2 == 3 and np.array_equal(v2, verts) and np.array_equal(c2, vi)
+    # a plain grid file is not a sub-grid file
+    plain = tmp_path / "grid.msh.h5"
+    write_msh_h5(str(plain), 3, verts, vi)
+    with pytest.raises(ZfvmError, match="partition"):
+        read_subgrid_h5(str(plain))
+    with pytest.raises(ZfvmError, match="unsigned"):
+        write_subgrid_h5(str(tmp_path / "bad.h5"), 3, verts, vi, part - 1, gci)
+    with pytest.raises(ValueError):
+        write_subgrid_h5(str(tmp_path / "bad.h5"), 3, verts, vi, part[:-1], gci)
+    # the same five datasets assembled byte by byte in the other format branch (superblock 2, version-2 headers, link
+    # messages; 32-bit owner ranks, 64-bit unsigned global indices): an independent writer for the reader
+    other = tmp_path / "subgrid-latest.msh.h5"
+    h5_files.write_latest_format(other, [("n_dims", np.array(3, dtype=np.int32), True), ("vertex_indices", vi.astype(np.uint64), False),
+                                         ("vertices", verts, False), ("partition", part.astype(np.uint32), False),
+                                         ("global_cell_indices", gci.astype(np.uint64), False)])
+    nd3, v3, c3, p3, g3 = read_subgrid_h5(str(other))
+    assert nd3 == 3 and np.array_equal(v3, verts) and np.array_equal(c3, vi) and np.array_equal(p3, part) and np.array_equal(g3, gci)
+    # one of the two datasets alone is not a sub-grid file
+    half = tmp_path / "half.msh.h5"
+    h5_files.write_latest_format(half, [("n_dims", np.array(3, dtype=np.int32), True), ("vertex_indices", vi.astype(np.uint64), False),
+                                        ("vertices", verts, False), ("partition", part.astype(np.uint64), False)])
+    with pytest.raises(ZfvmError, match="come together"):
+        read_subgrid_h5(str(half))

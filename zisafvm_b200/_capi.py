@@ -82,6 +82,10 @@ _SIGNATURES = {
     "zfvm_mesh_read_msh_h5": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), c_int64_p, C.POINTER(c_double_p), c_int64_p,
                                         C.POINTER(c_int32_p)]),
     "zfvm_mesh_write_msh_h5": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, c_double_p, C.c_int64, c_int32_p]),
+    "zfvm_mesh_read_subgrid_h5": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), c_int64_p, C.POINTER(c_double_p), c_int64_p,
+                                            C.POINTER(c_int32_p), C.POINTER(c_int64_p), C.POINTER(c_int64_p)]),
+    "zfvm_mesh_write_subgrid_h5": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, c_double_p, C.c_int64, c_int32_p, c_int64_p,
+                                             c_int64_p]),
     "zfvm_free": (None, [_vp]),
     "zfvm_stencils_compute": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.c_char_p, c_double_p, C.c_uint64, C.POINTER(_vp)]),
     "zfvm_stencils_get": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(C.c_int), c_int64_p]),

@@ -195,6 +195,58 @@ int zfvm_mesh_write_msh_h5(const char *path, int n_dims, int64_t n_vertices, con
   }
 }
 
+int zfvm_mesh_read_subgrid_h5(const char *path, int *n_dims, int64_t *n_vertices, double **vertices, int64_t *n_cells,
+                              int32_t **vertex_indices, int64_t **partition, int64_t **global_cell_indices) {
+  try {
+    RawMesh m;
+    read_msh_h5(path, m);
+    if (m.partition.empty())
+      return fail(std::string("zfvm_mesh_read_subgrid_h5: ") + path + " has no 'partition' / 'global_cell_indices' (a plain grid file?)");
+    *n_dims = m.n_dims;
+    const size_t nc = m.partition.size();
+    int64_t *pt = static_cast<int64_t *>(std::malloc(std::max<size_t>(nc, 1) * sizeof(int64_t)));
+    int64_t *gc = static_cast<int64_t *>(std::malloc(std::max<size_t>(nc, 1) * sizeof(int64_t)));
+    if (!pt || !gc) {
+      std::free(pt);
+      std::free(gc);
+      return fail("zfvm_mesh_read_subgrid_h5: out of memory");
+    }
+    std::memcpy(pt, m.partition.data(), nc * sizeof(int64_t));
+    std::memcpy(gc, m.global_cell_indices.data(), nc * sizeof(int64_t));
+    if (export_mesh(m, 0, n_vertices, vertices, n_cells, vertex_indices)) {
+      std::free(pt);
+      std::free(gc);
+      return 1;
+    }
+    *partition = pt;
+    *global_cell_indices = gc;
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_mesh_read_subgrid_h5: ") + e.what());
+  }
+}
+
+int zfvm_mesh_write_subgrid_h5(const char *path, int n_dims, int64_t n_vertices, const double *vertices, int64_t n_cells,
+                               const int32_t *vertex_indices, const int64_t *partition, const int64_t *global_cell_indices) {
+  try {
+    if (n_dims != 2 && n_dims != 3) return fail("zfvm_mesh_write_subgrid_h5: n_dims must be 2 or 3");
+    if (n_cells < 1) return fail("zfvm_mesh_write_subgrid_h5: an empty sub-grid");
+    for (int64_t i = 0; i < n_cells; ++i)
+      if (partition[i] < 0 || global_cell_indices[i] < 0)
+        return fail("zfvm_mesh_write_subgrid_h5: partition and global cell indices are unsigned in the reference (int_t)");
+    RawMesh m;
+    m.n_dims = n_dims;
+    m.vertices.assign(vertices, vertices + 3 * n_vertices);
+    m.vertex_indices.assign(vertex_indices, vertex_indices + (n_dims + 1) * n_cells);
+    m.partition.assign(partition, partition + n_cells);
+    m.global_cell_indices.assign(global_cell_indices, global_cell_indices + n_cells);
+    write_msh_h5(path, m);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(std::string("zfvm_mesh_write_subgrid_h5: ") + e.what());
+  }
+}
+
 void zfvm_free(void *p) { std::free(p); }
 
 int zfvm_stencils_compute(const zfvm_grid *grid, int n_stencils, const int *orders, const char *biases,

@@ -492,6 +492,22 @@ void read_msh_h5(const std::string &path, RawMesh &mesh) {
     if (idx[a] < 0 || idx[a] >= n_vertices) throw std::runtime_error(path + ": vertex index out of range");
     mesh.vertex_indices[a] = (i32)idx[a];
   }
+  // sub-grid files (subgrid-%04d.msh.h5, src/domain_decomposition.cpp:84-88) carry two more datasets of int_t per cell
+  Dataset pt, gc;
+  const bool has_pt = f.find("partition", pt), has_gc = f.find("global_cell_indices", gc);
+  mesh.partition.clear();
+  mesh.global_cell_indices.clear();
+  if (has_pt != has_gc) throw std::runtime_error(path + ": 'partition' and 'global_cell_indices' come together (sub-grid files)");
+  if (has_pt) {
+    const u64 n_cells = vi.dims[0];
+    if (pt.type_class != 0 || pt.rank != 1 || pt.dims[0] != n_cells || gc.type_class != 0 || gc.rank != 1 || gc.dims[0] != n_cells)
+      throw std::runtime_error(path + ": partition / global_cell_indices must be integer arrays [n_cells]");
+    mesh.partition = f.values<std::int64_t>(pt, "partition");
+    mesh.global_cell_indices = f.values<std::int64_t>(gc, "global_cell_indices");
+    for (size_t a = 0; a < mesh.partition.size(); ++a)
+      if (mesh.partition[a] < 0 || mesh.global_cell_indices[a] < 0)
+        throw std::runtime_error(path + ": negative partition / global cell index");
+  }
 }
 
 void write_msh_h5(const std::string &path, const RawMesh &mesh) {
@@ -499,11 +515,17 @@ void write_msh_h5(const std::string &path, const RawMesh &mesh) {
   const std::int32_t n_dims = mesh.n_dims;
   // the reference's int_t is std::size_t: 64-bit unsigned indices
   std::vector<u64> idx(mesh.vertex_indices.begin(), mesh.vertex_indices.end());
-  WDataset sets[3] = {
-      {"n_dims", 0, {0, 0}, 0, 4, true, &n_dims, 4},
-      {"vertex_indices", 2, {(u64)(idx.size() / (size_t)F), (u64)F}, 0, 8, false, idx.data(), idx.size() * 8},
-      {"vertices", 2, {(u64)(mesh.vertices.size() / 3), 3}, 1, 8, false, mesh.vertices.data(), mesh.vertices.size() * 8},
-  };  // already in strcmp order, as a symbol table node wants them
+  const bool sub = !mesh.partition.empty();
+  if (sub && (mesh.partition.size() != idx.size() / (size_t)F || mesh.global_cell_indices.size() != mesh.partition.size()))
+    throw std::runtime_error("write_msh_h5: partition / global_cell_indices must have one entry per cell");
+  std::vector<u64> part(mesh.partition.begin(), mesh.partition.end()), gci(mesh.global_cell_indices.begin(), mesh.global_cell_indices.end());
+  std::vector<WDataset> sets;  // in strcmp order, as a symbol table node wants them
+  if (sub) sets.push_back({"global_cell_indices", 1, {(u64)gci.size(), 0}, 0, 8, false, gci.data(), gci.size() * 8});
+  sets.push_back({"n_dims", 0, {0, 0}, 0, 4, true, &n_dims, 4});
+  if (sub) sets.push_back({"partition", 1, {(u64)part.size(), 0}, 0, 8, false, part.data(), part.size() * 8});
+  sets.push_back({"vertex_indices", 2, {(u64)(idx.size() / (size_t)F), (u64)F}, 0, 8, false, idx.data(), idx.size() * 8});
+  sets.push_back({"vertices", 2, {(u64)(mesh.vertices.size() / 3), 3}, 1, 8, false, mesh.vertices.data(), mesh.vertices.size() * 8});
+  const int NSETS = (int)sets.size();  // <= 2 K = 8 entries of one symbol table node
 
   Out o;
   // superblock, version 0 (96 bytes)
@@ -550,10 +572,10 @@ void write_msh_h5(const std::string &path, const RawMesh &mesh) {
   o.put(0, 8);
 
   // local heap: "" at offset 0, then the names, 8-byte aligned
-  u64 name_off[3];
+  u64 name_off[8];
   Out heap_data;
   heap_data.put(0, 8);
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < NSETS; ++k) {
     name_off[k] = heap_data.size();
     heap_data.bytes(sets[k].name.c_str(), sets[k].name.size() + 1);
     heap_data.pad8();
@@ -584,14 +606,14 @@ void write_msh_h5(const std::string &path, const RawMesh &mesh) {
   o.put(UNDEF, 8);
   o.put(0, 8);             // key 0: ""
   o.put(snod, 8);          // child 0
-  o.put(name_off[2], 8);   // key 1: the largest name in child 0
+  o.put(name_off[NSETS - 1], 8);   // key 1: the largest name in child 0
   while (o.size() < btree + btree_bytes) o.put(0, 1);
   o.bytes("SNOD", 4);
   o.put(1, 1);
   o.put(0, 1);
-  o.put(3, 2);
-  u64 at_entry_header[3];
-  for (int k = 0; k < 3; ++k) {
+  o.put((u64)NSETS, 2);
+  u64 at_entry_header[8];
+  for (int k = 0; k < NSETS; ++k) {
     o.put(name_off[k], 8);
     at_entry_header[k] = o.size();
     o.put(0, 8);
@@ -602,14 +624,14 @@ void write_msh_h5(const std::string &path, const RawMesh &mesh) {
   while (o.size() < snod + snod_bytes) o.put(0, 1);
 
   // dataset headers, then the raw data
-  u64 header[3], at_layout_addr[3];
-  for (int k = 0; k < 3; ++k) {
+  u64 header[8], at_layout_addr[8];
+  for (int k = 0; k < NSETS; ++k) {
     o.pad8();
     header[k] = o.size();
     dataset_header(o, sets[k], 0);
     at_layout_addr[k] = o.size() - 22;  // the layout message comes last: version, class, address, size, 6 bytes of padding
   }
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < NSETS; ++k) {
     o.pad8();
     const u64 addr = o.size();
     o.bytes(sets[k].data, (size_t)sets[k].bytes);

@@ -159,6 +159,9 @@ struct RawMesh {
   int n_dims = 0;
   std::vector<double> vertices;     // [nv][3]
   std::vector<i32> vertex_indices;  // [nc][n_dims+1]
+  // sub-grid files only (src/domain_decomposition.cpp:84-88, load_distributed_grid): owner rank and global index of every
+  // local cell; both empty for a plain grid file
+  std::vector<std::int64_t> partition, global_cell_indices;  // [nc]
 };
 /// [x0,x1]x[y0,y1], nx*ny squares split on alternating diagonals, interior vertices jittered.
 RawMesh make_square_mesh(int nx, int ny, double x0, double x1, double y0, double y1, double jitter,

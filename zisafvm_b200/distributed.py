@@ -8,6 +8,9 @@ Host-side mirror of the reference's distributed set-up:
 * ``extract_subdomain``       <->  ``extract_subgrid`` / ``extract_stencils`` / ``StencilBasedIndicator``
   (:300-326, :412-447): owned cells first, then the halo -- every cell a stencil of an owned cell or of a
   face-neighbour of an owned cell reads -- grouped contiguously per owner;
+* ``save_partitioned_grid`` / ``load_local_grid``  <->  the partition tool and its reader (src/domain_decomposition.cpp:36-113,
+  src/zisa/parallelization/local_grid.cpp:11-58): one ``subgrid-%04d.msh.h5`` per part, an oversized chunk with ``partition``
+  and ``global_cell_indices``;
 * ``HaloPlan`` / ``connect``  <->  ``make_mpi_halo_exchange`` (src/zisa/mpi/parallelization/
   mpi_halo_exchange.cpp:203-251): ranks tell each other which of their cells they need, by global index.
 
@@ -166,6 +169,72 @@ def extract_subdomain(n_dims: int, vertices: np.ndarray, vertex_indices: np.ndar
     need = [gidx[halo[b - n_owned: e - n_owned]].copy() for b, e in zip(recv_begin, recv_end)]
     plan = HaloPlan(peers, recv_begin, recv_end, need)
     return SubDomain(rank, n_ranks, grid, stencils, n_owned, gidx[sel].copy(), owner[sel].copy(), plan, sel)
+
+
+def subgrid_file(dirname: str, n_parts: int, rank: int) -> str:
+    """``<dirname>/partitioned/<n_parts>/subgrid-%04d.msh.h5`` (mpi_numerical_experiment.hpp:309-315)."""
+    import os
+
+    return os.path.join(dirname, "partitioned", str(int(n_parts)), "subgrid-%04d.msh.h5" % int(rank))
+
+
+def save_partitioned_grid(dirname: str, grid: Grid, owner: np.ndarray, n_parts: int, layers: int = 12) -> List[str]:
+    """The reference's partition tool (``save_partitioned_grid``, src/domain_decomposition.cpp:36-113): one sub-grid
+    file per part holding the part's cells followed by an *oversized* surrounding -- here every cell within ``layers``
+    face-neighbour layers of the part, grouped per owner -- with the owner (``partition``) and the global index
+    (``global_cell_indices``) of every cell.  The loading rank recomputes its stencils on that chunk and keeps what they
+    need (``load_local_grid``); the chunk must therefore contain the search region of the part's outermost stencils
+    (the reference oversizes with a large central stencil per owned cell, :466-505).  Returns the file names."""
+    import os
+
+    from .grid import write_subgrid_h5
+
+    owner = np.asarray(owner, dtype=np.int64)
+    nb = grid.array("neighbours")
+    verts, vi = grid.array("vertices"), grid.array("vertex_indices")
+    safe = np.maximum(nb, 0)
+    names = []
+    for p in range(int(n_parts)):
+        owned = owner == p
+        if not owned.any():
+            raise ValueError(f"save_partitioned_grid: part {p} owns no cell")
+        mask = owned.copy()
+        for _ in range(int(layers)):
+            grown = (mask[safe] & (nb >= 0)).any(axis=1)
+            if not (grown & ~mask).any():
+                break
+            mask |= grown
+        halo = np.nonzero(mask & ~owned)[0]
+        halo = halo[np.lexsort((halo, owner[halo]))]   # grouped per owner (make_halo reads runs of equal owners)
+        sel = np.concatenate([np.nonzero(owned)[0], halo])
+        used, inv = np.unique(vi[sel].reshape(-1), return_inverse=True)
+        name = subgrid_file(dirname, n_parts, p)
+        os.makedirs(os.path.dirname(name), exist_ok=True)
+        write_subgrid_h5(name, grid.n_dims, verts[used], inv.reshape(-1, grid.n_dims + 1), owner[sel], sel)
+        names.append(name)
+    return names
+
+
+def load_local_grid(path: str, rank: int, n_ranks: int, qr: QRDegrees, stencil_params, boundary_mask=None,
+                    seed: int = 0) -> SubDomain:
+    """``zisa::load_local_grid`` (src/zisa/parallelization/local_grid.cpp:11-58): read rank ``rank``'s oversized chunk,
+    mask everything it does not own (and the physical boundary cells ``boundary_mask`` marks) as ghost, compute the
+    stencil families on the chunk, keep the cells they need (``StencilBasedIndicator``), and extract grid, stencils and
+    the distributed-grid arrays for them.  ``boundary_mask``: boolean array over the chunk's cells, or a callable
+    ``(vertices, vertex_indices, global_cell_indices) -> mask``."""
+    from .grid import read_subgrid_h5
+
+    nd, verts, vi, part, gci = read_subgrid_h5(path)
+    n_mine = int((part == rank).sum())
+    if n_mine == 0 or not np.all(part[:n_mine] == rank):
+        raise ValueError(f"{path}: the cells of part {rank} must come first (is this rank {rank}'s file?)")
+    if int(part.max()) >= n_ranks:
+        raise ValueError(f"{path}: written for more than {n_ranks} parts")
+    phys = None
+    if boundary_mask is not None:
+        phys = boundary_mask(verts, vi, gci) if callable(boundary_mask) else np.asarray(boundary_mask, dtype=bool)
+    return extract_subdomain(nd, verts, vi, part.astype(np.int32), gci, rank, n_ranks, qr, stencil_params,
+                             physical_ghost=phys, seed=seed)
 
 
 def complete_halo_plan(sub: SubDomain, requests: Sequence[dict]) -> None:

@@ -128,6 +128,38 @@ def write_msh_h5(path: str, n_dims: int, vertices: np.ndarray, vertex_indices: n
                                      c.ctypes.data_as(_capi.c_int32_p)))
 
 
+def read_subgrid_h5(path: str):
+    """A sub-grid file ``subgrid-%04d.msh.h5`` of the reference's partition tool (src/domain_decomposition.cpp:70-88;
+    ``load_grid`` + ``load_distributed_grid``, src/zisa/parallelization/distributed_grid.cpp:10-17): ``(n_dims, vertices,
+    vertex_indices, partition, global_cell_indices)`` -- owner rank and global index of every local cell."""
+    nd, nv, nc = C.c_int(), C.c_int64(), C.c_int64()
+    verts, vi = _capi.c_double_p(), _capi.c_int32_p()
+    part, gci = _capi.c_int64_p(), _capi.c_int64_p()
+    check(lib.zfvm_mesh_read_subgrid_h5(str(path).encode(), C.byref(nd), C.byref(nv), C.byref(verts), C.byref(nc),
+                                        C.byref(vi), C.byref(part), C.byref(gci)))
+    p = np.ctypeslib.as_array(part, shape=(nc.value,)).copy()
+    g = np.ctypeslib.as_array(gci, shape=(nc.value,)).copy()
+    lib.zfvm_free(C.cast(part, C.c_void_p))
+    lib.zfvm_free(C.cast(gci, C.c_void_p))
+    v, c = _take_mesh(nv, verts, nc, vi, nd.value)
+    return nd.value, v, c, p, g
+
+
+def write_subgrid_h5(path: str, n_dims: int, vertices: np.ndarray, vertex_indices: np.ndarray, partition: np.ndarray,
+                     global_cell_indices: np.ndarray) -> None:
+    """Writes what src/domain_decomposition.cpp:80-88 writes: a grid file plus ``partition`` and ``global_cell_indices``
+    (64-bit unsigned, the reference's ``int_t``)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    c = np.ascontiguousarray(vertex_indices, dtype=np.int32)
+    p = np.ascontiguousarray(partition, dtype=np.int64)
+    g = np.ascontiguousarray(global_cell_indices, dtype=np.int64)
+    if p.shape != (c.shape[0],) or g.shape != (c.shape[0],):
+        raise ValueError("write_subgrid_h5: partition / global_cell_indices need one entry per cell")
+    check(lib.zfvm_mesh_write_subgrid_h5(str(path).encode(), int(n_dims), v.shape[0], _capi.ptr_f64(v), c.shape[0],
+                                         c.ctypes.data_as(_capi.c_int32_p), p.ctypes.data_as(_capi.c_int64_p),
+                                         g.ctypes.data_as(_capi.c_int64_p)))
+
+
 @dataclass
 class StencilFamilyParams:
     """``zisa::StencilFamilyParams{orders, biases, overfit_factors}``."""
