@@ -76,10 +76,10 @@ def _worker(rank, world, port, kind, out_dir, partitioner="sfc"):
     try:
         case, verts, vi, ghost = _global_case(kind)
         n = vi.shape[0]
-        if partitioner == "sfc_files":
+        if partitioner.endswith("_files"):
             # the reference's route: the partition tool writes one oversized sub-grid file per part, every rank loads
             # its own (src/domain_decomposition.cpp:36-113, local_grid.cpp:11-58)
-            part = zd.partition_by_sfc(n, world)
+            part = _partition(zd, case, partitioner[: -len("_files")], world)
             if rank == 0:
                 zd.save_partitioned_grid(out_dir, case.grid, part, world)
             dist.barrier()
@@ -124,7 +124,7 @@ def _worker(rank, world, port, kind, out_dir, partitioner="sfc"):
 
 @pytest.mark.parametrize("kind,partitioner", [("vortex2d", "sfc"), ("blast3d", "sfc"), ("vortex2d", "metis"),
                                               ("blast3d", "metis_faces"), ("vortex2d", "sfc_files"),
-                                              ("blast3d", "sfc_files")])
+                                              ("blast3d", "sfc_files"), ("vortex2d", "metis_files")])
 def test_two_ranks_reproduce_the_single_domain_run(kind, partitioner, tmp_path):
     import torch.multiprocessing as mp
 
